@@ -1,0 +1,187 @@
+"""Pin the CPU oracle (oracle/) against outputs of the reference itself.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py, which
+runs the unmodified reference classes on seeded inputs with injected noise.
+fp32 comparisons: the oracle restates the same fp32 torch ops, so samples agree
+to ~1e-6; the loss oracle replaces autograd double-backward by explicit jets, so
+losses/grads agree to fp32 round-off of a different summation order (1e-4 rel).
+"""
+import pytest
+import torch
+
+import oracle
+from oracle import losses as ol, nets as on, sampler as osamp, scatterometry as oscat, vp
+from oracle.weights import make_params
+from util import check_grads, load_golden, meta_hidden, surrogate_params
+
+
+@pytest.mark.parametrize("name", ["mlp_cde_linear", "mlp_cdiffe_scat", "mlp_synth", "mlp_small"])
+def test_mlp_forward(name):
+    fx = load_golden(name)
+    seed, xdim, ydim, out_dim = (int(v) for v in fx["meta"][:4])
+    params = make_params(seed, xdim + ydim + 1, out_dim, meta_hidden(fx, 4))
+    out = on.mlp(params, fx["x"], fx["y"], fx["t"])
+    assert torch.allclose(out, fx["out"], rtol=1e-5, atol=2e-6)
+    # single-tanh network must NOT match (double-tanh quirk)
+    W, b = params[0]
+    h = torch.tanh(torch.cat([fx["x"], fx["y"], fx["t"]], 1) @ W.T + b)
+    for W, b in params[1:-1]:
+        h = torch.tanh(h @ W.T + b)
+    single = h @ params[-1][0].T + params[-1][1]
+    assert (single - fx["out"]).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("name", ["sampler_cde_linear", "sampler_cde_linear_meanstd", "sampler_cde_scat",
+                                  "sampler_cde_synth", "sampler_cde_small"])
+def test_sampler_cde(name):
+    fx = load_golden(name)
+    seed, xdim, ydim, N, S = (int(v) for v in fx["meta"][:5])
+    params = make_params(seed, xdim + ydim + 1, xdim, meta_hidden(fx, 5))
+    mean, std = fx["mean_std"].tolist()
+    out = osamp.em_sampler_cde(params, fx["y"], fx["x0"] * std + mean, fx["noise"], S)
+    assert out.shape == (N, xdim)
+    assert (out - fx["out"]).abs().max() <= 1e-6 * fx["out"].abs().max() + 1e-6
+
+
+@pytest.mark.parametrize("name", ["sampler_cdiffe_linear", "sampler_cdiffe_scat"])
+def test_sampler_cdiffe(name):
+    fx = load_golden(name)
+    seed, xdim, ydim, N, S = (int(v) for v in fx["meta"][:5])
+    params = make_params(seed, xdim + ydim + 1, xdim + ydim, meta_hidden(fx, 5))
+    out = osamp.em_sampler_cdiffe(params, fx["y"], fx["x0"], fx["ynoise"], fx["noise"], S)
+    assert (out - fx["out"]).abs().max() <= 1e-6 * fx["out"].abs().max() + 1e-6
+
+
+def test_sampler_dps():
+    fx = load_golden("sampler_dps_scat")
+    seed, xdim, ydim, N, S = (int(v) for v in fx["meta"][:5])
+    hid = meta_hidden(fx, 5)
+    pp = make_params(seed, xdim + 1, xdim, hid)
+    lp = make_params(seed + 100, xdim + ydim + 1, xdim, hid)
+    out = osamp.em_sampler_dps(pp, lp, fx["y"], fx["x0"], fx["noise"], S)
+    assert (out - fx["out"]).abs().max() <= 2e-6 * fx["out"].abs().max() + 1e-6
+
+
+def _leaf(params):
+    return [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in params]
+
+
+LOSS_CASES = {
+    # name: (model, kind, kwargs, gain)
+    "loss_dsm_cde_linear": ("CDE", "DSM", {}, 1.0),
+    "loss_dsm_cdiffe_linear": ("CDiffE", "DSM", {}, 1.0),
+    "loss_dsm_cde_scat": ("CDE", "DSM", {}, 1.0),
+    "loss_dsm_small": ("CDE", "DSM", {}, 1.0),
+    "loss_pinn_cde_linear": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_cde_linear_g3": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 3.0),
+    "loss_pinn_cde_linear_l2l1": ("CDE", "PINN", dict(lam=0.5, lam2=0.7, pde_loss="FPE", ic_metric="L1", pde_metric="L2"), 1.0),
+    "loss_pinn_cde_linear_cfpe": ("CDE", "PINN", dict(lam=0.01, lam2=0.1, pde_loss="cScoreFPE", ic_metric="L2", pde_metric="L2"), 1.0),
+    "loss_pinn_cde_scat": ("CDE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_cdiffe_linear": ("CDiffE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_small": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_dsmpde_cde_linear": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="FPE", pde_metric="L1"), 1.0),
+    "loss_dsmpde_cde_linear_cfpe": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="cScoreFPE", pde_metric="L1"), 1.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_CASES))
+def test_losses(name):
+    model, kind, kw, gain = LOSS_CASES[name]
+    fx = load_golden(name, torch.float64)
+    seed, xdim, ydim, B = (int(v) for v in fx["meta"][:4])
+    out_dim = xdim if model == "CDE" else xdim + ydim
+    # fp64 oracle vs fp32 reference: removes the oracle's own round-off from the comparison
+    params = _leaf(make_params(seed, xdim + ydim + 1, out_dim, meta_hidden(fx, 4), gain=gain, dtype=torch.float64))
+    x, y, t, eps = fx["x"], fx["y"], fx["t"], fx["eps"]
+    if kind == "DSM":
+        loss, info = ol.dsm_loss(params, model, x, y, t, eps), {}
+    elif kind == "PINN":
+        loss, info = ol.pinn_loss(params, model, x, y, t, eps, fx["ic_target"], **kw)
+    else:
+        loss, info = ol.dsm_pde_loss(params, model, x, y, t, eps, **kw)
+    assert abs(loss.item() - fx["loss"].item()) <= 2e-4 * abs(fx["loss"].item()) + 1e-6
+    for k, v in info.items():
+        ref = fx["info_" + k.replace(" ", "_").replace("-", "_")].item()
+        assert abs(v.item() - ref) <= 3e-4 * abs(ref) + 1e-6, (k, v.item(), ref)
+    loss.backward()
+    check_grads(fx, [(W.grad, b.grad) for W, b in params], rtol=2e-3, atol_frac=2e-3)
+
+
+def test_pinn_scat_ic_target_matches_closed_form():
+    fx = load_golden("loss_pinn_cde_scat", torch.float64)
+    sp = surrogate_params(torch.float64)
+    ic = oscat.score_posterior(sp, fx["x"], fx["y"])
+    assert torch.allclose(ic, fx["ic_target"], rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["loss_posterior_scat", "loss_posterior_small"])
+def test_posterior_loss(name):
+    fx = load_golden(name, torch.float64)
+    seed, xdim, ydim, B = (int(v) for v in fx["meta"][:4])
+    hid = meta_hidden(fx, 4)
+    pp = _leaf(make_params(seed, xdim + 1, xdim, hid, dtype=torch.float64))
+    lp = _leaf(make_params(seed + 100, xdim + ydim + 1, xdim, hid, dtype=torch.float64))
+    sp = surrogate_params(torch.float64)
+    loss, info = ol.posterior_loss(pp, lp, sp, fx["x"], fx["y"], fx["t"], fx["eps"], float(fx["lam"]))
+    assert abs(loss.item() - fx["loss"].item()) <= 5e-4 * abs(fx["loss"].item())
+    assert abs(info["PriorLoss"].item() - fx["info_PriorLoss"].item()) <= 5e-4 * abs(fx["info_PriorLoss"].item())
+    assert abs(info["LikelihoodLoss"].item() - fx["info_LikelihoodLoss"].item()) <= 5e-4 * abs(fx["info_LikelihoodLoss"].item())
+    loss.backward()
+    check_grads(fx, [(W.grad, b.grad) for W, b in pp], prefix="prior_", rtol=3e-3, atol_frac=3e-3)
+    check_grads(fx, [(W.grad, b.grad) for W, b in lp], prefix="lik_", rtol=3e-3, atol_frac=3e-3)
+
+
+def test_scat_energy_and_grad():
+    fx = load_golden("scat_energy")
+    sp = surrogate_params()
+    assert torch.allclose(oscat.surrogate(sp, fx["x"]), fx["fx"], rtol=1e-5, atol=1e-5)
+    E, g = oscat.energy_and_grad(sp, fx["x"], fx["y"])
+    assert torch.allclose(E, fx["E"], rtol=2e-4, atol=1e-2)
+    assert torch.allclose(oscat.energy(sp, fx["x"], fx["y"]), fx["E"], rtol=1e-5, atol=1e-3)
+    scale = fx["grad"].abs().max()
+    assert (g - fx["grad"]).abs().max() <= 2e-4 * scale
+
+
+def test_vp_closed_forms():
+    fx = load_golden("vp_closed_forms")
+    t = fx["t"]
+    assert torch.allclose(vp.beta(t), fx["beta"])
+    assert torch.allclose(vp.mean_weight(t), fx["alpha"])
+    assert torch.allclose(vp.var(t), fx["var"])
+    yt, std, g = vp.perturb(t, fx["y0"], fx["eps"])
+    assert torch.allclose(yt, fx["yt"]) and torch.allclose(std, fx["std"]) and torch.allclose(g, fx["g"])
+    assert torch.allclose(vp.f(t, fx["y0"]), fx["f"])
+    assert torch.allclose(vp.mean_weight(t) ** 2 + vp.var(t), torch.ones_like(t), atol=1e-6)
+
+
+def test_philox_known_answers():
+    import numpy as np
+    r = oracle.philox.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in r] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]      # Random123 KAT
+    r = oracle.philox.philox4x32_10(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(v) for v in r] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    z = oracle.philox.normals(np.arange(200000), 7, 0, 6, 99)
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+
+
+def trained_cde_linear_params(dtype=torch.float32):
+    fx = load_golden("trained_cde_linear", dtype)
+    return [(fx[f"{k}_weight"], fx[f"{k}_bias"]) for k in (0, 3, 5, 7)]
+
+
+def test_sampler_trained_cde_linear_philox_noise():
+    """Reference default S=200 on a trained net, noise from the keyed Philox stream."""
+    import numpy as np
+    fx = load_golden("sampler_trained_cde_linear")
+    N, S, seed = (int(v) for v in fx["philox"])
+    gidx = np.arange(N)
+    x0 = torch.from_numpy(oracle.philox.normals(gidx, oracle.philox.STEP_INIT, 0, 2, seed))
+    noise = torch.from_numpy(np.stack([oracle.philox.normals(gidx, i, 0, 2, seed) for i in range(S)]))
+    out = osamp.em_sampler_cde(trained_cde_linear_params(), fx["y"], x0, noise, S)
+    assert (out - fx["out"]).abs().max() < 2e-5
+    # the trained model reproduces the analytic posterior (linear_problem.py:41-46)
+    assert (out.mean(0) - fx["post_mean"]).abs().max() < 0.08
+    assert (torch.cov(out.T) - fx["post_cov"]).abs().max() < 0.05
+    # score-MSE metric of main_diffusion_linear.py:78-83 on the stored probe points
+    s0 = on.mlp(trained_cde_linear_params(), fx["score_x"], fx["score_y"], torch.zeros(256, 1)) / 0.1 ** 0.5
+    assert torch.allclose(s0, fx["score_net"], rtol=1e-4, atol=1e-4)
