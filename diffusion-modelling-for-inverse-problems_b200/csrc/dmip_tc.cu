@@ -1,0 +1,678 @@
+// dmip_tc.cu — the tcgen05 path: persistent fused Euler–Maruyama sampler (K1) and score-net forward.
+//
+// One CTA per SM, 128 particles (rows) per tile, the whole S-step reverse SDE of a tile runs on chip:
+//
+//   warp 0      bulk-TMA producer: streams the net's bf16 weight stages (16 KB = 128 out-features x 64 k,
+//               K-major, 128B-swizzled — written in exactly that image by dmip_pack.cu) from L2 into a
+//               5-deep shared-memory ring, the same ~1.1 MB sequence every step.
+//   warp 1      MMA issuer (one elected lane): per layer, four N=128 accumulator chunks of
+//               tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM).  The activations are the A
+//               operand and ALTERNATE between shared memory and tensor memory from layer to layer
+//               (A0: smem -> H1: tmem -> H2: smem -> H3: tmem), so a layer's epilogue never overwrites the
+//               operand its own MMAs are still reading, and the epilogue of chunk c overlaps the MMAs of chunk
+//               c+1 (two 128-column accumulator buffers).
+//   warps 4-11  epilogue (two threads per particle row): tcgen05.ld accumulator -> +bias -> tanh (twice after
+//               layer 0) -> bf16 -> next layer's A operand (tcgen05.st, or swizzled st.shared).
+//               After the output layer: reverse-SDE drift/diffusion update of the fp32 state, Philox noise, and
+//               the next step's layer-0 operand.  y and t never enter the GEMM: they are constant over the
+//               rows of a tile and are folded, in fp32, into a per-step layer-0 bias b0 + W0[:,y]·y + tau·W0[:,t].
+//
+// Reference code replaced: models/diffusion.py:27-46,158-180; sdes.py:21-49,77-87; nets.py:17-57,143-157.
+#include "dmip_common.h"
+#include "dmip_ptx.cuh"
+#include "dmip_rng.cuh"
+
+namespace dmip {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kStageBytes = 16384;   // 128 rows x 64 k x bf16
+constexpr int kNumStages = 5;
+constexpr int kHBytes = 131072;      // 128 rows x 512 k x bf16 = 8 K-blocks
+constexpr int kThreads = 384;        // warps: 0 producer, 1 MMA, 2-3 spare, 4..11 epilogue
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemH = 0;       // 256 columns: 128 x 512 bf16 activations (A operand)
+constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
+
+// shared-memory map (offsets from a 1024-aligned base)
+constexpr int kOffH = 0;
+constexpr int kOffB = kOffH + kHBytes;
+constexpr int kOffB0 = kOffB + kNumStages * kStageBytes;  // float[512] effective layer-0 bias of the current pass
+constexpr int kOffU = kOffB0 + 2048;                      // float[2][512] b0 + W0[:,y]·y per net
+constexpr int kOffWt = kOffU + 4096;                      // float[2][512] W0[:,t] per net
+constexpr int kOffBar = kOffWt + 4096;
+constexpr int kNumBars = 2 * kNumStages + 2 + 2 + 4 + 1;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // + alignment slack
+
+enum { kModeSampler = 0, kModeForward = 1 };
+
+struct TcNetDev {
+  const uint8_t* stages;
+  const float* b0;
+  const float* b1;
+  const float* b2;
+  const float* b3;
+  const float* w0c;  // [512][n_const]
+  int kb0, ksteps0, dv, split, outpad, n_const, n_stages;
+};
+
+struct TcParams {
+  int mode, variant, n_nets;
+  TcNetDev net[2];
+  int xdim, ydim, n_obs, tiles_per_obs, S;
+  long long n_per_obs, n_tiles;
+  float T, bmin, bmax, mean, std, delta, sqrt_delta;
+  const float* y;
+  float* out;
+  int rng_mode;
+  unsigned long long seed, gidx_base;
+  const float* x0;
+  const float* noise;
+  const float* ynoise;
+  // forward mode
+  const float* fx;
+  const float* fcond;
+  const float* ft;
+  int fx_dim, fcond_dim, out_dim;
+};
+
+struct Bars {
+  uint64_t* full;       // [kNumStages]
+  uint64_t* empty;      // [kNumStages]
+  uint64_t* acc_full;   // [2]
+  uint64_t* acc_empty;  // [2]
+  uint64_t* hready;     // [4]
+  uint64_t* a0_ready;   // [1]
+};
+
+__device__ __forceinline__ float tau_of_step(int i, int S, float T) {
+  // T - linspace(0, 1, S+1)[i] * T in fp32, linspace evaluated symmetrically as torch does (models/diffusion.py:34)
+  const float step = 1.0f / static_cast<float>(S);
+  const int steps = S + 1;
+  const float l = (i < steps / 2) ? step * static_cast<float>(i) : 1.0f - step * static_cast<float>(steps - i - 1);
+  return T - l * T;
+}
+
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ hidden-layer epilogue
+// One thread: row `row` (TMEM lane), 64 of the 128 columns of accumulator chunk `chunk` (half `hh`).
+template <bool kDoubleTanh, bool kToTmem>
+__device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col, int hh, int row, int chunk,
+                                           const float* __restrict__ bias, uint8_t* sH, uint64_t* acc_empty,
+                                           uint64_t* hready) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(lane_taddr + acc_col + hh * 64, v0);
+  tmem_ld32(lane_taddr + acc_col + hh * 64 + 32, v1);
+  tc_wait_ld();
+  tc_fence_before();
+  mbar_arrive(acc_empty);  // accumulator chunk is in registers: the MMA warp may reuse the buffer
+  const int n0 = chunk * 128 + hh * 64;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 bq = *reinterpret_cast<const float4*>(bias + n0 + p * 32 + q * 4);
+      float a[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t raw = p == 0 ? v0[q * 4 + e] : v1[q * 4 + e];
+        const float bb = e == 0 ? bq.x : e == 1 ? bq.y : e == 2 ? bq.z : bq.w;
+        float t = tanh_fast(__uint_as_float(raw) + bb);
+        if (kDoubleTanh) t = tanh_fast(t);
+        a[e] = t;
+      }
+      pk[q * 2] = pack_bf16x2(a[0], a[1]);
+      pk[q * 2 + 1] = pack_bf16x2(a[2], a[3]);
+    }
+    if (kToTmem) {
+      tmem_st16(lane_taddr + kTmemH + static_cast<uint32_t>((n0 + p * 32) >> 1), pk);
+    } else {
+      // K index of these 32 values: n0 + p*32 .. +31  ->  K-block chunk*2+hh, 16-byte chunks p*4 .. p*4+3
+      uint8_t* rowp = sH + (chunk * 2 + hh) * kStageBytes + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4(rowp + (((p * 4 + q) ^ (row & 7)) << 4), pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    }
+  }
+  if (kToTmem) {
+    tc_wait_st();
+    tc_fence_before();
+  } else {
+    fence_proxy_async_smem();
+  }
+  mbar_arrive(hready);
+}
+
+// write one bf16 element of the layer-0 operand tile
+__device__ __forceinline__ void a0_store(uint8_t* sH, int row, int k, float v) {
+  const uint32_t off = sw128_offset(static_cast<uint32_t>(row), static_cast<uint32_t>(k), kStageBytes);
+  const unsigned short h = static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xFFFFu);
+  *reinterpret_cast<unsigned short*>(sH + off) = h;
+}
+// element `idx` (of dv row-varying inputs) with value v, under the layer-0 split scheme
+__device__ __forceinline__ void a0_put(uint8_t* sH, int row, int idx, int dv, int split, float v) {
+  const float hi = bf16_round(v);
+  a0_store(sH, row, idx, hi);
+  if (split >= 2) a0_store(sH, row, dv + idx, v - hi);
+  if (split >= 3) a0_store(sH, row, 2 * dv + idx, hi);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sH = smem + kOffH;
+  uint8_t* sB = smem + kOffB;
+  float* sB0 = reinterpret_cast<float*>(smem + kOffB0);
+  float* sU = reinterpret_cast<float*>(smem + kOffU);
+  float* sWt = reinterpret_cast<float*>(smem + kOffWt);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+  Bars B;
+  B.full = bars;
+  B.empty = bars + kNumStages;
+  B.acc_full = bars + 2 * kNumStages;
+  B.acc_empty = B.acc_full + 2;
+  B.hready = B.acc_empty + 2;
+  B.a0_ready = B.hready + 4;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kNumStages; ++i) {
+      mbar_init(&B.full[i], 1);
+      mbar_init(&B.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B.acc_full[i], 1);
+      mbar_init(&B.acc_empty[i], kEpiThreads);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], kEpiThreads);
+    mbar_init(B.a0_ready, kEpiThreads);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_holder);
+  // zero the activation region once: layer-0 K padding must be finite (it meets zero weights)
+  for (int i = threadIdx.x; i < kHBytes / 16; i += kThreads) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int n_pass = P.n_nets;
+  const int S = P.S;
+
+  if (warp == 0) {
+    // =============================================================== producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int step = 0; step < S; ++step) {
+          for (int p = 0; p < n_pass; ++p) {
+            const uint8_t* src = P.net[p].stages;
+            const int ns = P.net[p].n_stages;
+            for (int st = 0; st < ns; ++st) {
+              mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);
+              mbar_arrive_expect_tx(&B.full[s], kStageBytes);
+              bulk_g2s(sB + s * kStageBytes, src + static_cast<size_t>(st) * kStageBytes, kStageBytes, &B.full[s]);
+              if (++s == kNumStages) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t acc_uses[2] = {0, 0};
+      uint32_t hr_par[4] = {0, 0, 0, 0};
+      uint32_t a0_par = 0;
+      uint32_t job = 0;
+      const uint32_t sH_addr = smem_u32(sH);
+      const uint32_t sB_addr = smem_u32(sB);
+      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int step = 0; step < S; ++step) {
+          for (int p = 0; p < n_pass; ++p) {
+            const TcNetDev& net = P.net[p];
+            mbar_wait(B.a0_ready, a0_par, 0x200);
+            a0_par ^= 1u;
+#pragma unroll 1
+            for (int l = 0; l < 4; ++l) {
+              const int n_chunks = (l == 3) ? 1 : 4;
+              const int KB = (l == 0) ? net.kb0 : 8;
+              const uint32_t idesc = (l == 3) ? umma_idesc_bf16(128, static_cast<uint32_t>(net.outpad))
+                                              : umma_idesc_bf16(128, 128);
+              const bool a_in_smem = (l & 1) == 0;
+#pragma unroll 1
+              for (int c = 0; c < n_chunks; ++c, ++job) {
+                const int buf = job & 1;
+                mbar_wait(&B.acc_empty[buf], (acc_uses[buf] & 1u) ^ 1u, 0x300 + buf);
+                acc_uses[buf]++;
+                const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
+#pragma unroll 1
+                for (int kb = 0; kb < KB; ++kb) {
+                  if (l > 0 && c == 0 && (kb & 1) == 0) {
+                    mbar_wait(&B.hready[kb >> 1], hr_par[kb >> 1], 0x400 + (kb >> 1));
+                    hr_par[kb >> 1] ^= 1u;
+                  }
+                  mbar_wait(&B.full[s], ph, 0x500 + s);
+                  tc_fence_after();
+                  const int nk = (l == 0 && kb == KB - 1) ? (net.ksteps0 - 4 * (KB - 1)) : 4;
+                  for (int kk = 0; kk < nk; ++kk) {
+                    const uint64_t bdesc = umma_smem_desc_sw128(sB_addr + s * kStageBytes + kk * 32);
+                    const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+                    if (a_in_smem) {
+                      const uint64_t adesc = umma_smem_desc_sw128(sH_addr + kb * kStageBytes + kk * 32);
+                      umma_ss(d_tmem, adesc, bdesc, idesc, acc);
+                    } else {
+                      umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, acc);
+                    }
+                  }
+                  tc_commit(&B.empty[s]);
+                  if (++s == kNumStages) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(&B.acc_full[buf]);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================================================== epilogue (256 threads, 2 per row)
+    const int ew = warp - 4;
+    const int quarter = ew & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int hh = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const int et = threadIdx.x - 128;  // 0..255
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t acc_uses[2] = {0, 0};
+    uint32_t job = 0;
+    const float dbeta = P.bmax - P.bmin;
+    const long long n_total = static_cast<long long>(P.n_obs) * P.n_per_obs;
+
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int obs = static_cast<int>(tile / P.tiles_per_obs);
+      const long long prow = (tile % P.tiles_per_obs) * kTileM + row;
+      const bool valid = prow < P.n_per_obs;
+      const long long grow = static_cast<long long>(obs) * P.n_per_obs + prow;
+      const unsigned long long gidx = P.gidx_base + static_cast<unsigned long long>(grow);
+
+      // state-column ownership of this thread in the output-layer epilogue (8-column pieces)
+      const int np = P.net[n_pass - 1].outpad >> 3;
+      const int np0 = (np + 1) >> 1;
+      const int piece_lo = hh == 0 ? 0 : np0;
+      const int piece_hi = hh == 0 ? np0 : np;
+      const int j_lo = piece_lo * 8;
+      const int j_hi = min(piece_hi * 8, P.mode == kModeSampler ? P.xdim : P.out_dim);
+
+      // ---- tile init: per-observation layer-0 bias parts, x0, first A0
+      if (P.mode == kModeSampler) {
+        for (int p = 0; p < n_pass; ++p) {
+          const TcNetDev& net = P.net[p];
+          for (int n = et; n < 512; n += kEpiThreads) {
+            float u = net.b0[n];
+            const float* wr = net.w0c + static_cast<size_t>(n) * net.n_const;
+            for (int j = 0; j + 1 < net.n_const; ++j) u = fmaf(wr[j], P.y[obs * P.ydim + j], u);
+            sU[p * 512 + n] = u;
+            sWt[p * 512 + n] = wr[net.n_const - 1];
+          }
+        }
+        if (valid) {
+          for (int j0 = j_lo; j0 < j_hi; j0 += 4) {
+            float z[4];
+            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, kPhiloxStepInit, kStreamState, j0 >> 2, P.seed, z);
+            for (int e = 0; e < 4 && j0 + e < j_hi; ++e) {
+              const float zz = P.rng_mode == DMIP_RNG_PHILOX ? z[e] : P.x0[grow * P.xdim + j0 + e];
+              P.out[grow * P.xdim + j0 + e] = zz * P.std + P.mean;
+            }
+          }
+        }
+      }
+
+      const int n_steps = (P.mode == kModeSampler) ? S : 1;
+      for (int step = 0; step < n_steps; ++step) {
+        const float tau = tau_of_step(step, S, P.T);
+        const float beta = P.bmin + dbeta * tau;
+        const float sb = sqrtf(beta);
+        float stash[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) stash[e] = 0.f;
+
+        for (int p = 0; p < n_pass; ++p) {
+          const TcNetDev& net = P.net[p];
+          // ---- layer-0 operand + effective bias for this pass
+          if (P.mode == kModeSampler) {
+            for (int n = et; n < 512; n += kEpiThreads) sB0[n] = fmaf(tau, sWt[p * 512 + n], sU[p * 512 + n]);
+            if (valid) {
+              for (int j = j_lo; j < j_hi; ++j) a0_put(sH, row, j, net.dv, net.split, P.out[grow * P.xdim + j]);
+              if (P.variant == DMIP_CDIFFE) {
+                // y_t = alpha(tau) y + std(tau) eta   (sdes.py:37-49 via models/diffusion.py:172)
+                const float Bt = 0.5f * tau * tau * dbeta + tau * P.bmin;
+                const float alpha = __expf(-0.5f * Bt);
+                const float sd = sqrtf(1.0f - __expf(-Bt));
+                for (int q = hh; q * 4 < P.ydim; q += 2) {
+                  float z[4];
+                  if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, step, kStreamObs, q, P.seed, z);
+                  for (int e = 0; e < 4 && q * 4 + e < P.ydim; ++e) {
+                    const int jj = q * 4 + e;
+                    const float eta = P.rng_mode == DMIP_RNG_PHILOX
+                                          ? z[e]
+                                          : P.ynoise[(static_cast<long long>(step) * n_total + grow) * P.ydim + jj];
+                    a0_put(sH, row, P.xdim + jj, net.dv, net.split, fmaf(sd, eta, alpha * P.y[obs * P.ydim + jj]));
+                  }
+                }
+              }
+            }
+          } else {
+            for (int n = et; n < 512; n += kEpiThreads) sB0[n] = net.b0[n];
+            if (valid) {
+              const int in_dim = net.dv;
+              for (int k = hh; k < in_dim; k += 2) {
+                float v;
+                if (k < P.fx_dim) v = P.fx[grow * P.fx_dim + k];
+                else if (k < P.fx_dim + P.fcond_dim) v = P.fcond[grow * P.fcond_dim + (k - P.fx_dim)];
+                else v = P.ft[grow];
+                a0_put(sH, row, k, net.dv, net.split, v);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(B.a0_ready);
+          epi_bar_sync();  // sB0 visible to all epilogue threads
+
+          // ---- layers 0..2
+#pragma unroll 1
+          for (int l = 0; l < 3; ++l) {
+            const float* bias = (l == 0) ? sB0 : (l == 1 ? net.b1 : net.b2);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c, ++job) {
+              const int buf = job & 1;
+              mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x600 + buf);
+              acc_uses[buf]++;
+              tc_fence_after();
+              const uint32_t acc_col = kTmemAcc + buf * 128;
+              if (l == 0)
+                epi_hidden<true, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+              else if (l == 1)
+                epi_hidden<false, false>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+              else
+                epi_hidden<false, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+            }
+          }
+
+          // ---- output layer
+          {
+            const int buf = job & 1;
+            ++job;
+            mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x700 + buf);
+            acc_uses[buf]++;
+            tc_fence_after();
+            const uint32_t acc_col = kTmemAcc + buf * 128;
+            const bool last_pass = (p == n_pass - 1);
+            for (int pc = piece_lo; pc < piece_hi; ++pc) {
+              uint32_t v[8];
+              tmem_ld8(lane_taddr + acc_col + pc * 8, v);
+              tc_wait_ld();
+              if (!valid || pc * 8 >= j_hi) continue;
+              float z[8];
+              if (P.mode == kModeSampler && last_pass && P.rng_mode == DMIP_RNG_PHILOX) {
+                float z4[4];
+                philox_normal4(gidx, step, kStreamState, pc * 2, P.seed, z4);
+                z[0] = z4[0]; z[1] = z4[1]; z[2] = z4[2]; z[3] = z4[3];
+                if (pc * 8 + 4 < j_hi) {
+                  philox_normal4(gidx, step, kStreamState, pc * 2 + 1, P.seed, z4);
+                  z[4] = z4[0]; z[5] = z4[1]; z[6] = z4[2]; z[7] = z4[3];
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int j = pc * 8 + e;
+                if (j < j_hi) {
+                  float a = __uint_as_float(v[e]) + net.b3[j];
+                  if (P.mode == kModeForward) {
+                    P.out[grow * P.out_dim + j] = a;
+                  } else if (!last_pass) {
+                    if (pc == piece_lo) stash[e] = a;  // DPS: outpad == 16, at most one piece per thread
+                  } else {
+                    if (n_pass == 2 && pc == piece_lo) a += stash[e];
+                    // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
+                    // DPS: a_net = sqrt(beta) (prior + lik) (nets.py:155-157) => mu = beta (prior+lik) + beta x / 2
+                    const float ca = (P.variant == DMIP_DPS) ? beta : sb;
+                    const float x = P.out[grow * P.xdim + j];
+                    const float eps = P.rng_mode == DMIP_RNG_PHILOX
+                                          ? z[e]
+                                          : P.noise[(static_cast<long long>(step) * n_total + grow) * P.xdim + j];
+                    const float mu = ca * a + 0.5f * beta * x;
+                    P.out[grow * P.xdim + j] = x + P.delta * mu + (P.sqrt_delta * sb) * eps;
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(&B.acc_empty[buf]);
+          }
+        }  // pass
+      }    // step
+    }      // tile
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ self-test kernel
+// D(128 x n) = A(128 x k) W(n x k)^T through the same descriptors / layouts / TMEM access as the sampler.
+__global__ void __launch_bounds__(128, 1) k_debug_umma(int mode, const float* __restrict__ a, const float* __restrict__ w,
+                                                        float* __restrict__ d, int n, int k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                       // up to 4 K-blocks
+  uint8_t* sW = smem + 4 * kStageBytes;     // up to 4 K-blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * kStageBytes);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 8 * kStageBytes + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(holder);
+  for (int i = threadIdx.x; i < 8 * kStageBytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // operand images
+  for (int kk = 0; kk < k; ++kk) {
+    const unsigned short ha = static_cast<unsigned short>(pack_bf16x2(a[row * k + kk], 0.f) & 0xFFFFu);
+    *reinterpret_cast<unsigned short*>(sA + sw128_offset(row, kk, kStageBytes)) = ha;
+    if (row < n) {
+      const unsigned short hw = static_cast<unsigned short>(pack_bf16x2(w[row * k + kk], 0.f) & 0xFFFFu);
+      *reinterpret_cast<unsigned short*>(sW + sw128_offset(row, kk, kStageBytes)) = hw;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  if (mode == 1) {
+    // A into tensor memory: lane = row, 32-bit column c = elements (2c, 2c+1)
+    for (int c0 = 0; c0 < k / 2; c0 += 16) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(a[row * k + 2 * (c0 + j)], a[row * k + 2 * (c0 + j) + 1]);
+      tmem_st16(lane_taddr + kTmemH + c0, pk);
+    }
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(n));
+    const uint32_t d_tmem = tmem_base + kTmemAcc;
+    for (int kb = 0; kb < k / 64; ++kb)
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sW) + kb * kStageBytes + kk * 32);
+        const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+        if (mode == 0)
+          umma_ss(d_tmem, umma_smem_desc_sw128(smem_u32(sA) + kb * kStageBytes + kk * 32), bdesc, idesc, acc);
+        else
+          umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, acc);
+      }
+    tc_commit(bar);
+  }
+  mbar_wait(bar, 0, 0x900);
+  tc_fence_after();
+  for (int pc = 0; pc < n / 8; ++pc) {
+    uint32_t v[8];
+    tmem_ld8(lane_taddr + kTmemAcc + pc * 8, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[row * n + pc * 8 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+  (void)lane;
+}
+
+int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows, int split, TcNetDev* o) {
+  TcNetGeom g;
+  int rc = tc_net_geom(net, n_varying, out_rows, split, &g);
+  if (rc) return rc;
+  const uint8_t* base = static_cast<const uint8_t*>(packed);
+  const float* tail = reinterpret_cast<const float*>(base + g.stage_bytes());
+  o->stages = base;
+  o->b0 = tail;
+  o->b1 = tail + 512;
+  o->b2 = tail + 1024;
+  o->b3 = tail + 1536;
+  o->w0c = tail + 1664;
+  o->kb0 = g.kb0;
+  o->ksteps0 = g.k0pad / 16;
+  o->dv = g.n_varying;
+  o->split = g.split;
+  o->outpad = g.outpad;
+  o->n_const = g.n_const;
+  o->n_stages = g.n_stages;
+  return 0;
+}
+
+int launch(const TcParams& P, cudaStream_t s) {
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  }
+  const long long grid = P.n_tiles < n_sm ? P.n_tiles : n_sm;
+  if (grid <= 0) return DMIP_OK;
+  k_tc_mlp<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, s>>>(P);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
+}
+
+}  // namespace
+
+int launch_sampler_tc(const DmipSampler* d, cudaStream_t s) {
+  TcParams P = {};
+  P.mode = kModeSampler;
+  P.variant = d->variant;
+  const int dv = d->variant == DMIP_CDIFFE ? d->xdim + d->ydim : d->xdim;
+  int rc;
+  if (d->variant == DMIP_DPS) {
+    P.n_nets = 2;
+    DMIP_REQUIRE(d->packed2 != nullptr, "DPS sampler needs packed2 (prior_net image)");
+    DMIP_REQUIRE(d->xdim <= 8, "DPS tcgen05 sampler supports xdim <= 8 (got %d)", d->xdim);
+    if ((rc = fill_net(&d->net2, d->packed2, d->xdim, d->xdim, d->l0_split, &P.net[0]))) return rc;  // prior (MLP2)
+    if ((rc = fill_net(&d->net, d->packed, d->xdim, d->xdim, d->l0_split, &P.net[1]))) return rc;    // likelihood
+  } else {
+    P.n_nets = 1;
+    if ((rc = fill_net(&d->net, d->packed, dv, d->xdim, d->l0_split, &P.net[0]))) return rc;
+  }
+  P.xdim = d->xdim;
+  P.ydim = d->ydim;
+  P.n_obs = d->n_obs;
+  P.n_per_obs = d->n_per_obs;
+  P.tiles_per_obs = static_cast<int>((d->n_per_obs + kTileM - 1) / kTileM);
+  P.n_tiles = static_cast<long long>(P.tiles_per_obs) * d->n_obs;
+  P.S = d->num_steps;
+  P.T = d->T;
+  P.bmin = d->beta_min;
+  P.bmax = d->beta_max;
+  P.mean = d->mean;
+  P.std = d->std;
+  const double delta = static_cast<double>(d->T) / d->num_steps;  // models/diffusion.py:31
+  P.delta = static_cast<float>(delta);
+  P.sqrt_delta = static_cast<float>(sqrt(delta));
+  P.y = d->y;
+  P.out = d->out;
+  P.rng_mode = d->rng_mode;
+  P.seed = d->seed;
+  P.gidx_base = d->gidx_base;
+  P.x0 = d->x0;
+  P.noise = d->noise;
+  P.ynoise = d->ynoise;
+  return launch(P, s);
+}
+
+int launch_forward_tc(const DmipForward* d, cudaStream_t s) {
+  TcParams P = {};
+  P.mode = kModeForward;
+  P.variant = DMIP_CDE;
+  P.n_nets = 1;
+  int rc;
+  if ((rc = fill_net(&d->net, d->packed, d->net.in_dim, d->net.out_dim, d->l0_split, &P.net[0]))) return rc;
+  P.n_obs = 1;
+  P.n_per_obs = d->n;
+  P.tiles_per_obs = static_cast<int>((d->n + kTileM - 1) / kTileM);
+  P.n_tiles = P.tiles_per_obs;
+  P.S = 1;
+  P.T = 1.f;
+  P.out = d->out;
+  P.fx = d->x;
+  P.fcond = d->cond;
+  P.ft = d->t;
+  P.fx_dim = d->x_dim;
+  P.fcond_dim = d->cond_dim;
+  P.out_dim = d->net.out_dim;
+  return launch(P, s);
+}
+
+int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s) {
+  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256, "debug_umma: k must be 64, 128, 192 or 256");
+  DMIP_REQUIRE(n % 16 == 0 && n >= 16 && n <= 128, "debug_umma: n must be a multiple of 16 in [16,128]");
+  const int smem = 8 * kStageBytes + 64 + 1024;
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_debug_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_debug_umma<<<1, 128, smem, s>>>(mode, a, w, d, n, k);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
+}
+
+}  // namespace dmip

@@ -1,0 +1,190 @@
+"""Drop-in for the reference's `models/diffusion.py`: CDE, CDiffE (Batzolis et al. 2021) and
+PosteriorDiffusionEstimator (after Chung et al. 2022), same constructors, attributes and call signatures:
+
+    model = CDE(xdim, ydim, hidden_layers)
+    x = model(y, num_samples=2000, num_steps=200, mean=0, std=1)      # np.ndarray (num_samples, xdim) float32
+    loss, info = model.train_epoch(optimizer, loss_fn, epoch_data_loader)
+    model.sde, model.sde.a, model.sde.base_sde, model.sde.T, model.sde.debias
+
+`forward` replaces the reference's S x ~30-kernel Python loop (models/diffusion.py:38-42, :171-177) by ONE launch of
+the persistent fused Euler–Maruyama kernel (`dmip_sampler_em_vp`, include/dmip.h).  Extras beyond the reference
+signature are keyword-only: `precision` ('bf16' tcgen05 path | 'fp32' FFMA path), `seed` (Philox key; the
+reference uses torch's global RNG, which a fused kernel cannot consume — statistics are preserved, streams differ),
+`injected` (dict with 'x0', 'noise'[, 'ynoise'] standard-normal tensors: bit-for-bit the reference's draws, for
+parity tests), `gidx_base` (global particle offset for multi-GPU sharding), `return_tensor`.  `y` may also be a
+batch (n_obs, ydim): all observations are integrated in the same launch and (n_obs, num_samples, xdim) is returned.
+
+CDiffE.forward upstream raises TypeError (it omits `cond` when calling `sde.mu`); the intended call
+(`cond` = empty tensor, as the loss path does) is what is implemented here.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from .. import _lib
+from .. import sdes
+from ..losses import PosteriorLoss, fused_train_step
+from ..nets import MLP, MLP2, PosteriorScore
+
+device = 'cuda' if torch.cuda.is_available() else 'cpu'
+
+_VARIANT = {'CDE': _lib.CDE, 'CDiffE': _lib.CDIFFE, 'Posterior': _lib.DPS}
+
+
+class BaseClassDiffusionModel():
+
+    variant = 'CDE'
+
+    def __init__(self, xdim, ydim):
+        self.xdim = xdim
+        self.ydim = ydim
+        self.sde = None                      # set by subclasses
+        self.precision = 'bf16'
+        self.l0_split = 2
+        self._packed = (_lib.PackedNet(), _lib.PackedNet())
+        self._seed_counter = 0
+
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
+
+    # ------------------------------------------------------------------ sampling
+    def _nets(self):
+        """(net, net2): score net; for DPS (likelihood_net, prior_net)."""
+        return self.sde.a, None
+
+    def forward(self, y, num_samples=2000, num_steps=200, mean=0, std=1, *, precision=None, seed=None,
+                injected=None, gidx_base=0, return_tensor=False):
+        L = _lib.require_gpu()
+        net, net2 = self._nets()
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError("dmip samplers run on CUDA (sm_100a) only: move the model to the GPU (no CPU fallback)")
+        y = torch.as_tensor(y, dtype=torch.float32)
+        batched = y.ndim == 2
+        ys = y.reshape(-1, self.ydim).to(dev).contiguous()
+        n_obs = ys.shape[0]
+        n_total = n_obs * num_samples
+
+        keep = [ys]
+        d = _lib.DmipSampler()
+        d.variant = _VARIANT[self.variant]
+        prec = _lib.precision_code(self.precision if precision is None else precision)
+        if prec == _lib.PREC_BF16 and not (_lib.tc_supported(net) and (net2 is None or _lib.tc_supported(net2))
+                                            and (net2 is None or self.xdim <= 8)):
+            prec = _lib.PREC_F32             # other layer widths: fp32 FFMA kernels (still CUDA, never CPU)
+        d.precision = prec
+        d.xdim, d.ydim = self.xdim, self.ydim
+        d.n_obs, d.n_per_obs, d.num_steps = n_obs, num_samples, num_steps
+        d.T = float(self.sde.T)
+        d.beta_min, d.beta_max = float(self.sde.base_sde.beta_min), float(self.sde.base_sde.beta_max)
+        d.mean, d.std = float(mean), float(std)
+        d.net = _lib.mlp_desc(net, keep)
+        if net2 is not None:
+            d.net2 = _lib.mlp_desc(net2, keep)
+        d.l0_split = self.l0_split
+        d.y = ys.data_ptr()
+        out = torch.empty(n_total, self.xdim, device=dev, dtype=torch.float32)
+        d.out = out.data_ptr()
+        if injected is not None:
+            d.rng_mode = _lib.RNG_INJECTED
+            for name in ('x0', 'noise') + (('ynoise',) if self.variant == 'CDiffE' else ()):
+                tns = injected[name].to(dev, torch.float32).contiguous()
+                keep.append(tns)
+                setattr(d, name, tns.data_ptr())
+            assert injected['x0'].numel() == n_total * self.xdim, 'x0 must have shape (n_obs*num_samples, xdim)'
+            assert injected['noise'].numel() == num_steps * n_total * self.xdim, 'noise must be (S, N, xdim)'
+        else:
+            d.rng_mode = _lib.RNG_PHILOX
+            if seed is None:                 # fresh stream per call, like successive draws from a global RNG
+                seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._seed_counter + 1)) & (2 ** 64 - 1)
+                self._seed_counter += 1
+            d.seed = int(seed) & (2 ** 64 - 1)
+        d.gidx_base = int(gidx_base)
+        with torch.cuda.device(dev):
+            if prec == _lib.PREC_BF16:
+                dv = self.xdim + self.ydim if self.variant == 'CDiffE' else self.xdim
+                d.packed = self._packed[0].get(net, dv, self.xdim, self.l0_split).data_ptr()
+                if net2 is not None:
+                    d.packed2 = self._packed[1].get(net2, self.xdim, self.xdim, self.l0_split).data_ptr()
+            else:
+                ws = torch.empty(max(L.dmip_sampler_workspace_bytes(C.byref(d)), 16), dtype=torch.uint8, device=dev)
+                keep.append(ws)
+                d.workspace = ws.data_ptr()
+                d.workspace_bytes = ws.numel()
+            _lib.check(L.dmip_sampler_em_vp(C.byref(d), _lib.stream_ptr()))
+            self.last_launch_count = L.dmip_last_launch_count()
+        if batched:
+            out = out.view(n_obs, num_samples, self.xdim)
+        if return_tensor:
+            return out
+        return out.cpu().numpy()              # the reference's single device->host crossing (models/diffusion.py:44)
+
+    # ------------------------------------------------------------------ training
+    def sample_t(self, x, eps=1e-4):
+        if self.sde.debias:
+            t_ = self.sde.base_sde.sample_debiasing_t([x.size(0), ] + [1 for _ in range(x.ndim - 1)]) + eps
+            t_ = torch.where(t_ > self.sde.T, t_ - eps, t_).to(x)
+        else:
+            t_ = eps + torch.rand([x.size(0), ] + [1 for _ in range(x.ndim - 1)]).to(x) * self.sde.T
+            t_ = torch.where(t_ > self.sde.T, torch.full_like(t_, self.sde.T - eps), t_)
+        t_.requires_grad = True
+        return t_
+
+    def train_epoch(self, optimizer, loss_fn, epoch_data_loader):
+        mean_loss = 0
+        logger_info = {}
+        for k, (x, y) in enumerate(epoch_data_loader()):
+            t = self.sample_t(x)
+            loss, loss_info = fused_train_step(self, loss_fn, x, y, t)
+            for key, value in loss_info.items():
+                logger_info[key] = logger_info.get(key, 0) * k / (k + 1) + value.item() / (k + 1)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            mean_loss = mean_loss * k / (k + 1) + loss.detach() / (k + 1)
+        return mean_loss, logger_info
+
+
+class CDE(BaseClassDiffusionModel):
+    """Conditional denoising estimator: score net a(x_t, y, t) -> xdim."""
+
+    variant = 'CDE'
+
+    def __init__(self, xdim, ydim, hidden_layers):
+        super().__init__(xdim, ydim)
+        score_net = MLP(input_dim=xdim + ydim + 1, output_dim=xdim, hidden_layers=hidden_layers,
+                        activation=nn.Tanh()).to(device)
+        self.sde = sdes.PluginReverseSDE(sdes.VariancePreservingSDE(), score_net, T=1, debias=True)
+
+
+class CDiffE(BaseClassDiffusionModel):
+    """Conditional diffusive estimator: joint score of z = [x, y]; y is re-diffused at every sampling step."""
+
+    variant = 'CDiffE'
+
+    def __init__(self, xdim, ydim, hidden_layers):
+        super().__init__(xdim, ydim)
+        score_net = MLP(input_dim=xdim + ydim + 1, output_dim=xdim + ydim, hidden_layers=hidden_layers,
+                        activation=nn.Tanh()).to(device)
+        self.sde = sdes.PluginReverseSDE(sdes.VariancePreservingSDE(), score_net, T=1, debias=True)
+
+
+class PosteriorDiffusionEstimator(BaseClassDiffusionModel):
+    """Diffusion posterior sampler: drift = g * (prior_net(x,t) + likelihood_net(x,y,t))."""
+
+    variant = 'Posterior'
+
+    def __init__(self, xdim, ydim, hidden_layers):
+        super().__init__(xdim, ydim)
+        forward_process = sdes.VariancePreservingSDE()
+        prior_net = MLP2(input_dim=xdim + 1, output_dim=xdim, hidden_layers=hidden_layers,
+                         activation=nn.Tanh()).to(device)
+        likelihood_net = MLP(input_dim=xdim + ydim + 1, output_dim=xdim, hidden_layers=hidden_layers,
+                             activation=nn.Tanh()).to(device)
+        score_net = PosteriorScore(prior_net, likelihood_net, forward_process)
+        self.sde = sdes.PluginReverseSDE(forward_process, score_net, T=1, debias=True)
+        self.loss_fn = PosteriorLoss
+
+    def _nets(self):
+        return self.sde.a.likelihood_net, self.sde.a.prior_net

@@ -1,0 +1,93 @@
+"""Drop-in for the reference's `sdes.py` (VariancePreservingSDE :9-57, PluginReverseSDE :60-87).
+
+Same class names, constructor arguments, attributes and method signatures.  The closed forms below are only the
+*interface* (callers such as losses and evaluation scripts use them on small tensors); inside the sampler and the
+fused losses the same formulas are evaluated in-kernel (csrc/dmip_tc.cu, csrc/dmip_f32.cu).  The reference's dead
+methods `dsm` / `elbo_random_t_slice` (wrong arity) are not carried over.
+"""
+import math
+
+import torch
+
+
+def vp_truncated_inverse_cdf(u, beta_min, beta_max, t_epsilon, T):
+    """Inverse CDF of q(t) ∝ beta(t)/var(t), constant below t_epsilon — the distribution behind the reference's
+    `sample_vp_truncated_q` (sdes.py:57; the implementation lives in the un-vendored sdeflow-light, so this is
+    restated from its published form)."""
+    db = beta_max - beta_min
+
+    def big_b(t):
+        return 0.5 * t * t * db + t * beta_min
+
+    def antider(t):
+        b = big_b(t)
+        return math.log(1.0 - math.exp(-b)) + b
+
+    r_eps = (beta_min + db * t_epsilon) / (1.0 - math.exp(-big_b(t_epsilon)))
+    a_eps = antider(t_epsilon)
+    Z = r_eps * t_epsilon + antider(float(T)) - a_eps
+    lin = Z / r_eps * u
+    nl = (-beta_min + torch.sqrt(beta_min ** 2 + 2.0 * db * torch.log1p(torch.exp(Z * u + a_eps - r_eps * t_epsilon)))) / db
+    return torch.where(u <= t_epsilon * r_eps / Z, lin, nl)
+
+
+class VariancePreservingSDE(torch.nn.Module):
+    """VP-SDE of Song et al. 2021: dy = -beta(t)/2 y dt + sqrt(beta(t)) dW."""
+
+    def __init__(self, beta_min=0.1, beta_max=20.0, T=1.0, t_epsilon=0.001):
+        super().__init__()
+        self.beta_min = beta_min
+        self.beta_max = beta_max
+        self.T = T
+        self.t_epsilon = t_epsilon
+
+    def beta(self, t):
+        return self.beta_min + (self.beta_max - self.beta_min) * t
+
+    def _int_beta(self, t):
+        return 0.5 * t ** 2 * (self.beta_max - self.beta_min) + t * self.beta_min
+
+    def mean_weight(self, t):
+        return torch.exp(-0.5 * self._int_beta(t))
+
+    def var(self, t):
+        return 1. - torch.exp(-self._int_beta(t))
+
+    def f(self, t, y):
+        return -0.5 * self.beta(t) * y
+
+    def g(self, t, y):
+        return torch.ones_like(y) * self.beta(t) ** 0.5
+
+    def sample(self, t, y0, return_noise=False):
+        """y_t | y_0; with return_noise also (epsilon, std, g) as the losses need them."""
+        std = self.var(t) ** 0.5
+        epsilon = torch.randn_like(y0)
+        yt = epsilon * std + self.mean_weight(t) * y0
+        if not return_noise:
+            return yt
+        return yt, epsilon, std, self.g(t, yt)
+
+    def sample_debiasing_t(self, shape):
+        """t ~ q(t) ∝ g²/std² truncated at t_epsilon (importance sampling that removes the DSM weight)."""
+        u = torch.rand(*shape)
+        return vp_truncated_inverse_cdf(u.view(-1), self.beta_min, self.beta_max, self.t_epsilon, self.T).view(*shape)
+
+
+class PluginReverseSDE(torch.nn.Module):
+    """Reverse-time SDE with plug-in drift a = g * score:  mu = g a - f,  sigma = g  (time runs T - t)."""
+
+    def __init__(self, base_sde, drift_a, T, vtype='rademacher', debias=False):
+        super().__init__()
+        self.base_sde = base_sde
+        self.a = drift_a
+        self.T = T
+        self.vtype = vtype
+        self.debias = debias
+
+    def mu(self, t, x, cond, lmbd=0.):
+        s = self.T - t
+        return (1. - 0.5 * lmbd) * self.base_sde.g(s, x) * self.a(x, cond, s) - self.base_sde.f(s, x)
+
+    def sigma(self, t, y, lmbd=0.):
+        return (1. - lmbd) ** 0.5 * self.base_sde.g(self.T - t, y)

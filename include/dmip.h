@@ -1,0 +1,147 @@
+/*
+ * dmip.h — C ABI of libdmip_sm100.so, the B200 (sm_100a) hot path of
+ * maffos/Diffusion-Modelling-for-inverse-problems.
+ *
+ * The reference is pure Python/PyTorch and has NO plugin / FFI boundary
+ * (SURVEY.md §8b): its "API that stays as it is" is the Python class surface of
+ * models/diffusion.py, sdes.py, losses.py and nets.py.  This header is the new
+ * boundary a maintainer binds underneath those classes (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer
+ *     owned by the caller (e.g. a torch tensor's data_ptr()); the library never
+ *     allocates or frees device memory and keeps no pointer after returning;
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (as void*),
+ *     asynchronously, without internal synchronisation;
+ *   - return value 0 = ok, negative = DMIP_E*; dmip_last_error() gives the
+ *     message for the calling thread; no C++ exception crosses the boundary;
+ *   - fp32 row-major contiguous tensors unless a leading dimension is given;
+ *   - weights are nn.Linear layout: W (out_features, in_features), b (out_features).
+ */
+#ifndef DMIP_H_
+#define DMIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMIP_VERSION 100
+
+#define DMIP_OK 0
+#define DMIP_EINVAL (-1)     /* bad argument (reference: ValueError / assert, losses.py:79,86,97; nets.py:34) */
+#define DMIP_EARCH (-2)      /* device is not sm_100 */
+#define DMIP_EWORKSPACE (-3) /* workspace too small; see dmip_*_workspace_bytes */
+#define DMIP_ECUDA (-4)      /* CUDA runtime error; message carries cudaGetErrorString */
+
+#define DMIP_MAX_LAYERS 8
+
+/* precision of the score-net evaluation */
+#define DMIP_PREC_F32 0  /* fp32 FFMA kernels: any layer widths; matches the reference to fp32 round-off  */
+#define DMIP_PREC_BF16 1 /* tcgen05 kernels: bf16 operands / fp32 accumulate; hidden_layers == [512,512,512] */
+
+/* sampler variants: models/diffusion.py classes */
+#define DMIP_CDE 0    /* CDE  — BaseClassDiffusionModel.forward, models/diffusion.py:27-46                  */
+#define DMIP_CDIFFE 1 /* CDiffE.forward, models/diffusion.py:158-180 (with the `cond` fix)    */
+#define DMIP_DPS 2    /* PosteriorDiffusionEstimator: base forward with nets.py:155-157 PosteriorScore as a */
+
+#define DMIP_RNG_PHILOX 0   /* counter-based Philox4x32-10 keyed by global particle index                  */
+#define DMIP_RNG_INJECTED 1 /* caller supplies x0 / per-step noise (parity tests)            */
+
+/* A tanh MLP as built by nets.py:17-30 (MLP / MLP2): n_layers Linear layers, tanh after every layer but the
+ * last, and tanh applied TWICE after layer 0 (the Sequential 'act' quirk). */
+typedef struct DmipMlp {
+  int32_t n_layers; /* number of nn.Linear layers (= len(hidden_layers)+1), 2..DMIP_MAX_LAYERS   */
+  int32_t in_dim;   /* columns of cat[x, cond, t]                                                 */
+  int32_t out_dim;
+  int32_t width[DMIP_MAX_LAYERS]; /* out_features of layer l (width[n_layers-1] == out_dim)       */
+  const float* W[DMIP_MAX_LAYERS]; /* device, (width[l], width[l-1] or in_dim)                     */
+  const float* b[DMIP_MAX_LAYERS]; /* device, (width[l],)                                          */
+} DmipMlp;
+
+int dmip_version(void);
+const char* dmip_last_error(void);
+/* 1 if the current device can run the library (compute capability 10.x), else 0 */
+int dmip_device_ok(void);
+
+/* ---- weight packing for the tcgen05 path -------------------------------------------------------------
+ * Re-tiles one net into the bf16, 128B-swizzled, K-major stage images the sampler streams with bulk-TMA.
+ * `n_varying` = leading input columns that vary per row and therefore enter the layer-0 GEMM (the rest —
+ * y and/or t — are folded into an fp32 per-step bias by the kernel); `out_rows` = leading output rows kept
+ * (CDiffE needs only the first xdim outputs, models/diffusion.py:177); `l0_split` in {1,2,3}: layer-0
+ * operand splitting (1: bf16 x; 2: x = hi+lo, both bf16; 3: also W0 = hi+lo).  Call again after every
+ * optimizer.step().  Replaces nothing in the reference (its weights are read in place by addmm). */
+size_t dmip_pack_bytes(const DmipMlp* net, int32_t n_varying, int32_t out_rows, int32_t l0_split);
+int dmip_pack_mlp(const DmipMlp* net, int32_t n_varying, int32_t out_rows, int32_t l0_split, void* packed,
+                  size_t packed_bytes, void* stream);
+
+/* ---- reverse-SDE Euler–Maruyama posterior sampler -----------------------------------------------------
+ * Replaces the S-step loop of models/diffusion.py:38-42 / :171-177 together with sdes.py:77-87 (mu, sigma),
+ * sdes.py:21-35 (beta, f, g), sdes.py:37-49 (CDiffE re-diffusion of y) and nets.py:32-35/52-57/155-157.
+ * One call integrates n_obs * n_per_obs particles for num_steps steps; particles of observation o occupy
+ * rows [o*n_per_obs, (o+1)*n_per_obs) of every per-particle tensor. */
+typedef struct DmipSampler {
+  int32_t variant;   /* DMIP_CDE / DMIP_CDIFFE / DMIP_DPS                                          */
+  int32_t precision; /* DMIP_PREC_*                                                                 */
+  int32_t xdim, ydim;
+  int32_t n_obs;
+  int64_t n_per_obs;
+  int32_t num_steps;               /* S; reference default 200 (models/diffusion.py:27)            */
+  float T, beta_min, beta_max;     /* sdes.py:14-19 defaults 1, 0.1, 20                             */
+  float mean, std;                 /* x0 = randn*std + mean (models/diffusion.py:32-33)             */
+  DmipMlp net;                     /* CDE/CDiffE: sde.a ; DPS: likelihood_net (MLP on [x,y,t])      */
+  DmipMlp net2;                    /* DPS only: prior_net (MLP2 on [x,t])                           */
+  const void* packed;              /* DMIP_PREC_BF16: dmip_pack_mlp image of `net`                   */
+  const void* packed2;             /* DMIP_PREC_BF16 + DPS: image of `net2`                          */
+  int32_t l0_split;                /* must equal the value given to dmip_pack_mlp                    */
+  const float* y;                  /* device (n_obs, ydim)                                           */
+  float* out;                      /* device (n_obs*n_per_obs, xdim): final x_t (also the fp32 state)*/
+  int32_t rng_mode;                /* DMIP_RNG_*                                                     */
+  uint64_t seed;                   /* Philox key                                                     */
+  uint64_t gidx_base;              /* global index of this call's particle 0 (multi-GPU sharding)    */
+  const float* x0;                 /* injected: (n_obs*n_per_obs, xdim) standard normals             */
+  const float* noise;              /* injected: (S, n_obs*n_per_obs, xdim)                           */
+  const float* ynoise;             /* injected, CDiffE: (S, n_obs*n_per_obs, ydim)                   */
+  void* workspace;                 /* device scratch, dmip_sampler_workspace_bytes()                 */
+  size_t workspace_bytes;
+} DmipSampler;
+
+size_t dmip_sampler_workspace_bytes(const DmipSampler* d);
+int dmip_sampler_em_vp(const DmipSampler* d, void* stream);
+/* number of kernel launches the last dmip_* call on this thread enqueued (bench.py's gpu_launches) */
+int dmip_last_launch_count(void);
+
+/* ---- score-net forward  a(x, cond, t) ------------------------------------------------------------------
+ * Replaces MLP.forward / MLP2.forward (nets.py:32-35, :52-57): cat[x, cond, t] -> net.  `cond` may be NULL
+ * with cond_dim 0 (MLP2, or the empty tensor of losses.py:149).  out: (n, net.out_dim). */
+typedef struct DmipForward {
+  int32_t precision;
+  DmipMlp net;
+  const void* packed; /* DMIP_PREC_BF16: image packed with n_varying = in_dim, out_rows = out_dim */
+  int32_t l0_split;
+  int64_t n;
+  int32_t x_dim, cond_dim;
+  const float* x;    /* device (n, x_dim)    */
+  const float* cond; /* device (n, cond_dim) */
+  const float* t;    /* device (n,)          */
+  float* out;        /* device (n, out_dim)  */
+  void* workspace;
+  size_t workspace_bytes;
+} DmipForward;
+
+size_t dmip_forward_workspace_bytes(const DmipForward* d);
+int dmip_mlp_forward(const DmipForward* d, void* stream);
+
+/* ---- debug / self-test hooks (used by tests/ only) ------------------------------------------------------
+ * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
+ * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.
+ * k multiple of 64 (<=512), n multiple of 16 (<=128). */
+int dmip_debug_umma(int32_t mode, const float* a, const float* w, float* d, int32_t n, int32_t k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMIP_H_ */

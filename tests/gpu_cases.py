@@ -1,0 +1,200 @@
+"""GPU parity cases shared by the pytest suite (tests/test_gpu_*.py) and the staged diagnostic runner
+(tests/gpu_diag.py).  Every case calls the CUDA path through the C ABI (ctypes) or through the drop-in classes and
+compares with the CPU oracle / the reference-generated golden fixtures.  Tolerances are stated per case."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+import oracle
+from oracle import nets as on, sampler as osamp
+from oracle.weights import make_params, state_dict_from_params
+from util import load_golden, meta_hidden
+
+DEV = "cuda"
+
+
+def _dmip():
+    import dmip
+    from dmip import _lib
+    return dmip, _lib
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 building block
+def case_umma(mode, n, k, seed=0):
+    """128 x n x k bf16 GEMM via dmip_debug_umma.  bf16 products are exact in fp32, so only the summation order
+    differs from the fp64 reference on bf16-rounded operands: tolerance 1e-4 * sqrt(k)."""
+    _, _lib = _dmip()
+    L = _lib.require_gpu()
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(128, k, generator=g)
+    w = torch.randn(n, k, generator=g)
+    ref = (a.bfloat16().double() @ w.bfloat16().double().T).float()
+    ad, wd = a.to(DEV), w.to(DEV)
+    d = torch.full((128, n), float("nan"), device=DEV)
+    _lib.check(L.dmip_debug_umma(mode, ad.data_ptr(), wd.data_ptr(), d.data_ptr(), n, k, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (d.cpu() - ref).abs().max().item()
+    tol = 1e-4 * k ** 0.5
+    return err, tol, dict(d=d.cpu(), ref=ref)
+
+
+# ------------------------------------------------------------------------------------------- pack image
+def sw128_offset(row, k, kblock_bytes=16384):
+    kb, kin = k >> 6, k & 63
+    chunk = (kin >> 3) ^ (row & 7)
+    return kb * kblock_bytes + (row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (kin & 7) * 2
+
+
+def case_pack(xdim=3, ydim=23, out_dim=3, split=2, seed=3):
+    """The packed image must hold exactly bf16(W) at the swizzled positions the UMMA descriptor expects."""
+    _, _lib = _dmip()
+    L = _lib.require_gpu()
+    in_dim = xdim + ydim + 1
+    params = make_params(seed, in_dim, out_dim)
+    from dmip.nets import MLP
+    net = MLP(in_dim, out_dim, [512, 512, 512], torch.nn.Tanh())
+    net.load_state_dict(state_dict_from_params(params))
+    net.to(DEV)
+    dv = xdim
+    buf = _lib.PackedNet().get(net, dv, out_dim, split).cpu().numpy()
+    k0 = split * dv
+    k0pad = (k0 + 15) // 16 * 16
+    kb0 = (k0pad + 63) // 64
+    n_stages = 4 * kb0 + 72
+    assert buf.size >= n_stages * 16384 + (1664 + 512 * (in_dim - dv)) * 4
+    img = buf[: n_stages * 16384].view(np.uint16).reshape(n_stages, 8192)
+
+    def bf16_bits(x):
+        return (torch.as_tensor(x, dtype=torch.float32).bfloat16().view(torch.int16).numpy().astype(np.int64) & 0xFFFF)
+
+    bad = 0
+    W0, W1, W3 = params[0][0], params[1][0], params[3][0]
+    hi = W0.bfloat16().float()
+    lo = (W0 - hi).bfloat16().float()
+    rng = np.random.default_rng(0)
+    for _ in range(4000):
+        r, k = int(rng.integers(128)), int(rng.integers(64))
+        c, kb = int(rng.integers(4)), int(rng.integers(8))
+        # layer 1, chunk c, K-block kb
+        st = 4 * kb0 + c * 8 + kb
+        got = int(img[st, sw128_offset(r, k) // 2])
+        bad += got != int(bf16_bits(W1[c * 128 + r, kb * 64 + k]))
+        # output layer
+        st = 4 * kb0 + 64 + kb
+        want = int(bf16_bits(W3[r, kb * 64 + k])) if r < out_dim else 0
+        bad += int(img[st, sw128_offset(r, k) // 2]) != want
+        # layer 0, chunk c, K-block 0
+        st = c * kb0
+        kg = k
+        if kg < k0:
+            part, idx = divmod(kg, dv)
+            src = lo if (split == 3 and part == 2) else hi
+            want = int(bf16_bits(src[c * 128 + r, idx]))
+        else:
+            want = 0
+        bad += int(img[st, sw128_offset(r, k) // 2]) != want
+    tail = buf[n_stages * 16384:].view(np.float32)
+    ok_tail = np.array_equal(tail[:512], params[0][1].numpy()) and np.array_equal(tail[1536:1536 + out_dim], params[3][1].numpy()) \
+        and np.array_equal(tail[1664:1664 + 512 * (in_dim - dv)].reshape(512, -1), W0[:, dv:].numpy())
+    return bad + (0 if ok_tail else 1), 0, {}
+
+
+# ------------------------------------------------------------------------------------------- score-net forward
+def _load_net(cls_name, in_dim, out_dim, hidden, params):
+    from dmip import nets
+    net = getattr(nets, cls_name)(in_dim, out_dim, list(hidden), torch.nn.Tanh())
+    net.load_state_dict(state_dict_from_params(params))
+    return net.to(DEV)
+
+
+def case_forward(name, precision):
+    """a(x,y,t) vs the golden reference output.  fp32 path: 2e-5 (accumulation order).  bf16 path: operands rounded
+    to bf16 (rel 2^-9) through 4 layers and tanh.approx (2^-11): tolerance 5e-3 * max|out|."""
+    fx = load_golden(name)
+    seed, xdim, ydim, out_dim = (int(v) for v in fx["meta"][:4])
+    hidden = meta_hidden(fx, 4)
+    params = make_params(seed, xdim + ydim + 1, out_dim, hidden)
+    net = _load_net("MLP", xdim + ydim + 1, out_dim, hidden, params)
+    net.precision = precision
+    with torch.no_grad():
+        out = net(fx["x"].to(DEV), fx["y"].to(DEV), fx["t"].to(DEV)).cpu()
+    scale = fx["out"].abs().max().item()
+    err = (out - fx["out"]).abs().max().item()
+    tol = (2e-5 if precision == "fp32" else 5e-3) * scale
+    return err, tol, dict(out=out, ref=fx["out"])
+
+
+# ------------------------------------------------------------------------------------------- samplers
+def _model(kind, xdim, ydim, hidden, seed):
+    from dmip.models.diffusion import CDE, CDiffE, PosteriorDiffusionEstimator
+    if kind == "CDE":
+        m = CDE(xdim, ydim, list(hidden))
+        m.sde.a.load_state_dict(state_dict_from_params(make_params(seed, xdim + ydim + 1, xdim, hidden)))
+    elif kind == "CDiffE":
+        m = CDiffE(xdim, ydim, list(hidden))
+        m.sde.a.load_state_dict(state_dict_from_params(make_params(seed, xdim + ydim + 1, xdim + ydim, hidden)))
+    else:
+        m = PosteriorDiffusionEstimator(xdim, ydim, list(hidden))
+        m.sde.a.prior_net.load_state_dict(state_dict_from_params(make_params(seed, xdim + 1, xdim, hidden)))
+        m.sde.a.likelihood_net.load_state_dict(
+            state_dict_from_params(make_params(seed + 100, xdim + ydim + 1, xdim, hidden)))
+    m.sde.to(DEV)
+    return m
+
+
+def case_sampler(name, kind, precision, split=2):
+    """Injected-noise sampler parity vs the golden reference samples.
+
+    These fixtures use *untrained* nets, whose reverse dynamics expand (|x| reaches ~1e2) and amplify any
+    perturbation, so the error is measured relative to max|x|: fp32 path 1e-5, bf16 path 2e-3
+    (the contractive, trained case is `case_sampler_trained`)."""
+    fx = load_golden(name)
+    seed, xdim, ydim, N, S = (int(v) for v in fx["meta"][:5])
+    m = _model(kind, xdim, ydim, meta_hidden(fx, 5), seed)
+    m.l0_split = split
+    mean, std = (fx["mean_std"].tolist() if "mean_std" in fx else (0.0, 1.0))
+    inj = dict(x0=fx["x0"], noise=fx["noise"])
+    if kind == "CDiffE":
+        inj["ynoise"] = fx["ynoise"]
+    out = torch.from_numpy(m(fx["y"], num_samples=N, num_steps=S, mean=mean, std=std, precision=precision, injected=inj))
+    scale = fx["out"].abs().max().item()
+    err = (out - fx["out"]).abs().max().item()
+    tol = (1e-5 if precision == "fp32" else 2e-3) * scale
+    return err, tol, dict(out=out, ref=fx["out"])
+
+
+def trained_model():
+    from dmip.models.diffusion import CDE
+    fx = load_golden("trained_cde_linear")
+    m = CDE(2, 2, [512, 512, 512])
+    m.sde.a.load_state_dict({f"{k}.{n}": fx[f"{k}_{n}"] for k in (0, 3, 5, 7) for n in ("weight", "bias")})
+    m.sde.to(DEV)
+    return m
+
+
+def case_sampler_trained(precision, mode):
+    """Trained linear CDE, reference default S=200, N=512; noise = the keyed Philox stream.
+    mode 'injected': the numpy-generated stream is fed in;  mode 'philox': the kernel generates it itself
+    (gidx/step/quad keyed) — both must reproduce the reference samples.
+    Tolerance: fp32 5e-4 (Philox transcendental intrinsics differ from numpy by ~1e-6 per draw, over 200 steps),
+    bf16 1e-2 max abs, plus mean shift <= 3e-3 and std ratio within 5e-3."""
+    fx = load_golden("sampler_trained_cde_linear")
+    N, S, seed = (int(v) for v in fx["philox"])
+    m = trained_model()
+    kw = {}
+    if mode == "injected":
+        gidx = np.arange(N)
+        kw["injected"] = dict(
+            x0=torch.from_numpy(oracle.philox.normals(gidx, oracle.philox.STEP_INIT, 0, 2, seed)),
+            noise=torch.from_numpy(np.stack([oracle.philox.normals(gidx, i, 0, 2, seed) for i in range(S)])))
+    else:
+        kw["seed"] = seed
+    out = torch.from_numpy(m(fx["y"], num_samples=N, num_steps=S, precision=precision, **kw))
+    err = (out - fx["out"]).abs().max().item()
+    tol = 5e-4 if precision == "fp32" else 1e-2
+    dmean = (out.mean(0) - fx["out"].mean(0)).abs().max().item()
+    rstd = (out.std(0) / fx["out"].std(0) - 1).abs().max().item()
+    if precision == "bf16" and (dmean > 3e-3 or rstd > 5e-3):
+        err = max(err, 1.0)
+    return err, tol, dict(out=out, ref=fx["out"], dmean=dmean, rstd=rstd)

@@ -1,0 +1,49 @@
+"""GPU parity tests of the sampler / forward hot path (run on the B200 box: pytest -m gpu)."""
+import pytest
+
+import gpu_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ok(res):
+    err, tol, extra = res
+    assert err <= tol, (err, tol, {k: v for k, v in extra.items() if isinstance(v, float)})
+
+
+@pytest.mark.parametrize("mode,n,k", [(0, 128, 64), (0, 128, 256), (0, 16, 128), (1, 128, 64), (1, 128, 256), (1, 48, 128)])
+def test_umma_building_block(mode, n, k):
+    _ok(gc.case_umma(mode, n, k))
+
+
+@pytest.mark.parametrize("split", [1, 2, 3])
+def test_pack_image(split):
+    _ok(gc.case_pack(split=split))
+
+
+@pytest.mark.parametrize("name", ["mlp_cde_linear", "mlp_cdiffe_scat", "mlp_synth", "mlp_small"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward(name, precision):
+    _ok(gc.case_forward(name, precision))     # mlp_small + bf16 dispatches to the fp32 kernels (widths != 512)
+
+
+SAMPLERS = [("sampler_cde_linear", "CDE"), ("sampler_cde_linear_meanstd", "CDE"), ("sampler_cde_scat", "CDE"),
+            ("sampler_cde_synth", "CDE"), ("sampler_cde_small", "CDE"), ("sampler_cdiffe_linear", "CDiffE"),
+            ("sampler_cdiffe_scat", "CDiffE"), ("sampler_dps_scat", "Posterior")]
+
+
+@pytest.mark.parametrize("name,kind", SAMPLERS)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sampler_injected_noise(name, kind, precision):
+    _ok(gc.case_sampler(name, kind, precision))
+
+
+@pytest.mark.parametrize("split", [1, 3])
+def test_sampler_layer0_split_modes(split):
+    _ok(gc.case_sampler("sampler_cde_linear", "CDE", "bf16", split))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["injected", "philox"])
+def test_sampler_trained_reference_default_steps(precision, mode):
+    _ok(gc.case_sampler_trained(precision, mode))
