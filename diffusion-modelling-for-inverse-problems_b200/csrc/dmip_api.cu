@@ -93,7 +93,8 @@ int dmip_pack_mlp(const DmipMlp* net, int32_t n_varying, int32_t out_rows, int32
 }
 
 size_t dmip_sampler_workspace_bytes(const DmipSampler* d) {
-  if (!d || d->precision != DMIP_PREC_F32) return 0;
+  if (!d) return 0;
+  if (d->precision == DMIP_PREC_BF16) return sampler_tc_workspace();
   return sampler_f32_workspace(d);
 }
 
@@ -142,6 +143,10 @@ int dmip_mlp_forward(const DmipForward* d, void* stream) {
     return DMIP_EWORKSPACE;
   }
   return launch_forward_f32(d, s);
+}
+
+void dmip_debug_set_timeline(void* device_buf, int32_t capacity) {
+  debug_set_timeline(static_cast<unsigned long long*>(device_buf), capacity);
 }
 
 int dmip_debug_umma(int32_t mode, const float* a, const float* w, float* d, int32_t n, int32_t k, void* stream) {

@@ -37,7 +37,8 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 struct TcNetGeom {
   int n_varying;   // dv: leading input columns that enter the layer-0 GEMM
   int split;       // layer-0 operand split (1,2,3)
-  int k0;          // split * dv
+  int dvp;         // part stride of the split operand: round_up(dv, 8)
+  int k0;          // (split - 1) * dvp + dv
   int k0pad;       // k0 rounded up to 16
   int kb0;         // K-blocks (64) of layer 0
   int out_rows;    // leading output rows kept
@@ -61,6 +62,8 @@ int launch_sampler_f32(const DmipSampler* d, cudaStream_t s);
 int launch_forward_f32(const DmipForward* d, cudaStream_t s);
 size_t sampler_f32_workspace(const DmipSampler* d);
 size_t forward_f32_workspace(const DmipForward* d);
+size_t sampler_tc_workspace();
+void debug_set_timeline(unsigned long long* buf, int cap);
 int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s);
 
 }  // namespace dmip

@@ -19,7 +19,8 @@ int tc_net_geom(const DmipMlp* net, int n_varying, int out_rows, int split, TcNe
                "out_rows %d out of range (out_dim %d, max 128)", out_rows, net->out_dim);
   g->n_varying = n_varying;
   g->split = split;
-  g->k0 = split * n_varying;
+  g->dvp = round_up(n_varying, 8);
+  g->k0 = (split - 1) * g->dvp + n_varying;
   g->k0pad = round_up(g->k0, 16);
   DMIP_REQUIRE(g->k0pad <= 512, "layer-0 GEMM depth %d exceeds 512", g->k0pad);
   g->kb0 = ceil_div(g->k0pad, 64);
@@ -35,7 +36,7 @@ namespace {
 struct PackParams {
   const float* W[4];
   const float* b[4];
-  int in_dim, dv, split, k0, kb0, out_rows, n_const, n_stages;
+  int in_dim, dv, dvp, split, k0, kb0, out_rows, n_const, n_stages;
   uint8_t* stages;
   float* tail;
 };
@@ -59,8 +60,9 @@ __global__ void k_pack(const PackParams p) {
       const int kg = kb * 64 + k;
       float v = 0.f;
       if (l == 0) {
-        if (kg < p.k0) {
-          const int part = kg / p.dv, idx = kg - part * p.dv;
+        const int part = kg / p.dvp, idx = kg - part * p.dvp;
+        if (part < p.split && idx < p.dv) {
+          // operand parts [x_hi | x_lo | x_hi] meet weight parts [W_hi | W_hi | W_lo]
           const float w = p.W[0][static_cast<size_t>(n) * p.in_dim + idx];
           const float hi = bf16_round(w);
           v = (part == 2) ? (w - hi) : hi;
@@ -95,6 +97,7 @@ int launch_pack(const DmipMlp* net, const TcNetGeom& g, void* packed, cudaStream
   }
   p.in_dim = net->in_dim;
   p.dv = g.n_varying;
+  p.dvp = g.dvp;
   p.split = g.split;
   p.k0 = g.k0;
   p.kb0 = g.kb0;

@@ -11,7 +11,7 @@
 //               (A0: smem -> H1: tmem -> H2: smem -> H3: tmem), so a layer's epilogue never overwrites the
 //               operand its own MMAs are still reading, and the epilogue of chunk c overlaps the MMAs of chunk
 //               c+1 (two 128-column accumulator buffers).
-//   warps 4-11  epilogue (two threads per particle row): tcgen05.ld accumulator -> +bias -> tanh (twice after
+//   warps 2-9   epilogue (two threads per particle row): tcgen05.ld accumulator -> +bias -> tanh (twice after
 //               layer 0) -> bf16 -> next layer's A operand (tcgen05.st, or swizzled st.shared).
 //               After the output layer: reverse-SDE drift/diffusion update of the fp32 state, Philox noise, and
 //               the next step's layer-0 operand.  y and t never enter the GEMM: they are constant over the
@@ -30,7 +30,7 @@ constexpr int kTileM = 128;
 constexpr int kStageBytes = 16384;   // 128 rows x 64 k x bf16
 constexpr int kNumStages = 5;
 constexpr int kHBytes = 131072;      // 128 rows x 512 k x bf16 = 8 K-blocks
-constexpr int kThreads = 384;        // warps: 0 producer, 1 MMA, 2-3 spare, 4..11 epilogue
+constexpr int kThreads = 320;        // warps: 0 producer, 1 MMA, 2..9 epilogue
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemH = 0;       // 256 columns: 128 x 512 bf16 activations (A operand)
@@ -77,6 +77,9 @@ struct TcParams {
   const float* fcond;
   const float* ft;
   int fx_dim, fcond_dim, out_dim;
+  float* xs;                // fp32 state of the tiles in flight: [grid][16 pieces][128 rows][8]
+  unsigned long long* tl;   // optional timeline buffer (debug): [0] = count, then (clock << 16 | code)
+  int tl_cap;
 };
 
 struct Bars {
@@ -157,12 +160,49 @@ __device__ __forceinline__ void a0_store(uint8_t* sH, int row, int k, float v) {
   const unsigned short h = static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xFFFFu);
   *reinterpret_cast<unsigned short*>(sH + off) = h;
 }
-// element `idx` (of dv row-varying inputs) with value v, under the layer-0 split scheme
-__device__ __forceinline__ void a0_put(uint8_t* sH, int row, int idx, int dv, int split, float v) {
+// element `idx` (of dv row-varying inputs) with value v, under the layer-0 split scheme; the parts of the split
+// operand start at multiples of dvp = round_up(dv, 8) so that 8 consecutive inputs are one 16-byte chunk
+__device__ __forceinline__ void a0_put(uint8_t* sH, int row, int idx, int dvp, int split, float v) {
   const float hi = bf16_round(v);
   a0_store(sH, row, idx, hi);
-  if (split >= 2) a0_store(sH, row, dv + idx, v - hi);
-  if (split >= 3) a0_store(sH, row, 2 * dv + idx, hi);
+  if (split >= 2) a0_store(sH, row, dvp + idx, v - hi);
+  if (split >= 3) a0_store(sH, row, 2 * dvp + idx, hi);
+}
+// eight consecutive inputs idx0 .. idx0+7 (idx0 % 8 == 0): one 16-byte swizzled store per split part
+__device__ __forceinline__ void a0_put8(uint8_t* sH, int row, int idx0, int dvp, int split, const float (&v)[8]) {
+  float hi[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) hi[e] = bf16_round(v[e]);
+  const uint32_t h0 = pack_bf16x2(hi[0], hi[1]), h1 = pack_bf16x2(hi[2], hi[3]), h2 = pack_bf16x2(hi[4], hi[5]),
+                 h3 = pack_bf16x2(hi[6], hi[7]);
+  uint8_t* rowp = sH + (row >> 3) * 1024 + (row & 7) * 128;
+  auto chunk_ptr = [&](int k) { return rowp + (k >> 6) * kStageBytes + ((((k & 63) >> 3) ^ (row & 7)) << 4); };
+  st_shared_v4(chunk_ptr(idx0), h0, h1, h2, h3);
+  if (split >= 2)
+    st_shared_v4(chunk_ptr(dvp + idx0), pack_bf16x2(v[0] - hi[0], v[1] - hi[1]), pack_bf16x2(v[2] - hi[2], v[3] - hi[3]),
+                 pack_bf16x2(v[4] - hi[4], v[5] - hi[5]), pack_bf16x2(v[6] - hi[6], v[7] - hi[7]));
+  if (split >= 3) st_shared_v4(chunk_ptr(2 * dvp + idx0), h0, h1, h2, h3);
+}
+
+// layer-0 operand columns of one state piece.  CDiffE keeps re-diffused y_t in the columns right after x, written
+// by other threads, so there only the x columns themselves are touched.
+__device__ __forceinline__ void a0_put_piece(uint8_t* sH, int row, int pc, int dvp, int split, const float (&x)[8],
+                                             bool elementwise, int width) {
+  if (!elementwise) {
+    a0_put8(sH, row, pc * 8, dvp, split, x);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (pc * 8 + e < width) a0_put(sH, row, pc * 8 + e, dvp, split, x[e]);
+  }
+}
+
+__device__ __forceinline__ void tl_mark(const TcParams& P, uint32_t code) {
+  if (P.tl != nullptr && blockIdx.x == 0) {
+    const unsigned int i = atomicAdd(reinterpret_cast<unsigned int*>(P.tl), 1u);
+    if (i + 1 < static_cast<unsigned int>(P.tl_cap))
+      P.tl[i + 1] = (static_cast<unsigned long long>(clock64()) << 16) | code;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -250,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             const TcNetDev& net = P.net[p];
             mbar_wait(B.a0_ready, a0_par, 0x200);
             a0_par ^= 1u;
+            int jl = 0;
 #pragma unroll 1
             for (int l = 0; l < 4; ++l) {
               const int n_chunks = (l == 3) ? 1 : 4;
@@ -258,10 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                                               : umma_idesc_bf16(128, 128);
               const bool a_in_smem = (l & 1) == 0;
 #pragma unroll 1
-              for (int c = 0; c < n_chunks; ++c, ++job) {
+              for (int c = 0; c < n_chunks; ++c, ++job, ++jl) {
                 const int buf = job & 1;
                 mbar_wait(&B.acc_empty[buf], (acc_uses[buf] & 1u) ^ 1u, 0x300 + buf);
                 acc_uses[buf]++;
+                tl_mark(P, 0x100u | jl);
                 const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
 #pragma unroll 1
                 for (int kb = 0; kb < KB; ++kb) {
@@ -286,24 +328,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                   if (++s == kNumStages) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(&B.acc_full[buf]);
+                tl_mark(P, 0x200u | jl);
               }
             }
           }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // =============================================================== epilogue (256 threads, 2 per row)
-    const int ew = warp - 4;
-    const int quarter = ew & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // warp % 4: the TMEM lane quarter this warp may access
     const int hh = ew >> 2;
     const int row = quarter * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..255
+    const int et = threadIdx.x - 64;  // 0..255
+    const bool tl_on = (et == 0);
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_uses[2] = {0, 0};
     uint32_t job = 0;
     const float dbeta = P.bmax - P.bmin;
     const long long n_total = static_cast<long long>(P.n_obs) * P.n_per_obs;
+    const TcNetDev& net_last = P.net[n_pass - 1];
+    const int dvp = (net_last.dv + 7) & ~7;
+
+    // state-column ownership of this thread (8-column pieces of the output layer): hh = 0 takes the first half
+    const int np = net_last.outpad >> 3;
+    const int np0 = (np + 1) >> 1;
+    const int piece_lo = hh == 0 ? 0 : np0;
+    const int piece_hi = hh == 0 ? np0 : np;
+    const int width = P.mode == kModeSampler ? P.xdim : P.out_dim;   // valid output columns
+    const bool ew_put = (P.variant == DMIP_CDIFFE);
+    // fp32 state of the tiles in flight: xs[block][piece][row][8] (L2-resident, coalesced 32 B per thread)
+    float* xs_blk = P.xs + static_cast<size_t>(blockIdx.x) * 16 * kTileM * 8;
 
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       const int obs = static_cast<int>(tile / P.tiles_per_obs);
@@ -312,15 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       const long long grow = static_cast<long long>(obs) * P.n_per_obs + prow;
       const unsigned long long gidx = P.gidx_base + static_cast<unsigned long long>(grow);
 
-      // state-column ownership of this thread in the output-layer epilogue (8-column pieces)
-      const int np = P.net[n_pass - 1].outpad >> 3;
-      const int np0 = (np + 1) >> 1;
-      const int piece_lo = hh == 0 ? 0 : np0;
-      const int piece_hi = hh == 0 ? np0 : np;
-      const int j_lo = piece_lo * 8;
-      const int j_hi = min(piece_hi * 8, P.mode == kModeSampler ? P.xdim : P.out_dim);
-
-      // ---- tile init: per-observation layer-0 bias parts, x0, first A0
+      // ---- tile init: per-observation layer-0 bias parts, x0 -> state + layer-0 operand
       if (P.mode == kModeSampler) {
         for (int p = 0; p < n_pass; ++p) {
           const TcNetDev& net = P.net[p];
@@ -332,15 +380,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             sWt[p * 512 + n] = wr[net.n_const - 1];
           }
         }
-        if (valid) {
-          for (int j0 = j_lo; j0 < j_hi; j0 += 4) {
-            float z[4];
-            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, kPhiloxStepInit, kStreamState, j0 >> 2, P.seed, z);
-            for (int e = 0; e < 4 && j0 + e < j_hi; ++e) {
-              const float zz = P.rng_mode == DMIP_RNG_PHILOX ? z[e] : P.x0[grow * P.xdim + j0 + e];
-              P.out[grow * P.xdim + j0 + e] = zz * P.std + P.mean;
+        for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
+          float x[8];
+          float z4[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, kPhiloxStepInit, kStreamState, pc * 2 + h, P.seed, z4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = pc * 8 + h * 4 + e;
+              float zz = 0.f;
+              if (valid && j < width) zz = P.rng_mode == DMIP_RNG_PHILOX ? z4[e] : P.x0[grow * P.xdim + j];
+              x[h * 4 + e] = (valid && j < width) ? zz * P.std + P.mean : 0.f;   // models/diffusion.py:32-33
             }
           }
+          float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+          xp[0] = make_float4(x[0], x[1], x[2], x[3]);
+          xp[1] = make_float4(x[4], x[5], x[6], x[7]);
+          a0_put_piece(sH, row, pc, dvp, P.net[0].split, x, ew_put, width);
         }
       }
 
@@ -349,62 +406,72 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         const float tau = tau_of_step(step, S, P.T);
         const float beta = P.bmin + dbeta * tau;
         const float sb = sqrtf(beta);
+        const bool last_step = (step == n_steps - 1);
         float stash[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) stash[e] = 0.f;
 
         for (int p = 0; p < n_pass; ++p) {
           const TcNetDev& net = P.net[p];
-          // ---- layer-0 operand + effective bias for this pass
+          const bool last_pass = (p == n_pass - 1);
+          // ---- effective layer-0 bias of this pass; operand columns that are not carried state
           if (P.mode == kModeSampler) {
             for (int n = et; n < 512; n += kEpiThreads) sB0[n] = fmaf(tau, sWt[p * 512 + n], sU[p * 512 + n]);
-            if (valid) {
-              for (int j = j_lo; j < j_hi; ++j) a0_put(sH, row, j, net.dv, net.split, P.out[grow * P.xdim + j]);
-              if (P.variant == DMIP_CDIFFE) {
-                // y_t = alpha(tau) y + std(tau) eta   (sdes.py:37-49 via models/diffusion.py:172)
-                const float Bt = 0.5f * tau * tau * dbeta + tau * P.bmin;
-                const float alpha = __expf(-0.5f * Bt);
-                const float sd = sqrtf(1.0f - __expf(-Bt));
-                for (int q = hh; q * 4 < P.ydim; q += 2) {
-                  float z[4];
-                  if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, step, kStreamObs, q, P.seed, z);
-                  for (int e = 0; e < 4 && q * 4 + e < P.ydim; ++e) {
-                    const int jj = q * 4 + e;
-                    const float eta = P.rng_mode == DMIP_RNG_PHILOX
-                                          ? z[e]
-                                          : P.ynoise[(static_cast<long long>(step) * n_total + grow) * P.ydim + jj];
-                    a0_put(sH, row, P.xdim + jj, net.dv, net.split, fmaf(sd, eta, alpha * P.y[obs * P.ydim + jj]));
-                  }
+            if (p > 0) {
+              // second net of the step (DPS likelihood net): same x, rebuilt because H2 overwrote the operand
+              for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
+                const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+                const float4 q0 = xp[0], q1 = xp[1];
+                const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                a0_put_piece(sH, row, pc, dvp, net.split, x, ew_put, width);
+              }
+            }
+            if (P.variant == DMIP_CDIFFE && valid) {
+              // y_t = alpha(tau) y + std(tau) eta   (sdes.py:37-49 via models/diffusion.py:172)
+              const float Bt = 0.5f * tau * tau * dbeta + tau * P.bmin;
+              const float alpha = __expf(-0.5f * Bt);
+              const float sd = sqrtf(1.0f - __expf(-Bt));
+              for (int q = hh; q * 4 < P.ydim; q += 2) {
+                float z[4];
+                if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, step, kStreamObs, q, P.seed, z);
+                for (int e = 0; e < 4 && q * 4 + e < P.ydim; ++e) {
+                  const int jj = q * 4 + e;
+                  const float eta = P.rng_mode == DMIP_RNG_PHILOX
+                                        ? z[e]
+                                        : P.ynoise[(static_cast<long long>(step) * n_total + grow) * P.ydim + jj];
+                  a0_put(sH, row, P.xdim + jj, dvp, net.split, fmaf(sd, eta, alpha * P.y[obs * P.ydim + jj]));
                 }
               }
             }
           } else {
             for (int n = et; n < 512; n += kEpiThreads) sB0[n] = net.b0[n];
             if (valid) {
-              const int in_dim = net.dv;
-              for (int k = hh; k < in_dim; k += 2) {
+              for (int k = hh; k < net.dv; k += 2) {
                 float v;
                 if (k < P.fx_dim) v = P.fx[grow * P.fx_dim + k];
                 else if (k < P.fx_dim + P.fcond_dim) v = P.fcond[grow * P.fcond_dim + (k - P.fx_dim)];
                 else v = P.ft[grow];
-                a0_put(sH, row, k, net.dv, net.split, v);
+                a0_put(sH, row, k, dvp, net.split, v);
               }
             }
           }
           fence_proxy_async_smem();
           mbar_arrive(B.a0_ready);
+          if (tl_on) tl_mark(P, 0x500u);
           epi_bar_sync();  // sB0 visible to all epilogue threads
 
           // ---- layers 0..2
+          int jl = 0;
 #pragma unroll 1
           for (int l = 0; l < 3; ++l) {
             const float* bias = (l == 0) ? sB0 : (l == 1 ? net.b1 : net.b2);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c, ++job) {
+            for (int c = 0; c < 4; ++c, ++job, ++jl) {
               const int buf = job & 1;
               mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x600 + buf);
               acc_uses[buf]++;
               tc_fence_after();
+              if (tl_on) tl_mark(P, 0x300u | jl);
               const uint32_t acc_col = kTmemAcc + buf * 128;
               if (l == 0)
                 epi_hidden<true, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
@@ -412,6 +479,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                 epi_hidden<false, false>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               else
                 epi_hidden<false, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+              if (tl_on) tl_mark(P, 0x400u | jl);
+            }
+            if (l == 0 && last_pass && P.mode == kModeSampler) {
+              // ---- off the critical path (layers 1-2 are MMA-bound): the part of the Euler–Maruyama update that
+              // does not need the net:  x <- x + delta*beta/2*x + sqrt(delta*beta)*eps   (models/diffusion.py:42)
+              for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
+                float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+                const float4 q0 = xp[0], q1 = xp[1];
+                float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                float z4[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, step, kStreamState, pc * 2 + h, P.seed, z4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int j = pc * 8 + h * 4 + e;
+                    float eps = 0.f;
+                    if (valid && j < width)
+                      eps = P.rng_mode == DMIP_RNG_PHILOX
+                                ? z4[e]
+                                : P.noise[(static_cast<long long>(step) * n_total + grow) * P.xdim + j];
+                    const float xv = x[h * 4 + e];
+                    x[h * 4 + e] = xv + P.delta * (0.5f * beta * xv) + (P.sqrt_delta * sb) * eps;
+                  }
+                }
+                xp[0] = make_float4(x[0], x[1], x[2], x[3]);
+                xp[1] = make_float4(x[4], x[5], x[6], x[7]);
+              }
+              if (tl_on) tl_mark(P, 0x510u);
             }
           }
 
@@ -419,52 +515,63 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           {
             const int buf = job & 1;
             ++job;
+            // prefetch the pre-updated state of this thread's pieces while the last MMAs run
+            float xt[8][8];
+            if (P.mode == kModeSampler && last_pass) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int pc = piece_lo + i;
+                if (pc < piece_hi && pc * 8 < width) {
+                  const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+                  const float4 q0 = xp[0], q1 = xp[1];
+                  xt[i][0] = q0.x; xt[i][1] = q0.y; xt[i][2] = q0.z; xt[i][3] = q0.w;
+                  xt[i][4] = q1.x; xt[i][5] = q1.y; xt[i][6] = q1.z; xt[i][7] = q1.w;
+                }
+              }
+            }
             mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x700 + buf);
             acc_uses[buf]++;
             tc_fence_after();
+            if (tl_on) tl_mark(P, 0x300u | 12);
             const uint32_t acc_col = kTmemAcc + buf * 128;
-            const bool last_pass = (p == n_pass - 1);
-            for (int pc = piece_lo; pc < piece_hi; ++pc) {
-              uint32_t v[8];
-              tmem_ld8(lane_taddr + acc_col + pc * 8, v);
-              tc_wait_ld();
-              if (!valid || pc * 8 >= j_hi) continue;
-              float z[8];
-              if (P.mode == kModeSampler && last_pass && P.rng_mode == DMIP_RNG_PHILOX) {
-                float z4[4];
-                philox_normal4(gidx, step, kStreamState, pc * 2, P.seed, z4);
-                z[0] = z4[0]; z[1] = z4[1]; z[2] = z4[2]; z[3] = z4[3];
-                if (pc * 8 + 4 < j_hi) {
-                  philox_normal4(gidx, step, kStreamState, pc * 2 + 1, P.seed, z4);
-                  z[4] = z4[0]; z[5] = z4[1]; z[6] = z4[2]; z[7] = z4[3];
-                }
-              }
+            // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
+            // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
+            const float ca = P.delta * ((P.variant == DMIP_DPS) ? beta : sb);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int j = pc * 8 + e;
-                if (j < j_hi) {
-                  float a = __uint_as_float(v[e]) + net.b3[j];
-                  if (P.mode == kModeForward) {
-                    P.out[grow * P.out_dim + j] = a;
-                  } else if (!last_pass) {
-                    if (pc == piece_lo) stash[e] = a;  // DPS: outpad == 16, at most one piece per thread
-                  } else {
-                    if (n_pass == 2 && pc == piece_lo) a += stash[e];
-                    // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
-                    // DPS: a_net = sqrt(beta) (prior + lik) (nets.py:155-157) => mu = beta (prior+lik) + beta x / 2
-                    const float ca = (P.variant == DMIP_DPS) ? beta : sb;
-                    const float x = P.out[grow * P.xdim + j];
-                    const float eps = P.rng_mode == DMIP_RNG_PHILOX
-                                          ? z[e]
-                                          : P.noise[(static_cast<long long>(step) * n_total + grow) * P.xdim + j];
-                    const float mu = ca * a + 0.5f * beta * x;
-                    P.out[grow * P.xdim + j] = x + P.delta * mu + (P.sqrt_delta * sb) * eps;
+            for (int i = 0; i < 8; ++i) {
+              const int pc = piece_lo + i;
+              if (pc < piece_hi) {  // warp-uniform
+                uint32_t v[8];
+                tmem_ld8(lane_taddr + acc_col + pc * 8, v);
+                tc_wait_ld();
+                if (pc * 8 < width) {
+                  float xn[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int j = pc * 8 + e;
+                    const float a = __uint_as_float(v[e]) + (j < width ? net.b3[j] : 0.f);
+                    if (P.mode == kModeForward) {
+                      if (valid && j < width) P.out[grow * P.out_dim + j] = a;
+                    } else if (!last_pass) {
+                      if (i == 0) stash[e] = a;   // DPS: outpad == 16, one piece per thread
+                    } else {
+                      const float at = (n_pass == 2 && i == 0) ? a + stash[e] : a;
+                      xn[e] = (j < width) ? fmaf(ca, at, xt[i][e]) : 0.f;
+                      if (last_step && valid && j < width) P.out[grow * P.xdim + j] = xn[e];
+                    }
+                  }
+                  if (P.mode == kModeSampler && last_pass && !last_step) {
+                    float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+                    xp[0] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+                    xp[1] = make_float4(xn[4], xn[5], xn[6], xn[7]);
+                    a0_put_piece(sH, row, pc, dvp, P.net[0].split, xn, ew_put, width);   // next step's layer-0 operand
                   }
                 }
               }
             }
             tc_fence_before();
             mbar_arrive(&B.acc_empty[buf]);
+            if (tl_on) tl_mark(P, 0x400u | 12);
           }
         }  // pass
       }    // step
@@ -581,14 +688,26 @@ int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows
   return 0;
 }
 
-int launch(const TcParams& P, cudaStream_t s) {
-  static int n_sm = 0;
-  if (!n_sm) {
+int g_n_sm = 0;
+unsigned long long* g_tl = nullptr;
+int g_tl_cap = 0;
+
+int init_device() {
+  if (!g_n_sm) {
     int dev = 0;
     DMIP_CHECK_CUDA(cudaGetDevice(&dev));
-    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&g_n_sm, cudaDevAttrMultiProcessorCount, dev));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
+  return DMIP_OK;
+}
+
+int launch(TcParams& P, cudaStream_t s) {
+  int rc = init_device();
+  if (rc) return rc;
+  const int n_sm = g_n_sm;
+  P.tl = g_tl;
+  P.tl_cap = g_tl_cap;
   const long long grid = P.n_tiles < n_sm ? P.n_tiles : n_sm;
   if (grid <= 0) return DMIP_OK;
   k_tc_mlp<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, s>>>(P);
@@ -599,8 +718,22 @@ int launch(const TcParams& P, cudaStream_t s) {
 
 }  // namespace
 
+size_t sampler_tc_workspace() {
+  if (init_device()) return 0;
+  return static_cast<size_t>(g_n_sm) * 16 * kTileM * 8 * sizeof(float);   // fp32 state of the tiles in flight
+}
+
+void debug_set_timeline(unsigned long long* buf, int cap) {
+  g_tl = buf;
+  g_tl_cap = cap;
+}
+
 int launch_sampler_tc(const DmipSampler* d, cudaStream_t s) {
   TcParams P = {};
+  DMIP_REQUIRE(d->workspace && d->workspace_bytes >= sampler_tc_workspace() &&
+                   (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0,
+               "workspace too small or misaligned: need %zu bytes, 16-byte aligned", sampler_tc_workspace());
+  P.xs = static_cast<float*>(d->workspace);
   P.mode = kModeSampler;
   P.variant = d->variant;
   const int dv = d->variant == DMIP_CDIFFE ? d->xdim + d->ydim : d->xdim;

@@ -107,11 +107,10 @@ class BaseClassDiffusionModel():
                 d.packed = self._packed[0].get(net, dv, self.xdim, self.l0_split).data_ptr()
                 if net2 is not None:
                     d.packed2 = self._packed[1].get(net2, self.xdim, self.xdim, self.l0_split).data_ptr()
-            else:
-                ws = torch.empty(max(L.dmip_sampler_workspace_bytes(C.byref(d)), 16), dtype=torch.uint8, device=dev)
-                keep.append(ws)
-                d.workspace = ws.data_ptr()
-                d.workspace_bytes = ws.numel()
+            ws = torch.empty(max(L.dmip_sampler_workspace_bytes(C.byref(d)), 16), dtype=torch.uint8, device=dev)
+            keep.append(ws)
+            d.workspace = ws.data_ptr()
+            d.workspace_bytes = ws.numel()
             _lib.check(L.dmip_sampler_em_vp(C.byref(d), _lib.stream_ptr()))
             self.last_launch_count = L.dmip_last_launch_count()
         if batched:

@@ -105,7 +105,7 @@ typedef struct DmipSampler {
   const float* x0;                 /* injected: (n_obs*n_per_obs, xdim) standard normals             */
   const float* noise;              /* injected: (S, n_obs*n_per_obs, xdim)                           */
   const float* ynoise;             /* injected, CDiffE: (S, n_obs*n_per_obs, ydim)                   */
-  void* workspace;                 /* device scratch, dmip_sampler_workspace_bytes()                 */
+  void* workspace;                 /* device scratch, dmip_sampler_workspace_bytes(), 16-byte aligned */
   size_t workspace_bytes;
 } DmipSampler;
 
@@ -139,6 +139,9 @@ int dmip_mlp_forward(const DmipForward* d, void* stream);
  * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
  * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.
  * k multiple of 64 (<=512), n multiple of 16 (<=128). */
+/* Timeline hook: when set, CTA 0 of the tcgen05 kernels records (clock64 << 16 | event code) entries into
+ * device_buf[1..capacity) and the entry count into device_buf[0] (uint64).  Pass NULL to switch off. */
+void dmip_debug_set_timeline(void* device_buf, int32_t capacity);
 int dmip_debug_umma(int32_t mode, const float* a, const float* w, float* d, int32_t n, int32_t k, void* stream);
 
 #ifdef __cplusplus

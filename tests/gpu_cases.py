@@ -58,7 +58,8 @@ def case_pack(xdim=3, ydim=23, out_dim=3, split=2, seed=3):
     net.to(DEV)
     dv = xdim
     buf = _lib.PackedNet().get(net, dv, out_dim, split).cpu().numpy()
-    k0 = split * dv
+    dvp = (dv + 7) // 8 * 8
+    k0 = (split - 1) * dvp + dv
     k0pad = (k0 + 15) // 16 * 16
     kb0 = (k0pad + 63) // 64
     n_stages = 4 * kb0 + 72
@@ -87,9 +88,9 @@ def case_pack(xdim=3, ydim=23, out_dim=3, split=2, seed=3):
         # layer 0, chunk c, K-block 0
         st = c * kb0
         kg = k
-        if kg < k0:
-            part, idx = divmod(kg, dv)
-            src = lo if (split == 3 and part == 2) else hi
+        part, idx = divmod(kg, dvp)
+        if part < split and idx < dv:
+            src = lo if part == 2 else hi
             want = int(bf16_bits(src[c * 128 + r, idx]))
         else:
             want = 0
