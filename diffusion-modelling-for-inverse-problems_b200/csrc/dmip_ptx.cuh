@@ -11,6 +11,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp.  The single-thread instructions (tcgen05.mma / commit, bulk copies) are wrapped in
+// `if (elect_one())` while the surrounding loop is executed by the whole warp: operands then stay provably
+// warp-uniform and live in uniform registers.  (Issuing from inside an `if (lane == 0)` region instead makes ptxas
+// emit an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" loop around every UTCHMMA — measured 5x slower issue.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ watchdog
 // A dead-locked mbarrier wait would hang the GPU until the process is killed.  Every wait therefore
 // carries a clock64() watchdog: after ~4e9 cycles it records (tag, block) and traps, which surfaces
@@ -69,6 +83,27 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// same copy, delivered to the same CTA-relative offset (data and mbarrier) of every CTA in `cta_mask`
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ thread-block cluster
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ tensor memory
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder) {  // one full warp
@@ -89,6 +124,14 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 // all previously issued tcgen05.mma of this thread arrive (once) on `bar` when they complete
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// the same arrival delivered to the barrier at this CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
                : "memory");
 }
 

@@ -18,6 +18,8 @@
 //               rows of a tile and are folded, in fp32, into a per-step layer-0 bias b0 + W0[:,y]·y + tau·W0[:,t].
 //
 // Reference code replaced: models/diffusion.py:27-46,158-180; sdes.py:21-49,77-87; nets.py:17-57,143-157.
+#include <stdlib.h>
+
 #include "dmip_common.h"
 #include "dmip_ptx.cuh"
 #include "dmip_rng.cuh"
@@ -78,6 +80,8 @@ struct TcParams {
   const float* ft;
   int fx_dim, fcond_dim, out_dim;
   float* xs;                // fp32 state of the tiles in flight: [grid][16 pieces][128 rows][8]
+  int dbg;                  // debug bits (DMIP_DBG): 1 = no weight copies, 2 = no MMA issue, 4 = 3-deep ring
+  int cluster;              // CTAs per cluster sharing one multicast weight stream (1, 2 or 4)
   unsigned long long* tl;   // optional timeline buffer (debug): [0] = count, then (clock << 16 | code)
   int tl_cap;
 };
@@ -224,14 +228,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   B.hready = B.acc_empty + 2;
   B.a0_ready = B.hready + 4;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kNumStages; ++i) {
       mbar_init(&B.full[i], 1);
-      mbar_init(&B.empty[i], 1);
+      mbar_init(&B.empty[i], static_cast<uint32_t>(P.cluster));   // one tcgen05.commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&B.acc_full[i], 1);
@@ -248,43 +252,66 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler
+
+  // Cluster: the C CTAs of a cluster walk the same stage sequence in lock-step; each loads 1/C of every weight
+  // stage and multicasts it to all of them, so L2 serves each line once per cluster instead of once per SM.
+  const int C = P.cluster;
+  const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
+  if (C > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive / multicast
+  const long long tile_first = static_cast<long long>(blockIdx.x / C) * C;
+  const long long tile_stride = static_cast<long long>(gridDim.x);
 
   const int n_pass = P.n_nets;
   const int S = P.S;
+  const int n_ring = (P.dbg & 4) ? 3 : kNumStages;
 
   if (warp == 0) {
-    // =============================================================== producer
-    if (lane == 0) {
+    // =============================================================== producer (whole warp, one elected lane issues)
+    {
       int s = 0;
       uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const uint32_t part = kStageBytes / C;
+      for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
         for (int step = 0; step < S; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const uint8_t* src = P.net[p].stages;
             const int ns = P.net[p].n_stages;
             for (int st = 0; st < ns; ++st) {
-              mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);
-              mbar_arrive_expect_tx(&B.full[s], kStageBytes);
-              bulk_g2s(sB + s * kStageBytes, src + static_cast<size_t>(st) * kStageBytes, kStageBytes, &B.full[s]);
-              if (++s == kNumStages) { s = 0; ph ^= 1u; }
+              mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);   // slot s released by the MMA warps of ALL cluster CTAs
+              const uint8_t* g = src + static_cast<size_t>(st) * kStageBytes;
+              if (elect_one()) {
+                if (P.dbg & 1) {
+                  mbar_arrive(&B.full[s]);
+                } else {
+                  mbar_arrive_expect_tx(&B.full[s], kStageBytes);
+                  if (C == 1)
+                    bulk_g2s(sB + s * kStageBytes, g, kStageBytes, &B.full[s]);
+                  else
+                    bulk_g2s_multicast(sB + s * kStageBytes + crank * part, g + crank * part, part, &B.full[s], cmask);
+                }
+              }
+              __syncwarp();
+              if (++s == n_ring) { s = 0; ph ^= 1u; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================================================== MMA issuer
-    if (lane == 0) {
+    // =============================================================== MMA issuer (whole warp, one elected lane issues)
+    {
       int s = 0;
       uint32_t ph = 0;
-      uint32_t acc_uses[2] = {0, 0};
-      uint32_t hr_par[4] = {0, 0, 0, 0};
+      uint32_t acc_uses0 = 0, acc_uses1 = 0;
+      uint32_t hr_par = 0;   // bit c = parity of hready[c]
       uint32_t a0_par = 0;
       uint32_t job = 0;
       const uint32_t sH_addr = smem_u32(sH);
       const uint32_t sB_addr = smem_u32(sB);
-      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // everything but the address field
+      for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
         for (int step = 0; step < S; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const TcNetDev& net = P.net[p];
@@ -301,34 +328,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 #pragma unroll 1
               for (int c = 0; c < n_chunks; ++c, ++job, ++jl) {
                 const int buf = job & 1;
-                mbar_wait(&B.acc_empty[buf], (acc_uses[buf] & 1u) ^ 1u, 0x300 + buf);
-                acc_uses[buf]++;
-                tl_mark(P, 0x100u | jl);
+                const uint32_t uses = buf ? acc_uses1 : acc_uses0;
+                mbar_wait(&B.acc_empty[buf], (uses & 1u) ^ 1u, 0x300 + buf);
+                if (buf) ++acc_uses1; else ++acc_uses0;
+                if (lane == 0) tl_mark(P, 0x100u | jl);
                 const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
 #pragma unroll 1
                 for (int kb = 0; kb < KB; ++kb) {
                   if (l > 0 && c == 0 && (kb & 1) == 0) {
-                    mbar_wait(&B.hready[kb >> 1], hr_par[kb >> 1], 0x400 + (kb >> 1));
-                    hr_par[kb >> 1] ^= 1u;
+                    mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
+                    hr_par ^= 1u << (kb >> 1);
                   }
                   mbar_wait(&B.full[s], ph, 0x500 + s);
                   tc_fence_after();
                   const int nk = (l == 0 && kb == KB - 1) ? (net.ksteps0 - 4 * (KB - 1)) : 4;
-                  for (int kk = 0; kk < nk; ++kk) {
-                    const uint64_t bdesc = umma_smem_desc_sw128(sB_addr + s * kStageBytes + kk * 32);
-                    const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-                    if (a_in_smem) {
-                      const uint64_t adesc = umma_smem_desc_sw128(sH_addr + kb * kStageBytes + kk * 32);
-                      umma_ss(d_tmem, adesc, bdesc, idesc, acc);
-                    } else {
-                      umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, acc);
+                  const uint32_t b_lo = ((sB_addr + s * kStageBytes) & 0x3FFFFu) >> 4;
+                  const uint32_t a_lo = ((sH_addr + kb * kStageBytes) & 0x3FFFFu) >> 4;
+                  const uint32_t a_tm = tmem_base + kTmemH + kb * 32;
+                  if (elect_one()) {
+                    if (!(P.dbg & 2)) {
+#pragma unroll
+                      for (int kk = 0; kk < 4; ++kk) {
+                        if (kk < nk) {
+                          const uint64_t bdesc = desc_hi | (b_lo + kk * 2);   // +32 B per UMMA_K step
+                          const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+                          if (a_in_smem) umma_ss(d_tmem, desc_hi | (a_lo + kk * 2), bdesc, idesc, acc);
+                          else umma_ts(d_tmem, a_tm + kk * 8, bdesc, idesc, acc);
+                        }
+                      }
                     }
+                    if (C == 1) tc_commit(&B.empty[s]);
+                    else tc_commit_multicast(&B.empty[s], cmask);
+                    if (kb == KB - 1) tc_commit(&B.acc_full[buf]);
                   }
-                  tc_commit(&B.empty[s]);
-                  if (++s == kNumStages) { s = 0; ph ^= 1u; }
+                  __syncwarp();
+                  if (++s == n_ring) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(&B.acc_full[buf]);
-                tl_mark(P, 0x200u | jl);
+                if (lane == 0) tl_mark(P, 0x200u | jl);
               }
             }
           }
@@ -361,10 +397,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     // fp32 state of the tiles in flight: xs[block][piece][row][8] (L2-resident, coalesced 32 B per thread)
     float* xs_blk = P.xs + static_cast<size_t>(blockIdx.x) * 16 * kTileM * 8;
 
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
+      // a cluster whose last round has fewer tiles than CTAs still runs every CTA (lock-step), on masked rows
+      const bool tile_ok = tb + crank < P.n_tiles;
+      const long long tile = tile_ok ? tb + crank : P.n_tiles - 1;
       const int obs = static_cast<int>(tile / P.tiles_per_obs);
       const long long prow = (tile % P.tiles_per_obs) * kTileM + row;
-      const bool valid = prow < P.n_per_obs;
+      const bool valid = tile_ok && prow < P.n_per_obs;
       const long long grow = static_cast<long long>(obs) * P.n_per_obs + prow;
       const unsigned long long gidx = P.gidx_base + static_cast<unsigned long long>(grow);
 
@@ -515,19 +554,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           {
             const int buf = job & 1;
             ++job;
-            // prefetch the pre-updated state of this thread's pieces while the last MMAs run
-            float xt[8][8];
-            if (P.mode == kModeSampler && last_pass) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int pc = piece_lo + i;
-                if (pc < piece_hi && pc * 8 < width) {
-                  const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-                  const float4 q0 = xp[0], q1 = xp[1];
-                  xt[i][0] = q0.x; xt[i][1] = q0.y; xt[i][2] = q0.z; xt[i][3] = q0.w;
-                  xt[i][4] = q1.x; xt[i][5] = q1.y; xt[i][6] = q1.z; xt[i][7] = q1.w;
-                }
-              }
+            // software-pipelined over this thread's 8-column pieces: the pre-updated state of piece i+1 is fetched
+            // from L2 while piece i is combined with the net output
+            const bool upd = (P.mode == kModeSampler) && last_pass;
+            float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
+            if (upd && piece_lo < piece_hi && piece_lo * 8 < width) {
+              const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(piece_lo) * kTileM + row) * 8);
+              nx0 = xp[0];
+              nx1 = xp[1];
             }
             mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x700 + buf);
             acc_uses[buf]++;
@@ -537,35 +571,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
             // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
             const float ca = P.delta * ((P.variant == DMIP_DPS) ? beta : sb);
+#pragma unroll 1
+            for (int pc = piece_lo; pc < piece_hi; ++pc) {   // warp-uniform bounds
+              const float xt[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+              if (upd && pc + 1 < piece_hi && (pc + 1) * 8 < width) {
+                const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(pc + 1) * kTileM + row) * 8);
+                nx0 = xp[0];
+                nx1 = xp[1];
+              }
+              uint32_t v[8];
+              tmem_ld8(lane_taddr + acc_col + pc * 8, v);
+              tc_wait_ld();
+              if (pc * 8 < width) {
+                const float4 b0 = *reinterpret_cast<const float4*>(net.b3 + pc * 8);   // zero-padded to 128
+                const float4 b1 = *reinterpret_cast<const float4*>(net.b3 + pc * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float xn[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int pc = piece_lo + i;
-              if (pc < piece_hi) {  // warp-uniform
-                uint32_t v[8];
-                tmem_ld8(lane_taddr + acc_col + pc * 8, v);
-                tc_wait_ld();
-                if (pc * 8 < width) {
-                  float xn[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const int j = pc * 8 + e;
-                    const float a = __uint_as_float(v[e]) + (j < width ? net.b3[j] : 0.f);
-                    if (P.mode == kModeForward) {
-                      if (valid && j < width) P.out[grow * P.out_dim + j] = a;
-                    } else if (!last_pass) {
-                      if (i == 0) stash[e] = a;   // DPS: outpad == 16, one piece per thread
-                    } else {
-                      const float at = (n_pass == 2 && i == 0) ? a + stash[e] : a;
-                      xn[e] = (j < width) ? fmaf(ca, at, xt[i][e]) : 0.f;
-                      if (last_step && valid && j < width) P.out[grow * P.xdim + j] = xn[e];
-                    }
+                for (int e = 0; e < 8; ++e) {
+                  const int j = pc * 8 + e;
+                  const float a = __uint_as_float(v[e]) + bb[e];
+                  if (P.mode == kModeForward) {
+                    if (valid && j < width) P.out[grow * P.out_dim + j] = a;
+                  } else if (!last_pass) {
+                    stash[e] = a;   // DPS prior pass: outpad == 16, one piece per thread
+                  } else {
+                    const float at = (n_pass == 2) ? a + stash[e] : a;
+                    xn[e] = (j < width) ? fmaf(ca, at, xt[e]) : 0.f;
+                    if (last_step && valid && j < width) P.out[grow * P.xdim + j] = xn[e];
                   }
-                  if (P.mode == kModeSampler && last_pass && !last_step) {
-                    float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-                    xp[0] = make_float4(xn[0], xn[1], xn[2], xn[3]);
-                    xp[1] = make_float4(xn[4], xn[5], xn[6], xn[7]);
-                    a0_put_piece(sH, row, pc, dvp, P.net[0].split, xn, ew_put, width);   // next step's layer-0 operand
-                  }
+                }
+                if (upd && !last_step) {
+                  float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+                  xp[0] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+                  xp[1] = make_float4(xn[4], xn[5], xn[6], xn[7]);
+                  a0_put_piece(sH, row, pc, dvp, P.net[0].split, xn, ew_put, width);   // next step's layer-0 operand
                 }
               }
             }
@@ -581,6 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
@@ -689,6 +730,8 @@ int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows
 }
 
 int g_n_sm = 0;
+int g_dbg = 0;
+int g_cluster = 2;   // CTAs per multicast cluster (DMIP_CLUSTER=1|2|4 overrides)
 unsigned long long* g_tl = nullptr;
 int g_tl_cap = 0;
 
@@ -698,6 +741,9 @@ int init_device() {
     DMIP_CHECK_CUDA(cudaGetDevice(&dev));
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&g_n_sm, cudaDevAttrMultiProcessorCount, dev));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (getenv("DMIP_DBG")) g_dbg = atoi(getenv("DMIP_DBG"));
+    const char* e = getenv("DMIP_CLUSTER");
+    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) g_cluster = atoi(e);
   }
   return DMIP_OK;
 }
@@ -708,9 +754,27 @@ int launch(TcParams& P, cudaStream_t s) {
   const int n_sm = g_n_sm;
   P.tl = g_tl;
   P.tl_cap = g_tl_cap;
-  const long long grid = P.n_tiles < n_sm ? P.n_tiles : n_sm;
-  if (grid <= 0) return DMIP_OK;
-  k_tc_mlp<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, s>>>(P);
+  if (P.n_tiles <= 0) return DMIP_OK;
+  int C = g_cluster;
+  while (C > 1 && P.n_tiles < C) C >>= 1;
+  P.cluster = C;
+  P.dbg = g_dbg;
+  const long long want_clusters = (P.n_tiles + C - 1) / C;
+  const long long max_clusters = n_sm / C;
+  const long long n_clusters = want_clusters < max_clusters ? want_clusters : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * C));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(C);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp, P));
   DMIP_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DMIP_OK;
