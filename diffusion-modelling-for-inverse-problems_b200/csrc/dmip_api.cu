@@ -145,6 +145,13 @@ int dmip_mlp_forward(const DmipForward* d, void* stream) {
   return launch_forward_f32(d, s);
 }
 
+int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  return launch_debug_mma_bench(mode, n, k, iters, grid, static_cast<long long*>(cycles), static_cast<cudaStream_t>(stream));
+}
+
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity) {
   debug_set_timeline(static_cast<unsigned long long*>(device_buf), capacity);
 }

@@ -64,6 +64,7 @@ size_t sampler_f32_workspace(const DmipSampler* d);
 size_t forward_f32_workspace(const DmipForward* d);
 size_t sampler_tc_workspace();
 void debug_set_timeline(unsigned long long* buf, int cap);
+int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s);
 int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s);
 
 }  // namespace dmip

@@ -41,8 +41,8 @@ constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
 // shared-memory map (offsets from a 1024-aligned base)
 constexpr int kOffH = 0;
 constexpr int kOffB = kOffH + kHBytes;
-constexpr int kOffB0 = kOffB + kNumStages * kStageBytes;  // float[512] effective layer-0 bias of the current pass
-constexpr int kOffU = kOffB0 + 2048;                      // float[2][512] b0 + W0[:,y]·y per net
+constexpr int kOffB0 = kOffB + kNumStages * kStageBytes;  // float[2][512] effective layer-0 bias: current pass / next pass
+constexpr int kOffU = kOffB0 + 4096;                      // float[2][512] b0 + W0[:,y]·y per net
 constexpr int kOffWt = kOffU + 4096;                      // float[2][512] W0[:,t] per net
 constexpr int kOffBar = kOffWt + 4096;
 constexpr int kNumBars = 2 * kNumStages + 2 + 2 + 4 + 1;
@@ -113,11 +113,16 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 template <bool kDoubleTanh, bool kToTmem>
 __device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col, int hh, int row, int chunk,
                                            const float* __restrict__ bias, uint8_t* sH, uint64_t* acc_empty,
-                                           uint64_t* hready) {
+                                           uint64_t* hready, int dbg) {
   uint32_t v0[32], v1[32];
-  tmem_ld32(lane_taddr + acc_col + hh * 64, v0);
-  tmem_ld32(lane_taddr + acc_col + hh * 64 + 32, v1);
-  tc_wait_ld();
+  if (dbg & 8) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v0[i] = 0x3c000000u + row + i; v1[i] = 0x3c100000u + row * 3 + i; }
+  } else {
+    tmem_ld32(lane_taddr + acc_col + hh * 64, v0);
+    tmem_ld32(lane_taddr + acc_col + hh * 64 + 32, v1);
+    tc_wait_ld();
+  }
   tc_fence_before();
   mbar_arrive(acc_empty);  // accumulator chunk is in registers: the MMA warp may reuse the buffer
   const int n0 = chunk * 128 + hh * 64;
@@ -133,13 +138,15 @@ __device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col
         const uint32_t raw = p == 0 ? v0[q * 4 + e] : v1[q * 4 + e];
         const float bb = e == 0 ? bq.x : e == 1 ? bq.y : e == 2 ? bq.z : bq.w;
         float t = tanh_fast(__uint_as_float(raw) + bb);
-        if (kDoubleTanh) t = tanh_fast(t);
+        if (kDoubleTanh) t = tanh_unit_poly(t);   // second tanh (Q1) on the FMA pipe: the MUFU is the busy one
         a[e] = t;
       }
       pk[q * 2] = pack_bf16x2(a[0], a[1]);
       pk[q * 2 + 1] = pack_bf16x2(a[2], a[3]);
     }
-    if (kToTmem) {
+    if (dbg & 16) {
+      if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) hready[1] = pk[3];   // keep the math alive, store nothing
+    } else if (kToTmem) {
       tmem_st16(lane_taddr + kTmemH + static_cast<uint32_t>((n0 + p * 32) >> 1), pk);
     } else {
       // K index of these 32 values: n0 + p*32 .. +31  ->  K-block chunk*2+hh, 16-byte chunks p*4 .. p*4+3
@@ -308,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       uint32_t hr_par = 0;   // bit c = parity of hready[c]
       uint32_t a0_par = 0;
       uint32_t job = 0;
+      bool ready = false;   // result of the early probe of full[s]
       const uint32_t sH_addr = smem_u32(sH);
       const uint32_t sB_addr = smem_u32(sB);
       const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // everything but the address field
@@ -339,12 +347,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                     mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
                     hr_par ^= 1u << (kb >> 1);
                   }
-                  mbar_wait(&B.full[s], ph, 0x500 + s);
+                  if (!ready) mbar_wait(&B.full[s], ph, 0x500 + s);
                   tc_fence_after();
                   const int nk = (l == 0 && kb == KB - 1) ? (net.ksteps0 - 4 * (KB - 1)) : 4;
                   const uint32_t b_lo = ((sB_addr + s * kStageBytes) & 0x3FFFFu) >> 4;
                   const uint32_t a_lo = ((sH_addr + kb * kStageBytes) & 0x3FFFFu) >> 4;
                   const uint32_t a_tm = tmem_base + kTmemH + kb * 32;
+                  const int s_cur = s;
+                  if (++s == n_ring) { s = 0; ph ^= 1u; }
+                  // probe the NEXT stage's barrier now: its latency hides behind the MMA issue below
+                  ready = mbar_try_wait(&B.full[s], ph);
                   if (elect_one()) {
                     if (!(P.dbg & 2)) {
 #pragma unroll
@@ -357,12 +369,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                         }
                       }
                     }
-                    if (C == 1) tc_commit(&B.empty[s]);
-                    else tc_commit_multicast(&B.empty[s], cmask);
+                    if (C == 1) tc_commit(&B.empty[s_cur]);
+                    else tc_commit_multicast(&B.empty[s_cur], cmask);
                     if (kb == KB - 1) tc_commit(&B.acc_full[buf]);
                   }
                   __syncwarp();
-                  if (++s == n_ring) { s = 0; ph ^= 1u; }
                 }
                 if (lane == 0) tl_mark(P, 0x200u | jl);
               }
@@ -382,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_uses[2] = {0, 0};
     uint32_t job = 0;
+    uint32_t npass = 0;   // running pass counter: selects the layer-0 bias buffer
     const float dbeta = P.bmax - P.bmin;
     const long long n_total = static_cast<long long>(P.n_obs) * P.n_per_obs;
     const TcNetDev& net_last = P.net[n_pass - 1];
@@ -417,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             for (int j = 0; j + 1 < net.n_const; ++j) u = fmaf(wr[j], P.y[obs * P.ydim + j], u);
             sU[p * 512 + n] = u;
             sWt[p * 512 + n] = wr[net.n_const - 1];
+            if (p == 0) sB0[(npass & 1) * 512 + n] = fmaf(tau_of_step(0, S, P.T), wr[net.n_const - 1], u);
           }
         }
         for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
@@ -455,7 +468,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           const bool last_pass = (p == n_pass - 1);
           // ---- effective layer-0 bias of this pass; operand columns that are not carried state
           if (P.mode == kModeSampler) {
-            for (int n = et; n < 512; n += kEpiThreads) sB0[n] = fmaf(tau, sWt[p * 512 + n], sU[p * 512 + n]);
             if (p > 0) {
               // second net of the step (DPS likelihood net): same x, rebuilt because H2 overwrote the operand
               for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               }
             }
           } else {
-            for (int n = et; n < 512; n += kEpiThreads) sB0[n] = net.b0[n];
+            for (int n = et; n < 512; n += kEpiThreads) sB0[(npass & 1) * 512 + n] = net.b0[n];
             if (valid) {
               for (int k = hh; k < net.dv; k += 2) {
                 float v;
@@ -503,7 +515,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           int jl = 0;
 #pragma unroll 1
           for (int l = 0; l < 3; ++l) {
-            const float* bias = (l == 0) ? sB0 : (l == 1 ? net.b1 : net.b2);
+            const float* bias = (l == 0) ? sB0 + (npass & 1) * 512 : (l == 1 ? net.b1 : net.b2);
+            if (l == 1 && P.mode == kModeSampler) {
+              // next pass's effective layer-0 bias b0 + W0[:,y]·y + tau'·W0[:,t] into the other buffer (read after the
+              // epilogue barrier at the top of that pass)
+              const int pn = (p + 1 == n_pass) ? 0 : p + 1;
+              const float tau_n = (p + 1 == n_pass) ? tau_of_step(step + 1, S, P.T) : tau;
+              for (int n = et; n < 512; n += kEpiThreads)
+                sB0[((npass + 1) & 1) * 512 + n] = fmaf(tau_n, sWt[pn * 512 + n], sU[pn * 512 + n]);
+            }
 #pragma unroll 1
             for (int c = 0; c < 4; ++c, ++job, ++jl) {
               const int buf = job & 1;
@@ -513,49 +533,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               if (tl_on) tl_mark(P, 0x300u | jl);
               const uint32_t acc_col = kTmemAcc + buf * 128;
               if (l == 0)
-                epi_hidden<true, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+                epi_hidden<true, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
               else if (l == 1)
-                epi_hidden<false, false>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+                epi_hidden<false, false>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
               else
-                epi_hidden<false, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+                epi_hidden<false, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
               if (tl_on) tl_mark(P, 0x400u | jl);
-            }
-            if (l == 0 && last_pass && P.mode == kModeSampler) {
-              // ---- off the critical path (layers 1-2 are MMA-bound): the part of the Euler–Maruyama update that
-              // does not need the net:  x <- x + delta*beta/2*x + sqrt(delta*beta)*eps   (models/diffusion.py:42)
-              for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
-                float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-                const float4 q0 = xp[0], q1 = xp[1];
-                float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                float z4[4];
+              if (l >= 1 && last_pass && P.mode == kModeSampler) {
+                // ---- in the shadow of the MMA-bound layers 1-2, one 8-column piece per accumulator chunk: the part
+                // of the Euler–Maruyama update that does not need the net output,
+                //   x <- x + delta*beta/2*x + sqrt(delta*beta)*eps            (models/diffusion.py:42, sdes.py:77-87)
+                const int pc = piece_lo + (l - 1) * 4 + c;
+                if (pc < piece_hi && pc * 8 < width) {
+                  float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
+                  const float4 q0 = xp[0], q1 = xp[1];
+                  float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                  float za[4], zb[4];
+                  if (P.rng_mode == DMIP_RNG_PHILOX) {
+                    philox_normal4(gidx, step, kStreamState, pc * 2, P.seed, za);
+                    philox_normal4(gidx, step, kStreamState, pc * 2 + 1, P.seed, zb);
+                  }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, step, kStreamState, pc * 2 + h, P.seed, z4);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int j = pc * 8 + h * 4 + e;
+                  for (int e = 0; e < 8; ++e) {
+                    const int j = pc * 8 + e;
                     float eps = 0.f;
                     if (valid && j < width)
                       eps = P.rng_mode == DMIP_RNG_PHILOX
-                                ? z4[e]
+                                ? (e < 4 ? za[e & 3] : zb[e & 3])
                                 : P.noise[(static_cast<long long>(step) * n_total + grow) * P.xdim + j];
-                    const float xv = x[h * 4 + e];
-                    x[h * 4 + e] = xv + P.delta * (0.5f * beta * xv) + (P.sqrt_delta * sb) * eps;
+                    x[e] = x[e] + P.delta * (0.5f * beta * x[e]) + (P.sqrt_delta * sb) * eps;
                   }
+                  xp[0] = make_float4(x[0], x[1], x[2], x[3]);
+                  xp[1] = make_float4(x[4], x[5], x[6], x[7]);
                 }
-                xp[0] = make_float4(x[0], x[1], x[2], x[3]);
-                xp[1] = make_float4(x[4], x[5], x[6], x[7]);
               }
-              if (tl_on) tl_mark(P, 0x510u);
             }
           }
-
           // ---- output layer
           {
             const int buf = job & 1;
             ++job;
-            // software-pipelined over this thread's 8-column pieces: the pre-updated state of piece i+1 is fetched
-            // from L2 while piece i is combined with the net output
+            // this thread's columns (<= 64) come out of tensor memory in two loads; the pre-updated state of piece
+            // i+1 is fetched from L2 while piece i is combined with the net output
             const bool upd = (P.mode == kModeSampler) && last_pass;
             float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
             if (upd && piece_lo < piece_hi && piece_lo * 8 < width) {
@@ -571,6 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
             // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
             const float ca = P.delta * ((P.variant == DMIP_DPS) ? beta : sb);
+            // rolled on purpose: the loop-carried prefetch keeps the L2 latency of the state one piece ahead
 #pragma unroll 1
             for (int pc = piece_lo; pc < piece_hi; ++pc) {   // warp-uniform bounds
               const float xt[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
@@ -613,6 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             mbar_arrive(&B.acc_empty[buf]);
             if (tl_on) tl_mark(P, 0x400u | 12);
           }
+          ++npass;
         }  // pass
       }    // step
     }      // tile
@@ -705,6 +726,67 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma(int mode, const float* __
     tmem_dealloc<512>(tmem_base);
   }
   (void)lane;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA micro-benchmark
+// Issues `iters` x (k/16) back-to-back tcgen05.mma (M=128, N=n, K=16) from one elected lane and reports the
+// cycles from first issue to completion.  mode 0: A in shared memory, 1: A in tensor memory.  Operands are whatever
+// is in shared / tensor memory (zeros): only the timing matters.
+__global__ void __launch_bounds__(128, 1) k_debug_mma_bench(int mode, int n, int k, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + 4 * kStageBytes;   // up to 256 rows x 4 K-blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * kStageBytes);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 12 * kStageBytes + 8);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(holder);
+  for (int i = threadIdx.x; i < 12 * kStageBytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *holder, 0);
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(n));
+    const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+    const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(sW) & 0x3FFFFu) >> 4;
+    const uint32_t wkb = static_cast<uint32_t>(n) * 128u;   // bytes per K-block of the B image
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int kb = 0; kb < k / 64; ++kb) {
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = desc_hi | (b_lo0 + ((kb * wkb) >> 4) + kk * 2);
+            const uint32_t d_tmem = tmem_base + kTmemAcc + (it & 1) * 0;   // same accumulator: worst-case dependence
+            if (mode == 0) umma_ss(d_tmem, desc_hi | (a_lo0 + ((kb * kStageBytes) >> 4) + kk * 2), bdesc, idesc, 1u);
+            else umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, 1u);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit(bar);
+    __syncwarp();
+    const long long t1 = clock64();
+    mbar_wait(bar, 0, 0x901);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      cycles[blockIdx.x * 2] = t1 - t0;
+      cycles[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
 }
 
 int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows, int split, TcNetDev* o) {
@@ -859,6 +941,16 @@ int launch_forward_tc(const DmipForward* d, cudaStream_t s) {
   P.fcond_dim = d->cond_dim;
   P.out_dim = d->net.out_dim;
   return launch(P, s);
+}
+
+int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s) {
+  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256 && n % 16 == 0 && n >= 16 && n <= 256 && grid >= 1, "bad bench shape");
+  const int smem = 12 * kStageBytes + 64 + 1024;
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_debug_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_debug_mma_bench<<<grid, 128, smem, s>>>(mode, n, k, iters, cycles);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
 }
 
 int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s) {

@@ -139,6 +139,9 @@ int dmip_mlp_forward(const DmipForward* d, void* stream);
  * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
  * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.
  * k multiple of 64 (<=512), n multiple of 16 (<=128). */
+/* tcgen05.mma issue-rate micro-benchmark: `iters` x (k/16) MMAs of shape 128 x n x 16 per CTA on `grid` CTAs;
+ * cycles: device int64[2*grid] = (issue cycles, completion cycles) per CTA. */
+int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream);
 /* Timeline hook: when set, CTA 0 of the tcgen05 kernels records (clock64 << 16 | event code) entries into
  * device_buf[1..capacity) and the entry count into device_buf[0] (uint64).  Pass NULL to switch off. */
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity);

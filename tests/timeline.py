@@ -27,7 +27,7 @@ b = buf.cpu().numpy()
 n = int(b[0])
 ev = sorted(((int(v) >> 16) & ((1 << 47) - 1), int(v) & 0xFFFF) for v in b[1:n + 1])
 t0 = ev[0][0]
-names = {0x100: "mma_start", 0x200: "mma_issued", 0x300: "epi_accfull", 0x400: "epi_done", 0x500: "a0_arrive"}
+names = {0xA00: "kb_top", 0xB00: "kb_waited", 0xC00: "kb_probed", 0xD00: "kb_issued", 0x100: "mma_start", 0x200: "mma_issued", 0x300: "epi_accfull", 0x400: "epi_done", 0x500: "a0_arrive"}
 print("n events", n)
 # print steps 2..3 in detail
 a0 = [i for i, (t, c) in enumerate(ev) if c == 0x500]
@@ -37,3 +37,6 @@ for t, c in ev[lo:hi]:
     print(f"{t - ev[lo][0]:8d}  {nm:12s} job {c & 0xFF}")
 per_step = [(ev[a0[i + 1]][0] - ev[a0[i]][0]) for i in range(len(a0) - 1)]
 print("cycles per step:", per_step)
+fine = [(t, c) for t, c in ev if (c & 0xF00) >= 0xA00]
+for t, c in fine:
+    print(f"   fine {t - fine[0][0]:7d} {names[c & 0xF00]:10s} kb {c & 0xFF}")
