@@ -120,7 +120,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     # bounded sample of the same workload: same net, same SDE; ~10-30 s of CPU work per bench step
-    n, s = 32768, 20
+    n, s = 65536, 100
     for _ in range(min(args.warmup, 1)):
         cpu_sampler_rate(2048, 4)
     rates, secs = [], []
@@ -246,7 +246,7 @@ def run_ours(args, rank, world):
         "clocks": clk,
     }
     if not args.no_cpu_baseline and world == 1:
-        n, s = 32768, 20
+        n, s = 65536, 100
         r, cores, dt = cpu_sampler_rate(n, s)
         line["cpu_baseline"] = {"value": r, "unit": "evals/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} particles x {s} steps of the same net, torch CPU fp32, {dt:.1f} s"}
