@@ -145,6 +145,18 @@ int dmip_mlp_forward(const DmipForward* d, void* stream) {
   return launch_forward_f32(d, s);
 }
 
+size_t dmip_loss_workspace_bytes(const DmipLoss* d) { return d ? loss_workspace(d) : 0; }
+size_t dmip_loss_grad_floats(const DmipMlp* net) { return net ? loss_grad_floats(net) : 0; }
+
+int dmip_loss_fwd_bwd(const DmipLoss* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  DMIP_REQUIRE(d->batch >= 0, "negative batch");
+  return launch_loss(d, static_cast<cudaStream_t>(stream));
+}
+
 int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream) {
   reset_launch_count();
   int rc = require_device();

@@ -62,6 +62,9 @@ int launch_sampler_f32(const DmipSampler* d, cudaStream_t s);
 int launch_forward_f32(const DmipForward* d, cudaStream_t s);
 size_t sampler_f32_workspace(const DmipSampler* d);
 size_t forward_f32_workspace(const DmipForward* d);
+size_t loss_workspace(const DmipLoss* q);
+size_t loss_grad_floats(const DmipMlp* net);
+int launch_loss(const DmipLoss* q, cudaStream_t s);
 size_t sampler_tc_workspace();
 void debug_set_timeline(unsigned long long* buf, int cap);
 int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s);

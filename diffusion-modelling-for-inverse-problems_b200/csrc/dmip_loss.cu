@@ -1,0 +1,658 @@
+// dmip_loss.cu — fused score-training losses, forward + backward, fp32 (K2 DSM, K3 PINN / Score-FPE, DSM_PDE).
+//
+// Replaces, per training batch: VariancePreservingSDE.sample (sdes.py:37-49), the net evaluations, DSMLoss
+// (losses.py:49-52), ScoreFPELoss with exact divergence (losses.py:77-98: 2d+1 autograd double-backward passes),
+// ConditionalScoreFPELoss (losses.py:116-124), DSM_PDELoss (losses.py:143-164), PINNLoss (losses.py:214-242) and
+// the loss.backward() through that double-backward graph (models/diffusion.py:100-102).
+//
+// Method: forward-mode jets instead of reverse-over-reverse autograd.  Every sample is
+// expanded into "streams" that share the net's weights and therefore ride the same GEMMs as extra rows:
+//     P   primal at [z_t, cond, t]            I   primal at [x, y, 0]            (PINN initial condition)
+//     T   tangent along (dz_t/dt, 0, 1)       S_k tangents along e_k             Q_ik second-order pairs (i <= k)
+// ds/dt is the TOTAL derivative along z_t(t) at fixed eps (Q8); grad_x [div s + |s|^2 + x.s] is a constant in the
+// backward pass (Q9); the (B,)+(B,1) broadcast of the reference means mean(loss) = mean(dsm)+mean(ic)+mean(pde) (Q10).
+// Parameter gradients flow through P, I and T only; the T adjoint couples back into P through phi' and phi''.
+//
+// Three kernels: k_jets_fwd (one CTA = 32 stream-rows: GEMM per layer + jet activation in shared memory, per-sample
+// loss and top adjoints), k_jets_bwd (adjoint rows back through the layers), k_wgrad (dW_l = ADJ_l^T IN_l, split-K).
+#include "dmip_common.h"
+
+namespace dmip {
+
+namespace {
+
+constexpr int kRows = 32;
+constexpr int kLd = 36;
+constexpr int kMaxW = 512;
+constexpr int kThreadsL = 256;
+constexpr int kMaxD = 4;   // exact Score-FPE: state dimension of the diffused variable (d(d+1)/2 second-order streams)
+
+struct LossDev {
+  int kind, model, xdim, ydim, d, cdim, in_dim, out_dim, n_layers;
+  int width[DMIP_MAX_LAYERS];
+  const float* W[DMIP_MAX_LAYERS];    // original (out,in)
+  const float* Wt[DMIP_MAX_LAYERS];   // transposed (in,out)
+  const float* b[DMIP_MAX_LAYERS];
+  long long B;
+  float inv_B;                        // 1 / global batch
+  float bmin, bmax, lam, lam2;
+  int pde_loss, pde_metric, ic_metric;
+  int has_I, has_T, has_S;            // stream groups present
+  int n_streams, spt;                 // streams per sample, samples per tile
+  int n_adj;                          // adjoint streams per sample: P [, I] [, T]
+  const float* x;
+  const float* y;
+  const float* t;
+  const float* eps;
+  const float* ic_target;
+  float* losses;                      // [4] total, dsm, ic, pde
+  float* in_rows[DMIP_MAX_LAYERS];    // IN_l  [B*n_adj][K_l]   inputs of layer l for the adjoint streams
+  float* adj_rows[DMIP_MAX_LAYERS];   // ADJ_l [B*n_adj][N_l]   adjoints of layer l pre-activations
+  float* zdt[DMIP_MAX_LAYERS];        // ZDT_l [B][N_l]         pre-activation time tangent of hidden layer l
+  float* abar;                        // [B*n_adj][out_dim]     adjoints of the net outputs
+};
+
+// out[n*kLd + r] = sum_k in[k*kLd + r] * Wt[k*N + n], r < 32, n < N.  256 threads; ends with __syncthreads().
+__device__ void tile_gemm(const float* in, float* out, const float* __restrict__ Wt, int K, int N) {
+  const int t = threadIdx.x;
+  const int rg = t >> 6, ng = t & 63;
+  for (int nb = 0; nb < N; nb += 512) {
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+    const int ncols = (N - nb - ng + 63) >> 6;
+    if (ncols > 0) {
+      for (int k = 0; k < K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(in + k * kLd + rg * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(in + k * kLd + rg * 8 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = (i < ncols) ? __ldg(Wt + static_cast<size_t>(k) * N + nb + ng + 64 * i) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(a[r], w[i], acc[r][i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = nb + ng + 64 * i;
+      if (n < N) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) out[n * kLd + rg * 8 + r] = acc[r][i];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// activation jets: value h, first and second derivative of phi at pre-activation z (layer 0: tanh(tanh), else tanh)
+__device__ __forceinline__ void act_jet(float z, bool first, float& h, float& p1, float& p2) {
+  if (first) {
+    const float u = tanhf(z);
+    h = tanhf(u);
+    p1 = (1.f - h * h) * (1.f - u * u);
+    p2 = p1 * (-2.f * h * (1.f - u * u) - 2.f * u);
+  } else {
+    h = tanhf(z);
+    p1 = 1.f - h * h;
+    p2 = -2.f * h * p1;
+  }
+}
+
+__device__ __forceinline__ void vp_terms(float t, float bmin, float bmax, float& beta, float& alpha, float& var) {
+  const float db = bmax - bmin;
+  beta = bmin + db * t;
+  const float Bt = 0.5f * t * t * db + t * bmin;
+  alpha = expf(-0.5f * Bt);
+  var = 1.f - expf(-Bt);
+}
+
+// stream index layout inside a sample:  P | I? | T? | S_0..S_{d-1}? | Q_(i,k), i<=k ?
+__device__ __forceinline__ int q_index(int i, int k, int d) { return i * d - (i * (i - 1)) / 2 + (k - i); }
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant__ LossDev P) {
+  extern __shared__ float smem[];
+  float* buf0 = smem;
+  float* buf1 = smem + kMaxW * kLd;
+  __shared__ float red[4];
+  const int t = threadIdx.x;
+  const int ns = P.n_streams, spt = P.spt, d = P.d;
+  const int sI = 1, sT = 1 + P.has_I, sS = sT + P.has_T, sQ = sS + (P.has_S ? d : 0);
+  const long long n_tiles = (P.B + spt - 1) / spt;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long s0 = tile * spt;
+    if (t < 4) red[t] = 0.f;
+    // ---- layer-0 input rows
+    for (int idx = t; idx < kRows * P.in_dim; idx += kThreadsL) {
+      const int k = idx / kRows, r = idx % kRows;
+      const int sl = r / ns, st = r % ns;
+      const long long smp = s0 + sl;
+      float v = 0.f;
+      if (sl < spt && smp < P.B) {
+        const float tt = P.t[smp];
+        float beta, alpha, var;
+        vp_terms(tt, P.bmin, P.bmax, beta, alpha, var);
+        const float sd = sqrtf(var);
+        // clean / diffused state component k (k < d): CDE: z0 = x; CDiffE: z0 = [x, y]   (models/diffusion.py:80,129)
+        float z0k = 0.f, epsk = 0.f;
+        if (k < d) {
+          z0k = (k < P.xdim) ? P.x[smp * P.xdim + k] : P.y[smp * P.ydim + (k - P.xdim)];
+          epsk = P.eps[smp * d + k];
+        }
+        if (st == 0) {                       // P: [z_t, cond, t]
+          if (k < d) v = epsk * sd + alpha * z0k;                                  // sdes.py:43-46
+          else if (k < d + P.cdim) v = P.y[smp * P.ydim + (k - d)];
+          else v = tt;
+        } else if (P.has_I && st == sI) {    // I: [x, y, 0]                        (losses.py:221-223)
+          if (k < P.xdim) v = P.x[smp * P.xdim + k];
+          else if (k < P.xdim + P.ydim) v = P.y[smp * P.ydim + (k - P.xdim)];
+          else v = 0.f;
+        } else if (P.has_T && st == sT) {    // T: (dz_t/dt, 0, 1)                  
+          if (k < d) v = epsk * beta * (1.f - var) / (2.f * sd) - 0.5f * beta * alpha * z0k;
+          else if (k < d + P.cdim) v = 0.f;
+          else v = 1.f;
+        } else if (P.has_S && st >= sS && st < sQ) {
+          v = (k == st - sS) ? 1.f : 0.f;    // S_k: e_k
+        }                                    // Q: zero input
+        // inputs of layer 0 for the adjoint streams (wgrad operands)
+        const int aidx = (st == 0) ? 0 : (P.has_I && st == sI) ? 1 : (P.has_T && st == sT) ? (1 + P.has_I) : -1;
+        if (aidx >= 0) P.in_rows[0][(smp * P.n_adj + aidx) * P.in_dim + k] = v;
+      }
+      buf0[k * kLd + r] = v;
+    }
+    __syncthreads();
+
+    float* in = buf0;
+    float* out = buf1;
+    int K = P.in_dim;
+    for (int l = 0; l < P.n_layers; ++l) {
+      const int N = P.width[l];
+      tile_gemm(in, out, P.Wt[l], K, N);
+      const bool last = (l == P.n_layers - 1);
+      if (!last) {
+        // ---- jet activation, in place: one (column, sample) pair per thread iteration
+        for (int idx = t; idx < N * spt; idx += kThreadsL) {
+          const int n = idx % N, sl = idx / N;
+          const long long smp = s0 + sl;
+          float* col = out + n * kLd + sl * ns;
+          const float bias = P.b[l][n];
+          float h, p1, p2;
+          act_jet(col[0] + bias, l == 0, h, p1, p2);
+          const bool live = smp < P.B;
+          if (live) P.in_rows[l + 1][(smp * P.n_adj + 0) * N + n] = h;
+          col[0] = h;
+          if (P.has_I) {
+            float hi, q1, q2;
+            act_jet(col[sI] + bias, l == 0, hi, q1, q2);
+            col[sI] = hi;
+            if (live) P.in_rows[l + 1][(smp * P.n_adj + 1) * N + n] = hi;
+          }
+          if (P.has_T) {
+            const float zd = col[sT];
+            const float hd = p1 * zd;
+            col[sT] = hd;
+            if (live) {
+              P.zdt[l][smp * N + n] = zd;
+              P.in_rows[l + 1][(smp * P.n_adj + 1 + P.has_I) * N + n] = hd;
+            }
+          }
+          if (P.has_S) {
+            float zs[kMaxD];
+#pragma unroll
+            for (int k = 0; k < kMaxD; ++k)
+              if (k < d) zs[k] = col[sS + k];
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i)
+#pragma unroll
+              for (int k = i; k < kMaxD; ++k)
+                if (k < d) {
+                  const int q = sQ + q_index(i, k, d);
+                  col[q] = p1 * col[q] + p2 * zs[i] * zs[k];
+                }
+#pragma unroll
+            for (int k = 0; k < kMaxD; ++k)
+              if (k < d) col[sS + k] = p1 * zs[k];
+          }
+        }
+        __syncthreads();
+      }
+      float* tmp = in;
+      in = out;
+      out = tmp;
+      K = N;
+    }
+
+    // ---- per-sample loss terms and output adjoints (one thread per sample; `in` holds the raw last-layer rows)
+    if (t < spt && s0 + t < P.B) {
+      const long long smp = s0 + t;
+      const float* o = in + t * ns;            // o[j*kLd + stream]
+      const int L = P.n_layers - 1;
+      const int od = P.out_dim;
+      const float tt = P.t[smp];
+      float beta, alpha, var;
+      vp_terms(tt, P.bmin, P.bmax, beta, alpha, var);
+      const float sd = sqrtf(var), sb = sqrtf(beta), db = P.bmax - P.bmin;
+      float* abarP = P.abar + (smp * P.n_adj + 0) * od;
+      float l_dsm = 0.f, l_ic = 0.f, l_pde = 0.f;
+      // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                            (losses.py:49-52, Q3)
+      for (int j = 0; j < od; ++j) {
+        const float a = o[j * kLd + 0] + P.b[L][j];
+        const float r = a / sb * sd + P.eps[smp * d + j];
+        l_dsm += 0.5f * r * r;
+        abarP[j] = P.inv_B * r * sd / sb;
+      }
+      if (P.has_I) {                           // initial condition at t = 0          (losses.py:221-230)
+        float* abarI = P.abar + (smp * P.n_adj + 1) * od;
+        const float g0 = sqrtf(P.bmin);
+        for (int j = 0; j < od; ++j) {
+          float g = 0.f;
+          if (j < P.xdim) {
+            const float diff = (o[j * kLd + sI] + P.b[L][j]) / g0 - P.ic_target[smp * P.xdim + j];
+            if (P.ic_metric == 2) { l_ic += diff * diff; g = 2.f * diff; }
+            else { l_ic += fabsf(diff); g = (diff > 0.f) - (diff < 0.f); }
+            g *= P.lam2 / (P.xdim * g0);
+          }
+          abarI[j] = P.inv_B * g;
+        }
+        l_ic *= P.lam2 / P.xdim;
+      }
+      if (P.has_T) {
+        float* abarT = P.abar + (smp * P.n_adj + 1 + P.has_I) * od;
+        if (P.pde_loss == 0) {
+          // Score-FPE residual R = ds/dt - beta/2 grad_x[div s + |s|^2 + x.s], grad_x constant (losses.py:88-95, Q9)
+          float a[kMaxD], zt[kMaxD], J[kMaxD][kMaxD], gtr[kMaxD];
+#pragma unroll
+          for (int i = 0; i < kMaxD; ++i) {
+            a[i] = 0.f; zt[i] = 0.f; gtr[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMaxD; ++k) J[i][k] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < kMaxD; ++i)
+            if (i < d) {
+              a[i] = o[i * kLd + 0] + P.b[L][i];
+              const float z0 = (i < P.xdim) ? P.x[smp * P.xdim + i] : P.y[smp * P.ydim + (i - P.xdim)];
+              zt[i] = P.eps[smp * d + i] * sd + alpha * z0;
+#pragma unroll
+              for (int k = 0; k < kMaxD; ++k)
+                if (k < d) J[i][k] = o[i * kLd + 1 + P.has_I + P.has_T + k];     // d a_i / d x_k
+            }
+#pragma unroll
+          for (int i = 0; i < kMaxD; ++i)
+#pragma unroll
+            for (int k = i; k < kMaxD; ++k)
+              if (k < d) {
+                const int q = 1 + P.has_I + P.has_T + d + q_index(i, k, d);
+                gtr[k] += o[i * kLd + q];                    // d^2 a_i / dx_i dx_k
+                if (i != k) gtr[i] += o[k * kLd + q];        // d^2 a_k / dx_k dx_i
+              }
+          for (int k = 0; k < d; ++k) {
+            float JTa = 0.f, JTx = 0.f;
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i)
+              if (i < d) { JTa += J[i][k] * a[i]; JTx += J[i][k] * zt[i]; }
+            const float grad_x = gtr[k] / sb + 2.f * JTa / beta + (a[k] + JTx) / sb;
+            const float ds_dt = o[k * kLd + sT] / sb - a[k] * db / (2.f * beta * sb);
+            const float R = ds_dt - 0.5f * beta * grad_x;
+            float g;
+            if (P.pde_metric == 1) { l_pde += fabsf(R); g = (R > 0.f) - (R < 0.f); }
+            else { l_pde += R * R; g = 2.f * R; }
+            g *= P.lam / d * P.inv_B;
+            abarT[k] = g / sb;
+            abarP[k] += -g * db / (2.f * beta * sb);
+          }
+          l_pde *= P.lam / d;
+        } else {
+          // cScoreFPE: sum_j (std^3 ds/dt - eps beta alpha^2 / 2)^2                  (losses.py:116-124)
+          for (int j = 0; j < od; ++j) {
+            const float a = o[j * kLd + 0] + P.b[L][j];
+            const float ds_dt = o[j * kLd + sT] / sb - a * db / (2.f * beta * sb);
+            const float r = sd * sd * sd * ds_dt - 0.5f * P.eps[smp * d + j] * beta * alpha * alpha;
+            float g;
+            if (P.pde_metric == 2) { l_pde += r * r; g = 2.f * r; }
+            else { l_pde += fabsf(r); g = (r > 0.f) - (r < 0.f); }
+            g *= P.lam * sd * sd * sd * P.inv_B;
+            abarT[j] = g / sb;
+            abarP[j] += -g * db / (2.f * beta * sb);
+          }
+          l_pde *= P.lam;
+        }
+      }
+      atomicAdd(&red[1], l_dsm);
+      atomicAdd(&red[2], l_ic);
+      atomicAdd(&red[3], l_pde);
+    }
+    __syncthreads();
+    if (t == 0) {
+      atomicAdd(&P.losses[1], red[1] * P.inv_B);
+      atomicAdd(&P.losses[2], red[2] * P.inv_B);
+      atomicAdd(&P.losses[3], red[3] * P.inv_B);
+      atomicAdd(&P.losses[0], (red[1] + red[2] + red[3]) * P.inv_B);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// rows = (sample, adjoint stream); P and T rows of a sample are coupled through phi' and phi''.
+__global__ void __launch_bounds__(kThreadsL, 1) k_jets_bwd(const __grid_constant__ LossDev P) {
+  extern __shared__ float smem[];
+  float* buf0 = smem;
+  float* buf1 = smem + kMaxW * kLd;
+  const int t = threadIdx.x;
+  const int na = P.n_adj;
+  const int spt = kRows / na;
+  const int aT = 1 + P.has_I;
+  const long long n_tiles = (P.B + spt - 1) / spt;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long s0 = tile * spt;
+    const int L = P.n_layers - 1;
+    // adjoints of the outputs = adjoints of the last layer's pre-activations
+    for (int idx = t; idx < kRows * P.out_dim; idx += kThreadsL) {
+      const int n = idx / kRows, r = idx % kRows;
+      const int sl = r / na, st = r % na;
+      const long long smp = s0 + sl;
+      float v = 0.f;
+      if (sl < spt && smp < P.B) {
+        v = P.abar[(smp * na + st) * P.out_dim + n];
+        P.adj_rows[L][(smp * na + st) * P.out_dim + n] = v;
+      }
+      buf0[n * kLd + r] = v;
+    }
+    __syncthreads();
+    float* in = buf0;
+    float* out = buf1;
+    for (int l = L; l >= 1; --l) {
+      const int N = P.width[l], Kp = P.width[l - 1];
+      tile_gemm(in, out, P.W[l], N, Kp);      // hbar_{l-1}[k] = sum_n zbar_l[n] W_l[n][k]
+      for (int idx = t; idx < Kp * spt; idx += kThreadsL) {
+        const int k = idx % Kp, sl = idx / Kp;
+        const long long smp = s0 + sl;
+        if (smp >= P.B) continue;
+        float* col = out + k * kLd + sl * na;
+        // phi', phi'' of layer l-1 from its stored output h (layer 0: h = tanh(u), u = atanh(h), |h| < tanh(1))
+        const float h = P.in_rows[l][(smp * na + 0) * Kp + k];
+        float p1, p2;
+        if (l - 1 == 0) {
+          const float u = atanhf(h);
+          p1 = (1.f - h * h) * (1.f - u * u);
+          p2 = p1 * (-2.f * h * (1.f - u * u) - 2.f * u);
+        } else {
+          p1 = 1.f - h * h;
+          p2 = -2.f * h * p1;
+        }
+        float zP = p1 * col[0];
+        if (P.has_T) {
+          const float hdbar = col[aT];
+          zP += p2 * P.zdt[l - 1][smp * Kp + k] * hdbar;
+          const float zT = p1 * hdbar;
+          col[aT] = zT;
+          P.adj_rows[l - 1][(smp * na + aT) * Kp + k] = zT;
+        }
+        col[0] = zP;
+        P.adj_rows[l - 1][(smp * na + 0) * Kp + k] = zP;
+        if (P.has_I) {
+          const float hi = P.in_rows[l][(smp * na + 1) * Kp + k];
+          float q1;
+          if (l - 1 == 0) {
+            const float u = atanhf(hi);
+            q1 = (1.f - hi * hi) * (1.f - u * u);
+          } else {
+            q1 = 1.f - hi * hi;
+          }
+          const float zI = q1 * col[1];
+          col[1] = zI;
+          P.adj_rows[l - 1][(smp * na + 1) * Kp + k] = zI;
+        }
+      }
+      __syncthreads();
+      float* tmp = in;
+      in = out;
+      out = tmp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+// dW[n][k] += sum_r ADJ[r][n] * IN[r][k]   (r over B*n_adj rows), db[n] += sum_{r: stream is P or I} ADJ[r][n].
+// 64x64 output tile per CTA, split over row ranges (gridDim.z), fp32 atomics into the flat gradient buffer.
+__global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ adj, const float* __restrict__ inp, float* dW,
+                                               float* db, long long rows, int N, int K, int n_adj, int bias_streams,
+                                               long long rows_per_split) {
+  __shared__ float sA[16][64 + 4];
+  __shared__ float sI[16][64 + 4];
+  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const long long r_begin = static_cast<long long>(blockIdx.z) * rows_per_split;
+  const long long r_end = min(rows, r_begin + rows_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+    for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+      const int rr = idx >> 6, c = idx & 63;
+      const long long r = r0 + rr;
+      const bool ok = r < r_end;
+      sA[rr][c] = (ok && n0 + c < N) ? adj[r * N + n0 + c] : 0.f;
+      sI[rr][c] = (ok && k0 + c < K) ? inp[r * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[rr][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sI[rr][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (blockIdx.x == 0 && tx == 0 && ((r0 + rr) % n_adj) < bias_streams) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bsum[i] += a[i];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(&dW[static_cast<size_t>(n) * K + k], acc[i][j]);
+    }
+    if (blockIdx.x == 0 && tx == 0) atomicAdd(&db[n], bsum[i]);
+  }
+}
+
+__global__ void k_transpose_l(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? W[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) Wt[static_cast<size_t>(c) * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct LossPlan {
+  int d, cdim, n_streams, spt, n_adj, has_I, has_T, has_S;
+  size_t off_wt[DMIP_MAX_LAYERS], off_in[DMIP_MAX_LAYERS], off_adj[DMIP_MAX_LAYERS], off_zdt[DMIP_MAX_LAYERS], off_abar;
+  size_t bytes;
+};
+
+int make_plan(const DmipLoss* q, LossPlan* p) {
+  DMIP_REQUIRE(q != nullptr, "descriptor is NULL");
+  DMIP_REQUIRE(q->kind == DMIP_LOSS_DSM || q->kind == DMIP_LOSS_DSM_PDE || q->kind == DMIP_LOSS_PINN,
+               "No valid loss_fn was specified. Options are DMIP_LOSS_DSM, DMIP_LOSS_DSM_PDE, DMIP_LOSS_PINN.");
+  DMIP_REQUIRE(q->model == DMIP_CDE || q->model == DMIP_CDIFFE, "model must be DMIP_CDE or DMIP_CDIFFE");
+  const DmipMlp& net = q->net;
+  DMIP_REQUIRE(net.n_layers >= 2 && net.n_layers <= DMIP_MAX_LAYERS, "n_layers out of range");
+  DMIP_REQUIRE(net.in_dim == q->xdim + q->ydim + 1 && net.in_dim <= kMaxW, "net.in_dim must be xdim+ydim+1 (<= %d)", kMaxW);
+  for (int l = 0; l < net.n_layers; ++l)
+    DMIP_REQUIRE(net.width[l] >= 1 && net.width[l] <= kMaxW && net.W[l] && net.b[l], "layer %d: bad width or NULL", l);
+  p->d = (q->model == DMIP_CDE) ? q->xdim : q->xdim + q->ydim;
+  p->cdim = (q->model == DMIP_CDE) ? q->ydim : 0;
+  DMIP_REQUIRE(net.out_dim == p->d, "s and x_t need to have the same shape, but out_dim %d and %d was given", net.out_dim, p->d);
+  const bool pde = q->kind != DMIP_LOSS_DSM;
+  if (pde) {
+    DMIP_REQUIRE(q->pde_loss == DMIP_PDE_FPE || q->pde_loss == DMIP_PDE_CFPE, "pde_loss must be FPE or cScoreFPE");
+    DMIP_REQUIRE(q->pde_metric == DMIP_L1 || q->pde_metric == DMIP_L2,
+                 "No valid metric specified. Metric should be one of \"L1\" or \"L2\"");
+  }
+  if (q->kind == DMIP_LOSS_PINN) {
+    DMIP_REQUIRE(q->ic_metric == DMIP_L1 || q->ic_metric == DMIP_L2, "ic_metric should be one of \"L1\" or \"L2\"");
+    DMIP_REQUIRE(q->ic_target != nullptr, "PINNLoss needs ic_target = initial_condition(x, y)");
+  }
+  p->has_I = q->kind == DMIP_LOSS_PINN;
+  p->has_T = pde;
+  p->has_S = pde && q->pde_loss == DMIP_PDE_FPE;
+  if (p->has_S)
+    DMIP_REQUIRE(p->d <= kMaxD, "exact Score-FPE divergence supports d <= %d diffused dimensions (got %d); "
+                 "use pde_loss = cScoreFPE", kMaxD, p->d);
+  p->n_streams = 1 + p->has_I + p->has_T + (p->has_S ? p->d + p->d * (p->d + 1) / 2 : 0);
+  DMIP_REQUIRE(p->n_streams <= kRows, "too many jet streams (%d)", p->n_streams);
+  p->spt = kRows / p->n_streams;
+  p->n_adj = 1 + p->has_I + p->has_T;
+  size_t off = 0;
+  int k = net.in_dim;
+  const size_t B = static_cast<size_t>(q->batch);
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int n = net.width[l];
+    p->off_wt[l] = off;  off += align_up(sizeof(float) * k * n);
+    p->off_in[l] = off;  off += align_up(sizeof(float) * B * p->n_adj * k);
+    p->off_adj[l] = off; off += align_up(sizeof(float) * B * p->n_adj * n);
+    p->off_zdt[l] = off; off += (p->has_T && l < net.n_layers - 1) ? align_up(sizeof(float) * B * n) : 0;
+    k = n;
+  }
+  p->off_abar = off;
+  off += align_up(sizeof(float) * B * p->n_adj * net.out_dim);
+  p->bytes = off;
+  return DMIP_OK;
+}
+
+}  // namespace
+
+size_t loss_workspace(const DmipLoss* q) {
+  LossPlan p;
+  if (make_plan(q, &p)) return 0;
+  return p.bytes;
+}
+
+size_t loss_grad_floats(const DmipMlp* net) {
+  size_t n = 0;
+  int k = net->in_dim;
+  for (int l = 0; l < net->n_layers; ++l) {
+    n += static_cast<size_t>(k) * net->width[l] + net->width[l];
+    k = net->width[l];
+  }
+  return n;
+}
+
+int launch_loss(const DmipLoss* q, cudaStream_t s) {
+  LossPlan p;
+  int rc = make_plan(q, &p);
+  if (rc) return rc;
+  DMIP_REQUIRE(q->x && q->y && q->t && q->eps && q->out_losses && q->grad, "x / y / t / eps / out_losses / grad is NULL");
+  if (!q->workspace || q->workspace_bytes < p.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) {
+    set_error("workspace too small or misaligned: need %zu bytes", p.bytes);
+    return DMIP_EWORKSPACE;
+  }
+  static int n_sm = 0;
+  const int smem = 2 * kMaxW * kLd * 4;
+  if (!n_sm) {
+    int dev = 0;
+    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  const DmipMlp& net = q->net;
+  uint8_t* ws = static_cast<uint8_t*>(q->workspace);
+  LossDev D = {};
+  D.kind = q->kind; D.model = q->model; D.xdim = q->xdim; D.ydim = q->ydim;
+  D.d = p.d; D.cdim = p.cdim; D.in_dim = net.in_dim; D.out_dim = net.out_dim; D.n_layers = net.n_layers;
+  D.B = q->batch;
+  D.inv_B = 1.0f / static_cast<float>(q->batch_global > 0 ? q->batch_global : q->batch);
+  D.bmin = q->beta_min; D.bmax = q->beta_max; D.lam = q->lam; D.lam2 = q->lam2;
+  D.pde_loss = q->pde_loss; D.pde_metric = q->pde_metric; D.ic_metric = q->ic_metric;
+  D.has_I = p.has_I; D.has_T = p.has_T; D.has_S = p.has_S;
+  D.n_streams = p.n_streams; D.spt = p.spt; D.n_adj = p.n_adj;
+  D.x = q->x; D.y = q->y; D.t = q->t; D.eps = q->eps; D.ic_target = q->ic_target;
+  D.losses = q->out_losses;
+  D.abar = reinterpret_cast<float*>(ws + p.off_abar);
+  int k = net.in_dim;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int n = net.width[l];
+    D.width[l] = n;
+    D.W[l] = net.W[l];
+    D.b[l] = net.b[l];
+    float* wt = reinterpret_cast<float*>(ws + p.off_wt[l]);
+    D.Wt[l] = wt;
+    D.in_rows[l] = reinterpret_cast<float*>(ws + p.off_in[l]);
+    D.adj_rows[l] = reinterpret_cast<float*>(ws + p.off_adj[l]);
+    D.zdt[l] = reinterpret_cast<float*>(ws + p.off_zdt[l]);
+    dim3 grid(ceil_div(k, 32), ceil_div(n, 32)), block(32, 8);
+    k_transpose_l<<<grid, block, 0, s>>>(net.W[l], wt, n, k);
+    DMIP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    k = n;
+  }
+  DMIP_CHECK_CUDA(cudaMemsetAsync(q->out_losses, 0, 4 * sizeof(float), s));
+  DMIP_CHECK_CUDA(cudaMemsetAsync(q->grad, 0, loss_grad_floats(&net) * sizeof(float), s));
+  if (q->batch == 0) return DMIP_OK;
+
+  const long long tiles_f = (q->batch + p.spt - 1) / p.spt;
+  k_jets_fwd<<<static_cast<unsigned>(tiles_f < 4LL * n_sm ? tiles_f : 4LL * n_sm), kThreadsL, smem, s>>>(D);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  const int spt_b = kRows / p.n_adj;
+  const long long tiles_b = (q->batch + spt_b - 1) / spt_b;
+  k_jets_bwd<<<static_cast<unsigned>(tiles_b < 4LL * n_sm ? tiles_b : 4LL * n_sm), kThreadsL, smem, s>>>(D);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+
+  // weight / bias gradients, flat layout [W_0, b_0, W_1, b_1, ...]
+  float* g = q->grad;
+  k = net.in_dim;
+  const long long rows = q->batch * p.n_adj;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int n = net.width[l];
+    const int tiles = ceil_div(n, 64) * ceil_div(k, 64);
+    int split = (2 * n_sm + tiles - 1) / tiles;
+    const long long max_split = (rows + 255) / 256;
+    if (split > max_split) split = static_cast<int>(max_split);
+    if (split < 1) split = 1;
+    long long rps = (rows + split - 1) / split;
+    rps = (rps + p.n_adj * 16 - 1) / (p.n_adj * 16) * (p.n_adj * 16);   // keep stream phase aligned per split
+    split = static_cast<int>((rows + rps - 1) / rps);
+    dim3 grid(ceil_div(k, 64), ceil_div(n, 64), split);
+    k_wgrad<<<grid, 256, 0, s>>>(D.adj_rows[l], D.in_rows[l], g, g + static_cast<size_t>(n) * k, rows, n, k, p.n_adj,
+                                 1 + p.has_I, rps);
+    DMIP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    g += static_cast<size_t>(n) * k + n;
+    k = n;
+  }
+  return DMIP_OK;
+}
+
+}  // namespace dmip

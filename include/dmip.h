@@ -135,6 +135,48 @@ typedef struct DmipForward {
 size_t dmip_forward_workspace_bytes(const DmipForward* d);
 int dmip_mlp_forward(const DmipForward* d, void* stream);
 
+/* ---- fused score-training losses: forward + backward in one call -------------------------------------------
+ * Replaces, per batch, the body of CDE/CDiffE.train_epoch (models/diffusion.py:80-88, :129-139) up to and including
+ * loss.backward(): VariancePreservingSDE.sample with the Gaussian draw `eps` supplied by the caller, the net
+ * evaluations, DSMLoss (losses.py:49-52), ScoreFPELoss with exact divergence (losses.py:77-98),
+ * ConditionalScoreFPELoss (losses.py:116-124), DSM_PDELoss (losses.py:143-164), PINNLoss (losses.py:214-242).
+ * Outputs: out_losses[4] = {loss, mean DSM, mean initial-condition (x lam2), mean PDE (x lam)} — the reference's
+ * return value and info dict — and d loss / d parameters in `grad`, flat fp32 [W_0, b_0, W_1, b_1, ...] (both are
+ * overwritten).  Means divide by batch_global (>= batch; data-parallel ranks pass the global batch and all-reduce
+ * `grad` and `out_losses` with SUM).  fp32 FFMA kernels, any layer widths <= 512. */
+#define DMIP_LOSS_DSM 0     /* loss_fn.name == 'DSMLoss'                                   */
+#define DMIP_LOSS_DSM_PDE 1 /* DSM_PDELoss                                                 */
+#define DMIP_LOSS_PINN 2    /* PINNLoss                                                    */
+#define DMIP_PDE_FPE 0      /* pde_loss = 'FPE'  (needs xdim [+ydim for CDiffE] <= 4)      */
+#define DMIP_PDE_CFPE 1     /* pde_loss = 'cScoreFPE'                                      */
+#define DMIP_L1 1
+#define DMIP_L2 2
+
+typedef struct DmipLoss {
+  int32_t kind;  /* DMIP_LOSS_*                      */
+  int32_t model; /* DMIP_CDE or DMIP_CDIFFE          */
+  int32_t xdim, ydim;
+  int64_t batch;
+  int64_t batch_global; /* 0 = batch */
+  DmipMlp net;          /* sde.a */
+  float beta_min, beta_max;
+  float lam, lam2;
+  int32_t pde_loss, pde_metric, ic_metric;
+  const float* x;         /* device (batch, xdim)                                           */
+  const float* y;         /* device (batch, ydim)                                           */
+  const float* t;         /* device (batch,)  from sample_t (models/diffusion.py:48-58)     */
+  const float* eps;       /* device (batch, d) standard normals, d = xdim (CDE) | xdim+ydim */
+  const float* ic_target; /* device (batch, xdim) = initial_condition(x, y); PINN only      */
+  float* out_losses;      /* device float[4]                                                */
+  float* grad;            /* device float[dmip_loss_grad_floats(net)]                       */
+  void* workspace;        /* device, dmip_loss_workspace_bytes(), 16-byte aligned           */
+  size_t workspace_bytes;
+} DmipLoss;
+
+size_t dmip_loss_workspace_bytes(const DmipLoss* d);
+size_t dmip_loss_grad_floats(const DmipMlp* net);
+int dmip_loss_fwd_bwd(const DmipLoss* d, void* stream);
+
 /* ---- debug / self-test hooks (used by tests/ only) ------------------------------------------------------
  * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
  * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.

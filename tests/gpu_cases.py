@@ -199,3 +199,66 @@ def case_sampler_trained(precision, mode):
     if precision == "bf16" and (dmean > 3e-3 or rstd > 5e-3):
         err = max(err, 1.0)
     return err, tol, dict(out=out, ref=fx["out"], dmean=dmean, rstd=rstd)
+
+
+# ------------------------------------------------------------------------------------------- fused losses
+LOSS_CASES = {
+    # fixture: (model, kind, kwargs, weight gain)
+    "loss_dsm_cde_linear": ("CDE", "DSM", {}, 1.0),
+    "loss_dsm_cdiffe_linear": ("CDiffE", "DSM", {}, 1.0),
+    "loss_dsm_cde_scat": ("CDE", "DSM", {}, 1.0),
+    "loss_dsm_small": ("CDE", "DSM", {}, 1.0),
+    "loss_pinn_cde_linear": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_cde_linear_g3": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 3.0),
+    "loss_pinn_cde_linear_l2l1": ("CDE", "PINN", dict(lam=0.5, lam2=0.7, pde_loss="FPE", ic_metric="L1", pde_metric="L2"), 1.0),
+    "loss_pinn_cde_linear_cfpe": ("CDE", "PINN", dict(lam=0.01, lam2=0.1, pde_loss="cScoreFPE", ic_metric="L2", pde_metric="L2"), 1.0),
+    "loss_pinn_cde_scat": ("CDE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_cdiffe_linear": ("CDiffE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_small": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_dsmpde_cde_linear": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="FPE", pde_metric="L1"), 1.0),
+    "loss_dsmpde_cde_linear_cfpe": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="cScoreFPE", pde_metric="L1"), 1.0),
+}
+
+
+def case_loss(name):
+    """Fused loss forward+backward (fp32 kernels) vs the reference's autograd result stored in the fixture:
+    loss and every info-dict entry within 3e-4 relative; every parameter gradient within 3e-3 of its scale
+    (atomics make the fp32 summation order of the batch reductions non-deterministic)."""
+    from dmip import losses as dl
+    from util import check_grads
+    model_kind, kind, kw, gain = LOSS_CASES[name]
+    fx = load_golden(name)
+    seed, xdim, ydim, B = (int(v) for v in fx["meta"][:4])
+    hidden = meta_hidden(fx, 4)
+    from dmip.models.diffusion import CDE, CDiffE
+    m = (CDE if model_kind == "CDE" else CDiffE)(xdim, ydim, list(hidden))
+    out_dim = xdim if model_kind == "CDE" else xdim + ydim
+    m.sde.a.load_state_dict(state_dict_from_params(make_params(seed, xdim + ydim + 1, out_dim, hidden, gain=gain)))
+    m.sde.to(DEV)
+    x, y, t, eps = (fx[k].to(DEV) for k in ("x", "y", "t", "eps"))
+    info = {}
+    if kind == "DSM":
+        loss, _ = dl.dsm_fused(m, x, y, t, eps)
+    else:
+        if kind == "PINN":
+            ic = fx["ic_target"].to(DEV)
+            loss_fn = dl.PINNLoss(lambda xx, yy: ic, **kw)
+        else:
+            loss_fn = dl.DSM_PDELoss(**kw)
+        z = x if model_kind == "CDE" else torch.cat([x, y], 1)
+        loss, info = loss_fn(m.sde, x, y, z, t, eps, None, None)
+    m.sde.a.zero_grad()
+    loss.backward()
+    ref = fx["loss"].item()
+    err = abs(loss.item() - ref) / max(abs(ref), 1e-6)
+    for k, v in info.items():
+        r = fx["info_" + k.replace(" ", "_").replace("-", "_")].item()
+        err = max(err, abs(v.item() - r) / max(abs(r), 1e-6))
+    lins = [mod for mod in m.sde.a.children() if isinstance(mod, torch.nn.Linear)]
+    grads = [(l.weight.grad.cpu(), l.bias.grad.cpu()) for l in lins]
+    try:
+        check_grads(fx, grads, rtol=3e-3, atol_frac=3e-3)
+    except AssertionError as e:
+        print("  grad mismatch:", str(e)[:300])
+        err = max(err, 1.0)
+    return err, 3e-4, dict(loss=loss.item(), ref=ref)

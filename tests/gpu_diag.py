@@ -39,7 +39,11 @@ CASES = [
     ("trained_f32_philox", "case_sampler_trained('fp32', 'philox')"),
     ("trained_bf16_injected", "case_sampler_trained('bf16', 'injected')"),
     ("trained_bf16_philox", "case_sampler_trained('bf16', 'philox')"),
-]
+] + [("loss_" + n[5:], f"case_loss('{n}')") for n in [
+    "loss_dsm_small", "loss_dsm_cde_linear", "loss_dsm_cdiffe_linear", "loss_dsm_cde_scat",
+    "loss_pinn_small", "loss_pinn_cde_linear", "loss_pinn_cde_linear_g3", "loss_pinn_cde_linear_l2l1",
+    "loss_pinn_cde_linear_cfpe", "loss_pinn_cde_scat", "loss_pinn_cdiffe_linear",
+    "loss_dsmpde_cde_linear", "loss_dsmpde_cde_linear_cfpe"]]
 
 TEMPLATE = """
 import sys, torch
