@@ -157,6 +157,26 @@ int dmip_loss_fwd_bwd(const DmipLoss* d, void* stream) {
   return launch_loss(d, static_cast<cudaStream_t>(stream));
 }
 
+size_t dmip_surrogate_workspace_bytes(const DmipSurrogate* d) { return d ? surrogate_workspace(d) : 0; }
+
+int dmip_surrogate_score(const DmipSurrogate* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  return launch_surrogate(d, static_cast<cudaStream_t>(stream));
+}
+
+size_t dmip_posterior_loss_workspace_bytes(const DmipPosteriorLoss* d) { return d ? posterior_loss_workspace(d) : 0; }
+
+int dmip_posterior_loss_fwd_bwd(const DmipPosteriorLoss* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  return launch_posterior_loss(d, static_cast<cudaStream_t>(stream));
+}
+
 int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream) {
   reset_launch_count();
   int rc = require_device();

@@ -65,6 +65,10 @@ size_t forward_f32_workspace(const DmipForward* d);
 size_t loss_workspace(const DmipLoss* q);
 size_t loss_grad_floats(const DmipMlp* net);
 int launch_loss(const DmipLoss* q, cudaStream_t s);
+size_t posterior_loss_workspace(const DmipPosteriorLoss* q);
+int launch_posterior_loss(const DmipPosteriorLoss* q, cudaStream_t s);
+size_t surrogate_workspace(const DmipSurrogate* d);
+int launch_surrogate(const DmipSurrogate* d, cudaStream_t s);
 size_t sampler_tc_workspace();
 void debug_set_timeline(unsigned long long* buf, int cap);
 int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s);

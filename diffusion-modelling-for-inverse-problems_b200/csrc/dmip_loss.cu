@@ -16,15 +16,12 @@
 // Three kernels: k_jets_fwd (one CTA = 32 stream-rows: GEMM per layer + jet activation in shared memory, per-sample
 // loss and top adjoints), k_jets_bwd (adjoint rows back through the layers), k_wgrad (dW_l = ADJ_l^T IN_l, split-K).
 #include "dmip_common.h"
+#include "dmip_tile.cuh"
 
 namespace dmip {
 
 namespace {
 
-constexpr int kRows = 32;
-constexpr int kLd = 36;
-constexpr int kMaxW = 512;
-constexpr int kThreadsL = 256;
 constexpr int kMaxD = 4;   // exact Score-FPE: state dimension of the diffused variable (d(d+1)/2 second-order streams)
 
 struct LossDev {
@@ -37,7 +34,12 @@ struct LossDev {
   float inv_B;                        // 1 / global batch
   float bmin, bmax, lam, lam2;
   int pde_loss, pde_metric, ic_metric;
-  int has_I, has_T, has_S;            // stream groups present
+  int has_I, has_T, has_S, has_Q;     // stream groups present
+  int post;                           // 0: CDE/CDiffE losses; 1: DPS prior net pass; 2: DPS likelihood net pass
+  float* aux_s;                       // post=1 out: s_prior (B,d);  post=2 in: target (B,d)
+  float* aux_J;                       // post=1 out: J_s (B,d,d) row-major [i][k] = d s_i / d x_k
+  float* aux_x0;                      // post=1 out: Tweedie mean x0_hat (B,d)
+  float* aux_xt;                      // post=1 out: x_t (B,d)
   int n_streams, spt;                 // streams per sample, samples per tile
   int n_adj;                          // adjoint streams per sample: P [, I] [, T]
   const float* x;
@@ -51,43 +53,6 @@ struct LossDev {
   float* zdt[DMIP_MAX_LAYERS];        // ZDT_l [B][N_l]         pre-activation time tangent of hidden layer l
   float* abar;                        // [B*n_adj][out_dim]     adjoints of the net outputs
 };
-
-// out[n*kLd + r] = sum_k in[k*kLd + r] * Wt[k*N + n], r < 32, n < N.  256 threads; ends with __syncthreads().
-__device__ void tile_gemm(const float* in, float* out, const float* __restrict__ Wt, int K, int N) {
-  const int t = threadIdx.x;
-  const int rg = t >> 6, ng = t & 63;
-  for (int nb = 0; nb < N; nb += 512) {
-    float acc[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
-    const int ncols = (N - nb - ng + 63) >> 6;
-    if (ncols > 0) {
-      for (int k = 0; k < K; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(in + k * kLd + rg * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(in + k * kLd + rg * 8 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = (i < ncols) ? __ldg(Wt + static_cast<size_t>(k) * N + nb + ng + 64 * i) : 0.f;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(a[r], w[i], acc[r][i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int n = nb + ng + 64 * i;
-      if (n < N) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) out[n * kLd + rg * 8 + r] = acc[r][i];
-      }
-    }
-  }
-  __syncthreads();
-}
 
 // activation jets: value h, first and second derivative of phi at pre-activation z (layer 0: tanh(tanh), else tanh)
 __device__ __forceinline__ void act_jet(float z, bool first, float& h, float& p1, float& p2) {
@@ -123,6 +88,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
   const int t = threadIdx.x;
   const int ns = P.n_streams, spt = P.spt, d = P.d;
   const int sI = 1, sT = 1 + P.has_I, sS = sT + P.has_T, sQ = sS + (P.has_S ? d : 0);
+  (void)sQ;
   const long long n_tiles = (P.B + spt - 1) / spt;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -207,14 +173,16 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
 #pragma unroll
             for (int k = 0; k < kMaxD; ++k)
               if (k < d) zs[k] = col[sS + k];
+            if (P.has_Q) {
 #pragma unroll
-            for (int i = 0; i < kMaxD; ++i)
+              for (int i = 0; i < kMaxD; ++i)
 #pragma unroll
-              for (int k = i; k < kMaxD; ++k)
-                if (k < d) {
-                  const int q = sQ + q_index(i, k, d);
-                  col[q] = p1 * col[q] + p2 * zs[i] * zs[k];
-                }
+                for (int k = i; k < kMaxD; ++k)
+                  if (k < d) {
+                    const int q = sQ + q_index(i, k, d);
+                    col[q] = p1 * col[q] + p2 * zs[i] * zs[k];
+                  }
+            }
 #pragma unroll
             for (int k = 0; k < kMaxD; ++k)
               if (k < d) col[sS + k] = p1 * zs[k];
@@ -240,6 +208,28 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
       const float sd = sqrtf(var), sb = sqrtf(beta), db = P.bmax - P.bmin;
       float* abarP = P.abar + (smp * P.n_adj + 0) * od;
       float l_dsm = 0.f, l_ic = 0.f, l_pde = 0.f;
+      if (P.post == 1) {
+        // DPS prior net: s_prior = prior_net(x_t, t) IS the score (no 1/g); DSM on it; Tweedie mean and Jacobian
+        // for the likelihood target                                                   (losses.py:374-381)
+        for (int j = 0; j < od; ++j) {
+          const float sp = o[j * kLd + 0] + P.b[L][j];
+          const float xt = P.eps[smp * d + j] * sd + alpha * P.x[smp * P.xdim + j];
+          const float r = sp * sd + P.eps[smp * d + j];
+          l_dsm += 0.5f * r * r;
+          abarP[j] = P.inv_B * r * sd;
+          P.aux_s[smp * d + j] = sp;
+          P.aux_xt[smp * d + j] = xt;
+          P.aux_x0[smp * d + j] = (xt + var * sp) / alpha;
+          for (int k = 0; k < d; ++k) P.aux_J[(smp * d + j) * d + k] = o[j * kLd + sS + k];
+        }
+      } else if (P.post == 2) {
+        // DPS likelihood net: sum_j (alpha s_lik - target)^2, target detached           (losses.py:382)
+        for (int j = 0; j < od; ++j) {
+          const float r = alpha * (o[j * kLd + 0] + P.b[L][j]) - P.aux_s[smp * d + j];
+          l_ic += P.lam * r * r;
+          abarP[j] = P.inv_B * P.lam * 2.f * r * alpha;
+        }
+      } else
       // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                            (losses.py:49-52, Q3)
       for (int j = 0; j < od; ++j) {
         const float a = o[j * kLd + 0] + P.b[L][j];
@@ -477,70 +467,50 @@ __global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ adj, co
   }
 }
 
-__global__ void k_transpose_l(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
-  __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < rows && c < cols) ? W[static_cast<size_t>(r) * cols + c] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) Wt[static_cast<size_t>(c) * rows + r] = tile[threadIdx.x][i];
-  }
-}
 
-size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+// One "pass" = one net, one batch, one choice of jet streams: transposes, k_jets_fwd, k_jets_bwd, k_wgrad.
+struct PassCfg {
+  const DmipMlp* net;
+  int xdim, ydim, d, cdim;
+  int has_I, has_T, has_S, has_Q, post;
+  int kind, model, pde_loss, pde_metric, ic_metric;
+  long long batch, batch_global;
+  float bmin, bmax, lam, lam2;
+  const float *x, *y, *t, *eps, *ic_target;
+  float *losses, *grad;
+  float *aux_s, *aux_J, *aux_x0, *aux_xt;
+};
 
 struct LossPlan {
-  int d, cdim, n_streams, spt, n_adj, has_I, has_T, has_S;
+  int n_streams, spt, n_adj;
   size_t off_wt[DMIP_MAX_LAYERS], off_in[DMIP_MAX_LAYERS], off_adj[DMIP_MAX_LAYERS], off_zdt[DMIP_MAX_LAYERS], off_abar;
   size_t bytes;
 };
 
-int make_plan(const DmipLoss* q, LossPlan* p) {
-  DMIP_REQUIRE(q != nullptr, "descriptor is NULL");
-  DMIP_REQUIRE(q->kind == DMIP_LOSS_DSM || q->kind == DMIP_LOSS_DSM_PDE || q->kind == DMIP_LOSS_PINN,
-               "No valid loss_fn was specified. Options are DMIP_LOSS_DSM, DMIP_LOSS_DSM_PDE, DMIP_LOSS_PINN.");
-  DMIP_REQUIRE(q->model == DMIP_CDE || q->model == DMIP_CDIFFE, "model must be DMIP_CDE or DMIP_CDIFFE");
-  const DmipMlp& net = q->net;
-  DMIP_REQUIRE(net.n_layers >= 2 && net.n_layers <= DMIP_MAX_LAYERS, "n_layers out of range");
-  DMIP_REQUIRE(net.in_dim == q->xdim + q->ydim + 1 && net.in_dim <= kMaxW, "net.in_dim must be xdim+ydim+1 (<= %d)", kMaxW);
+int check_net(const DmipMlp& net, int want_in, const char* what) {
+  DMIP_REQUIRE(net.n_layers >= 2 && net.n_layers <= DMIP_MAX_LAYERS, "%s: n_layers out of range", what);
+  DMIP_REQUIRE(net.in_dim == want_in && net.in_dim <= kMaxW, "%s: in_dim must be %d (<= %d), got %d", what, want_in, kMaxW,
+               net.in_dim);
   for (int l = 0; l < net.n_layers; ++l)
-    DMIP_REQUIRE(net.width[l] >= 1 && net.width[l] <= kMaxW && net.W[l] && net.b[l], "layer %d: bad width or NULL", l);
-  p->d = (q->model == DMIP_CDE) ? q->xdim : q->xdim + q->ydim;
-  p->cdim = (q->model == DMIP_CDE) ? q->ydim : 0;
-  DMIP_REQUIRE(net.out_dim == p->d, "s and x_t need to have the same shape, but out_dim %d and %d was given", net.out_dim, p->d);
-  const bool pde = q->kind != DMIP_LOSS_DSM;
-  if (pde) {
-    DMIP_REQUIRE(q->pde_loss == DMIP_PDE_FPE || q->pde_loss == DMIP_PDE_CFPE, "pde_loss must be FPE or cScoreFPE");
-    DMIP_REQUIRE(q->pde_metric == DMIP_L1 || q->pde_metric == DMIP_L2,
-                 "No valid metric specified. Metric should be one of \"L1\" or \"L2\"");
-  }
-  if (q->kind == DMIP_LOSS_PINN) {
-    DMIP_REQUIRE(q->ic_metric == DMIP_L1 || q->ic_metric == DMIP_L2, "ic_metric should be one of \"L1\" or \"L2\"");
-    DMIP_REQUIRE(q->ic_target != nullptr, "PINNLoss needs ic_target = initial_condition(x, y)");
-  }
-  p->has_I = q->kind == DMIP_LOSS_PINN;
-  p->has_T = pde;
-  p->has_S = pde && q->pde_loss == DMIP_PDE_FPE;
-  if (p->has_S)
-    DMIP_REQUIRE(p->d <= kMaxD, "exact Score-FPE divergence supports d <= %d diffused dimensions (got %d); "
-                 "use pde_loss = cScoreFPE", kMaxD, p->d);
-  p->n_streams = 1 + p->has_I + p->has_T + (p->has_S ? p->d + p->d * (p->d + 1) / 2 : 0);
+    DMIP_REQUIRE(net.width[l] >= 1 && net.width[l] <= kMaxW && net.W[l] && net.b[l], "%s layer %d: bad width or NULL", what, l);
+  return DMIP_OK;
+}
+
+int plan_pass(const PassCfg& c, LossPlan* p) {
+  const DmipMlp& net = *c.net;
+  p->n_streams = 1 + c.has_I + c.has_T + (c.has_S ? c.d : 0) + (c.has_Q ? c.d * (c.d + 1) / 2 : 0);
   DMIP_REQUIRE(p->n_streams <= kRows, "too many jet streams (%d)", p->n_streams);
   p->spt = kRows / p->n_streams;
-  p->n_adj = 1 + p->has_I + p->has_T;
+  p->n_adj = 1 + c.has_I + c.has_T;
   size_t off = 0;
   int k = net.in_dim;
-  const size_t B = static_cast<size_t>(q->batch);
+  const size_t B = static_cast<size_t>(c.batch);
   for (int l = 0; l < net.n_layers; ++l) {
     const int n = net.width[l];
     p->off_wt[l] = off;  off += align_up(sizeof(float) * k * n);
     p->off_in[l] = off;  off += align_up(sizeof(float) * B * p->n_adj * k);
     p->off_adj[l] = off; off += align_up(sizeof(float) * B * p->n_adj * n);
-    p->off_zdt[l] = off; off += (p->has_T && l < net.n_layers - 1) ? align_up(sizeof(float) * B * n) : 0;
+    p->off_zdt[l] = off; off += (c.has_T && l < net.n_layers - 1) ? align_up(sizeof(float) * B * n) : 0;
     k = n;
   }
   p->off_abar = off;
@@ -549,55 +519,81 @@ int make_plan(const DmipLoss* q, LossPlan* p) {
   return DMIP_OK;
 }
 
-}  // namespace
-
-size_t loss_workspace(const DmipLoss* q) {
-  LossPlan p;
-  if (make_plan(q, &p)) return 0;
-  return p.bytes;
-}
-
-size_t loss_grad_floats(const DmipMlp* net) {
-  size_t n = 0;
-  int k = net->in_dim;
-  for (int l = 0; l < net->n_layers; ++l) {
-    n += static_cast<size_t>(k) * net->width[l] + net->width[l];
-    k = net->width[l];
-  }
-  return n;
-}
-
-int launch_loss(const DmipLoss* q, cudaStream_t s) {
-  LossPlan p;
-  int rc = make_plan(q, &p);
+// DmipLoss -> PassCfg (CDE / CDiffE losses), with the reference's argument checks
+int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
+  DMIP_REQUIRE(q != nullptr, "descriptor is NULL");
+  DMIP_REQUIRE(q->kind == DMIP_LOSS_DSM || q->kind == DMIP_LOSS_DSM_PDE || q->kind == DMIP_LOSS_PINN,
+               "No valid loss_fn was specified. Options are DMIP_LOSS_DSM, DMIP_LOSS_DSM_PDE, DMIP_LOSS_PINN.");
+  DMIP_REQUIRE(q->model == DMIP_CDE || q->model == DMIP_CDIFFE, "model must be DMIP_CDE or DMIP_CDIFFE");
+  DMIP_REQUIRE(q->xdim >= 1 && q->ydim >= 1 && q->batch >= 0, "xdim/ydim must be positive, batch >= 0");
+  int rc = check_net(q->net, q->xdim + q->ydim + 1, "net");
   if (rc) return rc;
-  DMIP_REQUIRE(q->x && q->y && q->t && q->eps && q->out_losses && q->grad, "x / y / t / eps / out_losses / grad is NULL");
-  if (!q->workspace || q->workspace_bytes < p.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) {
-    set_error("workspace too small or misaligned: need %zu bytes", p.bytes);
-    return DMIP_EWORKSPACE;
+  *c = PassCfg{};
+  c->net = &q->net;
+  c->xdim = q->xdim; c->ydim = q->ydim;
+  c->d = (q->model == DMIP_CDE) ? q->xdim : q->xdim + q->ydim;
+  c->cdim = (q->model == DMIP_CDE) ? q->ydim : 0;
+  DMIP_REQUIRE(q->net.out_dim == c->d, "s and x_t need to have the same shape, but out_dim %d and %d was given",
+               q->net.out_dim, c->d);
+  const bool pde = q->kind != DMIP_LOSS_DSM;
+  if (pde) {
+    DMIP_REQUIRE(q->pde_loss == DMIP_PDE_FPE || q->pde_loss == DMIP_PDE_CFPE, "pde_loss must be FPE or cScoreFPE");
+    DMIP_REQUIRE(q->pde_metric == DMIP_L1 || q->pde_metric == DMIP_L2,
+                 "No valid metric specified. Metric should be one of \"L1\" or \"L2\"");
   }
-  static int n_sm = 0;
-  const int smem = 2 * kMaxW * kLd * 4;
-  if (!n_sm) {
-    int dev = 0;
+  if (q->kind == DMIP_LOSS_PINN) {
+    DMIP_REQUIRE(q->ic_metric == DMIP_L1 || q->ic_metric == DMIP_L2, "ic_metric should be one of \"L1\" or \"L2\"");
+    DMIP_REQUIRE(q->ic_target != nullptr || q->batch == 0, "PINNLoss needs ic_target = initial_condition(x, y)");
+  }
+  c->has_I = q->kind == DMIP_LOSS_PINN;
+  c->has_T = pde;
+  c->has_S = pde && q->pde_loss == DMIP_PDE_FPE;
+  c->has_Q = c->has_S;
+  if (c->has_S)
+    DMIP_REQUIRE(c->d <= kMaxD, "exact Score-FPE divergence supports d <= %d diffused dimensions (got %d); "
+                 "use pde_loss = cScoreFPE", kMaxD, c->d);
+  c->kind = q->kind; c->model = q->model;
+  c->pde_loss = q->pde_loss; c->pde_metric = q->pde_metric; c->ic_metric = q->ic_metric;
+  c->batch = q->batch; c->batch_global = q->batch_global;
+  c->bmin = q->beta_min; c->bmax = q->beta_max; c->lam = q->lam; c->lam2 = q->lam2;
+  c->x = q->x; c->y = q->y; c->t = q->t; c->eps = q->eps; c->ic_target = q->ic_target;
+  c->losses = q->out_losses; c->grad = q->grad;
+  return DMIP_OK;
+}
+
+int g_loss_sm = 0;
+constexpr int kLossSmem = 2 * kMaxW * kLd * 4;
+
+int loss_init() {
+  if (!g_loss_sm) {
+    int dev = 0, n = 0;
     DMIP_CHECK_CUDA(cudaGetDevice(&dev));
-    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
+    g_loss_sm = n;
   }
-  const DmipMlp& net = q->net;
-  uint8_t* ws = static_cast<uint8_t*>(q->workspace);
+  return DMIP_OK;
+}
+
+// Enqueue one pass.  `ws` must hold p.bytes; c.grad is zeroed here, c.losses is NOT (the caller owns it).
+int run_pass(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
+  int rc = loss_init();
+  if (rc) return rc;
+  const int n_sm = g_loss_sm;
+  const DmipMlp& net = *c.net;
   LossDev D = {};
-  D.kind = q->kind; D.model = q->model; D.xdim = q->xdim; D.ydim = q->ydim;
-  D.d = p.d; D.cdim = p.cdim; D.in_dim = net.in_dim; D.out_dim = net.out_dim; D.n_layers = net.n_layers;
-  D.B = q->batch;
-  D.inv_B = 1.0f / static_cast<float>(q->batch_global > 0 ? q->batch_global : q->batch);
-  D.bmin = q->beta_min; D.bmax = q->beta_max; D.lam = q->lam; D.lam2 = q->lam2;
-  D.pde_loss = q->pde_loss; D.pde_metric = q->pde_metric; D.ic_metric = q->ic_metric;
-  D.has_I = p.has_I; D.has_T = p.has_T; D.has_S = p.has_S;
+  D.kind = c.kind; D.model = c.model; D.xdim = c.xdim; D.ydim = c.ydim;
+  D.d = c.d; D.cdim = c.cdim; D.in_dim = net.in_dim; D.out_dim = net.out_dim; D.n_layers = net.n_layers;
+  D.B = c.batch;
+  D.inv_B = 1.0f / static_cast<float>(c.batch_global > 0 ? c.batch_global : (c.batch > 0 ? c.batch : 1));
+  D.bmin = c.bmin; D.bmax = c.bmax; D.lam = c.lam; D.lam2 = c.lam2;
+  D.pde_loss = c.pde_loss; D.pde_metric = c.pde_metric; D.ic_metric = c.ic_metric;
+  D.has_I = c.has_I; D.has_T = c.has_T; D.has_S = c.has_S; D.has_Q = c.has_Q; D.post = c.post;
+  D.aux_s = c.aux_s; D.aux_J = c.aux_J; D.aux_x0 = c.aux_x0; D.aux_xt = c.aux_xt;
   D.n_streams = p.n_streams; D.spt = p.spt; D.n_adj = p.n_adj;
-  D.x = q->x; D.y = q->y; D.t = q->t; D.eps = q->eps; D.ic_target = q->ic_target;
-  D.losses = q->out_losses;
+  D.x = c.x; D.y = c.y; D.t = c.t; D.eps = c.eps; D.ic_target = c.ic_target;
+  D.losses = c.losses;
   D.abar = reinterpret_cast<float*>(ws + p.off_abar);
   int k = net.in_dim;
   for (int l = 0; l < net.n_layers; ++l) {
@@ -616,24 +612,23 @@ int launch_loss(const DmipLoss* q, cudaStream_t s) {
     count_launch();
     k = n;
   }
-  DMIP_CHECK_CUDA(cudaMemsetAsync(q->out_losses, 0, 4 * sizeof(float), s));
-  DMIP_CHECK_CUDA(cudaMemsetAsync(q->grad, 0, loss_grad_floats(&net) * sizeof(float), s));
-  if (q->batch == 0) return DMIP_OK;
+  DMIP_CHECK_CUDA(cudaMemsetAsync(c.grad, 0, loss_grad_floats(&net) * sizeof(float), s));
+  if (c.batch == 0) return DMIP_OK;
 
-  const long long tiles_f = (q->batch + p.spt - 1) / p.spt;
-  k_jets_fwd<<<static_cast<unsigned>(tiles_f < 4LL * n_sm ? tiles_f : 4LL * n_sm), kThreadsL, smem, s>>>(D);
+  const long long tiles_f = (c.batch + p.spt - 1) / p.spt;
+  k_jets_fwd<<<static_cast<unsigned>(tiles_f < 4LL * n_sm ? tiles_f : 4LL * n_sm), kThreadsL, kLossSmem, s>>>(D);
   DMIP_CHECK_CUDA(cudaGetLastError());
   count_launch();
   const int spt_b = kRows / p.n_adj;
-  const long long tiles_b = (q->batch + spt_b - 1) / spt_b;
-  k_jets_bwd<<<static_cast<unsigned>(tiles_b < 4LL * n_sm ? tiles_b : 4LL * n_sm), kThreadsL, smem, s>>>(D);
+  const long long tiles_b = (c.batch + spt_b - 1) / spt_b;
+  k_jets_bwd<<<static_cast<unsigned>(tiles_b < 4LL * n_sm ? tiles_b : 4LL * n_sm), kThreadsL, kLossSmem, s>>>(D);
   DMIP_CHECK_CUDA(cudaGetLastError());
   count_launch();
 
   // weight / bias gradients, flat layout [W_0, b_0, W_1, b_1, ...]
-  float* g = q->grad;
+  float* g = c.grad;
   k = net.in_dim;
-  const long long rows = q->batch * p.n_adj;
+  const long long rows = c.batch * p.n_adj;
   for (int l = 0; l < net.n_layers; ++l) {
     const int n = net.width[l];
     const int tiles = ceil_div(n, 64) * ceil_div(k, 64);
@@ -646,13 +641,153 @@ int launch_loss(const DmipLoss* q, cudaStream_t s) {
     split = static_cast<int>((rows + rps - 1) / rps);
     dim3 grid(ceil_div(k, 64), ceil_div(n, 64), split);
     k_wgrad<<<grid, 256, 0, s>>>(D.adj_rows[l], D.in_rows[l], g, g + static_cast<size_t>(n) * k, rows, n, k, p.n_adj,
-                                 1 + p.has_I, rps);
+                                 1 + c.has_I, rps);
     DMIP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     g += static_cast<size_t>(n) * k + n;
     k = n;
   }
   return DMIP_OK;
+}
+
+// target = std^2 J_s^T u + u  (losses.py:369)  — in place over u
+__global__ void k_post_target(const float* __restrict__ J, float* __restrict__ u, const float* __restrict__ t, long long B,
+                              int d, float bmin, float bmax) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float beta, alpha, var;
+  vp_terms(t[i], bmin, bmax, beta, alpha, var);
+  float uu[8], out[8];
+  for (int j = 0; j < d; ++j) uu[j] = u[i * d + j];
+  for (int k = 0; k < d; ++k) {
+    float acc = 0.f;
+    for (int j = 0; j < d; ++j) acc = fmaf(J[(i * d + j) * d + k], uu[j], acc);
+    out[k] = fmaf(var, acc, uu[k]);
+  }
+  for (int k = 0; k < d; ++k) u[i * d + k] = out[k];
+}
+
+struct PostPlan {
+  PassCfg c1, c2;
+  LossPlan p1, p2;
+  size_t off_pass, off_s, off_J, off_x0, off_xt, off_surr, bytes;
+  DmipSurrogate sd;
+};
+
+int plan_posterior(const DmipPosteriorLoss* q, PostPlan* P) {
+  DMIP_REQUIRE(q != nullptr, "descriptor is NULL");
+  DMIP_REQUIRE(q->xdim >= 1 && q->xdim <= kMaxD && q->ydim >= 1 && q->batch >= 0,
+               "PosteriorLoss: 1 <= xdim <= %d (Jacobian tangent streams), ydim >= 1", kMaxD);
+  int rc;
+  if ((rc = check_net(q->prior_net, q->xdim + 1, "prior_net"))) return rc;
+  if ((rc = check_net(q->lik_net, q->xdim + q->ydim + 1, "likelihood_net"))) return rc;
+  if ((rc = check_net(q->surrogate, q->xdim, "forward_model"))) return rc;
+  DMIP_REQUIRE(q->prior_net.out_dim == q->xdim && q->lik_net.out_dim == q->xdim && q->surrogate.out_dim == q->ydim,
+               "PosteriorLoss: prior/likelihood nets must output xdim columns and the forward model ydim");
+  PassCfg base = {};
+  base.xdim = q->xdim; base.ydim = q->ydim; base.d = q->xdim;
+  base.kind = DMIP_LOSS_DSM; base.model = DMIP_CDE;
+  base.batch = q->batch; base.batch_global = q->batch_global;
+  base.bmin = q->beta_min; base.bmax = q->beta_max; base.lam = q->lam;
+  base.x = q->x; base.y = q->y; base.t = q->t; base.eps = q->eps;
+  base.losses = q->out_losses;
+  P->c1 = base;
+  P->c1.net = &q->prior_net; P->c1.cdim = 0; P->c1.has_S = 1; P->c1.post = 1; P->c1.grad = q->grad_prior;
+  P->c2 = base;
+  P->c2.net = &q->lik_net; P->c2.cdim = q->ydim; P->c2.post = 2; P->c2.grad = q->grad_lik;
+  if ((rc = plan_pass(P->c1, &P->p1))) return rc;
+  if ((rc = plan_pass(P->c2, &P->p2))) return rc;
+  const size_t B = static_cast<size_t>(q->batch), d = q->xdim;
+  size_t off = 0;
+  P->off_pass = off; off += P->p1.bytes > P->p2.bytes ? P->p1.bytes : P->p2.bytes;   // the passes run one after the other
+  P->off_s = off;  off += align_up(sizeof(float) * B * d);
+  P->off_J = off;  off += align_up(sizeof(float) * B * d * d);
+  P->off_x0 = off; off += align_up(sizeof(float) * B * d);
+  P->off_xt = off; off += align_up(sizeof(float) * B * d);
+  P->sd = DmipSurrogate{};
+  P->sd.mode = DMIP_SURR_LIK_VJP;
+  P->sd.net = q->surrogate;
+  P->sd.a = q->a; P->sd.b = q->b; P->sd.lambd_bd = 0.f;
+  P->sd.n = q->batch;
+  P->off_surr = off; off += surrogate_workspace(&P->sd);
+  P->bytes = off;
+  return DMIP_OK;
+}
+
+}  // namespace
+
+size_t loss_workspace(const DmipLoss* q) {
+  PassCfg c;
+  LossPlan p;
+  if (cfg_from_loss(q, &c) || plan_pass(c, &p)) return 0;
+  return p.bytes;
+}
+
+size_t loss_grad_floats(const DmipMlp* net) {
+  size_t n = 0;
+  int k = net->in_dim;
+  for (int l = 0; l < net->n_layers; ++l) {
+    n += static_cast<size_t>(k) * net->width[l] + net->width[l];
+    k = net->width[l];
+  }
+  return n;
+}
+
+int launch_loss(const DmipLoss* q, cudaStream_t s) {
+  PassCfg c;
+  LossPlan p;
+  int rc = cfg_from_loss(q, &c);
+  if (rc) return rc;
+  if ((rc = plan_pass(c, &p))) return rc;
+  DMIP_REQUIRE(q->out_losses && q->grad, "out_losses / grad is NULL");
+  DMIP_REQUIRE(q->batch == 0 || (q->x && q->y && q->t && q->eps), "x / y / t / eps is NULL");
+  if (!q->workspace || q->workspace_bytes < p.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) {
+    set_error("workspace too small or misaligned: need %zu bytes", p.bytes);
+    return DMIP_EWORKSPACE;
+  }
+  DMIP_CHECK_CUDA(cudaMemsetAsync(q->out_losses, 0, 4 * sizeof(float), s));
+  return run_pass(c, p, static_cast<uint8_t*>(q->workspace), s);
+}
+
+size_t posterior_loss_workspace(const DmipPosteriorLoss* q) {
+  PostPlan P;
+  if (plan_posterior(q, &P)) return 0;
+  return P.bytes;
+}
+
+int launch_posterior_loss(const DmipPosteriorLoss* q, cudaStream_t s) {
+  PostPlan P;
+  int rc = plan_posterior(q, &P);
+  if (rc) return rc;
+  DMIP_REQUIRE(q->out_losses && q->grad_prior && q->grad_lik, "out_losses / grad_prior / grad_lik is NULL");
+  DMIP_REQUIRE(q->batch == 0 || (q->x && q->y && q->t && q->eps), "x / y / t / eps is NULL");
+  if (!q->workspace || q->workspace_bytes < P.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) {
+    set_error("workspace too small or misaligned: need %zu bytes", P.bytes);
+    return DMIP_EWORKSPACE;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(q->workspace);
+  float* aux_s = reinterpret_cast<float*>(ws + P.off_s);
+  float* aux_J = reinterpret_cast<float*>(ws + P.off_J);
+  float* aux_x0 = reinterpret_cast<float*>(ws + P.off_x0);
+  float* aux_xt = reinterpret_cast<float*>(ws + P.off_xt);
+  DMIP_CHECK_CUDA(cudaMemsetAsync(q->out_losses, 0, 4 * sizeof(float), s));
+  // 1. prior net: DSM + its gradient; s_prior, J_s, Tweedie mean x0_hat
+  P.c1.aux_s = aux_s; P.c1.aux_J = aux_J; P.c1.aux_x0 = aux_x0; P.c1.aux_xt = aux_xt;
+  if ((rc = run_pass(P.c1, P.p1, ws + P.off_pass, s))) return rc;
+  if (q->batch > 0) {
+    // 2. u = J_f(x0_hat)^T (-a^2 v1 + v2 + a^2 v3)  -> aux_s
+    P.sd.x = aux_x0; P.sd.y = q->y; P.sd.grad = aux_s;
+    P.sd.workspace = ws + P.off_surr; P.sd.workspace_bytes = surrogate_workspace(&P.sd);
+    if ((rc = launch_surrogate(&P.sd, s))) return rc;
+    // 3. target = std^2 J_s^T u + u
+    k_post_target<<<static_cast<unsigned>((q->batch + 255) / 256), 256, 0, s>>>(aux_J, aux_s, q->t, q->batch, q->xdim,
+                                                                                 q->beta_min, q->beta_max);
+    DMIP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  // 4. likelihood net: lam * sum (alpha s_lik - target)^2 + its gradient
+  P.c2.aux_s = aux_s;
+  return run_pass(P.c2, P.p2, ws + P.off_pass, s);
 }
 
 }  // namespace dmip

@@ -1,0 +1,202 @@
+// dmip_surrogate.cu — K4: forward + reverse sweep through the frozen scatterometry surrogate (ReLU MLP
+// 3 -> 256 -> 256 -> 256 -> 23, utils_scatterometry.py:9-16) fused with the cotangent that feeds it.
+//
+//   mode 0  energy E(x) = 1/2 sum log p + 1/2 sum (y-f)^2/p + lambd_bd sum [relu(x-1) + relu(-1-x)],
+//           p = (a f)^2 + b^2  (get_log_posterior, utils_scatterometry.py:30-38) and grad_x E
+//           (energy_grad, models/SNF.py:234-237); score_posterior = -grad_x E is the PINNLoss initial condition
+//           (main_diffusion_scatterometry.py:142-145).  Closed form: SURVEY.md App. A.6.
+//   mode 1  u = J_f(x)^T w with w = -a^2 f/p + (y-f)/p + a^2 (y-f)^2 f/p — the three VJPs of
+//           PosteriorLoss.likelihood_target (losses.py:349-371) merged into one sweep.
+//
+// One CTA = 32 rows.  The ReLU masks of the hidden layers are kept as one 32-bit word per (layer, unit) in shared
+// memory; the reverse sweep reuses the untransposed nn.Linear weights as [contraction][output].
+#include "dmip_common.h"
+#include "dmip_tile.cuh"
+
+namespace dmip {
+
+namespace {
+
+struct SurrDev {
+  int mode, n_layers, in_dim, out_dim;
+  int width[DMIP_MAX_LAYERS];
+  const float* W[DMIP_MAX_LAYERS];
+  const float* Wt[DMIP_MAX_LAYERS];
+  const float* b[DMIP_MAX_LAYERS];
+  float a, bb, lambd;
+  long long n;
+  const float* x;
+  const float* y;
+  float* energy;
+  float* grad;
+  float* fx;
+};
+
+__global__ void __launch_bounds__(kThreadsL, 1) k_surrogate(const __grid_constant__ SurrDev P) {
+  extern __shared__ float smem[];
+  float* buf0 = smem;
+  float* buf1 = smem + kMaxW * kLd;
+  uint32_t* masks = reinterpret_cast<uint32_t*>(buf1 + kMaxW * kLd);   // [n_layers-1][kMaxW]
+  const int t = threadIdx.x, lane = t & 31;
+  const long long n_tiles = (P.n + kRows - 1) / kRows;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long r0 = tile * kRows;
+    for (int idx = t; idx < kRows * P.in_dim; idx += kThreadsL) {
+      const int k = idx / kRows, r = idx % kRows;
+      buf0[k * kLd + r] = (r0 + r < P.n) ? P.x[(r0 + r) * P.in_dim + k] : 0.f;
+    }
+    __syncthreads();
+    float* in = buf0;
+    float* out = buf1;
+    int K = P.in_dim;
+    const int L = P.n_layers - 1;
+    for (int l = 0; l <= L; ++l) {
+      const int N = P.width[l];
+      tile_gemm(in, out, P.Wt[l], K, N);
+      for (int idx = t; idx < N * kRows; idx += kThreadsL) {      // a warp = one unit n, lane = row
+        const int n = idx >> 5;
+        float z = out[n * kLd + lane] + P.b[l][n];
+        if (l < L) {
+          const uint32_t m = __ballot_sync(0xffffffffu, z > 0.f);
+          if (lane == 0) masks[l * kMaxW + n] = m;
+          z = fmaxf(z, 0.f);
+        }
+        out[n * kLd + lane] = z;
+      }
+      __syncthreads();
+      float* tmp = in; in = out; out = tmp;
+      K = N;
+    }
+    // ---- per-row energy and cotangent d(.)/df  (in: f[j][row])
+    if (t < kRows) {
+      const long long row = r0 + t;
+      const bool live = row < P.n;
+      const float a2 = P.a * P.a;
+      float E = 0.f;
+      for (int j = 0; j < P.out_dim; ++j) {
+        const float f = in[j * kLd + t];
+        const float yv = live ? P.y[row * P.out_dim + j] : 0.f;
+        const float p = a2 * f * f + P.bb * P.bb;
+        const float r = yv - f;
+        float w;
+        if (P.mode == 0) {
+          E += 0.5f * logf(p) + 0.5f * r * r / p;
+          w = a2 * f / p - r / p - a2 * f * r * r / (p * p);       // dE/df  (App. A.6)
+        } else {
+          w = -a2 * f / p + r / p + a2 * r * r * f / p;            // -a^2 v1 + v2 + a^2 v3  (losses.py:354-368)
+        }
+        if (live && P.fx) P.fx[row * P.out_dim + j] = f;
+        in[j * kLd + t] = w;
+      }
+      if (P.mode == 0 && live && P.energy) {
+        for (int k = 0; k < P.in_dim; ++k) {
+          const float xv = P.x[row * P.in_dim + k];
+          E += P.lambd * (fmaxf(xv - 1.f, 0.f) + fmaxf(-1.f - xv, 0.f));
+        }
+        P.energy[row] = E;
+      }
+    }
+    __syncthreads();
+    // ---- reverse sweep
+    for (int l = L; l >= 0; --l) {
+      const int N = P.width[l];
+      const int Kp = (l == 0) ? P.in_dim : P.width[l - 1];
+      tile_gemm(in, out, P.W[l], N, Kp);
+      if (l > 0) {
+        for (int idx = t; idx < Kp * kRows; idx += kThreadsL) {
+          const int k = idx >> 5;
+          if (!((masks[(l - 1) * kMaxW + k] >> lane) & 1u)) out[k * kLd + lane] = 0.f;
+        }
+        __syncthreads();
+      }
+      float* tmp = in; in = out; out = tmp;
+    }
+    for (int idx = t; idx < kRows * P.in_dim; idx += kThreadsL) {
+      const int r = idx / P.in_dim, k = idx % P.in_dim;
+      const long long row = r0 + r;
+      if (row < P.n) {
+        float g = in[k * kLd + r];
+        if (P.mode == 0) {
+          const float xv = P.x[row * P.in_dim + k];
+          g += P.lambd * ((xv > 1.f ? 1.f : 0.f) - (xv < -1.f ? 1.f : 0.f));
+        }
+        P.grad[row * P.in_dim + k] = g;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+size_t surr_wt_floats(const DmipMlp* net) {
+  size_t n = 0;
+  int k = net->in_dim;
+  for (int l = 0; l < net->n_layers; ++l) {
+    n += static_cast<size_t>(k) * net->width[l];
+    k = net->width[l];
+  }
+  return n;
+}
+
+}  // namespace
+
+size_t surrogate_workspace(const DmipSurrogate* d) { return align_up(surr_wt_floats(&d->net) * sizeof(float)); }
+
+int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
+  const DmipMlp& net = d->net;
+  DMIP_REQUIRE(net.n_layers >= 2 && net.n_layers <= DMIP_MAX_LAYERS, "surrogate n_layers out of range");
+  DMIP_REQUIRE(net.in_dim >= 1 && net.in_dim <= kMaxW, "surrogate in_dim out of range");
+  for (int l = 0; l < net.n_layers; ++l)
+    DMIP_REQUIRE(net.width[l] >= 1 && net.width[l] <= kMaxW && net.W[l] && net.b[l], "surrogate layer %d: bad width or NULL", l);
+  DMIP_REQUIRE(d->mode == 0 || d->mode == 1, "surrogate mode must be 0 (energy + gradient) or 1 (likelihood VJP)");
+  DMIP_REQUIRE(d->n >= 0, "negative row count");
+  if (d->n == 0) return DMIP_OK;
+  DMIP_REQUIRE(d->x && d->y && d->grad, "x / y / grad is NULL");
+  if (!d->workspace || d->workspace_bytes < surrogate_workspace(d)) {
+    set_error("workspace too small: need %zu bytes", surrogate_workspace(d));
+    return DMIP_EWORKSPACE;
+  }
+  static int n_sm = 0;
+  const int smem = 2 * kMaxW * kLd * 4 + (DMIP_MAX_LAYERS - 1) * kMaxW * 4;
+  if (!n_sm) {
+    int dev = 0;
+    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+    DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_surrogate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  SurrDev P = {};
+  P.mode = d->mode;
+  P.n_layers = net.n_layers;
+  P.in_dim = net.in_dim;
+  P.out_dim = net.out_dim;
+  float* wt = static_cast<float*>(d->workspace);
+  int k = net.in_dim;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int n = net.width[l];
+    P.width[l] = n;
+    P.W[l] = net.W[l];
+    P.b[l] = net.b[l];
+    P.Wt[l] = wt;
+    dim3 grid(ceil_div(k, 32), ceil_div(n, 32)), block(32, 8);
+    k_transpose_l<<<grid, block, 0, s>>>(net.W[l], wt, n, k);
+    DMIP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    wt += static_cast<size_t>(k) * n;
+    k = n;
+  }
+  P.a = d->a;
+  P.bb = d->b;
+  P.lambd = d->lambd_bd;
+  P.n = d->n;
+  P.x = d->x;
+  P.y = d->y;
+  P.energy = d->energy;
+  P.grad = d->grad;
+  P.fx = d->fx;
+  const long long tiles = (d->n + kRows - 1) / kRows;
+  k_surrogate<<<static_cast<unsigned>(tiles < 4LL * n_sm ? tiles : 4LL * n_sm), kThreadsL, smem, s>>>(P);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
+}
+
+}  // namespace dmip

@@ -208,12 +208,32 @@ __device__ __forceinline__ void a0_put_piece(uint8_t* sH, int row, int pc, int d
   }
 }
 
-__device__ __forceinline__ void tl_mark(const TcParams& P, uint32_t code) {
-  if (P.tl != nullptr && blockIdx.x == 0) {
-    const unsigned int i = atomicAdd(reinterpret_cast<unsigned int*>(P.tl), 1u);
-    if (i + 1 < static_cast<unsigned int>(P.tl_cap))
-      P.tl[i + 1] = (static_cast<unsigned long long>(clock64()) << 16) | code;
+// Timeline hook (debug): each instrumented thread of CTA 0 owns a quarter of the buffer and appends
+// (clock64 << 16 | code) with plain stores — no atomics, so the probe costs a few cycles, not an L2 round trip.
+struct TlRole {
+  unsigned long long* p;
+  unsigned int n, cap;
+};
+__device__ __forceinline__ TlRole tl_role(const TcParams& P, int role, bool on) {
+  TlRole r;
+  r.p = nullptr;
+  r.n = 0;
+  r.cap = 0;
+  if (P.tl != nullptr && blockIdx.x == 0 && on) {
+    const int seg = P.tl_cap / 4;
+    r.p = P.tl + static_cast<size_t>(role) * seg;
+    r.cap = static_cast<unsigned int>(seg - 1);
   }
+  return r;
+}
+__device__ __forceinline__ void tl_mark(TlRole& r, uint32_t code) {
+  if (r.p != nullptr && r.n < r.cap) {
+    r.p[1 + r.n] = (static_cast<unsigned long long>(clock64()) << 16) | code;
+    ++r.n;
+  }
+}
+__device__ __forceinline__ void tl_finish(const TlRole& r) {
+  if (r.p != nullptr) r.p[0] = r.n;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -279,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     {
       int s = 0;
       uint32_t ph = 0;
+      TlRole tl = tl_role(P, 0, lane == 0);
       const uint32_t part = kStageBytes / C;
       for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
         for (int step = 0; step < S; ++step) {
@@ -287,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             const int ns = P.net[p].n_stages;
             for (int st = 0; st < ns; ++st) {
               mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);   // slot s released by the MMA warps of ALL cluster CTAs
+              tl_mark(tl, 0x600u | (st & 0xFF));
               const uint8_t* g = src + static_cast<size_t>(st) * kStageBytes;
               if (elect_one()) {
                 if (P.dbg & 1) {
@@ -305,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           }
         }
       }
+      tl_finish(tl);
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer (whole warp, one elected lane issues)
@@ -316,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       uint32_t a0_par = 0;
       uint32_t job = 0;
       bool ready = false;   // result of the early probe of full[s]
+      TlRole tl = tl_role(P, 1, lane == 0);
       const uint32_t sH_addr = smem_u32(sH);
       const uint32_t sB_addr = smem_u32(sB);
       const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // everything but the address field
@@ -323,7 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         for (int step = 0; step < S; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const TcNetDev& net = P.net[p];
+            tl_mark(tl, 0xD00u);
             mbar_wait(B.a0_ready, a0_par, 0x200);
+            tl_mark(tl, 0xE00u);
             a0_par ^= 1u;
             int jl = 0;
 #pragma unroll 1
@@ -337,17 +363,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               for (int c = 0; c < n_chunks; ++c, ++job, ++jl) {
                 const int buf = job & 1;
                 const uint32_t uses = buf ? acc_uses1 : acc_uses0;
-                mbar_wait(&B.acc_empty[buf], (uses & 1u) ^ 1u, 0x300 + buf);
+                if (!mbar_try_wait(&B.acc_empty[buf], (uses & 1u) ^ 1u)) {
+                  tl_mark(tl, 0xB00u | jl);   // accumulator buffer still being drained by the epilogue
+                  mbar_wait(&B.acc_empty[buf], (uses & 1u) ^ 1u, 0x300 + buf);
+                  tl_mark(tl, 0xC00u | jl);
+                }
                 if (buf) ++acc_uses1; else ++acc_uses0;
-                if (lane == 0) tl_mark(P, 0x100u | jl);
+                tl_mark(tl, 0x100u | jl);
                 const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
 #pragma unroll 1
                 for (int kb = 0; kb < KB; ++kb) {
                   if (l > 0 && c == 0 && (kb & 1) == 0) {
-                    mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
+                    if (!mbar_try_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u)) {
+                      tl_mark(tl, 0x900u | (jl << 4) | kb);   // waiting for the previous layer's epilogue
+                      mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
+                      tl_mark(tl, 0xA00u | (jl << 4) | kb);
+                    }
                     hr_par ^= 1u << (kb >> 1);
                   }
-                  if (!ready) mbar_wait(&B.full[s], ph, 0x500 + s);
+                  if (!ready) {
+                    tl_mark(tl, 0x700u | (jl << 4) | kb);   // ring underflow: the weight stage has not landed yet
+                    mbar_wait(&B.full[s], ph, 0x500 + s);
+                    tl_mark(tl, 0x800u | (jl << 4) | kb);
+                  }
                   tc_fence_after();
                   const int nk = (l == 0 && kb == KB - 1) ? (net.ksteps0 - 4 * (KB - 1)) : 4;
                   const uint32_t b_lo = ((sB_addr + s * kStageBytes) & 0x3FFFFu) >> 4;
@@ -375,12 +413,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                   }
                   __syncwarp();
                 }
-                if (lane == 0) tl_mark(P, 0x200u | jl);
+                tl_mark(tl, 0x200u | jl);
               }
             }
           }
         }
       }
+      tl_finish(tl);
     }
   } else {
     // =============================================================== epilogue (256 threads, 2 per row)
@@ -389,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     const int hh = ew >> 2;
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..255
-    const bool tl_on = (et == 0);
+    TlRole tl = tl_role(P, et == 0 ? 2 : 3, et == 0 || et == 128);
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_uses[2] = {0, 0};
     uint32_t job = 0;
@@ -508,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           }
           fence_proxy_async_smem();
           mbar_arrive(B.a0_ready);
-          if (tl_on) tl_mark(P, 0x500u);
+          tl_mark(tl, 0x500u);
           epi_bar_sync();  // sB0 visible to all epilogue threads
 
           // ---- layers 0..2
@@ -530,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x600 + buf);
               acc_uses[buf]++;
               tc_fence_after();
-              if (tl_on) tl_mark(P, 0x300u | jl);
+              tl_mark(tl, 0x300u | jl);
               const uint32_t acc_col = kTmemAcc + buf * 128;
               if (l == 0)
                 epi_hidden<true, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
@@ -538,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                 epi_hidden<false, false>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
               else
                 epi_hidden<false, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
-              if (tl_on) tl_mark(P, 0x400u | jl);
+              tl_mark(tl, 0x400u | jl);
               if (l >= 1 && last_pass && P.mode == kModeSampler) {
                 // ---- in the shadow of the MMA-bound layers 1-2, one 8-column piece per accumulator chunk: the part
                 // of the Euler–Maruyama update that does not need the net output,
@@ -585,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x700 + buf);
             acc_uses[buf]++;
             tc_fence_after();
-            if (tl_on) tl_mark(P, 0x300u | 12);
+            tl_mark(tl, 0x300u | 12);
             const uint32_t acc_col = kTmemAcc + buf * 128;
             // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
             // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
@@ -631,12 +670,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             }
             tc_fence_before();
             mbar_arrive(&B.acc_empty[buf]);
-            if (tl_on) tl_mark(P, 0x400u | 12);
+            tl_mark(tl, 0x400u | 12);
           }
           ++npass;
         }  // pass
       }    // step
     }      // tile
+    tl_finish(tl);
   }
 
   // ---- teardown

@@ -211,9 +211,9 @@ class PosteriorLoss(nn.Module):
         self.b = b
         self.lam = lam
 
-    def forward(self, model, x, y, t):
+    def forward(self, model, x, y, t, eps=None):
         from .posterior import posterior_loss_fused
-        return posterior_loss_fused(self, model, x, y, t)
+        return posterior_loss_fused(self, model, x, y, t, eps)
 
 
 def dsm_fused(model, x, y, t, eps, batch_global=0):

@@ -177,6 +177,68 @@ size_t dmip_loss_workspace_bytes(const DmipLoss* d);
 size_t dmip_loss_grad_floats(const DmipMlp* net);
 int dmip_loss_fwd_bwd(const DmipLoss* d, void* stream);
 
+/* ---- scatterometry surrogate: energy / posterior score / likelihood VJP (K4) ----------------------------------
+ * The frozen forward model f: R^3 -> R^23 is the ReLU MLP of utils_scatterometry.py:9-16 (surrogate.pt; relu after
+ * every layer but the last).  One call runs forward + reverse sweep through it for n rows.
+ *   mode DMIP_SURR_ENERGY   energy[i] = get_log_posterior(x_i, f, a, b, y_i, lambd_bd)  (utils_scatterometry.py:30-38)
+ *                           grad[i]   = d energy / d x_i = energy_grad (models/SNF.py:234-237);
+ *                           score_posterior = -grad is the PINNLoss initial condition
+ *                           (main_diffusion_scatterometry.py:142-145) and the drift of the Metropolis reference chain.
+ *   mode DMIP_SURR_LIK_VJP  grad[i] = J_f(x_i)^T (-a^2 v1 + v2 + a^2 v3), the three surrogate VJPs of
+ *                           PosteriorLoss.likelihood_target (losses.py:349-371) merged; `energy` unused.
+ * fx (optional): f(x) (n, out_dim).  Any widths <= 512, 2..DMIP_MAX_LAYERS layers. */
+#define DMIP_SURR_ENERGY 0
+#define DMIP_SURR_LIK_VJP 1
+
+typedef struct DmipSurrogate {
+  int32_t mode;
+  DmipMlp net;          /* the surrogate (ReLU MLP), in_dim = xdim, out_dim = ydim                    */
+  float a, b, lambd_bd; /* noise model p = (a f)^2 + b^2 and boundary weight (utils_scatterometry.py:19-21) */
+  int64_t n;
+  const float* x;       /* device (n, in_dim)  */
+  const float* y;       /* device (n, out_dim) */
+  float* energy;        /* device (n,) or NULL */
+  float* grad;          /* device (n, in_dim)  */
+  float* fx;            /* device (n, out_dim) or NULL */
+  void* workspace;      /* device, dmip_surrogate_workspace_bytes() */
+  size_t workspace_bytes;
+} DmipSurrogate;
+
+size_t dmip_surrogate_workspace_bytes(const DmipSurrogate* d);
+int dmip_surrogate_score(const DmipSurrogate* d, void* stream);
+
+/* ---- PosteriorLoss (DPS joint loss), forward + backward -------------------------------------------------------
+ * Replaces PosteriorLoss.forward + likelihood_target (losses.py:349-386) and the loss.backward() of
+ * PosteriorDiffusionEstimator.train_epoch (models/diffusion.py:204-229):
+ *   prior_loss = DSM(prior_net(x_t,t), std, eps);  x0_hat = (x_t + std^2 s_prior)/alpha;
+ *   target = (std^2 J_s^T + I) J_f(x0_hat)^T (-a^2 v1 + v2 + a^2 v3)   (constant in the backward pass: the reference
+ *   calls autograd.grad without create_graph);  lik_loss = sum_j (alpha s_lik - target)^2;
+ *   loss = mean(prior_loss + lam * lik_loss).
+ * out_losses[4] = {loss, mean prior_loss, lam * mean lik_loss, 0}; grad_prior / grad_lik: flat fp32 gradients of the
+ * two nets ([W_0,b_0,W_1,b_1,...]).  J_s comes from xdim forward-mode tangent streams through the prior net. */
+typedef struct DmipPosteriorLoss {
+  int32_t xdim, ydim;
+  int64_t batch;
+  int64_t batch_global;   /* 0 = batch */
+  DmipMlp prior_net;      /* MLP2 on [x_t, t]      */
+  DmipMlp lik_net;        /* MLP  on [x_t, y, t]   */
+  DmipMlp surrogate;      /* forward model f       */
+  float beta_min, beta_max;
+  float a, b, lam;
+  const float* x;         /* device (batch, xdim)  */
+  const float* y;         /* device (batch, ydim)  */
+  const float* t;         /* device (batch,)       */
+  const float* eps;       /* device (batch, xdim)  */
+  float* out_losses;      /* device float[4]       */
+  float* grad_prior;      /* device float[dmip_loss_grad_floats(prior_net)] */
+  float* grad_lik;        /* device float[dmip_loss_grad_floats(lik_net)]   */
+  void* workspace;
+  size_t workspace_bytes;
+} DmipPosteriorLoss;
+
+size_t dmip_posterior_loss_workspace_bytes(const DmipPosteriorLoss* d);
+int dmip_posterior_loss_fwd_bwd(const DmipPosteriorLoss* d, void* stream);
+
 /* ---- debug / self-test hooks (used by tests/ only) ------------------------------------------------------
  * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
  * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.

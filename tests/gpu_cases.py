@@ -262,3 +262,88 @@ def case_loss(name):
         print("  grad mismatch:", str(e)[:300])
         err = max(err, 1.0)
     return err, 3e-4, dict(loss=loss.item(), ref=ref)
+
+
+# ------------------------------------------------------------------------------------------- scatterometry surrogate (K4)
+def _surrogate_module():
+    from util import surrogate_params
+    sp = surrogate_params()
+    fm = torch.nn.Sequential(torch.nn.Linear(3, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                             torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 23))
+    fm.load_state_dict({f"{i}.{n}": (W if n == "weight" else b) for i, (W, b) in zip((0, 2, 4, 6), sp)
+                        for n in ("weight", "bias")})
+    for p in fm.parameters():
+        p.requires_grad = False
+    return fm.to(DEV), sp
+
+
+def case_surrogate_energy():
+    """get_log_posterior + energy_grad (utils_scatterometry.py:30-38, models/SNF.py:234-237) vs the reference's own
+    autograd values in scat_energy.npz.  fp32 kernels: f(x) 1e-5; E rel 2e-4 (+1e-2: E ~ 1e3 from the 1/b^2 terms);
+    grad 2e-4 of its scale."""
+    from dmip import utils_scatterometry as us
+    fx = load_golden("scat_energy")
+    fm, _ = _surrogate_module()
+    E, g, f = us.surrogate_call(fm, fx["x"].to(DEV), fx["y"].to(DEV), 0.2, 0.01, 1000.0, want_fx=True)
+    E, g, f = E.cpu(), g.cpu(), f.cpu()
+    e_f = (f - fx["fx"]).abs().max().item() / 1e-5
+    e_E = ((E - fx["E"]).abs() / (2e-4 * fx["E"].abs() + 1e-2)).max().item()
+    e_g = (g - fx["grad"]).abs().max().item() / (2e-4 * fx["grad"].abs().max().item())
+    # the public wrappers
+    E2 = us.get_log_posterior(fx["x"].to(DEV), fm, 0.2, 0.01, fx["y"].to(DEV), 1000.0).cpu()
+    s = us.make_score_posterior(fm, dict(a=0.2, b=0.01, lambd_bd=1000))(fx["x"].to(DEV), fx["y"].to(DEV)).cpu()
+    e_w = max((E2 - E).abs().max().item(), (s + g).abs().max().item()) * 1e6
+    return max(e_f, e_E, e_g, e_w), 1.0, dict(out=g, ref=fx["grad"], e_f=e_f, e_E=e_E, e_g=e_g)
+
+
+def case_surrogate_vjp():
+    """mode DMIP_SURR_LIK_VJP vs the oracle's explicit reverse sweep (oracle/scatterometry.py) — 2e-4 of the scale;
+    also ragged row counts (n not a multiple of the 32-row tile) and n = 1."""
+    from dmip import utils_scatterometry as us
+    from oracle import scatterometry as oscat
+    fx = load_golden("scat_energy")
+    fm, sp = _surrogate_module()
+    worst = 0.0
+    for n in (512, 77, 1):
+        x, y = fx["x"][:n], fx["y"][:n]
+        f = oscat.surrogate(sp, x)
+        pre = (0.2 * f) ** 2 + 0.01 ** 2
+        w = -0.04 * f / pre + (y - f) / pre + 0.04 * (y - f) ** 2 * f / pre
+        ref = oscat.surrogate_vjp(sp, x, w)
+        _, g, _ = us.surrogate_call(fm, x.to(DEV), y.to(DEV), 0.2, 0.01, mode=us.SURR_LIK_VJP)
+        worst = max(worst, (g.cpu() - ref).abs().max().item() / (2e-4 * ref.abs().max().item()))
+    return worst, 1.0, {}
+
+
+def case_posterior_loss(name):
+    """PosteriorLoss fused forward+backward vs the reference autograd values in the fixture: loss and both info
+    entries 5e-4 relative, every parameter gradient of both nets within 3e-3 of its scale."""
+    from dmip import losses as dl
+    from dmip.models.diffusion import PosteriorDiffusionEstimator
+    from util import check_grads
+    fx = load_golden(name)
+    seed, xdim, ydim, B = (int(v) for v in fx["meta"][:4])
+    hid = meta_hidden(fx, 4)
+    m = PosteriorDiffusionEstimator(xdim, ydim, list(hid))
+    m.sde.a.prior_net.load_state_dict(state_dict_from_params(make_params(seed, xdim + 1, xdim, hid)))
+    m.sde.a.likelihood_net.load_state_dict(state_dict_from_params(make_params(seed + 100, xdim + ydim + 1, xdim, hid)))
+    m.sde.to(DEV)
+    fm, _ = _surrogate_module()
+    loss_fn = dl.PosteriorLoss(fm, 0.2, 0.01, float(fx["lam"]))
+    loss, info = loss_fn(m.sde, fx["x"].to(DEV), fx["y"].to(DEV), fx["t"].to(DEV), fx["eps"].to(DEV))
+    m.sde.a.zero_grad()
+    loss.backward()
+    ref = fx["loss"].item()
+    err = abs(loss.item() - ref) / abs(ref)
+    for k in ("PriorLoss", "LikelihoodLoss"):
+        r = fx["info_" + k].item()
+        err = max(err, abs(info[k].item() - r) / abs(r))
+    for prefix, net in (("prior_", m.sde.a.prior_net), ("lik_", m.sde.a.likelihood_net)):
+        lins = [mod for mod in net.children() if isinstance(mod, torch.nn.Linear)]
+        grads = [(l.weight.grad.cpu(), l.bias.grad.cpu()) for l in lins]
+        try:
+            check_grads(fx, grads, prefix=prefix, rtol=3e-3, atol_frac=3e-3)
+        except AssertionError as e:
+            print("  grad mismatch:", prefix, str(e)[:300])
+            err = max(err, 1.0)
+    return err, 5e-4, dict(loss=loss.item(), ref=ref)

@@ -43,7 +43,12 @@ CASES = [
     "loss_dsm_small", "loss_dsm_cde_linear", "loss_dsm_cdiffe_linear", "loss_dsm_cde_scat",
     "loss_pinn_small", "loss_pinn_cde_linear", "loss_pinn_cde_linear_g3", "loss_pinn_cde_linear_l2l1",
     "loss_pinn_cde_linear_cfpe", "loss_pinn_cde_scat", "loss_pinn_cdiffe_linear",
-    "loss_dsmpde_cde_linear", "loss_dsmpde_cde_linear_cfpe"]]
+    "loss_dsmpde_cde_linear", "loss_dsmpde_cde_linear_cfpe"]] + [
+    ("surr_energy", "case_surrogate_energy()"),
+    ("surr_vjp", "case_surrogate_vjp()"),
+    ("loss_posterior_scat", "case_posterior_loss('loss_posterior_scat')"),
+    ("loss_posterior_small", "case_posterior_loss('loss_posterior_small')"),
+]
 
 TEMPLATE = """
 import sys, torch

@@ -1,0 +1,29 @@
+"""GPU parity tests of the fused score-training losses and the scatterometry surrogate kernel (pytest -m gpu)."""
+import pytest
+
+import gpu_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ok(res):
+    err, tol, extra = res
+    assert err <= tol, (err, tol, {k: v for k, v in extra.items() if isinstance(v, float)})
+
+
+@pytest.mark.parametrize("name", sorted(gc.LOSS_CASES))
+def test_fused_loss(name):
+    _ok(gc.case_loss(name))
+
+
+@pytest.mark.parametrize("name", ["loss_posterior_scat", "loss_posterior_small"])
+def test_posterior_loss(name):
+    _ok(gc.case_posterior_loss(name))
+
+
+def test_surrogate_energy_and_score():
+    _ok(gc.case_surrogate_energy())
+
+
+def test_surrogate_likelihood_vjp():
+    _ok(gc.case_surrogate_vjp())
