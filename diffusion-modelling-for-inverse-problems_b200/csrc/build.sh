@@ -1,13 +1,14 @@
 #!/bin/bash
 # Build libdmip_sm100.so in-tree (sm_100a only; nvcc cross-compiles without a GPU).
+# DMIP_DEBUG=1 bash build.sh  compiles the DMIP_DBG ablation bits and the kernel timeline in (slower issue loops).
 set -euo pipefail
 cd "$(dirname "$0")"
 OUT=../libdmip_sm100.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v ${DMIP_DEBUG:+-DDMIP_DEBUG}"
 mkdir -p build
 pids=()
-SRCS="dmip_api dmip_pack dmip_tc dmip_f32 dmip_loss dmip_surrogate"
+SRCS="dmip_api dmip_pack dmip_tc dmip_f32 dmip_loss dmip_surrogate dmip_debug"
 for f in $SRCS; do
   ( $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 || { cat build/$f.log; exit 1; } ) &
   pids+=($!)

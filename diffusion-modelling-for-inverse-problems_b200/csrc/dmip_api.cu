@@ -184,6 +184,22 @@ int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int3
   return launch_debug_mma_bench(mode, n, k, iters, grid, static_cast<long long*>(cycles), static_cast<cudaStream_t>(stream));
 }
 
+int dmip_debug_mma_bench2(int32_t cg, int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t stream_bytes, int32_t grid,
+                          const void* gsrc, void* cycles, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  return launch_debug_mma_bench2(cg, mode, n, k, iters, stream_bytes, grid, gsrc, static_cast<long long*>(cycles),
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int dmip_debug_prim_bench(int32_t iters, void* out, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  return launch_debug_prim_bench(iters, static_cast<long long*>(out), static_cast<cudaStream_t>(stream));
+}
+
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity) {
   debug_set_timeline(static_cast<unsigned long long*>(device_buf), capacity);
 }

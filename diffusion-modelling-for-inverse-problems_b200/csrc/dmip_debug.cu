@@ -1,0 +1,391 @@
+// dmip_debug.cu — tcgen05 design probes (tests/ only): MMA issue rate for single-CTA and CTA-pair instructions, A from
+// shared or tensor memory, with an optional concurrent bulk-TMA weight stream into the same shared memory.  The
+// numbers these print decide the sampler's tiling (DESIGN.md "K1 tiling").
+#include "dmip_common.h"
+#include "dmip_ptx.cuh"
+
+namespace dmip {
+
+namespace {
+
+constexpr int kKb = 16384;        // one 128-row x 64-k bf16 K-block
+constexpr int kRing = 2;
+
+struct BenchParams {
+  int cg;            // CTAs per MMA (1 or 2)
+  int a_tmem;        // 0: A from shared memory, 1: A from tensor memory
+  int alt_acc;       // 1: alternate between two accumulators (no D dependence between consecutive chunks)
+  int n;             // N of one instruction (whole pair)
+  int k;             // K per accumulation chain (multiple of 64, <= 256)
+  int iters;         // chains
+  int stream_bytes;  // bytes the producer warp copies global -> shared per K-block (0: no stream)
+  int rnd;           // 1: operands hold pseudo-random bf16 data instead of zeros (switching power)
+  int commit;        // 1: one tcgen05.commit per K-block (4 MMAs), as the sampler does
+  int readers;       // 1: warps 4-7 read the accumulators with tcgen05.ld in a loop (epilogue stand-in); 2: ld + st
+  int reader_iters;
+  int math;          // warps 8-23: 1 = MUFU.TANH loop, 2 = FFMA loop, 3 = both (row-warp stand-in without TMEM traffic)
+  int math_iters;
+  float* sink;
+  const uint8_t* gsrc;
+  long long* cycles; // [grid][4]: issue, complete, producer cycles, unused
+};
+
+// kCg is a template parameter: a kernel that CONTAINS cta_group::2 instructions can only be launched with an even
+// cluster dimension (launch fails with "cluster misconfiguration" otherwise), so the single-CTA probe is a separate kernel.
+template <int kCg>
+__global__ void __launch_bounds__(768, 1) k_mma_bench2(const __grid_constant__ BenchParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                          // 4 K-blocks x 16 KB
+  uint8_t* sW = smem + 4 * kKb;                // 4 K-blocks x (rows_per_cta x 128 B), rows_per_cta <= 256
+  uint8_t* sR = smem + 4 * kKb + 8 * kKb;      // stream ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + kRing * kKb);
+  uint64_t* done = bars;                       // MMA completion
+  uint64_t* rfull = bars + 1;                  // [kRing]
+  uint64_t* dummy = bars + 1 + kRing;          // per-K-block commits land here (nobody waits)
+  uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 2 + kRing);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = kCg == 2 ? cluster_ctarank() : 0u;
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    for (int i = 0; i < kRing; ++i) mbar_init(&rfull[i], 1);
+    mbar_init(dummy, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < (12 + kRing) * kKb / 16; i += 768) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (P.rnd) {   // bf16 values in (-2, 2) with random mantissas: 0x3f80..0x3fff / 0xbf80..0xbfff
+      uint32_t h = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+      auto nxt = [&]() { h = h * 1664525u + 1013904223u; return ((h >> 9) & 0x807F807Fu) | 0x3F803F80u; };
+      v = make_uint4(nxt(), nxt(), nxt(), nxt());
+    }
+    reinterpret_cast<uint4*>(smem)[i] = v;
+  }
+  fence_proxy_async_smem();
+  if (kCg == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) {
+    if (kCg == 2) tmem_alloc_pair<512>(holder); else tmem_alloc<512>(holder);
+  }
+  tc_fence_before();
+  if (kCg == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *holder, 0);
+  if (P.rnd && warp < 4) {   // A operand image in tensor memory columns 0..127
+    const uint32_t lt = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+      uint32_t pk[16];
+      uint32_t h = (threadIdx.x * 2654435761u) ^ (c0 * 97u);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { h = h * 1664525u + 1013904223u; pk[j] = ((h >> 9) & 0x807F807Fu) | 0x3F803F80u; }
+      tmem_st16(lt + c0, pk);
+    }
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const int rows_b = P.n / kCg;               // B rows held by this CTA
+  long long t_issue = 0, t_done = 0, t_prod = 0;
+  if (warp == 0 && crank == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128u * kCg, static_cast<uint32_t>(P.n));
+    const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+    const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(sW) & 0x3FFFFu) >> 4;
+    const uint32_t wkb = static_cast<uint32_t>(rows_b) * 128u;
+    const long long t0 = clock64();
+    for (int it = 0; it < P.iters; ++it) {
+      const uint32_t d_tmem = tmem_base + 256 + ((P.alt_acc && (it & 1)) ? static_cast<uint32_t>(P.n <= 128 ? 128 : 0) : 0u);
+      for (int kb = 0; kb < P.k / 64; ++kb) {
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = desc_hi | (b_lo0 + ((kb * wkb) >> 4) + kk * 2);
+            const uint64_t adesc = desc_hi | (a_lo0 + ((kb * kKb) >> 4) + kk * 2);
+            const uint32_t a_tm = tmem_base + kb * 32 + kk * 8;
+            if (kCg == 2) {
+              if (P.a_tmem) umma_ts_pair(d_tmem, a_tm, bdesc, idesc, 1u);
+              else umma_ss_pair(d_tmem, adesc, bdesc, idesc, 1u);
+            } else {
+              if (P.a_tmem) umma_ts(d_tmem, a_tm, bdesc, idesc, 1u);
+              else umma_ss(d_tmem, adesc, bdesc, idesc, 1u);
+            }
+          }
+          if (P.commit) {
+            if (kCg == 2) tc_commit_pair(dummy, 0x1); else tc_commit(dummy);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) {
+      if (kCg == 2) tc_commit_pair(done, 0x3); else tc_commit(done);
+    }
+    __syncwarp();
+    t_issue = clock64() - t0;
+    mbar_wait(done, 0, 0x901);
+    t_done = clock64() - t0;
+  } else if (warp == 0) {
+    mbar_wait(done, 0, 0x902);                 // peer CTA: its tensor core works for the leader's instructions
+  } else if (warp == 1 && P.stream_bytes > 0) {
+    // weight-stream stand-in: stream_bytes per K-block into a 2-slot ring, next copy issued when the previous one
+    // into that slot has landed (self-paced: as fast as L2 / shared memory allow, capped at the MMA count)
+    const long long t0 = clock64();
+    const int n_copies = P.iters * (P.k / 64);
+    uint32_t ph = 0;
+    int s = 0;
+    const size_t span = 8u << 20;
+    size_t off = (static_cast<size_t>(blockIdx.x) * 65536) % span;
+    for (int i = 0; i < n_copies; ++i) {
+      if (i >= kRing) mbar_wait(&rfull[s], ph, 0x903);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&rfull[s], static_cast<uint32_t>(P.stream_bytes));
+        bulk_g2s(sR + s * kKb, P.gsrc + off, static_cast<uint32_t>(P.stream_bytes), &rfull[s]);
+      }
+      __syncwarp();
+      off = (off + P.stream_bytes) % span;
+      if (++s == kRing) { s = 0; if (i >= kRing) ph ^= 1u; }
+    }
+    // drain
+    for (int i = 0; i < kRing && i < n_copies; ++i) {
+      mbar_wait(&rfull[s], ph, 0x904);
+      if (++s == kRing) { s = 0; ph ^= 1u; }
+    }
+    t_prod = clock64() - t0;
+  } else if (warp >= 8) {
+    if (P.math > 0) {
+      float a0 = threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f;
+      for (int it = 0; it < P.math_iters; ++it) {
+        if (P.math & 1) {
+          asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a0));
+          asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a1));
+          asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a2));
+          asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a3));
+        }
+        if (P.math & 2) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            a0 = fmaf(a0, 1.0001f, 0.5f); a1 = fmaf(a1, 1.0001f, 0.5f); a2 = fmaf(a2, 1.0001f, 0.5f); a3 = fmaf(a3, 1.0001f, 0.5f);
+          }
+        }
+      }
+      if (a0 + a1 + a2 + a3 == 123.456f) P.sink[threadIdx.x] = a0;
+    }
+  } else if (warp >= 4 && P.readers > 0) {
+    // epilogue stand-in: lane quarter (warp % 4) reads 2 x 32 accumulator columns per iteration, optionally writes 16
+    const uint32_t lt = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    for (int it = 0; it < P.reader_iters; ++it) {
+      uint32_t v[32];
+      tmem_ld32(lt + 256 + (it & 1) * 64, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= v[j];
+      if (P.readers > 1) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = v[j] ^ v[j + 16];
+        tmem_st16(lt + 128 + (it & 3) * 16, pk);
+        tc_wait_st();
+      }
+    }
+    if (acc == 0x12345678u) P.cycles[blockIdx.x * 4 + 3] = acc;
+  }
+  if (lane == 0 && warp == 0 && crank == 0) {
+    P.cycles[blockIdx.x * 4] = t_issue;
+    P.cycles[blockIdx.x * 4 + 1] = t_done;
+  }
+  if (lane == 0 && warp == 1) P.cycles[blockIdx.x * 4 + 2] = t_prod;
+  tc_fence_before();
+  if (kCg == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    if (kCg == 2) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ primitive costs
+// One warp, `iters` iterations of a small sequence of the synchronisation primitives the sampler's producer / issuer
+// loops are made of; cycles per iteration for each sequence.  out[m] for m = 0..7.
+struct PrimParams {
+  int iters;
+  int a, b, c;       // read inside the loops (constant-bank loads the compiler cannot hoist over "memory" clobbers)
+  long long* out;
+  unsigned long long* sink;
+};
+
+__global__ void __launch_bounds__(64, 1) k_prim_bench(const __grid_constant__ PrimParams P) {
+  __shared__ uint64_t bar_done[2];   // phase 0 completed before the loop
+  __shared__ uint64_t bar_self;      // count 1: every arrive completes a phase
+  __shared__ uint32_t holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done[0], 1);
+    mbar_init(&bar_done[1], 1);
+    mbar_init(&bar_self, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { mbar_arrive(&bar_done[0]); mbar_arrive(&bar_done[1]); }
+  if (warp == 0) tmem_alloc<32>(&holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp != 0) return;
+  unsigned long long acc = 0;
+  for (int m = 0; m < 10; ++m) {
+    __syncwarp();
+    const long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int i = 0; i < P.iters; ++i) {
+      switch (m) {
+        case 0: mbar_wait(&bar_done[0], 0, 1); break;                              // try_wait on a long-completed phase
+        case 1: if (elect_one()) mbar_arrive(&bar_self); __syncwarp(); break;      // elect + arrive
+        case 2: if (elect_one()) mbar_arrive(&bar_self); __syncwarp();             // arrive then wait for that phase
+                mbar_wait(&bar_self, ph, 2); ph ^= 1u; break;
+        case 3: acc += clock64(); break;                                           // CS2R
+        case 4: if (elect_one()) tc_commit(&bar_self); __syncwarp(); break;        // tcgen05.commit (nothing pending)
+        case 5: if (elect_one()) tc_commit(&bar_self); __syncwarp();               // commit then wait for its arrival
+                mbar_wait(&bar_self, ph, 3); ph ^= 1u; break;
+        case 6: tc_fence_after(); break;
+        case 7: asm volatile("" ::: "memory"); acc += P.a + P.b + P.c; break;      // constant-bank reloads
+        case 8: mbar_wait(&bar_done[0], 0, 1); tc_fence_after();                   // the issuer's per-K-block skeleton
+                if (elect_one()) tc_commit(&bar_self); __syncwarp(); break;
+        case 9: mbar_wait(&bar_done[1], 0, 1);                                     // the producer's per-stage skeleton
+                if (elect_one()) mbar_arrive_expect_tx(&bar_self, 0); __syncwarp(); break;
+      }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) P.out[m] = t1 - t0;
+    // leave bar_self in a known phase: it completes a phase per arrive; re-sync parity for the next sequence
+    __syncwarp();
+    if (m == 1 || m == 4 || m == 8 || m == 9) {
+      // unknown parity: re-initialise
+      if (lane == 0) { mbar_init(&bar_self, 1); fence_barrier_init(); }
+      __syncwarp();
+    }
+  }
+  if (acc == 0x1234567ull) P.sink[0] = acc;
+  tc_fence_before();
+  __syncwarp();
+  tmem_dealloc<32>(holder);
+}
+
+
+// ------------------------------------------------------------------------------------------------ wake-up latency
+// Two warps ping-pong over two mbarriers: cycles per round trip (= 2 x arrive -> the other warp notices).
+// mode 0: mbarrier.try_wait (hardware suspend), 1: mbarrier.test_wait spin, 2: try_wait with a 0 ns suspend hint.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void wait_mode(int mode, uint64_t* bar, uint32_t parity) {
+  if (mode == 0) { while (!mbar_try_wait(bar, parity)) {} }
+  else if (mode == 1) { while (!mbar_test_wait(bar, parity)) {} }
+  else { while (!mbar_try_wait_hint(bar, parity, 0)) {} }
+}
+
+__global__ void __launch_bounds__(64, 1) k_pingpong(int iters, long long* out) {
+  __shared__ uint64_t ping, pong;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int mode = 0; mode < 3; ++mode) {
+    if (threadIdx.x == 0) {
+      mbar_init(&ping, 1);
+      mbar_init(&pong, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int i = 0; i < iters; ++i) {
+      if (warp == 0) {
+        if (elect_one()) mbar_arrive(&ping);
+        __syncwarp();
+        wait_mode(mode, &pong, ph);
+      } else {
+        wait_mode(mode, &ping, ph);
+        if (elect_one()) mbar_arrive(&pong);
+        __syncwarp();
+      }
+      ph ^= 1u;
+    }
+    const long long t1 = clock64();
+    if (warp == 0 && lane == 0) out[20 + mode] = t1 - t0;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int stream_bytes, int grid, const void* gsrc,
+                            long long* cycles, cudaStream_t s) {
+  DMIP_REQUIRE(cg == 1 || cg == 2, "cg must be 1 or 2");
+  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256, "k must be 64..256");
+  DMIP_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && n / cg <= 256, "bad n");
+  DMIP_REQUIRE(stream_bytes >= 0 && stream_bytes <= kKb && stream_bytes % 16 == 0, "stream_bytes must be <= 16384, multiple of 16");
+  DMIP_REQUIRE(grid >= cg && grid % cg == 0, "grid must be a multiple of cg");
+  DMIP_REQUIRE(stream_bytes == 0 || gsrc != nullptr, "gsrc (>= 8 MB + 64 KB) needed when streaming");
+  const int smem = (12 + kRing) * kKb + 256 + 1024;
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_mma_bench2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_mma_bench2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  BenchParams P = {};
+  P.cg = cg; P.a_tmem = mode & 1; P.alt_acc = (mode >> 1) & 1; P.n = n; P.k = k; P.iters = iters;
+  P.rnd = (mode >> 2) & 1; P.commit = (mode >> 3) & 1; P.readers = (mode >> 4) & 3;
+  P.reader_iters = iters * (k / 16) / 2;
+  P.math = (mode >> 6) & 3;
+  P.math_iters = iters * (k / 16) * 8;
+  P.sink = reinterpret_cast<float*>(cycles);
+  P.stream_bytes = stream_bytes;
+  P.gsrc = static_cast<const uint8_t*>(gsrc);
+  P.cycles = cycles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(768);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cg);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cg > 1 ? 1 : 0;
+  if (cg == 2) DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_mma_bench2<2>, P));
+  else DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_mma_bench2<1>, P));
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
+}
+
+int launch_debug_prim_bench(int iters, long long* out, cudaStream_t s) {
+  PrimParams P = {};
+  P.iters = iters; P.a = 1; P.b = 2; P.c = 3;
+  P.out = out;
+  P.sink = reinterpret_cast<unsigned long long*>(out + 16);
+  k_prim_bench<<<1, 64, 0, s>>>(P);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  k_pingpong<<<1, 64, 0, s>>>(iters, out);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return DMIP_OK;
+}
+
+}  // namespace dmip

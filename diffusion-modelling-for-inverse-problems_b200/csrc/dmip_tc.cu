@@ -1,21 +1,29 @@
 // dmip_tc.cu — the tcgen05 path: persistent fused Euler–Maruyama sampler (K1) and score-net forward.
 //
-// One CTA per SM, 128 particles (rows) per tile, the whole S-step reverse SDE of a tile runs on chip:
+// One CTA per SM, 128 particles (rows) per tile, the whole S-step reverse SDE of a tile runs on chip.  20 warps:
 //
-//   warp 0      bulk-TMA producer: streams the net's bf16 weight stages (16 KB = 128 out-features x 64 k,
-//               K-major, 128B-swizzled — written in exactly that image by dmip_pack.cu) from L2 into a
-//               5-deep shared-memory ring, the same ~1.1 MB sequence every step.
-//   warp 1      MMA issuer (one elected lane): per layer, four N=128 accumulator chunks of
-//               tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM).  The activations are the A
-//               operand and ALTERNATE between shared memory and tensor memory from layer to layer
-//               (A0: smem -> H1: tmem -> H2: smem -> H3: tmem), so a layer's epilogue never overwrites the
-//               operand its own MMAs are still reading, and the epilogue of chunk c overlaps the MMAs of chunk
-//               c+1 (two 128-column accumulator buffers).
-//   warps 2-9   epilogue (two threads per particle row): tcgen05.ld accumulator -> +bias -> tanh (twice after
-//               layer 0) -> bf16 -> next layer's A operand (tcgen05.st, or swizzled st.shared).
-//               After the output layer: reverse-SDE drift/diffusion update of the fp32 state, Philox noise, and
-//               the next step's layer-0 operand.  y and t never enter the GEMM: they are constant over the
-//               rows of a tile and are folded, in fp32, into a per-step layer-0 bias b0 + W0[:,y]·y + tau·W0[:,t].
+//   warps 0-15    ROW warps, four threads per particle row (warp w: TMEM lane quarter w % 4, column group w / 4).
+//                 Hidden layers: tcgen05.ld accumulator -> +bias -> tanh (twice after layer 0) -> bf16 ->
+//                 next layer's A operand (tcgen05.st, or swizzled st.shared); 4 warps per scheduler keep the MUFU pipe
+//                 (the epilogue's bound: one tanh per activation) busy while the tensor pipe runs the next chunk.
+//                 State: each thread keeps its share of the particle's fp32 SDE state in REGISTERS for the whole
+//                 integration, draws the Philox noise and applies the drift/diffusion update in the shadow of the
+//                 MMA-bound layers, reads the output layer's accumulator and builds the next step's layer-0 operand
+//                 (bf16 hi/lo split).  y and t never enter the GEMM: they are constant over a tile and are folded,
+//                 in fp32, into a per-step layer-0 bias  b0 + W0[:,y]·y + tau·W0[:,t].
+//   warp 16       bulk-TMA producer: streams the net's bf16 weight stages (16 KB = 128 out-features x 64 k, K-major,
+//                 128B-swizzled — written in exactly that image by dmip_pack.cu) from L2 into a 5-deep shared-memory
+//                 ring, the same ~1.3 MB sequence every step; the two CTAs of a cluster each fetch half of every stage
+//                 and multicast it to both.
+//   warp 17       MMA issuer (one elected lane): per layer four N=128 accumulator chunks of
+//                 tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM).  The activations are the A operand
+//                 and ALTERNATE between shared memory and tensor memory from layer to layer
+//                 (A0: smem -> H1: tmem -> H2: smem -> H3: tmem), so an epilogue never overwrites the operand its own
+//                 layer's MMAs still read, and the epilogue of chunk c overlaps the MMAs of chunk c+1.
+//                 Producer and issuer sit at the HIGHEST warp ids: the warp scheduler prefers high ids, and an issuer
+//                 at warp 1 was measured starved by the math warps (200 instead of 75 cycles per MMA).
+//   warps 18-19   idle: registers are allocated in units of four warps, so they exist anyway; setmaxnreg hands the
+//                 spare registers of warps 16-19 to the row warps.
 //
 // Reference code replaced: models/diffusion.py:27-46,158-180; sdes.py:21-49,77-87; nets.py:17-57,143-157.
 #include <stdlib.h>
@@ -32,8 +40,14 @@ constexpr int kTileM = 128;
 constexpr int kStageBytes = 16384;   // 128 rows x 64 k x bf16
 constexpr int kNumStages = 5;
 constexpr int kHBytes = 131072;      // 128 rows x 512 k x bf16 = 8 K-blocks
-constexpr int kThreads = 320;        // warps: 0 producer, 1 MMA, 2..9 epilogue
-constexpr int kEpiThreads = 256;
+constexpr int kThreads = 640;        // warps: 0-15 row warps (epilogue + state), 16 producer, 17 MMA, 18-19 idle
+constexpr int kRegsSmall = 40;       // registers are allocated per 4 warps (18 warps are billed as 20), so the kernel
+constexpr int kRegsRow = 104;        // launches with 640 x 96 and setmaxnreg moves 128 x 56 of them to the row warps
+constexpr int kNumRowWarps = 16;
+constexpr int kRowThreads = 512;
+constexpr int kProducerWarp = 16;
+constexpr int kMmaWarp = 17;
+constexpr int kCluster = 2;          // CTAs per cluster sharing one multicast weight stream
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemH = 0;       // 256 columns: 128 x 512 bf16 activations (A operand)
 constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
@@ -42,10 +56,9 @@ constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
 constexpr int kOffH = 0;
 constexpr int kOffB = kOffH + kHBytes;
 constexpr int kOffB0 = kOffB + kNumStages * kStageBytes;  // float[2][512] effective layer-0 bias: current pass / next pass
-constexpr int kOffU = kOffB0 + 4096;                      // float[2][512] b0 + W0[:,y]·y per net
-constexpr int kOffWt = kOffU + 4096;                      // float[2][512] W0[:,t] per net
-constexpr int kOffBar = kOffWt + 4096;
-constexpr int kNumBars = 2 * kNumStages + 2 + 2 + 4 + 1;
+constexpr int kOffB3 = kOffB0 + 4096;                     // float[2][128] output-layer bias per net
+constexpr int kOffBar = kOffB3 + 1024;
+constexpr int kNumBars = 2 * kNumStages + 2 + 2 + 1 + 1 + 1 + 4 + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // + alignment slack
 
@@ -79,21 +92,43 @@ struct TcParams {
   const float* fcond;
   const float* ft;
   int fx_dim, fcond_dim, out_dim;
-  float* xs;                // fp32 state of the tiles in flight: [grid][16 pieces][128 rows][8]
   int dbg;                  // debug bits (DMIP_DBG): 1 = no weight copies, 2 = no MMA issue, 4 = 3-deep ring
   int cluster;              // CTAs per cluster sharing one multicast weight stream (1, 2 or 4)
-  unsigned long long* tl;   // optional timeline buffer (debug): [0] = count, then (clock << 16 | code)
+  unsigned long long* tl;   // optional timeline buffer (debug): 4 role segments of [count, (clock << 16 | code)...]
   int tl_cap;
 };
 
 struct Bars {
-  uint64_t* full;       // [kNumStages]
-  uint64_t* empty;      // [kNumStages]
-  uint64_t* acc_full;   // [2]
-  uint64_t* acc_empty;  // [2]
-  uint64_t* hready;     // [4]
-  uint64_t* a0_ready;   // [1]
+  uint64_t* full;       // [kNumStages]  weight stage landed            (tx bytes)
+  uint64_t* empty;      // [kNumStages]  weight stage consumed          (one tcgen05.commit per cluster CTA)
+  uint64_t* acc_full;   // [2]           hidden accumulator chunk complete  (tcgen05.commit)
+  uint64_t* acc_empty;  // [2]           hidden chunk drained               (16 row warps)
+  uint64_t* out_full;   // [1]           output-layer chunk complete        (tcgen05.commit)
+  uint64_t* out_empty;  // [1]           output-layer chunk drained         (16 row warps)
+  uint64_t* sh_free;    // [1]           layer 2 has consumed the shared-memory operand region (tcgen05.commit)
+  uint64_t* hready;     // [4]           K-blocks 2c, 2c+1 of the next A operand written (16 row warps)
+  uint64_t* a0_ready;   // [1]           layer-0 operand + bias of the next pass written (16 row warps)
 };
+
+// Kernel parameters live in the constant bank; ptxas re-materialises them with an LDC at every use after an asm with a
+// "memory" clobber (all mbarrier / tcgen05 / TMA wrappers) — ~40 cycles each in the producer's and the issuer's
+// dependent chains.  A value that went through a warp shuffle cannot be re-materialised and stays in a register.
+// (All lanes hold the same parameter value, so the shuffle is the identity.)
+__device__ __forceinline__ int keep(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ long long keep(long long v) {
+  const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(v), 0);
+  const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(v) >> 32), 0);
+  return static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+}
+template <class T>
+__device__ __forceinline__ const T* keep(const T* p) {
+  return reinterpret_cast<const T*>(keep(static_cast<long long>(reinterpret_cast<uintptr_t>(p))));
+}
+
+template <int kRegs>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 __device__ __forceinline__ float tau_of_step(int i, int S, float T) {
   // T - linspace(0, 1, S+1)[i] * T in fp32, linspace evaluated symmetrically as torch does (models/diffusion.py:34)
@@ -106,63 +141,60 @@ __device__ __forceinline__ float tau_of_step(int i, int S, float T) {
 __device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ hidden-layer epilogue
-// One thread: row `row` (TMEM lane), 64 of the 128 columns of accumulator chunk `chunk` (half `hh`).
+// One thread: row `row` (TMEM lane), 32 of the 128 columns of accumulator chunk `chunk` (column group `cgp`), as two
+// 16-column halves so that the second half's tcgen05.ld is in flight while the first half's tanh runs.
+template <bool kDoubleTanh>
+__device__ __forceinline__ void tanh_pack16(const uint32_t (&v)[16], const float* __restrict__ bias, uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bq = *reinterpret_cast<const float4*>(bias + q * 4);
+    float a[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float bb = e == 0 ? bq.x : e == 1 ? bq.y : e == 2 ? bq.z : bq.w;
+      float t = tanh_fast(__uint_as_float(v[q * 4 + e]) + bb);
+      if (kDoubleTanh) t = tanh_unit_poly(t);   // second tanh (Q1) on the FMA pipe: the MUFU is the busy one
+      a[e] = t;
+    }
+    pk[q * 2] = pack_bf16x2(a[0], a[1]);
+    pk[q * 2 + 1] = pack_bf16x2(a[2], a[3]);
+  }
+}
+
 template <bool kDoubleTanh, bool kToTmem>
-__device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col, int hh, int row, int chunk,
+__device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col, int cgp, int row, int chunk, int lane,
                                            const float* __restrict__ bias, uint8_t* sH, uint64_t* acc_empty,
-                                           uint64_t* hready, int dbg) {
-  uint32_t v0[32], v1[32];
-  if (dbg & 8) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { v0[i] = 0x3c000000u + row + i; v1[i] = 0x3c100000u + row * 3 + i; }
-  } else {
-    tmem_ld32(lane_taddr + acc_col + hh * 64, v0);
-    tmem_ld32(lane_taddr + acc_col + hh * 64 + 32, v1);
-    tc_wait_ld();
-  }
+                                           uint64_t* hready) {
+  uint32_t v0[16], v1[16];
+  tmem_ld16(lane_taddr + acc_col + cgp * 32, v0);
+  tmem_ld16(lane_taddr + acc_col + cgp * 32 + 16, v1);
+  tc_wait_ld();
   tc_fence_before();
-  mbar_arrive(acc_empty);  // accumulator chunk is in registers: the MMA warp may reuse the buffer
-  const int n0 = chunk * 128 + hh * 64;
-#pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    uint32_t pk[16];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 bq = *reinterpret_cast<const float4*>(bias + n0 + p * 32 + q * 4);
-      float a[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t raw = p == 0 ? v0[q * 4 + e] : v1[q * 4 + e];
-        const float bb = e == 0 ? bq.x : e == 1 ? bq.y : e == 2 ? bq.z : bq.w;
-        float t = tanh_fast(__uint_as_float(raw) + bb);
-        if (kDoubleTanh) t = tanh_unit_poly(t);   // second tanh (Q1) on the FMA pipe: the MUFU is the busy one
-        a[e] = t;
-      }
-      pk[q * 2] = pack_bf16x2(a[0], a[1]);
-      pk[q * 2 + 1] = pack_bf16x2(a[2], a[3]);
-    }
-    if (dbg & 16) {
-      if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) hready[1] = pk[3];   // keep the math alive, store nothing
-    } else if (kToTmem) {
-      tmem_st16(lane_taddr + kTmemH + static_cast<uint32_t>((n0 + p * 32) >> 1), pk);
-    } else {
-      // K index of these 32 values: n0 + p*32 .. +31  ->  K-block chunk*2+hh, 16-byte chunks p*4 .. p*4+3
-      uint8_t* rowp = sH + (chunk * 2 + hh) * kStageBytes + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        st_shared_v4(rowp + (((p * 4 + q) ^ (row & 7)) << 4), pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-    }
-  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(acc_empty);  // this warp's part of the chunk is in registers: the buffer may be reused
+  const int n0 = chunk * 128 + cgp * 32;
+  uint32_t pk0[8], pk1[8];
+  tanh_pack16<kDoubleTanh>(v0, bias + n0, pk0);
+  tanh_pack16<kDoubleTanh>(v1, bias + n0 + 16, pk1);
   if (kToTmem) {
+    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1), pk0);
+    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1) + 8, pk1);
     tc_wait_st();
     tc_fence_before();
   } else {
+    // K index of these 32 values: n0 .. n0+31  ->  K-block chunk*2 + (cgp>>1), 16-byte chunks (cgp&1)*4 .. +3
+    uint8_t* rowp = sH + (chunk * 2 + (cgp >> 1)) * kStageBytes + (row >> 3) * 1024 + (row & 7) * 128;
+    const int c0 = (cgp & 1) * 4;
+    st_shared_v4(rowp + (((c0 + 0) ^ (row & 7)) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
+    st_shared_v4(rowp + (((c0 + 1) ^ (row & 7)) << 4), pk0[4], pk0[5], pk0[6], pk0[7]);
+    st_shared_v4(rowp + (((c0 + 2) ^ (row & 7)) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
+    st_shared_v4(rowp + (((c0 + 3) ^ (row & 7)) << 4), pk1[4], pk1[5], pk1[6], pk1[7]);
     fence_proxy_async_smem();
   }
-  mbar_arrive(hready);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(hready);
 }
 
 // write one bf16 element of the layer-0 operand tile
@@ -180,7 +212,7 @@ __device__ __forceinline__ void a0_put(uint8_t* sH, int row, int idx, int dvp, i
   if (split >= 3) a0_store(sH, row, 2 * dvp + idx, hi);
 }
 // eight consecutive inputs idx0 .. idx0+7 (idx0 % 8 == 0): one 16-byte swizzled store per split part
-__device__ __forceinline__ void a0_put8(uint8_t* sH, int row, int idx0, int dvp, int split, const float (&v)[8]) {
+__device__ __forceinline__ void a0_put8(uint8_t* sH, int row, int idx0, int dvp, int split, const float* v) {
   float hi[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) hi[e] = bf16_round(v[e]);
@@ -195,30 +227,19 @@ __device__ __forceinline__ void a0_put8(uint8_t* sH, int row, int idx0, int dvp,
   if (split >= 3) st_shared_v4(chunk_ptr(2 * dvp + idx0), h0, h1, h2, h3);
 }
 
-// layer-0 operand columns of one state piece.  CDiffE keeps re-diffused y_t in the columns right after x, written
-// by other threads, so there only the x columns themselves are touched.
-__device__ __forceinline__ void a0_put_piece(uint8_t* sH, int row, int pc, int dvp, int split, const float (&x)[8],
-                                             bool elementwise, int width) {
-  if (!elementwise) {
-    a0_put8(sH, row, pc * 8, dvp, split, x);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (pc * 8 + e < width) a0_put(sH, row, pc * 8 + e, dvp, split, x[e]);
-  }
-}
-
 // Timeline hook (debug): each instrumented thread of CTA 0 owns a quarter of the buffer and appends
 // (clock64 << 16 | code) with plain stores — no atomics, so the probe costs a few cycles, not an L2 round trip.
 struct TlRole {
   unsigned long long* p;
   unsigned int n, cap;
+  bool minimal;   // DMIP_DBG bit 64: record only the pass boundaries (a probe costs ~90 cycles: clock64 is slow)
 };
 __device__ __forceinline__ TlRole tl_role(const TcParams& P, int role, bool on) {
   TlRole r;
   r.p = nullptr;
   r.n = 0;
   r.cap = 0;
+  r.minimal = __shfl_sync(0xffffffffu, (P.dbg & 64) != 0 ? 1 : 0, 0) != 0;   // pinned (see keep())
   if (P.tl != nullptr && blockIdx.x == 0 && on) {
     const int seg = P.tl_cap / 4;
     r.p = P.tl + static_cast<size_t>(role) * seg;
@@ -226,25 +247,37 @@ __device__ __forceinline__ TlRole tl_role(const TcParams& P, int role, bool on) 
   }
   return r;
 }
-__device__ __forceinline__ void tl_mark(TlRole& r, uint32_t code) {
-  if (r.p != nullptr && r.n < r.cap) {
+__device__ __forceinline__ void tl_mark_impl(TlRole& r, uint32_t code) {
+  if (r.p != nullptr && r.n < r.cap && (!r.minimal || code == 0xD00u || (code & 0xF00u) == 0x100u || code == 0xE00u)) {
     r.p[1 + r.n] = (static_cast<unsigned long long>(clock64()) << 16) | code;
     ++r.n;
   }
 }
-__device__ __forceinline__ void tl_finish(const TlRole& r) {
+__device__ __forceinline__ void tl_finish_impl(const TlRole& r) {
   if (r.p != nullptr) r.p[0] = r.n;
 }
+#ifdef DMIP_DEBUG
+#define tl_mark(r, code) tl_mark_impl(r, code)
+#define tl_finish(r) tl_finish_impl(r)
+#else
+#define tl_mark(r, code) ((void)0)
+#define tl_finish(r) ((void)0)
+#endif
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// NP = 8-column pieces of the fp32 state per particle (xdim <= 8 NP); a row thread keeps ceil(NP / 4) of them.
+// VAR = sampler variant (DMIP_CDE also serves the forward mode): decides which per-thread state exists at all.
+template <int NP, int VAR>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ TcParams P) {
+  constexpr int kOwn = (NP + 3) / 4;
+  constexpr bool cdiffe = (VAR == DMIP_CDIFFE);
+  constexpr bool dps = (VAR == DMIP_DPS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sH = smem + kOffH;
   uint8_t* sB = smem + kOffB;
   float* sB0 = reinterpret_cast<float*>(smem + kOffB0);
-  float* sU = reinterpret_cast<float*>(smem + kOffU);
-  float* sWt = reinterpret_cast<float*>(smem + kOffWt);
+  float* sB3 = reinterpret_cast<float*>(smem + kOffB3);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   Bars B;
@@ -252,29 +285,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   B.empty = bars + kNumStages;
   B.acc_full = bars + 2 * kNumStages;
   B.acc_empty = B.acc_full + 2;
-  B.hready = B.acc_empty + 2;
+  B.out_full = B.acc_empty + 2;
+  B.out_empty = B.out_full + 1;
+  B.sh_free = B.out_empty + 1;
+  B.hready = B.sh_free + 1;
   B.a0_ready = B.hready + 4;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < kNumStages; ++i) {
       mbar_init(&B.full[i], 1);
-      mbar_init(&B.empty[i], static_cast<uint32_t>(P.cluster));   // one tcgen05.commit per CTA of the cluster
+      mbar_init(&B.empty[i], static_cast<uint32_t>(kCluster));   // one tcgen05.commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&B.acc_full[i], 1);
-      mbar_init(&B.acc_empty[i], kEpiThreads);
+      mbar_init(&B.acc_empty[i], kNumRowWarps);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], kEpiThreads);
-    mbar_init(B.a0_ready, kEpiThreads);
+    mbar_init(B.out_full, 1);
+    mbar_init(B.out_empty, kNumRowWarps);
+    mbar_init(B.sh_free, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], kNumRowWarps);
+    mbar_init(B.a0_ready, kNumRowWarps);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_holder);
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_holder);
   // zero the activation region once: layer-0 K padding must be finite (it meets zero weights)
   for (int i = threadIdx.x; i < kHBytes / 16; i += kThreads) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 256; i += kThreads) sB3[i] = (i >> 7) < P.n_nets ? P.net[i >> 7].b3[i & 127] : 0.f;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -283,35 +323,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 
   // Cluster: the C CTAs of a cluster walk the same stage sequence in lock-step; each loads 1/C of every weight
   // stage and multicasts it to all of them, so L2 serves each line once per cluster instead of once per SM.
-  const int C = P.cluster;
+  constexpr int C = kCluster;
+#ifdef DMIP_DEBUG
+  const int dbg = P.dbg;
+#else
+  constexpr int dbg = 0;   // the DMIP_DBG ablation bits and the timeline exist only in -DDMIP_DEBUG builds: a run-time
+#endif                     // flag costs a constant-bank re-load (~40 cycles) at every use inside the issue loops
+  const long long n_tiles = keep(P.n_tiles);
   const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
   if (C > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive / multicast
   const long long tile_first = static_cast<long long>(blockIdx.x / C) * C;
-  const long long tile_stride = static_cast<long long>(gridDim.x);
+  const long long tile_stride = keep(static_cast<long long>(gridDim.x));
 
-  const int n_pass = P.n_nets;
-  const int S = P.S;
-  const int n_ring = (P.dbg & 4) ? 3 : kNumStages;
+  const int n_pass = keep(P.n_nets);
+  const int S = keep(P.S);
+  const int n_steps = keep((P.mode == kModeSampler) ? S : 1);
+  const int n_ring = keep((dbg & 4) ? 3 : kNumStages);
 
-  if (warp == 0) {
-    // =============================================================== producer (whole warp, one elected lane issues)
-    {
+  if (warp >= kNumRowWarps) {
+    reg_dealloc<kRegsSmall>();
+    if (warp == kProducerWarp) {
+      // ============================================================= producer (whole warp, one elected lane issues)
       int s = 0;
       uint32_t ph = 0;
       TlRole tl = tl_role(P, 0, lane == 0);
       const uint32_t part = kStageBytes / C;
-      for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
-        for (int step = 0; step < S; ++step) {
+      for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
+        for (int step = 0; step < n_steps; ++step) {
           for (int p = 0; p < n_pass; ++p) {
-            const uint8_t* src = P.net[p].stages;
-            const int ns = P.net[p].n_stages;
+            const uint8_t* src = keep(P.net[p].stages);
+            const int ns = keep(P.net[p].n_stages);
             for (int st = 0; st < ns; ++st) {
               mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);   // slot s released by the MMA warps of ALL cluster CTAs
               tl_mark(tl, 0x600u | (st & 0xFF));
               const uint8_t* g = src + static_cast<size_t>(st) * kStageBytes;
               if (elect_one()) {
-                if (P.dbg & 1) {
+                if (dbg & 1) {
                   mbar_arrive(&B.full[s]);
                 } else {
                   mbar_arrive_expect_tx(&B.full[s], kStageBytes);
@@ -328,25 +376,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         }
       }
       tl_finish(tl);
-    }
-  } else if (warp == 1) {
-    // =============================================================== MMA issuer (whole warp, one elected lane issues)
-    {
+    } else if (warp == kMmaWarp) {
+      // ============================================================= MMA issuer (whole warp, one elected lane issues)
       int s = 0;
       uint32_t ph = 0;
-      uint32_t acc_uses0 = 0, acc_uses1 = 0;
+      uint32_t job = 0;
       uint32_t hr_par = 0;   // bit c = parity of hready[c]
       uint32_t a0_par = 0;
-      uint32_t job = 0;
-      bool ready = false;   // result of the early probe of full[s]
+      uint32_t ch0 = 0, ch1 = 0, n_out = 0;          // hidden uses of accumulator buffer 0/1; output jobs so far
+      uint32_t lastkind = 0;                         // 2 bits per buffer: 0 never used, 1 hidden job, 2 output job
       TlRole tl = tl_role(P, 1, lane == 0);
       const uint32_t sH_addr = smem_u32(sH);
       const uint32_t sB_addr = smem_u32(sB);
       const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // everything but the address field
-      for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
-        for (int step = 0; step < S; ++step) {
+      for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
+        for (int step = 0; step < n_steps; ++step) {
           for (int p = 0; p < n_pass; ++p) {
-            const TcNetDev& net = P.net[p];
+            const int net_kb0 = keep(P.net[p].kb0), net_ksteps0 = keep(P.net[p].ksteps0);
+            const int net_outpad = keep(P.net[p].outpad);
             tl_mark(tl, 0xD00u);
             mbar_wait(B.a0_ready, a0_par, 0x200);
             tl_mark(tl, 0xE00u);
@@ -355,48 +402,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 #pragma unroll 1
             for (int l = 0; l < 4; ++l) {
               const int n_chunks = (l == 3) ? 1 : 4;
-              const int KB = (l == 0) ? net.kb0 : 8;
-              const uint32_t idesc = (l == 3) ? umma_idesc_bf16(128, static_cast<uint32_t>(net.outpad))
+              const int KB = (l == 0) ? net_kb0 : 8;
+              const uint32_t idesc = (l == 3) ? umma_idesc_bf16(128, static_cast<uint32_t>(net_outpad))
                                               : umma_idesc_bf16(128, 128);
               const bool a_in_smem = (l & 1) == 0;
 #pragma unroll 1
               for (int c = 0; c < n_chunks; ++c, ++job, ++jl) {
                 const int buf = job & 1;
-                const uint32_t uses = buf ? acc_uses1 : acc_uses0;
-                if (!mbar_try_wait(&B.acc_empty[buf], (uses & 1u) ^ 1u)) {
-                  tl_mark(tl, 0xB00u | jl);   // accumulator buffer still being drained by the epilogue
-                  mbar_wait(&B.acc_empty[buf], (uses & 1u) ^ 1u, 0x300 + buf);
-                  tl_mark(tl, 0xC00u | jl);
-                }
-                if (buf) ++acc_uses1; else ++acc_uses0;
+                // the buffer's previous user has drained it (a hidden chunk, or the latest output chunk)
+                const uint32_t lk = (lastkind >> (2 * buf)) & 3u;
+                tl_mark(tl, 0xB00u | jl);
+                if (lk == 1u) mbar_wait(&B.acc_empty[buf], ((buf ? ch1 : ch0) - 1u) & 1u, 0x300 + buf);
+                else if (lk == 2u) mbar_wait(B.out_empty, (n_out - 1u) & 1u, 0x310 + buf);
                 tl_mark(tl, 0x100u | jl);
+                if (l == 3) ++n_out; else { if (buf) ++ch1; else ++ch0; }
+                lastkind = (lastkind & ~(3u << (2 * buf))) | ((l == 3 ? 2u : 1u) << (2 * buf));
                 const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
 #pragma unroll 1
                 for (int kb = 0; kb < KB; ++kb) {
                   if (l > 0 && c == 0 && (kb & 1) == 0) {
-                    if (!mbar_try_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u)) {
-                      tl_mark(tl, 0x900u | (jl << 4) | kb);   // waiting for the previous layer's epilogue
-                      mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
-                      tl_mark(tl, 0xA00u | (jl << 4) | kb);
-                    }
+                    tl_mark(tl, 0x900u | (jl << 4) | kb);
+                    mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
+                    tl_mark(tl, 0xA00u | (jl << 4) | kb);
                     hr_par ^= 1u << (kb >> 1);
                   }
-                  if (!ready) {
-                    tl_mark(tl, 0x700u | (jl << 4) | kb);   // ring underflow: the weight stage has not landed yet
-                    mbar_wait(&B.full[s], ph, 0x500 + s);
-                    tl_mark(tl, 0x800u | (jl << 4) | kb);
-                  }
+                  if (dbg & 32) tl_mark(tl, 0x700u | (jl << 4) | kb);
+                  mbar_wait(&B.full[s], ph, 0x500 + s);
+                  if (dbg & 32) tl_mark(tl, 0x800u | (jl << 4) | kb);
                   tc_fence_after();
-                  const int nk = (l == 0 && kb == KB - 1) ? (net.ksteps0 - 4 * (KB - 1)) : 4;
+                  const int nk = (l == 0 && kb == KB - 1) ? (net_ksteps0 - 4 * (KB - 1)) : 4;
                   const uint32_t b_lo = ((sB_addr + s * kStageBytes) & 0x3FFFFu) >> 4;
                   const uint32_t a_lo = ((sH_addr + kb * kStageBytes) & 0x3FFFFu) >> 4;
                   const uint32_t a_tm = tmem_base + kTmemH + kb * 32;
-                  const int s_cur = s;
-                  if (++s == n_ring) { s = 0; ph ^= 1u; }
-                  // probe the NEXT stage's barrier now: its latency hides behind the MMA issue below
-                  ready = mbar_try_wait(&B.full[s], ph);
+                  if (dbg & 32) tl_mark(tl, 0xF10u);
                   if (elect_one()) {
-                    if (!(P.dbg & 2)) {
+                    if (!(dbg & 2)) {
 #pragma unroll
                       for (int kk = 0; kk < 4; ++kk) {
                         if (kk < nk) {
@@ -407,11 +447,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                         }
                       }
                     }
-                    if (C == 1) tc_commit(&B.empty[s_cur]);
-                    else tc_commit_multicast(&B.empty[s_cur], cmask);
-                    if (kb == KB - 1) tc_commit(&B.acc_full[buf]);
+                    if (dbg & 32) tl_mark(tl, 0xF20u);
+                    if (C == 1) tc_commit(&B.empty[s]);
+                    else tc_commit_multicast(&B.empty[s], cmask);
+                    if (kb == KB - 1) {
+                      if (l == 3) tc_commit(B.out_full);
+                      else tc_commit(&B.acc_full[buf]);
+                      if (l == 2 && c == 3) tc_commit(B.sh_free);
+                    }
+                    if (dbg & 32) tl_mark(tl, 0xF30u);
                   }
                   __syncwarp();
+                  if (dbg & 32) tl_mark(tl, 0xF40u);
+                  if (++s == n_ring) { s = 0; ph ^= 1u; }
                 }
                 tl_mark(tl, 0x200u | jl);
               }
@@ -422,257 +470,328 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       tl_finish(tl);
     }
   } else {
-    // =============================================================== epilogue (256 threads, 2 per row)
-    const int ew = warp - 2;
+    // =============================================================== row warps (512 threads, 4 per particle row)
+    reg_alloc<kRegsRow>();
     const int quarter = warp & 3;  // warp % 4: the TMEM lane quarter this warp may access
-    const int hh = ew >> 2;
+    const int cgp = warp >> 2;     // column group: 32 of a chunk's 128 columns; a quarter of the state pieces
     const int row = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..255
-    TlRole tl = tl_role(P, et == 0 ? 2 : 3, et == 0 || et == 128);
+    const int et = threadIdx.x;    // 0..511: owner of hidden unit `et` of the effective layer-0 bias
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint32_t acc_uses[2] = {0, 0};
-    uint32_t job = 0;
-    uint32_t npass = 0;   // running pass counter: selects the layer-0 bias buffer
+    TlRole tl = tl_role(P, warp == 0 ? 2 : 3, lane == 0 && (warp == 0 || warp == 12));
+    uint32_t job = 0;     // global job counter (13 per pass; accumulator buffer = job & 1)
+    uint32_t npass = 0;   // running pass counter: layer-0 bias buffer, parity of the once-per-pass barriers
+    uint32_t cf0 = 0, cf1 = 0;   // hidden chunks seen in accumulator buffer 0 / 1
     const float dbeta = P.bmax - P.bmin;
     const long long n_total = static_cast<long long>(P.n_obs) * P.n_per_obs;
     const TcNetDev& net_last = P.net[n_pass - 1];
     const int dvp = (net_last.dv + 7) & ~7;
+    const int split = P.net[0].split;
+    const bool sampler = (P.mode == kModeSampler);
+    const int xdim = P.xdim;
+    // state pieces (8 columns) of this row owned by this thread: [piece_lo, piece_lo + n_own)
+    const int np = sampler ? (xdim + 7) >> 3 : 0;
+    const int pbase = np >> 2, prem = np & 3;
+    const int n_own = pbase + (cgp < prem ? 1 : 0);
+    const int piece_lo = cgp * pbase + (cgp < prem ? cgp : prem);
+    float xs[kOwn * 8];   // fp32 SDE state
+    float yt[cdiffe ? 8 : 1];   // CDiffE: re-diffused observation columns 4 cgp .. +3 and 4 (cgp + 4) .. +3 of the next step
+    float myU[2], myWt[2];      // [1] is used by DPS only
+#pragma unroll
+    for (int j = 0; j < kOwn * 8; ++j) xs[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < (cdiffe ? 8 : 1); ++j) yt[j] = 0.f;
+    myU[0] = myU[1] = myWt[0] = myWt[1] = 0.f;
 
-    // state-column ownership of this thread (8-column pieces of the output layer): hh = 0 takes the first half
-    const int np = net_last.outpad >> 3;
-    const int np0 = (np + 1) >> 1;
-    const int piece_lo = hh == 0 ? 0 : np0;
-    const int piece_hi = hh == 0 ? np0 : np;
-    const int width = P.mode == kModeSampler ? P.xdim : P.out_dim;   // valid output columns
-    const bool ew_put = (P.variant == DMIP_CDIFFE);
-    // fp32 state of the tiles in flight: xs[block][piece][row][8] (L2-resident, coalesced 32 B per thread)
-    float* xs_blk = P.xs + static_cast<size_t>(blockIdx.x) * 16 * kTileM * 8;
-
-    for (long long tb = tile_first; tb < P.n_tiles; tb += tile_stride) {
+    for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
       // a cluster whose last round has fewer tiles than CTAs still runs every CTA (lock-step), on masked rows
-      const bool tile_ok = tb + crank < P.n_tiles;
-      const long long tile = tile_ok ? tb + crank : P.n_tiles - 1;
+      const bool tile_ok = tb + crank < n_tiles;
+      const long long tile = tile_ok ? tb + crank : n_tiles - 1;
       const int obs = static_cast<int>(tile / P.tiles_per_obs);
       const long long prow = (tile % P.tiles_per_obs) * kTileM + row;
       const bool valid = tile_ok && prow < P.n_per_obs;
       const long long grow = static_cast<long long>(obs) * P.n_per_obs + prow;
       const unsigned long long gidx = P.gidx_base + static_cast<unsigned long long>(grow);
 
-      // ---- tile init: per-observation layer-0 bias parts, x0 -> state + layer-0 operand
-      if (P.mode == kModeSampler) {
-        for (int p = 0; p < n_pass; ++p) {
-          const TcNetDev& net = P.net[p];
-          for (int n = et; n < 512; n += kEpiThreads) {
-            float u = net.b0[n];
-            const float* wr = net.w0c + static_cast<size_t>(n) * net.n_const;
-            for (int j = 0; j + 1 < net.n_const; ++j) u = fmaf(wr[j], P.y[obs * P.ydim + j], u);
-            sU[p * 512 + n] = u;
-            sWt[p * 512 + n] = wr[net.n_const - 1];
-            if (p == 0) sB0[(npass & 1) * 512 + n] = fmaf(tau_of_step(0, S, P.T), wr[net.n_const - 1], u);
-          }
-        }
-        for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
-          float x[8];
-          float z4[4];
+      // y_t = alpha(tau) y + std(tau) eta   (sdes.py:37-49 via models/diffusion.py:172): quads cgp and cgp + 4
+      auto diffuse_y = [&](int stp) {
+        if (!cdiffe) return;
+        const float tau = tau_of_step(stp, S, P.T);
+        const float Bt = 0.5f * tau * tau * dbeta + tau * P.bmin;
+        const float alpha = __expf(-0.5f * Bt);
+        const float sd = sqrtf(1.0f - __expf(-Bt));
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, kPhiloxStepInit, kStreamState, pc * 2 + h, P.seed, z4);
+        for (int h = 0; h < 2; ++h) {
+          const int q = cgp + 4 * h;
+          if (q * 4 < P.ydim) {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, stp, kStreamObs, q, P.seed, z);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int j = pc * 8 + h * 4 + e;
-              float zz = 0.f;
-              if (valid && j < width) zz = P.rng_mode == DMIP_RNG_PHILOX ? z4[e] : P.x0[grow * P.xdim + j];
-              x[h * 4 + e] = (valid && j < width) ? zz * P.std + P.mean : 0.f;   // models/diffusion.py:32-33
+              const int jj = q * 4 + e;
+              float v = 0.f;
+              if (valid && jj < P.ydim) {
+                const float eta = P.rng_mode == DMIP_RNG_PHILOX
+                                      ? z[e]
+                                      : P.ynoise[(static_cast<long long>(stp) * n_total + grow) * P.ydim + jj];
+                v = fmaf(sd, eta, alpha * P.y[obs * P.ydim + jj]);
+              }
+              yt[cdiffe ? h * 4 + e : 0] = v;
             }
           }
-          float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-          xp[0] = make_float4(x[0], x[1], x[2], x[3]);
-          xp[1] = make_float4(x[4], x[5], x[6], x[7]);
-          a0_put_piece(sH, row, pc, dvp, P.net[0].split, x, ew_put, width);
+        }
+      };
+      auto put_yt = [&]() {
+        if (!cdiffe) return;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = (cgp + 4 * h) * 4 + e;
+            if (jj < P.ydim) a0_put(sH, row, xdim + jj, dvp, split, yt[cdiffe ? h * 4 + e : 0]);
+          }
+      };
+      // layer-0 operand columns of this thread's state pieces
+      auto put_x = [&]() {
+#pragma unroll
+        for (int i = 0; i < kOwn; ++i) {
+          if (i < n_own) {
+            const int pc = piece_lo + i;
+            if (cdiffe) {   // the columns right after x hold y_t: touch only the x elements
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (pc * 8 + e < xdim) a0_put(sH, row, pc * 8 + e, dvp, split, xs[i * 8 + e]);
+            } else {
+              a0_put8(sH, row, pc * 8, dvp, split, &xs[i * 8]);
+            }
+          }
+        }
+      };
+
+      // ---- tile init
+      if (sampler) {
+        // per-observation parts of the effective layer-0 bias of hidden unit `et`
+        for (int p = 0; p < n_pass; ++p) {
+          const TcNetDev& net = P.net[p];
+          float u = net.b0[et];
+          const float* wr = net.w0c + static_cast<size_t>(et) * net.n_const;
+          for (int j = 0; j + 1 < net.n_const; ++j) u = fmaf(wr[j], P.y[obs * P.ydim + j], u);
+          const float wt = wr[net.n_const - 1];
+          if (p == 0) { myU[0] = u; myWt[0] = wt; } else if (dps) { myU[1] = u; myWt[1] = wt; }
+          if (p == 0) sB0[(npass & 1) * 512 + et] = fmaf(tau_of_step(0, S, P.T), wt, u);
+        }
+#pragma unroll
+        for (int i = 0; i < kOwn; ++i) {
+          if (i < n_own) {
+            const int pc = piece_lo + i;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float z4[4] = {0.f, 0.f, 0.f, 0.f};
+              if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, kPhiloxStepInit, kStreamState, pc * 2 + h, P.seed, z4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = pc * 8 + h * 4 + e;
+                float v = 0.f;
+                if (valid && j < xdim) {
+                  const float zz = P.rng_mode == DMIP_RNG_PHILOX ? z4[e] : P.x0[grow * xdim + j];
+                  v = zz * P.std + P.mean;   // models/diffusion.py:32-33
+                }
+                xs[i * 8 + h * 4 + e] = v;
+              }
+            }
+          }
+        }
+        put_x();
+        if (cdiffe) {
+          diffuse_y(0);
+          put_yt();
+        }
+      } else {
+        const TcNetDev& net = P.net[0];
+        sB0[(npass & 1) * 512 + et] = net.b0[et];
+        if (valid) {
+          for (int k = cgp; k < net.dv; k += 4) {
+            float v;
+            if (k < P.fx_dim) v = P.fx[grow * P.fx_dim + k];
+            else if (k < P.fx_dim + P.fcond_dim) v = P.fcond[grow * P.fcond_dim + (k - P.fx_dim)];
+            else v = P.ft[grow];
+            a0_put(sH, row, k, dvp, split, v);
+          }
         }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.a0_ready);
+      tl_mark(tl, 0x500u);
 
-      const int n_steps = (P.mode == kModeSampler) ? S : 1;
       for (int step = 0; step < n_steps; ++step) {
         const float tau = tau_of_step(step, S, P.T);
         const float beta = P.bmin + dbeta * tau;
         const float sb = sqrtf(beta);
         const bool last_step = (step == n_steps - 1);
-        float stash[8];
+        float stash[dps ? 8 : 1];   // DPS: prior-net output of this step
 #pragma unroll
-        for (int e = 0; e < 8; ++e) stash[e] = 0.f;
+        for (int e = 0; e < (dps ? 8 : 1); ++e) stash[e] = 0.f;
 
-        for (int p = 0; p < n_pass; ++p) {
+        for (int p = 0; p < n_pass; ++p, ++npass) {
           const TcNetDev& net = P.net[p];
           const bool last_pass = (p == n_pass - 1);
-          // ---- effective layer-0 bias of this pass; operand columns that are not carried state
-          if (P.mode == kModeSampler) {
-            if (p > 0) {
-              // second net of the step (DPS likelihood net): same x, rebuilt because H2 overwrote the operand
-              for (int pc = piece_lo; pc < piece_hi && pc * 8 < width; ++pc) {
-                const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-                const float4 q0 = xp[0], q1 = xp[1];
-                const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                a0_put_piece(sH, row, pc, dvp, net.split, x, ew_put, width);
-              }
-            }
-            if (P.variant == DMIP_CDIFFE && valid) {
-              // y_t = alpha(tau) y + std(tau) eta   (sdes.py:37-49 via models/diffusion.py:172)
-              const float Bt = 0.5f * tau * tau * dbeta + tau * P.bmin;
-              const float alpha = __expf(-0.5f * Bt);
-              const float sd = sqrtf(1.0f - __expf(-Bt));
-              for (int q = hh; q * 4 < P.ydim; q += 2) {
-                float z[4];
-                if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, step, kStreamObs, q, P.seed, z);
-                for (int e = 0; e < 4 && q * 4 + e < P.ydim; ++e) {
-                  const int jj = q * 4 + e;
-                  const float eta = P.rng_mode == DMIP_RNG_PHILOX
-                                        ? z[e]
-                                        : P.ynoise[(static_cast<long long>(step) * n_total + grow) * P.ydim + jj];
-                  a0_put(sH, row, P.xdim + jj, dvp, net.split, fmaf(sd, eta, alpha * P.y[obs * P.ydim + jj]));
-                }
-              }
-            }
-          } else {
-            for (int n = et; n < 512; n += kEpiThreads) sB0[(npass & 1) * 512 + n] = net.b0[n];
-            if (valid) {
-              for (int k = hh; k < net.dv; k += 2) {
-                float v;
-                if (k < P.fx_dim) v = P.fx[grow * P.fx_dim + k];
-                else if (k < P.fx_dim + P.fcond_dim) v = P.fcond[grow * P.fcond_dim + (k - P.fx_dim)];
-                else v = P.ft[grow];
-                a0_put(sH, row, k, dvp, net.split, v);
-              }
-            }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(B.a0_ready);
-          tl_mark(tl, 0x500u);
-          epi_bar_sync();  // sB0 visible to all epilogue threads
-
           // ---- layers 0..2
           int jl = 0;
 #pragma unroll 1
           for (int l = 0; l < 3; ++l) {
             const float* bias = (l == 0) ? sB0 + (npass & 1) * 512 : (l == 1 ? net.b1 : net.b2);
-            if (l == 1 && P.mode == kModeSampler) {
-              // next pass's effective layer-0 bias b0 + W0[:,y]·y + tau'·W0[:,t] into the other buffer (read after the
-              // epilogue barrier at the top of that pass)
-              const int pn = (p + 1 == n_pass) ? 0 : p + 1;
-              const float tau_n = (p + 1 == n_pass) ? tau_of_step(step + 1, S, P.T) : tau;
-              for (int n = et; n < 512; n += kEpiThreads)
-                sB0[((npass + 1) & 1) * 512 + n] = fmaf(tau_n, sWt[pn * 512 + n], sU[pn * 512 + n]);
+            if (l == 1 && sampler) {
+              // next pass's effective layer-0 bias b0 + W0[:,y]·y + tau'·W0[:,t] into the other buffer
+              const bool wrap = (p + 1 == n_pass);
+              const float tau_n = wrap ? tau_of_step(step + 1, S, P.T) : tau;
+              const float u = (wrap || !dps) ? myU[0] : myU[1];
+              const float wt = (wrap || !dps) ? myWt[0] : myWt[1];
+              sB0[((npass + 1) & 1) * 512 + et] = fmaf(tau_n, wt, u);
             }
 #pragma unroll 1
             for (int c = 0; c < 4; ++c, ++job, ++jl) {
               const int buf = job & 1;
-              mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x600 + buf);
-              acc_uses[buf]++;
+              mbar_wait(&B.acc_full[buf], (buf ? cf1 : cf0) & 1u, 0x800 + buf);
+              if (buf) ++cf1; else ++cf0;
               tc_fence_after();
               tl_mark(tl, 0x300u | jl);
               const uint32_t acc_col = kTmemAcc + buf * 128;
-              if (l == 0)
-                epi_hidden<true, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
+              if (dbg & 8) {   // debug: no epilogue work at all, only the handshakes
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&B.acc_empty[buf]); mbar_arrive(&B.hready[c]); }
+              } else if (l == 0)
+                epi_hidden<true, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               else if (l == 1)
-                epi_hidden<false, false>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
+                epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               else
-                epi_hidden<false, true>(lane_taddr, acc_col, hh, row, c, bias, sH, &B.acc_empty[buf], &B.hready[c], P.dbg);
+                epi_hidden<false, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               tl_mark(tl, 0x400u | jl);
-              if (l >= 1 && last_pass && P.mode == kModeSampler) {
-                // ---- in the shadow of the MMA-bound layers 1-2, one 8-column piece per accumulator chunk: the part
-                // of the Euler–Maruyama update that does not need the net output,
-                //   x <- x + delta*beta/2*x + sqrt(delta*beta)*eps            (models/diffusion.py:42, sdes.py:77-87)
-                const int pc = piece_lo + (l - 1) * 4 + c;
-                if (pc < piece_hi && pc * 8 < width) {
-                  float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-                  const float4 q0 = xp[0], q1 = xp[1];
-                  float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                  float za[4], zb[4];
-                  if (P.rng_mode == DMIP_RNG_PHILOX) {
-                    philox_normal4(gidx, step, kStreamState, pc * 2, P.seed, za);
-                    philox_normal4(gidx, step, kStreamState, pc * 2 + 1, P.seed, zb);
-                  }
+              if (sampler && last_pass && !(dbg & 16)) {
+                if (l == 1) {
+                  // ---- in the shadow of the MMA-bound layers, one state piece per accumulator chunk: the part of the
+                  // Euler–Maruyama update that does not need the net output,
+                  //   x <- x + delta*beta/2*x + sqrt(delta*beta)*eps            (models/diffusion.py:42, sdes.py:77-87)
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const int j = pc * 8 + e;
-                    float eps = 0.f;
-                    if (valid && j < width)
-                      eps = P.rng_mode == DMIP_RNG_PHILOX
-                                ? (e < 4 ? za[e & 3] : zb[e & 3])
-                                : P.noise[(static_cast<long long>(step) * n_total + grow) * P.xdim + j];
-                    x[e] = x[e] + P.delta * (0.5f * beta * x[e]) + (P.sqrt_delta * sb) * eps;
+                  for (int i = 0; i < kOwn; ++i) {
+                    if (i == c && i < n_own) {
+                      const int pc = piece_lo + i;
+                      float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
+                      if (P.rng_mode == DMIP_RNG_PHILOX) {
+                        philox_normal4(gidx, step, kStreamState, pc * 2, P.seed, za);
+                        philox_normal4(gidx, step, kStreamState, pc * 2 + 1, P.seed, zb);
+                      }
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) {
+                        const int j = pc * 8 + e;
+                        float eps = 0.f;
+                        if (valid && j < xdim)
+                          eps = P.rng_mode == DMIP_RNG_PHILOX
+                                    ? (e < 4 ? za[e & 3] : zb[e & 3])
+                                    : P.noise[(static_cast<long long>(step) * n_total + grow) * xdim + j];
+                        const float xv = xs[i * 8 + e];
+                        xs[i * 8 + e] = xv + P.delta * (0.5f * beta * xv) + (P.sqrt_delta * sb) * eps;
+                      }
+                    }
                   }
-                  xp[0] = make_float4(x[0], x[1], x[2], x[3]);
-                  xp[1] = make_float4(x[4], x[5], x[6], x[7]);
+                } else if (l == 2 && c == 0 && cdiffe && !last_step) {
+                  diffuse_y(step + 1);
                 }
               }
+            }
+          }
+          // ---- layer 2 has consumed the shared-memory operand region: operand columns that do not depend on this
+          // pass's output can be written now
+          tl_mark(tl, 0x310u);
+          mbar_wait(B.sh_free, npass & 1u, 0x600);
+          if (sampler) {
+            if (!last_pass) {
+              put_x();   // DPS: same x for the likelihood net (H2 overwrote the operand)
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(B.a0_ready);
+            } else if (cdiffe && !last_step) {
+              put_yt();
             }
           }
           // ---- output layer
-          {
-            const int buf = job & 1;
-            ++job;
-            // this thread's columns (<= 64) come out of tensor memory in two loads; the pre-updated state of piece
-            // i+1 is fetched from L2 while piece i is combined with the net output
-            const bool upd = (P.mode == kModeSampler) && last_pass;
-            float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
-            if (upd && piece_lo < piece_hi && piece_lo * 8 < width) {
-              const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(piece_lo) * kTileM + row) * 8);
-              nx0 = xp[0];
-              nx1 = xp[1];
-            }
-            mbar_wait(&B.acc_full[buf], acc_uses[buf] & 1u, 0x700 + buf);
-            acc_uses[buf]++;
-            tc_fence_after();
-            tl_mark(tl, 0x300u | 12);
-            const uint32_t acc_col = kTmemAcc + buf * 128;
-            // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
-            // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
-            const float ca = P.delta * ((P.variant == DMIP_DPS) ? beta : sb);
-            // rolled on purpose: the loop-carried prefetch keeps the L2 latency of the state one piece ahead
-#pragma unroll 1
-            for (int pc = piece_lo; pc < piece_hi; ++pc) {   // warp-uniform bounds
-              const float xt[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
-              if (upd && pc + 1 < piece_hi && (pc + 1) * 8 < width) {
-                const float4* xp = reinterpret_cast<const float4*>(xs_blk + (static_cast<size_t>(pc + 1) * kTileM + row) * 8);
-                nx0 = xp[0];
-                nx1 = xp[1];
-              }
+          tl_mark(tl, 0x320u);
+          mbar_wait(B.out_full, npass & 1u, 0x700);
+          tc_fence_after();
+          tl_mark(tl, 0x300u | 12);
+          const uint32_t acc_col = kTmemAcc + (job & 1u) * 128;
+          ++job;
+          const float* b3 = sB3 + p * 128;
+          if (!sampler) {
+            for (int pc = cgp; pc * 8 < P.out_dim; pc += 4) {
               uint32_t v[8];
               tmem_ld8(lane_taddr + acc_col + pc * 8, v);
               tc_wait_ld();
-              if (pc * 8 < width) {
-                const float4 b0 = *reinterpret_cast<const float4*>(net.b3 + pc * 8);   // zero-padded to 128
-                const float4 b1 = *reinterpret_cast<const float4*>(net.b3 + pc * 8 + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float xn[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int j = pc * 8 + e;
+                if (valid && j < P.out_dim) P.out[grow * P.out_dim + j] = __uint_as_float(v[e]) + b3[j];
+              }
+            }
+          } else if (!last_pass) {
+            if (n_own > 0) {   // DPS prior pass: xdim <= 8, the single piece belongs to column group 0
+              uint32_t v[8];
+              tmem_ld8(lane_taddr + acc_col, v);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) stash[dps ? e : 0] = __uint_as_float(v[e]) + b3[e];
+            }
+          } else {
+            // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
+            // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
+            const float ca = P.delta * (dps ? beta : sb);
+            uint32_t v[kOwn][8];
+#pragma unroll
+            for (int i = 0; i < kOwn; ++i)
+              if (i < n_own) tmem_ld8(lane_taddr + acc_col + (piece_lo + i) * 8, v[i]);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < kOwn; ++i) {
+              if (i < n_own) {
+                const int pc = piece_lo + i;
+                const float4 q0 = *reinterpret_cast<const float4*>(b3 + pc * 8);
+                const float4 q1 = *reinterpret_cast<const float4*>(b3 + pc * 8 + 4);
+                const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const int j = pc * 8 + e;
-                  const float a = __uint_as_float(v[e]) + bb[e];
-                  if (P.mode == kModeForward) {
-                    if (valid && j < width) P.out[grow * P.out_dim + j] = a;
-                  } else if (!last_pass) {
-                    stash[e] = a;   // DPS prior pass: outpad == 16, one piece per thread
-                  } else {
-                    const float at = (n_pass == 2) ? a + stash[e] : a;
-                    xn[e] = (j < width) ? fmaf(ca, at, xt[e]) : 0.f;
-                    if (last_step && valid && j < width) P.out[grow * P.xdim + j] = xn[e];
-                  }
-                }
-                if (upd && !last_step) {
-                  float4* xp = reinterpret_cast<float4*>(xs_blk + (static_cast<size_t>(pc) * kTileM + row) * 8);
-                  xp[0] = make_float4(xn[0], xn[1], xn[2], xn[3]);
-                  xp[1] = make_float4(xn[4], xn[5], xn[6], xn[7]);
-                  a0_put_piece(sH, row, pc, dvp, P.net[0].split, xn, ew_put, width);   // next step's layer-0 operand
+                  float a = __uint_as_float(v[i][e]) + bb[e];
+                  if (dps) a += stash[dps ? e : 0];
+                  xs[i * 8 + e] = (valid && j < xdim) ? fmaf(ca, a, xs[i * 8 + e]) : 0.f;
                 }
               }
             }
-            tc_fence_before();
-            mbar_arrive(&B.acc_empty[buf]);
-            tl_mark(tl, 0x400u | 12);
           }
-          ++npass;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(B.out_empty);
+          tl_mark(tl, 0x400u | 12);
+          if (sampler && last_pass) {
+            if (last_step) {
+              if (valid) {
+#pragma unroll
+                for (int i = 0; i < kOwn; ++i)
+                  if (i < n_own) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      const int j = (piece_lo + i) * 8 + e;
+                      if (j < xdim) P.out[grow * xdim + j] = xs[i * 8 + e];
+                    }
+                  }
+              }
+            } else {
+              put_x();   // next step's layer-0 operand
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(B.a0_ready);
+              tl_mark(tl, 0x500u);
+            }
+          }
         }  // pass
       }    // step
     }      // tile
@@ -683,7 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (C > 1) cluster_sync_all();   // no CTA leaves while a peer may still signal its barriers
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
@@ -853,7 +972,6 @@ int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows
 
 int g_n_sm = 0;
 int g_dbg = 0;
-int g_cluster = 2;   // CTAs per multicast cluster (DMIP_CLUSTER=1|2|4 overrides)
 unsigned long long* g_tl = nullptr;
 int g_tl_cap = 0;
 
@@ -862,10 +980,16 @@ int init_device() {
     int dev = 0;
     DMIP_CHECK_CUDA(cudaGetDevice(&dev));
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&g_n_sm, cudaDevAttrMultiProcessorCount, dev));
-    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tc_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+#define DMIP_SET_SMEM(NP, VAR) \
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tc_mlp<NP, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes))
+    DMIP_SET_SMEM(1, DMIP_CDE);
+    DMIP_SET_SMEM(1, DMIP_CDIFFE);
+    DMIP_SET_SMEM(1, DMIP_DPS);
+    DMIP_SET_SMEM(4, DMIP_CDE);
+    DMIP_SET_SMEM(4, DMIP_CDIFFE);
+    DMIP_SET_SMEM(13, DMIP_CDE);
+#undef DMIP_SET_SMEM
     if (getenv("DMIP_DBG")) g_dbg = atoi(getenv("DMIP_DBG"));
-    const char* e = getenv("DMIP_CLUSTER");
-    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) g_cluster = atoi(e);
   }
   return DMIP_OK;
 }
@@ -877,8 +1001,7 @@ int launch(TcParams& P, cudaStream_t s) {
   P.tl = g_tl;
   P.tl_cap = g_tl_cap;
   if (P.n_tiles <= 0) return DMIP_OK;
-  int C = g_cluster;
-  while (C > 1 && P.n_tiles < C) C >>= 1;
+  const int C = kCluster;   // a lone tile still launches a pair: the second CTA runs masked rows
   P.cluster = C;
   P.dbg = g_dbg;
   const long long want_clusters = (P.n_tiles + C - 1) / C;
@@ -896,7 +1019,18 @@ int launch(TcParams& P, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp, P));
+  const int state_cols = (P.mode == kModeSampler) ? P.xdim : 1;
+  const int var = (P.mode == kModeSampler) ? P.variant : DMIP_CDE;
+  if (var == DMIP_DPS) {
+    DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp<1, DMIP_DPS>, P));
+  } else if (var == DMIP_CDIFFE) {
+    if (state_cols <= 8) DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp<1, DMIP_CDIFFE>, P));
+    else DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp<4, DMIP_CDIFFE>, P));
+  } else {
+    if (state_cols <= 8) DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp<1, DMIP_CDE>, P));
+    else if (state_cols <= 32) DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp<4, DMIP_CDE>, P));
+    else DMIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_tc_mlp<13, DMIP_CDE>, P));
+  }
   DMIP_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DMIP_OK;
@@ -905,8 +1039,7 @@ int launch(TcParams& P, cudaStream_t s) {
 }  // namespace
 
 size_t sampler_tc_workspace() {
-  if (init_device()) return 0;
-  return static_cast<size_t>(g_n_sm) * 16 * kTileM * 8 * sizeof(float);   // fp32 state of the tiles in flight
+  return 256;   // the state lives in registers, activations in shared / tensor memory: no device scratch is needed
 }
 
 void debug_set_timeline(unsigned long long* buf, int cap) {
@@ -916,10 +1049,10 @@ void debug_set_timeline(unsigned long long* buf, int cap) {
 
 int launch_sampler_tc(const DmipSampler* d, cudaStream_t s) {
   TcParams P = {};
-  DMIP_REQUIRE(d->workspace && d->workspace_bytes >= sampler_tc_workspace() &&
-                   (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0,
-               "workspace too small or misaligned: need %zu bytes, 16-byte aligned", sampler_tc_workspace());
-  P.xs = static_cast<float*>(d->workspace);
+  DMIP_REQUIRE(d->xdim <= 104, "tcgen05 sampler keeps the state in registers: xdim <= 104 (got %d); use DMIP_PREC_F32", d->xdim);
+  if (d->variant == DMIP_CDIFFE)
+    DMIP_REQUIRE(d->xdim <= 32 && d->ydim <= 24, "tcgen05 CDiffE sampler supports xdim <= 32, ydim <= 24 (got %d, %d); "
+                 "use DMIP_PREC_F32", d->xdim, d->ydim);
   P.mode = kModeSampler;
   P.variant = d->variant;
   const int dv = d->variant == DMIP_CDIFFE ? d->xdim + d->ydim : d->xdim;

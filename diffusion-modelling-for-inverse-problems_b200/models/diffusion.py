@@ -71,8 +71,9 @@ class BaseClassDiffusionModel():
         d.variant = _VARIANT[self.variant]
         prec = _lib.precision_code(self.precision if precision is None else precision)
         if prec == _lib.PREC_BF16 and not (_lib.tc_supported(net) and (net2 is None or _lib.tc_supported(net2))
-                                            and (net2 is None or self.xdim <= 8)):
-            prec = _lib.PREC_F32             # other layer widths: fp32 FFMA kernels (still CUDA, never CPU)
+                                            and (net2 is None or self.xdim <= 8) and self.xdim <= 104
+                                            and (self.variant != 'CDiffE' or (self.xdim <= 32 and self.ydim <= 24))):
+            prec = _lib.PREC_F32             # other layer widths / state sizes: fp32 FFMA kernels (still CUDA, never CPU)
         d.precision = prec
         d.xdim, d.ydim = self.xdim, self.ydim
         d.n_obs, d.n_per_obs, d.num_steps = n_obs, num_samples, num_steps

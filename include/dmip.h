@@ -246,6 +246,13 @@ int dmip_posterior_loss_fwd_bwd(const DmipPosteriorLoss* d, void* stream);
 /* tcgen05.mma issue-rate micro-benchmark: `iters` x (k/16) MMAs of shape 128 x n x 16 per CTA on `grid` CTAs;
  * cycles: device int64[2*grid] = (issue cycles, completion cycles) per CTA. */
 int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream);
+/* Same probe for CTA-pair instructions and with a concurrent bulk-TMA stream: cg = CTAs per MMA (1|2; M = 128*cg),
+ * mode bit 0: A from tensor memory, bit 1: alternate accumulators; stream_bytes copied global->shared per K-block by a
+ * second warp (gsrc: device buffer >= 8 MB + 64 KB).  cycles: device int64[4*grid] = (issue, complete, producer, -). */
+int dmip_debug_mma_bench2(int32_t cg, int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t stream_bytes, int32_t grid,
+                          const void* gsrc, void* cycles, void* stream);
+/* Cost of the synchronisation primitives (cycles for `iters` iterations of ten small sequences; out: device int64[32]). */
+int dmip_debug_prim_bench(int32_t iters, void* out, void* stream);
 /* Timeline hook: when set, CTA 0 of the tcgen05 kernels records (clock64 << 16 | event code) entries into
  * device_buf[1..capacity) and the entry count into device_buf[0] (uint64).  Pass NULL to switch off. */
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity);

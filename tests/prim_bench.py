@@ -1,0 +1,24 @@
+"""Cycles per iteration of the synchronisation primitives the sampler's producer / issuer loops are made of."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dmip import _lib
+
+L = _lib.require_gpu()
+L.dmip_debug_prim_bench.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+names = ["try_wait (completed phase)", "elect + arrive", "arrive + wait for it", "clock64", "tcgen05.commit (idle)",
+         "commit + wait for it", "tcgen05.fence::after", "3 constant-bank loads", "issuer skeleton (wait+fence+commit)",
+         "producer skeleton (wait+expect_tx)"]
+iters = 2000
+out = torch.zeros(32, dtype=torch.int64, device="cuda")
+for _ in range(2):
+    _lib.check(L.dmip_debug_prim_bench(iters, out.data_ptr(), None))
+    torch.cuda.synchronize()
+for n, v in zip(names, out.cpu().tolist()):
+    print(f"{n:40s} {v / iters:8.1f} cycles")
+r = out.cpu().tolist()
+for i, n in enumerate(["try_wait (hardware suspend)", "test_wait spin", "try_wait, 0 ns suspend hint"]):
+    print(f"ping-pong round trip, {n:30s} {r[20 + i] / iters:8.1f} cycles")

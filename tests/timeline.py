@@ -74,7 +74,7 @@ if len(starts) > 3:
           [(t, "epi1", c) for t, c in roles[3] if lo <= t <= hi]
     names = {0x100: "mma_start", 0x200: "mma_issued", 0x300: "accfull", 0x400: "epi_done", 0x500: "a0_arrive",
              0x700: "stage_wait", 0x800: "stage_ok", 0x900: "hready_wait", 0xA00: "hready_ok", 0xB00: "acc_wait",
-             0xC00: "acc_ok", 0xD00: "a0_wait", 0xE00: "a0_ok"}
+             0xC00: "acc_ok", 0xD00: "a0_wait", 0xE00: "a0_ok", 0xF00: "issue_pt"}
     for t, who, c in sorted(evs):
         k = c & 0xF00
         arg = f"job {(c >> 4) & 0xF} kb {c & 0xF}" if k in (0x700, 0x800, 0x900, 0xA00) else f"job {c & 0xFF}"
@@ -85,3 +85,9 @@ if len(prod) > 200:
     d = [prod[i + 1][0] - prod[i][0] for i in range(100, len(prod) - 1)]
     d.sort()
     print(f"\nproducer: cycles between stage issues  median {d[len(d)//2]}  p10 {d[len(d)//10]}  p90 {d[9*len(d)//10]}")
+# ---- producer vs issuer lag (stages issued by the producer before each job starts)
+if len(starts) > 3 and prod:
+    lo, hi = mma[starts[2]][0], mma[starts[3]][0]
+    pj = [(t - lo, c & 0xFF) for t, c in prod if lo - 3000 <= t <= hi]
+    print("\nproducer stage issues (cycle, stage index) around pass 2:")
+    print("  " + " ".join(f"{t}:{st}" for t, st in pj[:120]))
