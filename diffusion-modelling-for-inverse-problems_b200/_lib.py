@@ -10,7 +10,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libdmip_sm100.so")
+_LIB_PATH = os.environ.get("DMIP_LIB") or os.path.join(_HERE, "libdmip_sm100.so")   # DMIP_LIB: experiment builds
 _lib = None
 
 MAX_LAYERS = 8

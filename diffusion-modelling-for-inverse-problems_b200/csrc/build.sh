@@ -3,9 +3,9 @@
 # DMIP_DEBUG=1 bash build.sh  compiles the DMIP_DBG ablation bits and the kernel timeline in (slower issue loops).
 set -euo pipefail
 cd "$(dirname "$0")"
-OUT=../libdmip_sm100.so
+OUT=${DMIP_OUT:-../libdmip_sm100.so}
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v ${DMIP_DEBUG:+-DDMIP_DEBUG}"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v ${DMIP_DEBUG:+-DDMIP_DEBUG} ${DMIP_EXP:+-DDMIP_EXP=$DMIP_EXP}"
 mkdir -p build
 pids=()
 SRCS="dmip_api dmip_pack dmip_tc dmip_f32 dmip_loss dmip_surrogate dmip_debug"

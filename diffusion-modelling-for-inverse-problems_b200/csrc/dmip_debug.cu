@@ -23,6 +23,7 @@ struct BenchParams {
   int commit;        // 1: one tcgen05.commit per K-block (4 MMAs), as the sampler does
   int readers;       // 1: warps 4-7 read the accumulators with tcgen05.ld in a loop (epilogue stand-in); 2: ld + st
   int reader_iters;
+  int kbwait;        // n: n mbarrier waits on an already-completed phase (+ tcgen05.fence::after) before every K-block
   int math;          // warps 8-23: 1 = MUFU.TANH loop, 2 = FFMA loop, 3 = both (row-warp stand-in without TMEM traffic)
   int math_iters;
   float* sink;
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(768, 1) k_mma_bench2(const __grid_constant__ B
   uint64_t* done = bars;                       // MMA completion
   uint64_t* rfull = bars + 1;                  // [kRing]
   uint64_t* dummy = bars + 1 + kRing;          // per-K-block commits land here (nobody waits)
-  uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 2 + kRing);
+  uint64_t* ready = bars + 2 + kRing;          // phase 0 completed during setup
+  uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 3 + kRing);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t crank = kCg == 2 ? cluster_ctarank() : 0u;
@@ -51,7 +53,9 @@ __global__ void __launch_bounds__(768, 1) k_mma_bench2(const __grid_constant__ B
     mbar_init(done, 1);
     for (int i = 0; i < kRing; ++i) mbar_init(&rfull[i], 1);
     mbar_init(dummy, 1);
+    mbar_init(ready, 1);
     fence_barrier_init();
+    mbar_arrive(ready);
   }
   for (int i = threadIdx.x; i < (12 + kRing) * kKb / 16; i += 768) {
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -96,6 +100,10 @@ __global__ void __launch_bounds__(768, 1) k_mma_bench2(const __grid_constant__ B
     for (int it = 0; it < P.iters; ++it) {
       const uint32_t d_tmem = tmem_base + 256 + ((P.alt_acc && (it & 1)) ? static_cast<uint32_t>(P.n <= 128 ? 128 : 0) : 0u);
       for (int kb = 0; kb < P.k / 64; ++kb) {
+        for (int w = 0; w < P.kbwait; ++w) {
+          mbar_wait(ready, 0, 0x905);
+          tc_fence_after();
+        }
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -351,6 +359,7 @@ int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int strea
   P.rnd = (mode >> 2) & 1; P.commit = (mode >> 3) & 1; P.readers = (mode >> 4) & 3;
   P.reader_iters = iters * (k / 16) / 2;
   P.math = (mode >> 6) & 3;
+  P.kbwait = (mode >> 8) & 7;
   P.math_iters = iters * (k / 16) * 8;
   P.sink = reinterpret_cast<float*>(cycles);
   P.stream_bytes = stream_bytes;

@@ -37,8 +37,10 @@ namespace dmip {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = 16384;   // 128 rows x 64 k x bf16
-constexpr int kNumStages = 5;
+constexpr int kStageBytes = 16384;   // 128 rows x 64 k x bf16: one K-block of a 128-feature chunk
+constexpr int kNumSlots = 6;         // ring of 16 KB slots, filled / waited for / released in PAIRS (32 KB = 8 MMAs):
+constexpr int kNumPairs = kNumSlots / 2;   // a barrier wait costs ~85 cycles in the issuing thread and the tensor core
+constexpr int kPairBytes = 2 * kStageBytes;  // queues only ~1 MMA ahead, so waits per MMA decide the MMA rate
 constexpr int kHBytes = 131072;      // 128 rows x 512 k x bf16 = 8 K-blocks
 constexpr int kThreads = 640;        // warps: 0-15 row warps (epilogue + state), 16 producer, 17 MMA, 18-19 idle
 constexpr int kRegsSmall = 40;       // registers are allocated per 4 warps (18 warps are billed as 20), so the kernel
@@ -52,15 +54,14 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemH = 0;       // 256 columns: 128 x 512 bf16 activations (A operand)
 constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
 
-// shared-memory map (offsets from a 1024-aligned base)
+// shared-memory map (offsets from the 1024-aligned dynamic shared memory base; 231.6 of the 232.4 KB a CTA may have)
 constexpr int kOffH = 0;
 constexpr int kOffB = kOffH + kHBytes;
-constexpr int kOffB0 = kOffB + kNumStages * kStageBytes;  // float[2][512] effective layer-0 bias: current pass / next pass
-constexpr int kOffB3 = kOffB0 + 4096;                     // float[2][128] output-layer bias per net
-constexpr int kOffBar = kOffB3 + 1024;
-constexpr int kNumBars = 2 * kNumStages + 2 + 2 + 1 + 1 + 1 + 4 + 1;
+constexpr int kOffB0 = kOffB + kNumSlots * kStageBytes;   // float[512] effective layer-0 bias of the coming pass
+constexpr int kOffBar = kOffB0 + 2048;
+constexpr int kNumBars = 2 * kNumPairs + 2 + 2 + 1 + 1 + 1 + 4 + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // + alignment slack
+constexpr int kSmemBytes = kOffTmem + 16;
 
 enum { kModeSampler = 0, kModeForward = 1 };
 
@@ -99,8 +100,8 @@ struct TcParams {
 };
 
 struct Bars {
-  uint64_t* full;       // [kNumStages]  weight stage landed            (tx bytes)
-  uint64_t* empty;      // [kNumStages]  weight stage consumed          (one tcgen05.commit per cluster CTA)
+  uint64_t* full;       // [kNumPairs]   weight slot pair landed        (tx bytes)
+  uint64_t* empty;      // [kNumPairs]   weight slot pair consumed      (one tcgen05.commit per cluster CTA)
   uint64_t* acc_full;   // [2]           hidden accumulator chunk complete  (tcgen05.commit)
   uint64_t* acc_empty;  // [2]           hidden chunk drained               (16 row warps)
   uint64_t* out_full;   // [1]           output-layer chunk complete        (tcgen05.commit)
@@ -234,12 +235,12 @@ struct TlRole {
   unsigned int n, cap;
   bool minimal;   // DMIP_DBG bit 64: record only the pass boundaries (a probe costs ~90 cycles: clock64 is slow)
 };
-__device__ __forceinline__ TlRole tl_role(const TcParams& P, int role, bool on) {
+__device__ __forceinline__ TlRole tl_role(const TcParams& P, int dbg, int role, bool on) {
   TlRole r;
   r.p = nullptr;
   r.n = 0;
   r.cap = 0;
-  r.minimal = __shfl_sync(0xffffffffu, (P.dbg & 64) != 0 ? 1 : 0, 0) != 0;   // pinned (see keep())
+  r.minimal = (dbg & 64) != 0;
   if (P.tl != nullptr && blockIdx.x == 0 && on) {
     const int seg = P.tl_cap / 4;
     r.p = P.tl + static_cast<size_t>(role) * seg;
@@ -272,18 +273,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   constexpr int kOwn = (NP + 3) / 4;
   constexpr bool cdiffe = (VAR == DMIP_CDIFFE);
   constexpr bool dps = (VAR == DMIP_DPS);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window base
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();       // itself is the swizzle-atom (1024 B) aligned address
   uint8_t* sH = smem + kOffH;
   uint8_t* sB = smem + kOffB;
   float* sB0 = reinterpret_cast<float*>(smem + kOffB0);
-  float* sB3 = reinterpret_cast<float*>(smem + kOffB3);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   Bars B;
   B.full = bars;
-  B.empty = bars + kNumStages;
-  B.acc_full = bars + 2 * kNumStages;
+  B.empty = bars + kNumPairs;
+  B.acc_full = bars + 2 * kNumPairs;
   B.acc_empty = B.acc_full + 2;
   B.out_full = B.acc_empty + 2;
   B.out_empty = B.out_full + 1;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 
   // ---- one-time setup
   if (warp == kProducerWarp && lane == 0) {
-    for (int i = 0; i < kNumStages; ++i) {
+    for (int i = 0; i < kNumPairs; ++i) {
       mbar_init(&B.full[i], 1);
       mbar_init(&B.empty[i], static_cast<uint32_t>(kCluster));   // one tcgen05.commit per CTA of the cluster
     }
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_holder);
   // zero the activation region once: layer-0 K padding must be finite (it meets zero weights)
   for (int i = threadIdx.x; i < kHBytes / 16; i += kThreads) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 256; i += kThreads) sB3[i] = (i >> 7) < P.n_nets ? P.net[i >> 7].b3[i & 127] : 0.f;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -325,10 +324,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   // stage and multicasts it to all of them, so L2 serves each line once per cluster instead of once per SM.
   constexpr int C = kCluster;
 #ifdef DMIP_DEBUG
-  const int dbg = P.dbg;
+  // masked with a value read from shared memory so that ptxas cannot re-materialise it from the constant bank
+  const int dbg = P.dbg & static_cast<int>(*reinterpret_cast<volatile uint32_t*>(tmem_holder) == 0xFFFFFFFFu ? 0u : 0xFFFFFFFFu);
 #else
-  constexpr int dbg = 0;   // the DMIP_DBG ablation bits and the timeline exist only in -DDMIP_DEBUG builds: a run-time
-#endif                     // flag costs a constant-bank re-load (~40 cycles) at every use inside the issue loops
+  // The DMIP_DBG ablation bits and the timeline exist only in -DDMIP_DEBUG builds: a run-time flag costs a constant-bank
+  // re-load (~40 cycles) at every use inside the issue loops.  -DDMIP_EXP=<bits> bakes the same bits in at compile time
+  // (timing experiments on otherwise unchanged production code): 1 no weight copies, 2 no MMA issue, 8 no epilogue
+  // math, 16 no state pre-update.
+#ifndef DMIP_EXP
+#define DMIP_EXP 0
+#endif
+  constexpr int dbg = DMIP_EXP;
+#endif
   const long long n_tiles = keep(P.n_tiles);
   const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   const int n_pass = keep(P.n_nets);
   const int S = keep(P.S);
   const int n_steps = keep((P.mode == kModeSampler) ? S : 1);
-  const int n_ring = keep((dbg & 4) ? 3 : kNumStages);
+  constexpr int n_ring = kNumPairs;
 
   if (warp >= kNumRowWarps) {
     reg_dealloc<kRegsSmall>();
@@ -347,26 +354,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       // ============================================================= producer (whole warp, one elected lane issues)
       int s = 0;
       uint32_t ph = 0;
-      TlRole tl = tl_role(P, 0, lane == 0);
-      const uint32_t part = kStageBytes / C;
+      TlRole tl = tl_role(P, dbg, 0, lane == 0);
+      constexpr uint32_t part = kPairBytes / C;
       for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
         for (int step = 0; step < n_steps; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const uint8_t* src = keep(P.net[p].stages);
-            const int ns = keep(P.net[p].n_stages);
-            for (int st = 0; st < ns; ++st) {
-              mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);   // slot s released by the MMA warps of ALL cluster CTAs
-              tl_mark(tl, 0x600u | (st & 0xFF));
-              const uint8_t* g = src + static_cast<size_t>(st) * kStageBytes;
+            const int npairs = keep(P.net[p].n_stages >> 1);   // 4 kb0 + 72 blocks: always even
+            for (int pr = 0; pr < npairs; ++pr) {
+              mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);   // pair s released by the MMA warps of ALL cluster CTAs
+              tl_mark(tl, 0x600u | (pr & 0xFF));
+              const uint8_t* g = src + static_cast<size_t>(pr) * kPairBytes;
               if (elect_one()) {
                 if (dbg & 1) {
                   mbar_arrive(&B.full[s]);
                 } else {
-                  mbar_arrive_expect_tx(&B.full[s], kStageBytes);
+                  mbar_arrive_expect_tx(&B.full[s], kPairBytes);
                   if (C == 1)
-                    bulk_g2s(sB + s * kStageBytes, g, kStageBytes, &B.full[s]);
+                    bulk_g2s(sB + s * kPairBytes, g, kPairBytes, &B.full[s]);
                   else
-                    bulk_g2s_multicast(sB + s * kStageBytes + crank * part, g + crank * part, part, &B.full[s], cmask);
+                    bulk_g2s_multicast(sB + s * kPairBytes + crank * part, g + crank * part, part, &B.full[s], cmask);
                 }
               }
               __syncwarp();
@@ -378,87 +385,118 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       tl_finish(tl);
     } else if (warp == kMmaWarp) {
       // ============================================================= MMA issuer (whole warp, one elected lane issues)
-      int s = 0;
+      // The tensor core queues only about one instruction ahead of the issuing thread, so every cycle this loop spends
+      // between two MMAs beyond ~1 MMA duration is a cycle the tensor pipe idles: the loop is kept to the bare
+      // sequence  wait(pair) / 8 x (descriptor add, UTCHMMA) / commit  with all addressing as immediates.
+      int s = 0;             // ring pair being consumed
       uint32_t ph = 0;
       uint32_t job = 0;
       uint32_t hr_par = 0;   // bit c = parity of hready[c]
       uint32_t a0_par = 0;
       uint32_t ch0 = 0, ch1 = 0, n_out = 0;          // hidden uses of accumulator buffer 0/1; output jobs so far
       uint32_t lastkind = 0;                         // 2 bits per buffer: 0 never used, 1 hidden job, 2 output job
-      TlRole tl = tl_role(P, 1, lane == 0);
-      const uint32_t sH_addr = smem_u32(sH);
-      const uint32_t sB_addr = smem_u32(sB);
+      uint32_t blk = 0;                              // 16 KB weight blocks consumed by layer 0 of this pass
+      TlRole tl = tl_role(P, dbg, 1, lane == 0);
+      const uint32_t a_base = (smem_u32(sH) & 0x3FFFFu) >> 4;    // descriptor address fields (16-byte units)
+      const uint32_t b_base = (smem_u32(sB) & 0x3FFFFu) >> 4;
       const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // everything but the address field
+      constexpr uint32_t kBlk16 = kStageBytes >> 4, kPair16 = kPairBytes >> 4;
+
+      // wait until the accumulator buffer's previous user has drained it, then book this use
+      auto acquire_acc = [&](int buf, bool is_out, int jl) {
+        const uint32_t lk = (lastkind >> (2 * buf)) & 3u;
+        tl_mark(tl, 0xB00u | jl);
+        if (lk == 1u) mbar_wait(&B.acc_empty[buf], ((buf ? ch1 : ch0) - 1u) & 1u, 0x300 + buf);
+        else if (lk == 2u) mbar_wait(B.out_empty, (n_out - 1u) & 1u, 0x310 + buf);   // = the latest output job
+        tl_mark(tl, 0x100u | jl);
+        if (is_out) ++n_out; else { if (buf) ++ch1; else ++ch0; }
+        lastkind = (lastkind & ~(3u << (2 * buf))) | ((is_out ? 2u : 1u) << (2 * buf));
+      };
+
       for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
         for (int step = 0; step < n_steps; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const int net_kb0 = keep(P.net[p].kb0), net_ksteps0 = keep(P.net[p].ksteps0);
-            const int net_outpad = keep(P.net[p].outpad);
+            const uint32_t idesc_out = umma_idesc_bf16(128, static_cast<uint32_t>(keep(P.net[p].outpad)));
+            constexpr uint32_t idesc_hid = umma_idesc_bf16(128, 128);
             tl_mark(tl, 0xD00u);
             mbar_wait(B.a0_ready, a0_par, 0x200);
             tl_mark(tl, 0xE00u);
             a0_par ^= 1u;
             int jl = 0;
+            // ---- layer 0: A0 (shared memory) x W0 chunks; K = 16 ksteps0 is arbitrary, blocks may straddle ring pairs
+            blk = 0;
 #pragma unroll 1
-            for (int l = 0; l < 4; ++l) {
+            for (int c = 0; c < 4; ++c, ++job, ++jl) {
+              const int buf = job & 1;
+              acquire_acc(buf, false, jl);
+              const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
+#pragma unroll 1
+              for (int kb = 0; kb < net_kb0; ++kb, ++blk) {
+                const uint32_t half = blk & 1u;   // which 16 KB slot of the pair
+                if (half == 0u) mbar_wait(&B.full[s], ph, 0x500 + s);
+                tc_fence_after();
+                const int nk = (kb == net_kb0 - 1) ? (net_ksteps0 - 4 * (net_kb0 - 1)) : 4;
+                const uint32_t b_lo = b_base + s * kPair16 + half * kBlk16;
+                const uint32_t a_lo = a_base + kb * kBlk16;
+                if (elect_one()) {
+                  if (!(dbg & 2)) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                      if (kk < nk)
+                        umma_ss(d_tmem, desc_hi | (a_lo + kk * 2), desc_hi | (b_lo + kk * 2), idesc_hid, (kb | kk) != 0 ? 1u : 0u);
+                  }
+                  if (half == 1u) tc_commit_multicast(&B.empty[s], cmask);
+                  if (kb == net_kb0 - 1) tc_commit(&B.acc_full[buf]);
+                }
+                __syncwarp();
+                if (half == 1u) { if (++s == n_ring) { s = 0; ph ^= 1u; } }
+              }
+              tl_mark(tl, 0x200u | jl);
+            }
+            // ---- layers 1..3: K = 512 = 4 ring pairs per chunk, pair-aligned (layer 0 consumed 4 kb0 blocks)
+#pragma unroll 1
+            for (int l = 1; l < 4; ++l) {
               const int n_chunks = (l == 3) ? 1 : 4;
-              const int KB = (l == 0) ? net_kb0 : 8;
-              const uint32_t idesc = (l == 3) ? umma_idesc_bf16(128, static_cast<uint32_t>(net_outpad))
-                                              : umma_idesc_bf16(128, 128);
-              const bool a_in_smem = (l & 1) == 0;
+              const uint32_t idesc = (l == 3) ? idesc_out : idesc_hid;
 #pragma unroll 1
               for (int c = 0; c < n_chunks; ++c, ++job, ++jl) {
                 const int buf = job & 1;
-                // the buffer's previous user has drained it (a hidden chunk, or the latest output chunk)
-                const uint32_t lk = (lastkind >> (2 * buf)) & 3u;
-                tl_mark(tl, 0xB00u | jl);
-                if (lk == 1u) mbar_wait(&B.acc_empty[buf], ((buf ? ch1 : ch0) - 1u) & 1u, 0x300 + buf);
-                else if (lk == 2u) mbar_wait(B.out_empty, (n_out - 1u) & 1u, 0x310 + buf);
-                tl_mark(tl, 0x100u | jl);
-                if (l == 3) ++n_out; else { if (buf) ++ch1; else ++ch0; }
-                lastkind = (lastkind & ~(3u << (2 * buf))) | ((l == 3 ? 2u : 1u) << (2 * buf));
+                acquire_acc(buf, l == 3, jl);
                 const uint32_t d_tmem = tmem_base + kTmemAcc + buf * 128;
 #pragma unroll 1
-                for (int kb = 0; kb < KB; ++kb) {
-                  if (l > 0 && c == 0 && (kb & 1) == 0) {
-                    tl_mark(tl, 0x900u | (jl << 4) | kb);
-                    mbar_wait(&B.hready[kb >> 1], (hr_par >> (kb >> 1)) & 1u, 0x400 + (kb >> 1));
-                    tl_mark(tl, 0xA00u | (jl << 4) | kb);
-                    hr_par ^= 1u << (kb >> 1);
+                for (int pr = 0; pr < 4; ++pr) {
+                  if (c == 0) {   // K-blocks 2 pr, 2 pr + 1 of this layer's A operand come from chunk pr of the previous epilogue
+                    mbar_wait(&B.hready[pr], (hr_par >> pr) & 1u, 0x400 + pr);
+                    hr_par ^= 1u << pr;
                   }
-                  if (dbg & 32) tl_mark(tl, 0x700u | (jl << 4) | kb);
                   mbar_wait(&B.full[s], ph, 0x500 + s);
-                  if (dbg & 32) tl_mark(tl, 0x800u | (jl << 4) | kb);
                   tc_fence_after();
-                  const int nk = (l == 0 && kb == KB - 1) ? (net_ksteps0 - 4 * (KB - 1)) : 4;
-                  const uint32_t b_lo = ((sB_addr + s * kStageBytes) & 0x3FFFFu) >> 4;
-                  const uint32_t a_lo = ((sH_addr + kb * kStageBytes) & 0x3FFFFu) >> 4;
-                  const uint32_t a_tm = tmem_base + kTmemH + kb * 32;
-                  if (dbg & 32) tl_mark(tl, 0xF10u);
+                  const uint32_t b_lo = b_base + s * kPair16;
                   if (elect_one()) {
                     if (!(dbg & 2)) {
+                      if (l == 2) {          // A = H2 in shared memory
+                        const uint32_t a_lo = a_base + pr * kPair16;
 #pragma unroll
-                      for (int kk = 0; kk < 4; ++kk) {
-                        if (kk < nk) {
-                          const uint64_t bdesc = desc_hi | (b_lo + kk * 2);   // +32 B per UMMA_K step
-                          const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-                          if (a_in_smem) umma_ss(d_tmem, desc_hi | (a_lo + kk * 2), bdesc, idesc, acc);
-                          else umma_ts(d_tmem, a_tm + kk * 8, bdesc, idesc, acc);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                          umma_ss(d_tmem, desc_hi | (a_lo + (j >> 2) * kBlk16 + (j & 3) * 2),
+                                  desc_hi | (b_lo + (j >> 2) * kBlk16 + (j & 3) * 2), idesc, (pr | j) != 0 ? 1u : 0u);
+                      } else {               // A = H1 / H3 in tensor memory
+                        const uint32_t a_tm = tmem_base + kTmemH + pr * 64;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                          umma_ts(d_tmem, a_tm + j * 8, desc_hi | (b_lo + (j >> 2) * kBlk16 + (j & 3) * 2), idesc,
+                                  (pr | j) != 0 ? 1u : 0u);
                       }
                     }
-                    if (dbg & 32) tl_mark(tl, 0xF20u);
-                    if (C == 1) tc_commit(&B.empty[s]);
-                    else tc_commit_multicast(&B.empty[s], cmask);
-                    if (kb == KB - 1) {
+                    tc_commit_multicast(&B.empty[s], cmask);
+                    if (pr == 3) {
                       if (l == 3) tc_commit(B.out_full);
                       else tc_commit(&B.acc_full[buf]);
                       if (l == 2 && c == 3) tc_commit(B.sh_free);
                     }
-                    if (dbg & 32) tl_mark(tl, 0xF30u);
                   }
                   __syncwarp();
-                  if (dbg & 32) tl_mark(tl, 0xF40u);
                   if (++s == n_ring) { s = 0; ph ^= 1u; }
                 }
                 tl_mark(tl, 0x200u | jl);
@@ -477,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x;    // 0..511: owner of hidden unit `et` of the effective layer-0 bias
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    TlRole tl = tl_role(P, warp == 0 ? 2 : 3, lane == 0 && (warp == 0 || warp == 12));
+    TlRole tl = tl_role(P, dbg, warp == 0 ? 2 : 3, lane == 0 && (warp == 0 || warp == 12));
     uint32_t job = 0;     // global job counter (13 per pass; accumulator buffer = job & 1)
     uint32_t npass = 0;   // running pass counter: layer-0 bias buffer, parity of the once-per-pass barriers
     uint32_t cf0 = 0, cf1 = 0;   // hidden chunks seen in accumulator buffer 0 / 1
@@ -577,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           for (int j = 0; j + 1 < net.n_const; ++j) u = fmaf(wr[j], P.y[obs * P.ydim + j], u);
           const float wt = wr[net.n_const - 1];
           if (p == 0) { myU[0] = u; myWt[0] = wt; } else if (dps) { myU[1] = u; myWt[1] = wt; }
-          if (p == 0) sB0[(npass & 1) * 512 + et] = fmaf(tau_of_step(0, S, P.T), wt, u);
+          if (p == 0) sB0[et] = fmaf(tau_of_step(0, S, P.T), wt, u);   // the previous tile's last pass has drained it
         }
 #pragma unroll
         for (int i = 0; i < kOwn; ++i) {
@@ -607,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         }
       } else {
         const TcNetDev& net = P.net[0];
-        sB0[(npass & 1) * 512 + et] = net.b0[et];
+        sB0[et] = net.b0[et];
         if (valid) {
           for (int k = cgp; k < net.dv; k += 4) {
             float v;
@@ -639,15 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           int jl = 0;
 #pragma unroll 1
           for (int l = 0; l < 3; ++l) {
-            const float* bias = (l == 0) ? sB0 + (npass & 1) * 512 : (l == 1 ? net.b1 : net.b2);
-            if (l == 1 && sampler) {
-              // next pass's effective layer-0 bias b0 + W0[:,y]·y + tau'·W0[:,t] into the other buffer
-              const bool wrap = (p + 1 == n_pass);
-              const float tau_n = wrap ? tau_of_step(step + 1, S, P.T) : tau;
-              const float u = (wrap || !dps) ? myU[0] : myU[1];
-              const float wt = (wrap || !dps) ? myWt[0] : myWt[1];
-              sB0[((npass + 1) & 1) * 512 + et] = fmaf(tau_n, wt, u);
-            }
+            const float* bias = (l == 0) ? sB0 : (l == 1 ? net.b1 : net.b2);
 #pragma unroll 1
             for (int c = 0; c < 4; ++c, ++job, ++jl) {
               const int buf = job & 1;
@@ -705,6 +735,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           tl_mark(tl, 0x310u);
           mbar_wait(B.sh_free, npass & 1u, 0x600);
           if (sampler) {
+            // layer 2 is done, so every row warp has left this pass's layer-0 epilogue: the single bias buffer may take
+            // the next pass's effective layer-0 bias  b0 + W0[:,y]·y + tau'·W0[:,t]
+            const bool wrap = (p + 1 == n_pass);
+            const float tau_n = wrap ? tau_of_step(step + 1, S, P.T) : tau;
+            const float u = (wrap || !dps) ? myU[0] : myU[1];
+            const float wt = (wrap || !dps) ? myWt[0] : myWt[1];
+            sB0[et] = fmaf(tau_n, wt, u);
+          }
+          if (sampler) {
             if (!last_pass) {
               put_x();   // DPS: same x for the likelihood net (H2 overwrote the operand)
               fence_proxy_async_smem();
@@ -721,7 +760,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           tl_mark(tl, 0x300u | 12);
           const uint32_t acc_col = kTmemAcc + (job & 1u) * 128;
           ++job;
-          const float* b3 = sB3 + p * 128;
+          const float* b3 = net.b3;   // zero-padded to 128 floats in the packed image
           if (!sampler) {
             for (int pc = cgp; pc * 8 < P.out_dim; pc += 4) {
               uint32_t v[8];

@@ -16,9 +16,9 @@ grid = 148
 iters, k = 256, 256
 
 
-def run(cg, a_tmem, n, alt=0, stream=0, rnd=0, commit=0, readers=0, math=0):
+def run(cg, a_tmem, n, alt=0, stream=0, rnd=0, commit=0, readers=0, math=0, kbwait=0):
     buf = torch.zeros(4 * grid, dtype=torch.int64, device="cuda")
-    mode = a_tmem | (alt << 1) | (rnd << 2) | (commit << 3) | (readers << 4) | (math << 6)
+    mode = a_tmem | (alt << 1) | (rnd << 2) | (commit << 3) | (readers << 4) | (math << 6) | (kbwait << 8)
     _lib.check(L.dmip_debug_mma_bench2(cg, mode, n, k, iters, stream, grid, src.data_ptr(), buf.data_ptr(), None))
     torch.cuda.synchronize()
     c = buf.cpu().view(grid, 4).double()
@@ -34,8 +34,8 @@ full = len(sys.argv) > 1 and sys.argv[1] == "full"
 for cg in ((1, 2) if full else (1,)):
     for a_tmem in (0, 1):
         for n in (128, 256):
-            for (stream, rnd, commit, readers, math) in [(0, 0, 0, 0, 0), (0, 0, 0, 0, 1), (0, 0, 0, 0, 2), (0, 0, 0, 0, 3),
-                                                         (16384, 1, 1, 2, 3)]:
-                cyc, flop = run(cg, a_tmem, n, 0, stream, rnd, commit, readers, math)
+            for (stream, rnd, commit, readers, math, kbwait) in [(0, 0, 0, 0, 0, 0), (0, 0, 1, 0, 0, 1), (0, 0, 1, 0, 0, 2),
+                                                                 (0, 0, 1, 0, 0, 3), (0, 0, 1, 0, 0, 4), (16384, 1, 1, 2, 3, 1)]:
+                cyc, flop = run(cg, a_tmem, n, 0, stream, rnd, commit, readers, math, kbwait)
                 print(f"cg{cg} A-{'tmem' if a_tmem else 'smem'} N={n:3d} stream={stream:5d} rnd={rnd} commit={commit} readers={readers} "
-                      f"math={math}{'':7s} {cyc:8.1f} {flop:12.0f}")
+                      f"math={math} kbwait={kbwait} {cyc:8.1f} {flop:12.0f}")
