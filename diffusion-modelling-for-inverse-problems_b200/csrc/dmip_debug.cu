@@ -341,6 +341,44 @@ __global__ void __launch_bounds__(64, 1) k_pingpong(int iters, long long* out) {
   }
 }
 
+
+// Wake-up latency of a sleeping waiter as a function of how long it has been asleep: warp 1 arrives `delay` cycles after
+// warp 0 started waiting; out[24 + 4*k + mode] = cycles between the arrive and warp 0 noticing, for delays 2^k * 250.
+__global__ void __launch_bounds__(64, 1) k_wakeup(long long* out) {
+  __shared__ uint64_t bar, go;
+  __shared__ long long t_arrive;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int mode = 0; mode < 3; ++mode) {
+    for (int k = 0; k < 6; ++k) {
+      const long long delay = 250LL << k;
+      if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_init(&go, 1);
+        fence_barrier_init();
+      }
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) mbar_arrive(&go);
+        __syncwarp();
+        wait_mode(mode, &bar, 0);
+        const long long t1 = clock64();
+        __syncwarp();
+        if (lane == 0) out[24 + 4 * k + mode] = t1 - t_arrive;
+      } else {
+        wait_mode(0, &go, 0);
+        const long long t0 = clock64();
+        while (clock64() - t0 < delay) {}
+        if (lane == 0) {
+          t_arrive = clock64();
+          mbar_arrive(&bar);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int stream_bytes, int grid, const void* gsrc,
@@ -393,7 +431,9 @@ int launch_debug_prim_bench(int iters, long long* out, cudaStream_t s) {
   DMIP_CHECK_CUDA(cudaGetLastError());
   k_pingpong<<<1, 64, 0, s>>>(iters, out);
   DMIP_CHECK_CUDA(cudaGetLastError());
-  count_launch(2);
+  k_wakeup<<<1, 64, 0, s>>>(out);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch(3);
   return DMIP_OK;
 }
 

@@ -126,6 +126,12 @@ __device__ __forceinline__ const T* keep(const T* p) {
   return reinterpret_cast<const T*>(keep(static_cast<long long>(reinterpret_cast<uintptr_t>(p))));
 }
 
+// identity the compiler cannot see through or move: ties a computation to this point of the instruction stream
+__device__ __forceinline__ uint32_t pin_here(uint32_t v) {
+  asm volatile("" : "+r"(v) :: "memory");
+  return v;
+}
+
 template <int kRegs>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
@@ -260,9 +266,16 @@ __device__ __forceinline__ void tl_finish_impl(const TlRole& r) {
 #ifdef DMIP_DEBUG
 #define tl_mark(r, code) tl_mark_impl(r, code)
 #define tl_finish(r) tl_finish_impl(r)
+#define job_mark(r, code) ((void)0)
+#elif defined(DMIP_JOBMARKS)
+// production code path + four probes per accumulator job (~90 cycles each): -DDMIP_JOBMARKS timing builds
+#define tl_mark(r, code) ((void)0)
+#define tl_finish(r) tl_finish_impl(r)
+#define job_mark(r, code) tl_mark_impl(r, code)
 #else
 #define tl_mark(r, code) ((void)0)
 #define tl_finish(r) ((void)0)
+#define job_mark(r, code) ((void)0)
 #endif
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -409,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         if (lk == 1u) mbar_wait(&B.acc_empty[buf], ((buf ? ch1 : ch0) - 1u) & 1u, 0x300 + buf);
         else if (lk == 2u) mbar_wait(B.out_empty, (n_out - 1u) & 1u, 0x310 + buf);   // = the latest output job
         tl_mark(tl, 0x100u | jl);
+        job_mark(tl, 0x100u | jl);
         if (is_out) ++n_out; else { if (buf) ++ch1; else ++ch0; }
         lastkind = (lastkind & ~(3u << (2 * buf))) | ((is_out ? 2u : 1u) << (2 * buf));
       };
@@ -420,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             const uint32_t idesc_out = umma_idesc_bf16(128, static_cast<uint32_t>(keep(P.net[p].outpad)));
             constexpr uint32_t idesc_hid = umma_idesc_bf16(128, 128);
             tl_mark(tl, 0xD00u);
+            job_mark(tl, 0xD00u);
             mbar_wait(B.a0_ready, a0_par, 0x200);
             tl_mark(tl, 0xE00u);
             a0_par ^= 1u;
@@ -453,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                 if (half == 1u) { if (++s == n_ring) { s = 0; ph ^= 1u; } }
               }
               tl_mark(tl, 0x200u | jl);
+              job_mark(tl, 0x200u | jl);
             }
             // ---- layers 1..3: K = 512 = 4 ring pairs per chunk, pair-aligned (layer 0 consumed 4 kb0 blocks)
 #pragma unroll 1
@@ -500,6 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                   if (++s == n_ring) { s = 0; ph ^= 1u; }
                 }
                 tl_mark(tl, 0x200u | jl);
+                job_mark(tl, 0x200u | jl);
               }
             }
           }
@@ -562,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           const int q = cgp + 4 * h;
           if (q * 4 < P.ydim) {
             float z[4] = {0.f, 0.f, 0.f, 0.f};
-            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, stp, kStreamObs, q, P.seed, z);
+            if (P.rng_mode == DMIP_RNG_PHILOX) philox_normal4(gidx, pin_here(static_cast<uint32_t>(stp)), kStreamObs, q, P.seed, z);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int jj = q * 4 + e;
@@ -681,10 +698,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 #pragma unroll 1
             for (int c = 0; c < 4; ++c, ++job, ++jl) {
               const int buf = job & 1;
+              job_mark(tl, 0x600u | jl);
               mbar_wait(&B.acc_full[buf], (buf ? cf1 : cf0) & 1u, 0x800 + buf);
               if (buf) ++cf1; else ++cf0;
               tc_fence_after();
               tl_mark(tl, 0x300u | jl);
+              job_mark(tl, 0x300u | jl);
               const uint32_t acc_col = kTmemAcc + buf * 128;
               if (dbg & 8) {   // debug: no epilogue work at all, only the handshakes
                 tc_fence_before();
@@ -697,6 +716,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               else
                 epi_hidden<false, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               tl_mark(tl, 0x400u | jl);
+              job_mark(tl, 0x400u | jl);
               if (sampler && last_pass && !(dbg & 16)) {
                 if (l == 1) {
                   // ---- in the shadow of the MMA-bound layers, one state piece per accumulator chunk: the part of the
@@ -706,10 +726,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                   for (int i = 0; i < kOwn; ++i) {
                     if (i == c && i < n_own) {
                       const int pc = piece_lo + i;
+                      // the output layer's bias joins here too (x += ca * b3), off the step boundary's critical path
+                      const float ca = P.delta * (dps ? beta : sb);
+                      const float4 q0 = *reinterpret_cast<const float4*>(net.b3 + pc * 8);
+                      const float4 q1 = *reinterpret_cast<const float4*>(net.b3 + pc * 8 + 4);
+                      const float b3v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                       float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
                       if (P.rng_mode == DMIP_RNG_PHILOX) {
-                        philox_normal4(gidx, step, kStreamState, pc * 2, P.seed, za);
-                        philox_normal4(gidx, step, kStreamState, pc * 2 + 1, P.seed, zb);
+                        // `here` pins the draw to this point of the schedule: the generator only depends on
+                        // (particle, step, piece), and the compiler otherwise hoists ALL of a step's draws to the top
+                        // of the step — 7800 cycles in front of the layer-0 epilogue instead of in the MMAs' shadow
+                        const uint32_t here = pin_here(static_cast<uint32_t>(step));
+                        philox_normal4(gidx, here, kStreamState, pc * 2, P.seed, za);
+                        philox_normal4(gidx, here, kStreamState, pc * 2 + 1, P.seed, zb);
                       }
 #pragma unroll
                       for (int e = 0; e < 8; ++e) {
@@ -720,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                                     ? (e < 4 ? za[e & 3] : zb[e & 3])
                                     : P.noise[(static_cast<long long>(step) * n_total + grow) * xdim + j];
                         const float xv = xs[i * 8 + e];
-                        xs[i * 8 + e] = xv + P.delta * (0.5f * beta * xv) + (P.sqrt_delta * sb) * eps;
+                        xs[i * 8 + e] = xv + P.delta * (0.5f * beta * xv) + (P.sqrt_delta * sb) * eps + ca * b3v[e];
                       }
                     }
                   }
@@ -758,6 +787,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           mbar_wait(B.out_full, npass & 1u, 0x700);
           tc_fence_after();
           tl_mark(tl, 0x300u | 12);
+          job_mark(tl, 0x300u | 12);
           const uint32_t acc_col = kTmemAcc + (job & 1u) * 128;
           ++job;
           const float* b3 = net.b3;   // zero-padded to 128 floats in the packed image
@@ -793,13 +823,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             for (int i = 0; i < kOwn; ++i) {
               if (i < n_own) {
                 const int pc = piece_lo + i;
-                const float4 q0 = *reinterpret_cast<const float4*>(b3 + pc * 8);
-                const float4 q1 = *reinterpret_cast<const float4*>(b3 + pc * 8 + 4);
-                const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const int j = pc * 8 + e;
-                  float a = __uint_as_float(v[i][e]) + bb[e];
+                  float a = __uint_as_float(v[i][e]);   // + b3: already folded into x by the pre-update
                   if (dps) a += stash[dps ? e : 0];
                   xs[i * 8 + e] = (valid && j < xdim) ? fmaf(ca, a, xs[i * 8 + e]) : 0.f;
                 }
@@ -829,6 +856,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               __syncwarp();
               if (lane == 0) mbar_arrive(B.a0_ready);
               tl_mark(tl, 0x500u);
+              job_mark(tl, 0x500u);
             }
           }
         }  // pass

@@ -13,7 +13,7 @@ names = ["try_wait (completed phase)", "elect + arrive", "arrive + wait for it",
          "commit + wait for it", "tcgen05.fence::after", "3 constant-bank loads", "issuer skeleton (wait+fence+commit)",
          "producer skeleton (wait+expect_tx)"]
 iters = 2000
-out = torch.zeros(32, dtype=torch.int64, device="cuda")
+out = torch.zeros(64, dtype=torch.int64, device="cuda")
 for _ in range(2):
     _lib.check(L.dmip_debug_prim_bench(iters, out.data_ptr(), None))
     torch.cuda.synchronize()
@@ -22,3 +22,6 @@ for n, v in zip(names, out.cpu().tolist()):
 r = out.cpu().tolist()
 for i, n in enumerate(["try_wait (hardware suspend)", "test_wait spin", "try_wait, 0 ns suspend hint"]):
     print(f"ping-pong round trip, {n:30s} {r[20 + i] / iters:8.1f} cycles")
+print("wake-up latency (cycles) after sleeping for D cycles:   try_wait   test_wait spin   try_wait hint 0")
+for k in range(6):
+    print(f"  D = {250 << k:6d}: {r[24 + 4 * k]:10d} {r[24 + 4 * k + 1]:14d} {r[24 + 4 * k + 2]:16d}")
