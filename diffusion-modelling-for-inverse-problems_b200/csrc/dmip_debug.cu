@@ -379,6 +379,51 @@ __global__ void __launch_bounds__(64, 1) k_wakeup(long long* out) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ XU pipe rates
+// 16 warps per SM each issue `iters` x 8 independent instructions of one kind; out[40 + kind] = cycles.
+// kind 0 MUFU.TANH, 1 MUFU.EX2, 2 MUFU.RCP, 3 F2FP.BF16 pack, 4 FFMA, 5 MUFU.TANH + F2FP interleaved (epilogue mix)
+template <int kind>
+__device__ __forceinline__ long long xu_loop(int iters, float (&a)[8], uint32_t& pk) {
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (kind == 0) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[j]));
+      else if (kind == 1) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+      else if (kind == 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+      else if (kind == 3) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[j]), "f"(a[(j + 1) & 7])); pk ^= r; }
+      else if (kind == 4) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(a[j]));
+      else {
+        asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[j]));
+        if (j & 1) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[j]), "f"(a[j - 1])); pk ^= r; }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  return t1 - t0;
+}
+
+__global__ void __launch_bounds__(512, 1) k_xu_rate(int iters, long long* out, float* sink) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = threadIdx.x * 1e-3f + j * 0.01f;
+  uint32_t pk = 0;
+  long long t[6];
+  t[0] = xu_loop<0>(iters, a, pk);
+  t[1] = xu_loop<1>(iters, a, pk);
+  t[2] = xu_loop<2>(iters, a, pk);
+  t[3] = xu_loop<3>(iters, a, pk);
+  t[4] = xu_loop<4>(iters, a, pk);
+  t[5] = xu_loop<5>(iters, a, pk);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 6; ++k) out[40 + k] = t[k];
+  if (a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7] + __uint_as_float(pk) == 123.f) sink[0] = a[0];
+}
+
 }  // namespace
 
 int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int stream_bytes, int grid, const void* gsrc,
@@ -433,7 +478,9 @@ int launch_debug_prim_bench(int iters, long long* out, cudaStream_t s) {
   DMIP_CHECK_CUDA(cudaGetLastError());
   k_wakeup<<<1, 64, 0, s>>>(out);
   DMIP_CHECK_CUDA(cudaGetLastError());
-  count_launch(3);
+  k_xu_rate<<<1, 512, 0, s>>>(iters, out, reinterpret_cast<float*>(out + 60));
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch(4);
   return DMIP_OK;
 }
 

@@ -58,7 +58,8 @@ constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
 constexpr int kOffH = 0;
 constexpr int kOffB = kOffH + kHBytes;
 constexpr int kOffB0 = kOffB + kNumSlots * kStageBytes;   // float[512] effective layer-0 bias of the coming pass
-constexpr int kOffBar = kOffB0 + 2048;
+constexpr int kOffB3 = kOffB0 + 2048;                     // float[128] output-layer bias (DPS: [0,8) prior net, [8,16) likelihood net)
+constexpr int kOffBar = kOffB3 + 512;
 constexpr int kNumBars = 2 * kNumPairs + 2 + 2 + 1 + 1 + 1 + 4 + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
@@ -156,7 +157,9 @@ template <bool kDoubleTanh>
 __device__ __forceinline__ void tanh_pack16(const uint32_t (&v)[16], const float* __restrict__ bias, uint32_t (&pk)[8]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 bq = *reinterpret_cast<const float4*>(bias + q * 4);
+    // layer 0 (double tanh): the per-step effective bias in shared memory; layers 1-2: global, read-only path
+    const float4 bq = kDoubleTanh ? *reinterpret_cast<const float4*>(bias + q * 4)
+                                  : __ldg(reinterpret_cast<const float4*>(bias + q * 4));
     float a[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   uint8_t* sH = smem + kOffH;
   uint8_t* sB = smem + kOffB;
   float* sB0 = reinterpret_cast<float*>(smem + kOffB0);
+  float* sB3 = reinterpret_cast<float*>(smem + kOffB3);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   Bars B;
@@ -327,6 +331,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_holder);
   // zero the activation region once: layer-0 K padding must be finite (it meets zero weights)
   for (int i = threadIdx.x; i < kHBytes / 16; i += kThreads) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 128; i += kThreads) {
+    if (dps) sB3[i] = i < 16 ? P.net[i >> 3].b3[i & 7] : 0.f;
+    else sB3[i] = P.net[0].b3[i];   // zero-padded to 128 floats in the packed image
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -728,8 +736,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                       const int pc = piece_lo + i;
                       // the output layer's bias joins here too (x += ca * b3), off the step boundary's critical path
                       const float ca = P.delta * (dps ? beta : sb);
-                      const float4 q0 = *reinterpret_cast<const float4*>(net.b3 + pc * 8);
-                      const float4 q1 = *reinterpret_cast<const float4*>(net.b3 + pc * 8 + 4);
+                      const float* b3s = sB3 + (dps ? 8 : pc * 8);   // DPS: one piece, the likelihood net's bias
+                      const float4 q0 = *reinterpret_cast<const float4*>(b3s);
+                      const float4 q1 = *reinterpret_cast<const float4*>(b3s + 4);
                       const float b3v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                       float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
                       if (P.rng_mode == DMIP_RNG_PHILOX) {
@@ -790,8 +799,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           job_mark(tl, 0x300u | 12);
           const uint32_t acc_col = kTmemAcc + (job & 1u) * 128;
           ++job;
-          const float* b3 = net.b3;   // zero-padded to 128 floats in the packed image
           if (!sampler) {
+            const float* b3 = net.b3;   // zero-padded to 128 floats in the packed image
             for (int pc = cgp; pc * 8 < P.out_dim; pc += 4) {
               uint32_t v[8];
               tmem_ld8(lane_taddr + acc_col + pc * 8, v);
@@ -808,11 +817,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               tmem_ld8(lane_taddr + acc_col, v);
               tc_wait_ld();
 #pragma unroll
-              for (int e = 0; e < 8; ++e) stash[dps ? e : 0] = __uint_as_float(v[e]) + b3[e];
+              for (int e = 0; e < 8; ++e) stash[dps ? e : 0] = __uint_as_float(v[e]) + sB3[e];
             }
           } else {
             // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
-            // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2
+            // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2.
+            // The bias b3 is already in x (pre-update).  No masks: padded columns meet zero weights and zero noise and
+            // stay zero; rows past the end of the tile integrate a harmless deterministic path and are never written.
             const float ca = P.delta * (dps ? beta : sb);
             uint32_t v[kOwn][8];
 #pragma unroll
@@ -822,13 +833,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < kOwn; ++i) {
               if (i < n_own) {
-                const int pc = piece_lo + i;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  const int j = pc * 8 + e;
-                  float a = __uint_as_float(v[i][e]);   // + b3: already folded into x by the pre-update
+                  float a = __uint_as_float(v[i][e]);
                   if (dps) a += stash[dps ? e : 0];
-                  xs[i * 8 + e] = (valid && j < xdim) ? fmaf(ca, a, xs[i * 8 + e]) : 0.f;
+                  xs[i * 8 + e] = fmaf(ca, a, xs[i * 8 + e]);
                 }
               }
             }
