@@ -347,3 +347,70 @@ def case_posterior_loss(name):
             print("  grad mismatch:", prefix, str(e)[:300])
             err = max(err, 1.0)
     return err, 5e-4, dict(loss=loss.item(), ref=ref)
+
+
+# ------------------------------------------------------------------------------------------- sharding / statistics
+def case_shards_are_bit_identical(precision="bf16"):
+    """Philox counters are keyed by the GLOBAL particle index: integrating [0,N) in one call or as three ragged shards
+    with gidx_base = shard start gives bit-identical samples (what makes multi-GPU runs independent of the GPU count)."""
+    m = trained_model()
+    fx = load_golden("sampler_trained_cde_linear")
+    N, S, seed = 1000, 40, 99
+    full = m(fx["y"], num_samples=N, num_steps=S, precision=precision, seed=seed, return_tensor=True)
+    parts, start = [], 0
+    for count in (300, 129, 571):
+        parts.append(m(fx["y"], num_samples=count, num_steps=S, precision=precision, seed=seed, gidx_base=start,
+                       return_tensor=True))
+        start += count
+    err = (torch.cat(parts) - full).abs().max().item()
+    # the same through the public sharding helper (world size 1 -> the whole range)
+    from dmip.distributed import sample_sharded
+    one = sample_sharded(m, fx["y"], num_samples=N, num_steps=S, seed=seed, precision=precision)
+    err = max(err, (one - full).abs().max().item())
+    return err, 0.0, {}
+
+
+def case_batched_observations():
+    """y of shape (n_obs, ydim): all observations in one launch == one call per observation with the matching
+    global-index offset (config 4 layout: observation o occupies rows [o N, (o+1) N))."""
+    m = trained_model()
+    g = torch.Generator().manual_seed(5)
+    ys = torch.randn(3, 2, generator=g)
+    N, S, seed = 200, 30, 7
+    batched = m(ys, num_samples=N, num_steps=S, seed=seed, return_tensor=True)
+    assert batched.shape == (3, N, 2)
+    err = 0.0
+    for o in range(3):
+        single = m(ys[o], num_samples=N, num_steps=S, seed=seed, gidx_base=o * N, return_tensor=True)
+        err = max(err, (single - batched[o]).abs().max().item())
+    return err, 0.0, {}
+
+
+def case_posterior_statistics():
+    """Statistics of the bf16 tensor-core sampler on the DSM-trained linear CDE, 65,536 particles, reference-default
+    200 steps, in-kernel Philox noise, against (a) the fp32 kernel on the same noise and (b) the analytic posterior
+    (linear_problem.py:41-46).  Tolerances: |mean shift| <= 3e-3 and |std ratio - 1| <= 5e-3 vs fp32 (SURVEY.md §8d);
+    the reference's own quality metric — histogram KL with 75 bins on [-3.5, 3.5]^2 (main_diffusion_linear.py:86-117) —
+    between the two precisions <= 2e-3 (two independent fp32 runs of this size differ by ~3e-2: sampling noise);
+    mean / covariance vs the analytic posterior within the trained model's own error (0.08 / 0.05)."""
+    import numpy as np
+    fx = load_golden("sampler_trained_cde_linear")
+    m = trained_model()
+    N, S, seed = 65536, 200, 2024
+    lo = m(fx["y"], num_samples=N, num_steps=S, precision="bf16", seed=seed)
+    hi = m(fx["y"], num_samples=N, num_steps=S, precision="fp32", seed=seed)
+    dmean = float(np.abs(lo.mean(0) - hi.mean(0)).max())
+    rstd = float(np.abs(lo.std(0) / hi.std(0) - 1).max())
+
+    def hist(a):
+        h, _ = np.histogramdd(a, bins=(75, 75), range=((-3.5, 3.5), (-3.5, 3.5)))
+        h = h / h.sum() + 1e-10
+        return h / h.sum()
+
+    p, q = hist(hi), hist(lo)
+    kl = float((p * np.log(p / q)).sum())
+    post_mean, post_cov = fx["post_mean"].numpy(), fx["post_cov"].numpy()
+    emean = float(np.abs(lo.mean(0) - post_mean).max())
+    ecov = float(np.abs(np.cov(lo.T) - post_cov).max())
+    err = max(dmean / 3e-3, rstd / 5e-3, kl / 2e-3, emean / 0.08, ecov / 0.05)
+    return err, 1.0, dict(dmean=dmean, rstd=rstd, kl=kl, emean=emean, ecov=ecov)

@@ -48,6 +48,10 @@ CASES = [
     ("surr_vjp", "case_surrogate_vjp()"),
     ("loss_posterior_scat", "case_posterior_loss('loss_posterior_scat')"),
     ("loss_posterior_small", "case_posterior_loss('loss_posterior_small')"),
+    ("shards_bf16", "case_shards_are_bit_identical('bf16')"),
+    ("shards_fp32", "case_shards_are_bit_identical('fp32')"),
+    ("batched_obs", "case_batched_observations()"),
+    ("posterior_stats", "case_posterior_statistics()"),
 ]
 
 TEMPLATE = """

@@ -47,3 +47,16 @@ def test_sampler_layer0_split_modes(split):
 @pytest.mark.parametrize("mode", ["injected", "philox"])
 def test_sampler_trained_reference_default_steps(precision, mode):
     _ok(gc.case_sampler_trained(precision, mode))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_shards_reproduce_the_single_gpu_run_bit_for_bit(precision):
+    _ok(gc.case_shards_are_bit_identical(precision))
+
+
+def test_batched_observations_match_per_observation_calls():
+    _ok(gc.case_batched_observations())
+
+
+def test_posterior_statistics_preserved_at_64k_particles():
+    _ok(gc.case_posterior_statistics())
