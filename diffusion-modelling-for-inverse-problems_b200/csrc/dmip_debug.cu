@@ -396,9 +396,37 @@ __device__ __forceinline__ long long xu_loop(int iters, float (&a)[8], uint32_t&
       else if (kind == 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
       else if (kind == 3) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[j]), "f"(a[(j + 1) & 7])); pk ^= r; }
       else if (kind == 4) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(a[j]));
-      else {
+      else if (kind == 5) {
         asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[j]));
         if (j & 1) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[j]), "f"(a[j - 1])); pk ^= r; }
+      } else if (kind == 6) {   // 32 x 32 -> 64 multiply (IMAD.WIDE.U32): the Philox round primitive
+        unsigned long long w;
+        uint32_t x = __float_as_uint(a[j]);
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x), "r"(0xD2511F53u));
+        a[j] = __uint_as_float(static_cast<uint32_t>(w) ^ static_cast<uint32_t>(w >> 32));
+      } else if (kind == 7) {   // mul.hi.u32 alone
+        uint32_t x = __float_as_uint(a[j]), h;
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0xD2511F53u));
+        a[j] = __uint_as_float(h);
+      } else if (kind == 8) {   // mul.lo.u32 alone
+        uint32_t x = __float_as_uint(a[j]), h;
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(0xD2511F53u));
+        a[j] = __uint_as_float(h);
+      } else if (kind == 9) {   // u32 -> f32 conversion
+        uint32_t x = __float_as_uint(a[j]);
+        asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(a[j]) : "r"(x));
+      } else if (kind == 10) {  // packed half tanh: two activations per MUFU instruction
+        uint32_t x = __float_as_uint(a[j]);
+        asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(x));
+        a[j] = __uint_as_float(x);
+      } else if (kind == 11) {  // packed bf16 tanh
+        uint32_t x = __float_as_uint(a[j]);
+        asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(x));
+        a[j] = __uint_as_float(x);
+      } else {                  // f32 pair -> f16x2 pack
+        uint32_t r;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[j]), "f"(a[(j + 1) & 7]));
+        pk ^= r;
       }
     }
   }
@@ -412,7 +440,14 @@ __global__ void __launch_bounds__(512, 1) k_xu_rate(int iters, long long* out, f
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = threadIdx.x * 1e-3f + j * 0.01f;
   uint32_t pk = 0;
-  long long t[6];
+  long long t[13];
+  t[10] = xu_loop<10>(iters, a, pk);
+  t[11] = xu_loop<11>(iters, a, pk);
+  t[12] = xu_loop<12>(iters, a, pk);
+  t[6] = xu_loop<6>(iters, a, pk);
+  t[7] = xu_loop<7>(iters, a, pk);
+  t[8] = xu_loop<8>(iters, a, pk);
+  t[9] = xu_loop<9>(iters, a, pk);
   t[0] = xu_loop<0>(iters, a, pk);
   t[1] = xu_loop<1>(iters, a, pk);
   t[2] = xu_loop<2>(iters, a, pk);
@@ -420,7 +455,7 @@ __global__ void __launch_bounds__(512, 1) k_xu_rate(int iters, long long* out, f
   t[4] = xu_loop<4>(iters, a, pk);
   t[5] = xu_loop<5>(iters, a, pk);
   if (threadIdx.x == 0)
-    for (int k = 0; k < 6; ++k) out[40 + k] = t[k];
+    for (int k = 0; k < 13; ++k) out[40 + k] = t[k];
   if (a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7] + __uint_as_float(pk) == 123.f) sink[0] = a[0];
 }
 

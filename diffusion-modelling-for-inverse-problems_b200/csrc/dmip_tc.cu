@@ -173,10 +173,17 @@ __device__ __forceinline__ void tanh_pack16(const uint32_t (&v)[16], const float
   }
 }
 
-template <bool kDoubleTanh, bool kToTmem>
+struct NoExtra {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// `extra` runs between the accumulator read and the tanh math, in the same straight-line block: independent ALU work
+// placed there (the Philox draw of the state pre-update) is interleaved by the scheduler with the MUFU-bound tanh
+// sequence instead of running after it.
+template <bool kDoubleTanh, bool kToTmem, class Extra = NoExtra>
 __device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col, int cgp, int row, int chunk, int lane,
                                            const float* __restrict__ bias, uint8_t* sH, uint64_t* acc_empty,
-                                           uint64_t* hready) {
+                                           uint64_t* hready, Extra extra = NoExtra()) {
   uint32_t v0[16], v1[16];
   tmem_ld16(lane_taddr + acc_col + cgp * 32, v0);
   tmem_ld16(lane_taddr + acc_col + cgp * 32 + 16, v1);
@@ -184,6 +191,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(acc_empty);  // this warp's part of the chunk is in registers: the buffer may be reused
+  extra();
   const int n0 = chunk * 128 + cgp * 32;
   uint32_t pk0[8], pk1[8];
   tanh_pack16<kDoubleTanh>(v0, bias + n0, pk0);
@@ -698,6 +706,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         for (int p = 0; p < n_pass; ++p, ++npass) {
           const TcNetDev& net = P.net[p];
           const bool last_pass = (p == n_pass - 1);
+          const bool fuse_draw = sampler && last_pass && !(dbg & 16) && P.rng_mode == DMIP_RNG_PHILOX;
+          float zdraw[4] = {0.f, 0.f, 0.f, 0.f}, zdraw4[4] = {0.f, 0.f, 0.f, 0.f};   // noise of the piece updated after chunk c
           // ---- layers 0..2
           int jl = 0;
 #pragma unroll 1
@@ -719,8 +729,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                 if (lane == 0) { mbar_arrive(&B.acc_empty[buf]); mbar_arrive(&B.hready[c]); }
               } else if (l == 0)
                 epi_hidden<true, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
-              else if (l == 1)
-                epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+              else if (l == 1) {
+                if (fuse_draw && c < kOwn) {
+                  // the Philox / Box-Muller draw of state piece c rides inside the epilogue's instruction stream
+                  const int pc = piece_lo + c;
+                  epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c],
+                                           [&]() {
+                                             const uint32_t here = pin_here(static_cast<uint32_t>(step));
+                                             philox_normal4(gidx, here, kStreamState, pc * 2, P.seed, zdraw);
+                                             philox_normal4(gidx, here, kStreamState, pc * 2 + 1, P.seed, zdraw4);
+                                           });
+                } else {
+                  epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+                }
+              }
               else
                 epi_hidden<false, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               tl_mark(tl, 0x400u | jl);
@@ -740,15 +762,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                       const float4 q0 = *reinterpret_cast<const float4*>(b3s);
                       const float4 q1 = *reinterpret_cast<const float4*>(b3s + 4);
                       const float b3v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                      float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
-                      if (P.rng_mode == DMIP_RNG_PHILOX) {
-                        // `here` pins the draw to this point of the schedule: the generator only depends on
-                        // (particle, step, piece), and the compiler otherwise hoists ALL of a step's draws to the top
-                        // of the step — 7800 cycles in front of the layer-0 epilogue instead of in the MMAs' shadow
-                        const uint32_t here = pin_here(static_cast<uint32_t>(step));
-                        philox_normal4(gidx, here, kStreamState, pc * 2, P.seed, za);
-                        philox_normal4(gidx, here, kStreamState, pc * 2 + 1, P.seed, zb);
-                      }
+                      // The draw itself was made inside this chunk's epilogue (fuse_draw); pin_here ties it to that
+                      // point of the schedule: the generator only depends on (particle, step, piece), and the compiler
+                      // otherwise hoists ALL of a step's draws to the top of the step — 7800 cycles in front of the
+                      // layer-0 epilogue instead of in the MMAs' shadow.
+                      float za[4], zb[4];
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) { za[e] = zdraw[e]; zb[e] = zdraw4[e]; }
 #pragma unroll
                       for (int e = 0; e < 8; ++e) {
                         const int j = pc * 8 + e;

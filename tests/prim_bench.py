@@ -26,6 +26,8 @@ print("wake-up latency (cycles) after sleeping for D cycles:   try_wait   test_w
 for k in range(6):
     print(f"  D = {250 << k:6d}: {r[24 + 4 * k]:10d} {r[24 + 4 * k + 1]:14d} {r[24 + 4 * k + 2]:16d}")
 print("XU / FMA pipe rates with 16 warps (4 per scheduler), lanes per clock per SM:")
-for i, n in enumerate(["MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "F2FP.BF16 pack", "FFMA", "TANH + pack mix (1.5 instr)"]):
+for i, n in enumerate(["MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "F2FP.BF16 pack", "FFMA", "TANH + pack mix (1.5 instr)",
+                       "mul.wide.u32 (IMAD.WIDE)", "mul.hi.u32", "mul.lo.u32", "cvt.rn.f32.u32 (I2F)",
+                       "tanh.approx.f16x2 (2 per instr)", "tanh.approx.bf16x2 (2 per instr)", "cvt.rn.f16x2.f32 pack"]):
     cyc = r[40 + i]
     print(f"  {n:28s} {cyc / (iters * 8):7.2f} cycles per warp-instruction per scheduler x4 warps -> {512 * iters * 8 / cyc:6.1f} lanes/clk/SM")
