@@ -43,8 +43,8 @@ constexpr int kNumPairs = kNumSlots / 2;   // a barrier wait costs ~85 cycles in
 constexpr int kPairBytes = 2 * kStageBytes;  // queues only ~1 MMA ahead, so waits per MMA decide the MMA rate
 constexpr int kHBytes = 131072;      // 128 rows x 512 k x bf16 = 8 K-blocks
 constexpr int kThreads = 640;        // warps: 0-15 row warps (epilogue + state), 16 producer, 17 MMA, 18-19 idle
-constexpr int kRegsSmall = 40;       // registers are allocated per 4 warps (18 warps are billed as 20), so the kernel
-constexpr int kRegsRow = 104;        // launches with 640 x 96 and setmaxnreg moves 128 x 56 of them to the row warps
+constexpr int kRegsSmall = 32;       // registers are allocated per 4 warps (18 warps are billed as 20), so the kernel
+constexpr int kRegsRow = 112;        // launches with 640 x 96 and setmaxnreg moves 128 x 64 of them to the row warps
 constexpr int kNumRowWarps = 16;
 constexpr int kRowThreads = 512;
 constexpr int kProducerWarp = 16;
@@ -193,22 +193,24 @@ __device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col
   if (lane == 0) mbar_arrive(acc_empty);  // this warp's part of the chunk is in registers: the buffer may be reused
   extra();
   const int n0 = chunk * 128 + cgp * 32;
-  uint32_t pk0[8], pk1[8];
-  tanh_pack16<kDoubleTanh>(v0, bias + n0, pk0);
-  tanh_pack16<kDoubleTanh>(v1, bias + n0 + 16, pk1);
+  uint32_t pk[8];   // one 16-column half at a time: its packed result is stored before the next half is computed
   if (kToTmem) {
-    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1), pk0);
-    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1) + 8, pk1);
+    tanh_pack16<kDoubleTanh>(v0, bias + n0, pk);
+    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1), pk);
+    tanh_pack16<kDoubleTanh>(v1, bias + n0 + 16, pk);
+    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1) + 8, pk);
     tc_wait_st();
     tc_fence_before();
   } else {
     // K index of these 32 values: n0 .. n0+31  ->  K-block chunk*2 + (cgp>>1), 16-byte chunks (cgp&1)*4 .. +3
     uint8_t* rowp = sH + (chunk * 2 + (cgp >> 1)) * kStageBytes + (row >> 3) * 1024 + (row & 7) * 128;
     const int c0 = (cgp & 1) * 4;
-    st_shared_v4(rowp + (((c0 + 0) ^ (row & 7)) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
-    st_shared_v4(rowp + (((c0 + 1) ^ (row & 7)) << 4), pk0[4], pk0[5], pk0[6], pk0[7]);
-    st_shared_v4(rowp + (((c0 + 2) ^ (row & 7)) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
-    st_shared_v4(rowp + (((c0 + 3) ^ (row & 7)) << 4), pk1[4], pk1[5], pk1[6], pk1[7]);
+    tanh_pack16<kDoubleTanh>(v0, bias + n0, pk);
+    st_shared_v4(rowp + (((c0 + 0) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(rowp + (((c0 + 1) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+    tanh_pack16<kDoubleTanh>(v1, bias + n0 + 16, pk);
+    st_shared_v4(rowp + (((c0 + 2) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(rowp + (((c0 + 3) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
     fence_proxy_async_smem();
   }
   __syncwarp();
@@ -769,16 +771,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                       float za[4], zb[4];
 #pragma unroll
                       for (int e = 0; e < 4; ++e) { za[e] = zdraw[e]; zb[e] = zdraw4[e]; }
+                      const float kx = P.delta * 0.5f * beta, ke = P.sqrt_delta * sb;
 #pragma unroll
                       for (int e = 0; e < 8; ++e) {
                         const int j = pc * 8 + e;
                         float eps = 0.f;
                         if (valid && j < xdim)
-                          eps = P.rng_mode == DMIP_RNG_PHILOX
-                                    ? (e < 4 ? za[e & 3] : zb[e & 3])
-                                    : P.noise[(static_cast<long long>(step) * n_total + grow) * xdim + j];
+                          eps = fuse_draw ? (e < 4 ? za[e & 3] : zb[e & 3])
+                                          : P.noise[(static_cast<long long>(step) * n_total + grow) * xdim + j];
                         const float xv = xs[i * 8 + e];
-                        xs[i * 8 + e] = xv + P.delta * (0.5f * beta * xv) + (P.sqrt_delta * sb) * eps + ca * b3v[e];
+                        xs[i * 8 + e] = fmaf(kx, xv, xv) + fmaf(ke, eps, ca * b3v[e]);
                       }
                     }
                   }
@@ -866,6 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(B.out_empty);
           tl_mark(tl, 0x400u | 12);
+          job_mark(tl, 0x400u | 12);
           if (sampler && last_pass) {
             if (last_step) {
               if (valid) {
