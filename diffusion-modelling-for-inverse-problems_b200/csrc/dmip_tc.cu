@@ -367,12 +367,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 #endif
   constexpr int dbg = DMIP_EXP;
 #endif
-  const long long n_tiles = keep(P.n_tiles);
+  const int n_tiles = keep(static_cast<int>(P.n_tiles));   // < 2^31 tiles (checked on the host)
   const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
   if (C > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive / multicast
-  const long long tile_first = static_cast<long long>(blockIdx.x / C) * C;
-  const long long tile_stride = keep(static_cast<long long>(gridDim.x));
+  const int tile_first = static_cast<int>(blockIdx.x / C) * C;
+  const int tile_stride = keep(static_cast<int>(gridDim.x));
 
   const int n_pass = keep(P.n_nets);
   const int S = keep(P.S);
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       uint32_t ph = 0;
       TlRole tl = tl_role(P, dbg, 0, lane == 0);
       constexpr uint32_t part = kPairBytes / C;
-      for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
+      for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
         for (int step = 0; step < n_steps; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const uint8_t* src = keep(P.net[p].stages);
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         lastkind = (lastkind & ~(3u << (2 * buf))) | ((is_out ? 2u : 1u) << (2 * buf));
       };
 
-      for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
+      for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
         for (int step = 0; step < n_steps; ++step) {
           for (int p = 0; p < n_pass; ++p) {
             const int net_kb0 = keep(P.net[p].kb0), net_ksteps0 = keep(P.net[p].ksteps0);
@@ -555,7 +555,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     uint32_t npass = 0;   // running pass counter: layer-0 bias buffer, parity of the once-per-pass barriers
     uint32_t cf0 = 0, cf1 = 0;   // hidden chunks seen in accumulator buffer 0 / 1
     const float dbeta = P.bmax - P.bmin;
-    const long long n_total = static_cast<long long>(P.n_obs) * P.n_per_obs;
     const TcNetDev& net_last = P.net[n_pass - 1];
     const int dvp = (net_last.dv + 7) & ~7;
     const int split = P.net[0].split;
@@ -575,12 +574,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     for (int j = 0; j < (cdiffe ? 8 : 1); ++j) yt[j] = 0.f;
     myU[0] = myU[1] = myWt[0] = myWt[1] = 0.f;
 
-    for (long long tb = tile_first; tb < n_tiles; tb += tile_stride) {
+    for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
       // a cluster whose last round has fewer tiles than CTAs still runs every CTA (lock-step), on masked rows
-      const bool tile_ok = tb + crank < n_tiles;
-      const long long tile = tile_ok ? tb + crank : n_tiles - 1;
+      const bool tile_ok = tb + static_cast<int>(crank) < n_tiles;
+      const int tile = tile_ok ? tb + static_cast<int>(crank) : n_tiles - 1;
       const int obs = static_cast<int>(tile / P.tiles_per_obs);
-      const long long prow = (tile % P.tiles_per_obs) * kTileM + row;
+      const long long prow = static_cast<long long>(tile % P.tiles_per_obs) * kTileM + row;
       const bool valid = tile_ok && prow < P.n_per_obs;
       const long long grow = static_cast<long long>(obs) * P.n_per_obs + prow;
       const unsigned long long gidx = P.gidx_base + static_cast<unsigned long long>(grow);
@@ -605,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               if (valid && jj < P.ydim) {
                 const float eta = P.rng_mode == DMIP_RNG_PHILOX
                                       ? z[e]
-                                      : P.ynoise[(static_cast<long long>(stp) * n_total + grow) * P.ydim + jj];
+                                      : P.ynoise[(static_cast<long long>(stp) * (static_cast<long long>(P.n_obs) * P.n_per_obs) + grow) * P.ydim + jj];
                 v = fmaf(sd, eta, alpha * P.y[obs * P.ydim + jj]);
               }
               yt[cdiffe ? h * 4 + e : 0] = v;
@@ -731,32 +730,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                 if (lane == 0) { mbar_arrive(&B.acc_empty[buf]); mbar_arrive(&B.hready[c]); }
               } else if (l == 0)
                 epi_hidden<true, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
-              else if (l == 1) {
-                if (fuse_draw && c < kOwn) {
-                  // the Philox / Box-Muller draw of state piece c rides inside the epilogue's instruction stream
-                  const int pc = piece_lo + c;
-                  epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c],
-                                           [&]() {
-                                             const uint32_t here = pin_here(static_cast<uint32_t>(step));
-                                             philox_normal4(gidx, here, kStreamState, pc * 2, P.seed, zdraw);
-                                             philox_normal4(gidx, here, kStreamState, pc * 2 + 1, P.seed, zdraw4);
-                                           });
+              else {
+                // State piece i is drawn and pre-updated at chunk (l, c) = (1 + i/2, 2 (i%2)): never in two consecutive
+                // chunks and never in a layer's last chunk, whose epilogue the next layer's MMAs are waiting for.
+                const int ip = (l - 1) * 2 + (c >> 1);
+                const bool draw_here = fuse_draw && (c & 1) == 0 && ip < kOwn;
+                const int pc = piece_lo + ip;
+                // the Philox / Box-Muller draw rides inside the epilogue's instruction stream
+                auto draw = [&]() {
+                  const uint32_t here = pin_here(static_cast<uint32_t>(step));
+                  philox_normal4(gidx, here, kStreamState, pc * 2, P.seed, zdraw);
+                  philox_normal4(gidx, here, kStreamState, pc * 2 + 1, P.seed, zdraw4);
+                };
+                if (l == 1) {
+                  if (draw_here)
+                    epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c], draw);
+                  else
+                    epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
                 } else {
-                  epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
+                  if (draw_here)
+                    epi_hidden<false, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c], draw);
+                  else
+                    epi_hidden<false, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
                 }
               }
-              else
-                epi_hidden<false, true>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c]);
               tl_mark(tl, 0x400u | jl);
               job_mark(tl, 0x400u | jl);
               if (sampler && last_pass && !(dbg & 16)) {
-                if (l == 1) {
+                if (l >= 1 && (c & 1) == 0) {
                   // ---- in the shadow of the MMA-bound layers, one state piece per accumulator chunk: the part of the
                   // Euler–Maruyama update that does not need the net output,
                   //   x <- x + delta*beta/2*x + sqrt(delta*beta)*eps            (models/diffusion.py:42, sdes.py:77-87)
 #pragma unroll
                   for (int i = 0; i < kOwn; ++i) {
-                    if (i == c && i < n_own) {
+                    if (i == (l - 1) * 2 + (c >> 1) && i < n_own) {
                       const int pc = piece_lo + i;
                       // the output layer's bias joins here too (x += ca * b3), off the step boundary's critical path
                       const float ca = P.delta * (dps ? beta : sb);
@@ -778,15 +785,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                         float eps = 0.f;
                         if (valid && j < xdim)
                           eps = fuse_draw ? (e < 4 ? za[e & 3] : zb[e & 3])
-                                          : P.noise[(static_cast<long long>(step) * n_total + grow) * xdim + j];
+                                          : P.noise[(static_cast<long long>(step) * (static_cast<long long>(P.n_obs) * P.n_per_obs) + grow) * xdim + j];
                         const float xv = xs[i * 8 + e];
                         xs[i * 8 + e] = fmaf(kx, xv, xv) + fmaf(ke, eps, ca * b3v[e]);
                       }
                     }
                   }
-                } else if (l == 2 && c == 0 && cdiffe && !last_step) {
-                  diffuse_y(step + 1);
                 }
+                if (l == 2 && c == 1 && cdiffe && !last_step) diffuse_y(step + 1);
               }
             }
           }
@@ -1100,6 +1106,7 @@ int launch(TcParams& P, cudaStream_t s) {
   P.tl = g_tl;
   P.tl_cap = g_tl_cap;
   if (P.n_tiles <= 0) return DMIP_OK;
+  DMIP_REQUIRE(P.n_tiles < (1LL << 31), "too many particle tiles in one call (%lld); split the call", P.n_tiles);
   const int C = kCluster;   // a lone tile still launches a pair: the second CTA runs masked rows
   P.cluster = C;
   P.dbg = g_dbg;
