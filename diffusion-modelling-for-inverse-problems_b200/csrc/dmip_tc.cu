@@ -184,31 +184,33 @@ template <bool kDoubleTanh, bool kToTmem, class Extra = NoExtra>
 __device__ __forceinline__ void epi_hidden(uint32_t lane_taddr, uint32_t acc_col, int cgp, int row, int chunk, int lane,
                                            const float* __restrict__ bias, uint8_t* sH, uint64_t* acc_empty,
                                            uint64_t* hready, Extra extra = NoExtra()) {
-  uint32_t v0[16], v1[16];
-  tmem_ld16(lane_taddr + acc_col + cgp * 32, v0);
-  tmem_ld16(lane_taddr + acc_col + cgp * 32 + 16, v1);
+  // Two 16-column halves, one in registers at a time (the particle state and the noise draw live in registers too):
+  // the accumulator buffer is released after the second half's load — the issuer needs it two chunks later.
+  const int n0 = chunk * 128 + cgp * 32;
+  uint32_t v[16], pk[8];
+  tmem_ld16(lane_taddr + acc_col + cgp * 32, v);
+  tc_wait_ld();
+  extra();
+  tanh_pack16<kDoubleTanh>(v, bias + n0, pk);
+  uint8_t* rowp = sH + (chunk * 2 + (cgp >> 1)) * kStageBytes + (row >> 3) * 1024 + (row & 7) * 128;
+  const int c0 = (cgp & 1) * 4;   // K index n0 .. n0+31 -> K-block chunk*2 + (cgp>>1), 16-byte chunks c0 .. c0+3
+  if (kToTmem) {
+    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1), pk);
+  } else {
+    st_shared_v4(rowp + (((c0 + 0) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(rowp + (((c0 + 1) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+  }
+  tmem_ld16(lane_taddr + acc_col + cgp * 32 + 16, v);
   tc_wait_ld();
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(acc_empty);  // this warp's part of the chunk is in registers: the buffer may be reused
-  extra();
-  const int n0 = chunk * 128 + cgp * 32;
-  uint32_t pk[8];   // one 16-column half at a time: its packed result is stored before the next half is computed
+  tanh_pack16<kDoubleTanh>(v, bias + n0 + 16, pk);
   if (kToTmem) {
-    tanh_pack16<kDoubleTanh>(v0, bias + n0, pk);
-    tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1), pk);
-    tanh_pack16<kDoubleTanh>(v1, bias + n0 + 16, pk);
     tmem_st8(lane_taddr + kTmemH + static_cast<uint32_t>(n0 >> 1) + 8, pk);
     tc_wait_st();
     tc_fence_before();
   } else {
-    // K index of these 32 values: n0 .. n0+31  ->  K-block chunk*2 + (cgp>>1), 16-byte chunks (cgp&1)*4 .. +3
-    uint8_t* rowp = sH + (chunk * 2 + (cgp >> 1)) * kStageBytes + (row >> 3) * 1024 + (row & 7) * 128;
-    const int c0 = (cgp & 1) * 4;
-    tanh_pack16<kDoubleTanh>(v0, bias + n0, pk);
-    st_shared_v4(rowp + (((c0 + 0) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-    st_shared_v4(rowp + (((c0 + 1) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
-    tanh_pack16<kDoubleTanh>(v1, bias + n0 + 16, pk);
     st_shared_v4(rowp + (((c0 + 2) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
     st_shared_v4(rowp + (((c0 + 3) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
     fence_proxy_async_smem();
