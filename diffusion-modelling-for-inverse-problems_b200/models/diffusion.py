@@ -44,6 +44,7 @@ class BaseClassDiffusionModel():
         self.l0_split = 2
         self._packed = (_lib.PackedNet(), _lib.PackedNet())
         self._seed_counter = 0
+        self._stage = None                   # pinned host staging buffer of the sampler's result
 
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
@@ -118,7 +119,14 @@ class BaseClassDiffusionModel():
             out = out.view(n_obs, num_samples, self.xdim)
         if return_tensor:
             return out
-        return out.cpu().numpy()              # the reference's single device->host crossing (models/diffusion.py:44)
+        # the reference's single device->host crossing (models/diffusion.py:44), through a cached pinned staging buffer
+        # (a pageable .cpu() of 1M x 100 samples costs 0.2 s; pinned DMA + one host memcpy 0.06 s)
+        n = out.numel()
+        if self._stage is None or self._stage.numel() < n:
+            self._stage = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        self._stage[:n].copy_(out.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return self._stage[:n].view(out.shape).numpy().copy()
 
     # ------------------------------------------------------------------ training
     def sample_t(self, x, eps=1e-4):
