@@ -414,3 +414,29 @@ def case_posterior_statistics():
     ecov = float(np.abs(np.cov(lo.T) - post_cov).max())
     err = max(dmean / 3e-3, rstd / 5e-3, kl / 2e-3, emean / 0.08, ecov / 0.05)
     return err, 1.0, dict(dmean=dmean, rstd=rstd, kl=kl, emean=emean, ecov=ecov)
+
+
+def case_edge_shapes():
+    """Ragged and degenerate shapes through the public call: empty result, a single particle, one SDE step, particle
+    counts that straddle the 128-row tile, a lone tile (the second CTA of the cluster runs masked), and an invalid
+    argument.  bf16 path vs fp32 path on the same Philox stream, relative to max|x|: 2e-2 — with 1-3 SDE steps the step size
+    delta*beta reaches 20 and amplifies the bf16 rounding of the net output (measured 1e-2 at S=3, 6e-4 at S=50): these
+    cases check shapes and masking, the accuracy cases are `case_sampler_trained` / `case_posterior_statistics`."""
+    import numpy as np
+    m = trained_model()
+    fx = load_golden("sampler_trained_cde_linear")
+    y = fx["y"]
+    out = m(y, num_samples=0, num_steps=5, seed=1)
+    assert out.shape == (0, 2) and out.dtype == np.float32
+    worst = 0.0
+    for N, S in ((1, 1), (1, 7), (127, 3), (128, 3), (129, 3), (257, 2), (148 * 128 + 5, 2)):
+        lo = m(y, num_samples=N, num_steps=S, precision="bf16", seed=3)
+        hi = m(y, num_samples=N, num_steps=S, precision="fp32", seed=3)
+        assert lo.shape == (N, 2) and np.isfinite(lo).all()
+        worst = max(worst, float(np.abs(lo - hi).max() / np.abs(hi).max()))
+    try:
+        m(y, num_samples=4, num_steps=0, seed=1)
+        worst = 1.0                                   # num_steps = 0 must be rejected (DMIP_EINVAL -> ValueError)
+    except ValueError:
+        pass
+    return worst, 2e-2, {}

@@ -52,6 +52,7 @@ CASES = [
     ("shards_fp32", "case_shards_are_bit_identical('fp32')"),
     ("batched_obs", "case_batched_observations()"),
     ("posterior_stats", "case_posterior_statistics()"),
+    ("edge_shapes", "case_edge_shapes()"),
 ]
 
 TEMPLATE = """

@@ -60,3 +60,7 @@ def test_batched_observations_match_per_observation_calls():
 
 def test_posterior_statistics_preserved_at_64k_particles():
     _ok(gc.case_posterior_statistics())
+
+
+def test_edge_shapes_and_invalid_arguments():
+    _ok(gc.case_edge_shapes())
