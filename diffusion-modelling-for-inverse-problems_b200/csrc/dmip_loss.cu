@@ -411,56 +411,93 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_bwd(const __grid_constant
 
 // ------------------------------------------------------------------------------------------------ weight gradients
 // dW[n][k] += sum_r ADJ[r][n] * IN[r][k]   (r over B*n_adj rows), db[n] += sum_{r: stream is P or I} ADJ[r][n].
-// 64x64 output tile per CTA, split over row ranges (gridDim.z), fp32 atomics into the flat gradient buffer.
+// 128 x 128 output tile per CTA (256 threads, 8 x 8 outputs each, operands staged through double-buffered shared
+// memory 8 rows at a time), split over row ranges (gridDim.z), fp32 atomics into the flat gradient buffer.
+constexpr int kWgT = 128;   // tile edge
+constexpr int kWgR = 8;     // rows per stage
+
 __global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ adj, const float* __restrict__ inp, float* dW,
                                                float* db, long long rows, int N, int K, int n_adj, int bias_streams,
                                                long long rows_per_split) {
-  __shared__ float sA[16][64 + 4];
-  __shared__ float sI[16][64 + 4];
-  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  __shared__ __align__(16) float sA[2][kWgR][kWgT];
+  __shared__ __align__(16) float sI[2][kWgR][kWgT];
+  const int n0 = blockIdx.y * kWgT, k0 = blockIdx.x * kWgT;
   const long long r_begin = static_cast<long long>(blockIdx.z) * rows_per_split;
   const long long r_end = min(rows, r_begin + rows_per_split);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4];
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;          // outputs: n = n0 + ty*4 + {0..3} and + 64; k = k0 + tx*4 + {0..3} and + 64
+  const int lr = t >> 5, lc = (t & 31) * 4;    // loader: row lr of the stage, columns lc .. lc+3
+  const bool vecA = (N & 3) == 0, vecI = (K & 3) == 0;
+
+  auto load = [&](const float* __restrict__ src, int ld, int c0, bool vec, long long r, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (r < r_end) {
+      const int c = c0 + lc;
+      const float* p = src + r * ld + c;
+      if (vec && c + 3 < ld) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
-    for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
-      const int rr = idx >> 6, c = idx & 63;
-      const long long r = r0 + rr;
-      const bool ok = r < r_end;
-      sA[rr][c] = (ok && n0 + c < N) ? adj[r * N + n0 + c] : 0.f;
-      sI[rr][c] = (ok && k0 + c < K) ? inp[r * K + k0 + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[rr][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sI[rr][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      if (blockIdx.x == 0 && tx == 0 && ((r0 + rr) % n_adj) < bias_streams) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bsum[i] += a[i];
+        for (int e = 0; e < 4; ++e)
+          if (c + e < ld) v[e] = __ldg(p + e);
       }
     }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float bsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+
+  float va[4], vi[4];
+  load(adj, N, n0, vecA, r_begin + lr, va);
+  load(inp, K, k0, vecI, r_begin + lr, vi);
+  *reinterpret_cast<float4*>(&sA[0][lr][lc]) = make_float4(va[0], va[1], va[2], va[3]);
+  *reinterpret_cast<float4*>(&sI[0][lr][lc]) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+  __syncthreads();
+  int cur = 0;
+  for (long long r0 = r_begin; r0 < r_end; r0 += kWgR) {
+    const bool more = r0 + kWgR < r_end;
+    if (more) {   // global loads of the next stage fly while this stage is multiplied
+      load(adj, N, n0, vecA, r0 + kWgR + lr, va);
+      load(inp, K, k0, vecI, r0 + kWgR + lr, vi);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kWgR; ++rr) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[cur][rr][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[cur][rr][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sI[cur][rr][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sI[cur][rr][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (blockIdx.x == 0 && tx == 0 && ((r0 + rr) % n_adj) < bias_streams) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bsum[i] += a[i];
+      }
+    }
+    if (more) {
+      *reinterpret_cast<float4*>(&sA[cur ^ 1][lr][lc]) = make_float4(va[0], va[1], va[2], va[3]);
+      *reinterpret_cast<float4*>(&sI[cur ^ 1][lr][lc]) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+    }
     __syncthreads();
+    cur ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = n0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (n >= N) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (k < K) atomicAdd(&dW[static_cast<size_t>(n) * K + k], acc[i][j]);
     }
     if (blockIdx.x == 0 && tx == 0) atomicAdd(&db[n], bsum[i]);
@@ -631,15 +668,15 @@ int run_pass(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
   const long long rows = c.batch * p.n_adj;
   for (int l = 0; l < net.n_layers; ++l) {
     const int n = net.width[l];
-    const int tiles = ceil_div(n, 64) * ceil_div(k, 64);
+    const int tiles = ceil_div(n, kWgT) * ceil_div(k, kWgT);
     int split = (2 * n_sm + tiles - 1) / tiles;
     const long long max_split = (rows + 255) / 256;
     if (split > max_split) split = static_cast<int>(max_split);
     if (split < 1) split = 1;
     long long rps = (rows + split - 1) / split;
-    rps = (rps + p.n_adj * 16 - 1) / (p.n_adj * 16) * (p.n_adj * 16);   // keep stream phase aligned per split
+    rps = (rps + p.n_adj * kWgR - 1) / (p.n_adj * kWgR) * (p.n_adj * kWgR);   // keep stream phase aligned per split
     split = static_cast<int>((rows + rps - 1) / rps);
-    dim3 grid(ceil_div(k, 64), ceil_div(n, 64), split);
+    dim3 grid(ceil_div(k, kWgT), ceil_div(n, kWgT), split);
     k_wgrad<<<grid, 256, 0, s>>>(D.adj_rows[l], D.in_rows[l], g, g + static_cast<size_t>(n) * k, rows, n, k, p.n_adj,
                                  1 + c.has_I, rps);
     DMIP_CHECK_CUDA(cudaGetLastError());
