@@ -81,9 +81,10 @@ __device__ __forceinline__ int q_index(int i, int k, int d) { return i * d - (i 
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant__ LossDev P) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = smem + kMaxW * kLd;
+  float* wbuf = buf1 + kMaxW * kLd;   // weight slabs of the staged GEMM
   __shared__ float red[4];
   const int t = threadIdx.x;
   const int ns = P.n_streams, spt = P.spt, d = P.d;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
     int K = P.in_dim;
     for (int l = 0; l < P.n_layers; ++l) {
       const int N = P.width[l];
-      tile_gemm(in, out, P.Wt[l], K, N);
+      tile_gemm(in, out, P.Wt[l], K, N, wbuf);
       const bool last = (l == P.n_layers - 1);
       if (!last) {
         // ---- jet activation, in place: one (column, sample) pair per thread iteration
@@ -332,9 +333,10 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
 // ------------------------------------------------------------------------------------------------ backward
 // rows = (sample, adjoint stream); P and T rows of a sample are coupled through phi' and phi''.
 __global__ void __launch_bounds__(kThreadsL, 1) k_jets_bwd(const __grid_constant__ LossDev P) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = smem + kMaxW * kLd;
+  float* wbuf = buf1 + kMaxW * kLd;   // weight slabs of the staged GEMM
   const int t = threadIdx.x;
   const int na = P.n_adj;
   const int spt = kRows / na;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_bwd(const __grid_constant
     float* out = buf1;
     for (int l = L; l >= 1; --l) {
       const int N = P.width[l], Kp = P.width[l - 1];
-      tile_gemm(in, out, P.W[l], N, Kp);      // hbar_{l-1}[k] = sum_n zbar_l[n] W_l[n][k]
+      tile_gemm(in, out, P.W[l], N, Kp, wbuf);      // hbar_{l-1}[k] = sum_n zbar_l[n] W_l[n][k]
       for (int idx = t; idx < Kp * spt; idx += kThreadsL) {
         const int k = idx % Kp, sl = idx / Kp;
         const long long smp = s0 + sl;
@@ -599,7 +601,7 @@ int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
 }
 
 int g_loss_sm = 0;
-constexpr int kLossSmem = 2 * kMaxW * kLd * 4;
+constexpr int kLossSmem = (2 * kMaxW * kLd + kWbufFloats) * 4;
 
 int loss_init() {
   if (!g_loss_sm) {

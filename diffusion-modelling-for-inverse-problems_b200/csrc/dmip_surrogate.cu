@@ -33,10 +33,11 @@ struct SurrDev {
 };
 
 __global__ void __launch_bounds__(kThreadsL, 1) k_surrogate(const __grid_constant__ SurrDev P) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = smem + kMaxW * kLd;
-  uint32_t* masks = reinterpret_cast<uint32_t*>(buf1 + kMaxW * kLd);   // [n_layers-1][kMaxW]
+  float* wbuf = buf1 + kMaxW * kLd;                                     // weight slabs of the staged GEMM
+  uint32_t* masks = reinterpret_cast<uint32_t*>(wbuf + kWbufFloats);    // [n_layers-1][kMaxW]
   const int t = threadIdx.x, lane = t & 31;
   const long long n_tiles = (P.n + kRows - 1) / kRows;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_surrogate(const __grid_constan
     const int L = P.n_layers - 1;
     for (int l = 0; l <= L; ++l) {
       const int N = P.width[l];
-      tile_gemm(in, out, P.Wt[l], K, N);
+      tile_gemm(in, out, P.Wt[l], K, N, wbuf);
       for (int idx = t; idx < N * kRows; idx += kThreadsL) {      // a warp = one unit n, lane = row
         const int n = idx >> 5;
         float z = out[n * kLd + lane] + P.b[l][n];
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_surrogate(const __grid_constan
     for (int l = L; l >= 0; --l) {
       const int N = P.width[l];
       const int Kp = (l == 0) ? P.in_dim : P.width[l - 1];
-      tile_gemm(in, out, P.W[l], N, Kp);
+      tile_gemm(in, out, P.W[l], N, Kp, wbuf);
       if (l > 0) {
         for (int idx = t; idx < Kp * kRows; idx += kThreadsL) {
           const int k = idx >> 5;
@@ -156,7 +157,7 @@ int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
     return DMIP_EWORKSPACE;
   }
   static int n_sm = 0;
-  const int smem = 2 * kMaxW * kLd * 4 + (DMIP_MAX_LAYERS - 1) * kMaxW * 4;
+  const int smem = (2 * kMaxW * kLd + kWbufFloats) * 4 + (DMIP_MAX_LAYERS - 1) * kMaxW * 4;
   if (!n_sm) {
     int dev = 0;
     DMIP_CHECK_CUDA(cudaGetDevice(&dev));
