@@ -440,3 +440,56 @@ def case_edge_shapes():
     except ValueError:
         pass
     return worst, 2e-2, {}
+
+
+# ------------------------------------------------------------------------------------------- training loop (a10)
+def case_train_epoch(loss_name):
+    """CDE.train_epoch with the reference's call signature (models/diffusion.py:74-105) on the linear toy problem
+    (linear_problem.py:10-16: y = A x + b + 0.3 eps): Adam steps through the fused loss kernels must reduce the loss,
+    and the DSM-trained net's posterior mean must move to the analytic posterior (linear_problem.py:41-46)."""
+    import numpy as np
+    from dmip import losses as dl
+    from dmip.models.diffusion import CDE
+    torch.manual_seed(0)
+    A = torch.tensor([[1.0, 0.5], [-0.3, 1.2]])
+    b = torch.tensor([0.2, -0.1])
+    sig = 0.3
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(16000, 2, generator=g)
+    Y = X @ A.T + b + sig * torch.randn(16000, 2, generator=g)
+    X, Y = X.to(DEV), Y.to(DEV)
+    m = CDE(2, 2, [512, 512, 512])
+    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3 if loss_name == "DSM" else 3e-4)
+    if loss_name == "DSM":
+        loss_fn = dl.DSMLoss()
+    else:
+        cov = torch.linalg.inv(torch.eye(2) + A.T @ A / sig ** 2).to(DEV)
+
+        def score_posterior(x, y):              # analytic posterior score (linear_problem.py:61-65)
+            mean = (cov @ (A.T.to(DEV) @ (y - b.to(DEV)).T / sig ** 2)).T
+            return -(x - mean) @ torch.linalg.inv(cov).T
+
+        loss_fn = dl.PINNLoss(score_posterior, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+
+    def loader():
+        perm = torch.randperm(X.shape[0], device=DEV)
+        for i in range(0, X.shape[0], 1000):
+            idx = perm[i:i + 1000]
+            yield X[idx], Y[idx]
+
+    losses = []
+    for epoch in range(12 if loss_name == "DSM" else 4):
+        loss, info = m.train_epoch(opt, loss_fn, loader)
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    if loss_name != "DSM":
+        assert set(info) == {"PDE-Loss", "Initial Condition", "DSM-Loss"}
+        return (0.0 if losses[-1] < losses[0] else 1.0), 0.5, dict(first=losses[0], last=losses[-1])
+    # posterior check for one observation
+    y0 = torch.tensor([0.7, -0.4])
+    cov = torch.linalg.inv(torch.eye(2) + A.T @ A / sig ** 2)
+    mean = cov @ (A.T @ (y0 - b) / sig ** 2)
+    xs = m(y0, num_samples=20000, num_steps=200, seed=11)
+    emean = float(np.abs(xs.mean(0) - mean.numpy()).max())
+    ok = losses[-1] < 0.8 * losses[0] and emean < 0.15
+    return (0.0 if ok else 1.0), 0.5, dict(first=losses[0], last=losses[-1], emean=emean)

@@ -53,6 +53,8 @@ CASES = [
     ("batched_obs", "case_batched_observations()"),
     ("posterior_stats", "case_posterior_statistics()"),
     ("edge_shapes", "case_edge_shapes()"),
+    ("train_dsm", "case_train_epoch('DSM')"),
+    ("train_pinn", "case_train_epoch('PINN')"),
 ]
 
 TEMPLATE = """
