@@ -296,12 +296,14 @@ int prep_net(const DmipMlp* net, float* ws, NetDev* o, cudaStream_t s) {
 
 int launch_f32(const F32Params& P, cudaStream_t s) {
   static int n_sm = 0;
+  static bool ready[64] = {};   // cudaFuncSetAttribute is per device
   const int smem = (2 * kMaxW + 128) * kLd * 4;
-  if (!n_sm) {
-    int dev = 0;
-    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  int dev = 0;
+  DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !ready[dev]) {
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_f32_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) ready[dev] = true;
   }
   const long long grid = P.n_tiles < n_sm ? P.n_tiles : n_sm;
   if (grid <= 0) return DMIP_OK;

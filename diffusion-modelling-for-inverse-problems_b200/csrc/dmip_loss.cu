@@ -601,16 +601,19 @@ int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
 }
 
 int g_loss_sm = 0;
+bool g_loss_ready[64] = {};   // cudaFuncSetAttribute is per device
 constexpr int kLossSmem = (2 * kMaxW * kLd + kWbufFloats) * 4;
 
 int loss_init() {
-  if (!g_loss_sm) {
-    int dev = 0, n = 0;
-    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  int dev = 0;
+  DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !g_loss_ready[dev]) {
+    int n = 0;
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
     g_loss_sm = n;
+    if (dev >= 0 && dev < 64) g_loss_ready[dev] = true;
   }
   return DMIP_OK;
 }

@@ -157,12 +157,14 @@ int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
     return DMIP_EWORKSPACE;
   }
   static int n_sm = 0;
+  static bool ready[64] = {};   // cudaFuncSetAttribute is per device
   const int smem = (2 * kMaxW * kLd + kWbufFloats) * 4 + (DMIP_MAX_LAYERS - 1) * kMaxW * 4;
-  if (!n_sm) {
-    int dev = 0;
-    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  int dev = 0;
+  DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !ready[dev]) {
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_surrogate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) ready[dev] = true;
   }
   SurrDev P = {};
   P.mode = d->mode;

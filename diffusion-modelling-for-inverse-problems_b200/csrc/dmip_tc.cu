@@ -1082,10 +1082,12 @@ int g_dbg = 0;
 unsigned long long* g_tl = nullptr;
 int g_tl_cap = 0;
 
+bool g_dev_ready[64] = {};   // cudaFuncSetAttribute is per device: one process may drive several GPUs
+
 int init_device() {
-  if (!g_n_sm) {
-    int dev = 0;
-    DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  int dev = 0;
+  DMIP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !g_dev_ready[dev]) {
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&g_n_sm, cudaDevAttrMultiProcessorCount, dev));
 #define DMIP_SET_SMEM(NP, VAR) \
   DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tc_mlp<NP, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes))
@@ -1097,6 +1099,7 @@ int init_device() {
     DMIP_SET_SMEM(13, DMIP_CDE);
 #undef DMIP_SET_SMEM
     if (getenv("DMIP_DBG")) g_dbg = atoi(getenv("DMIP_DBG"));
+    if (dev >= 0 && dev < 64) g_dev_ready[dev] = true;
   }
   return DMIP_OK;
 }
