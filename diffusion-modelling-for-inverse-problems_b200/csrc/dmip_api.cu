@@ -177,6 +177,21 @@ int dmip_posterior_loss_fwd_bwd(const DmipPosteriorLoss* d, void* stream) {
   return launch_posterior_loss(d, static_cast<cudaStream_t>(stream));
 }
 
+int dmip_histogramdd(const DmipHistogram* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  return launch_histogramdd(d, static_cast<cudaStream_t>(stream));
+}
+
+int dmip_hist_kl(const void* hist_p, const void* hist_q, int64_t n_bins_total, double epsilon, double* out, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  return launch_hist_kl(hist_p, hist_q, n_bins_total, epsilon, out, static_cast<cudaStream_t>(stream));
+}
+
 int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream) {
   reset_launch_count();
   int rc = require_device();

@@ -67,6 +67,8 @@ size_t loss_grad_floats(const DmipMlp* net);
 int launch_loss(const DmipLoss* q, cudaStream_t s);
 size_t posterior_loss_workspace(const DmipPosteriorLoss* q);
 int launch_posterior_loss(const DmipPosteriorLoss* q, cudaStream_t s);
+int launch_histogramdd(const DmipHistogram* d, cudaStream_t s);
+int launch_hist_kl(const void* hp, const void* hq, long long m, double epsilon, double* out, cudaStream_t s);
 size_t surrogate_workspace(const DmipSurrogate* d);
 int launch_surrogate(const DmipSurrogate* d, cudaStream_t s);
 size_t sampler_tc_workspace();

@@ -239,6 +239,25 @@ typedef struct DmipPosteriorLoss {
 size_t dmip_posterior_loss_workspace_bytes(const DmipPosteriorLoss* d);
 int dmip_posterior_loss_fwd_bwd(const DmipPosteriorLoss* d, void* stream);
 
+/* ---- evaluation metrics next to the sampler ------------------------------------------------------
+ * dmip_histogramdd: np.histogramdd(x, bins, range) of main_diffusion_linear.py:85-88 /
+ * main_diffusion_scatterometry.py:72-75, bit-exact (per dimension searchsorted(edges, x, 'right') - 1, last edge
+ * inclusive, out-of-range samples dropped); `counts` (uint64, prod(bins), C order) is ACCUMULATED into, which is the
+ * reference's `hist_sum += hist` over repeats.  edges[d]: device double[bins[d] + 1] (np.linspace(lo, hi, bins + 1)).
+ * dmip_hist_kl: sum(rel_entr(p, q)) with the reference's normalisation (h / sum, + epsilon, / sum;
+ * main_diffusion_linear.py:108-116): out = device double[3] {KL, sum(hp), sum(hq)}. */
+typedef struct DmipHistogram {
+  int32_t dim;               /* 1..4                         */
+  int32_t bins[4];
+  const double* edges[4];    /* device                       */
+  int64_t n;
+  const float* x;            /* device (n, dim)              */
+  void* counts;              /* device uint64[prod(bins)]    */
+} DmipHistogram;
+
+int dmip_histogramdd(const DmipHistogram* d, void* stream);
+int dmip_hist_kl(const void* hist_p, const void* hist_q, int64_t n_bins_total, double epsilon, double* out, void* stream);
+
 /* ---- debug / self-test hooks (used by tests/ only) ------------------------------------------------------
  * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
  * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.

@@ -493,3 +493,39 @@ def case_train_epoch(loss_name):
     emean = float(np.abs(xs.mean(0) - mean.numpy()).max())
     ok = losses[-1] < 0.8 * losses[0] and emean < 0.15
     return (0.0 if ok else 1.0), 0.5, dict(first=losses[0], last=losses[-1], emean=emean)
+
+
+# ------------------------------------------------------------------------------------------- evaluation metrics (N2)
+def case_histogram_kl():
+    """GPU histogramdd / KL vs numpy + scipy (the reference's evaluate loop): counts bit-exact — including samples on
+    bin edges, on the right-most edge, outside the range and NaN — for 2-D (linear, 75 bins on [-3.5, 3.5]) and 3-D
+    (scatterometry, 75 bins on [-1.2, 1.2]); KL within 1e-12."""
+    import numpy as np
+    from dmip import metrics as dmet
+    from oracle import metrics as omet
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for dim, lim in ((2, 3.5), (3, 1.2)):
+        bins, ranges = (75,) * dim, ((-lim, lim),) * dim
+        edges = np.linspace(-lim, lim, 76)
+        sets_true, sets_model = [], []
+        acc = dmet.HistogramKL(bins, ranges)
+        for rep in range(3):
+            a = (rng.standard_normal((30000, dim)) * lim * 0.45).astype(np.float32)
+            b = (rng.standard_normal((30000, dim)) * lim * 0.5 + 0.1).astype(np.float32)
+            a[:200, 0] = edges[rng.integers(0, 76, 200)].astype(np.float32)      # exactly on edges (after fp32 rounding)
+            a[200:210, 1] = np.float32(lim)                                      # right-most edge: inclusive
+            a[210:215, 0] = np.float32(-lim)
+            a[215:220, 1] = np.nan
+            b[:50] *= 10.0                                                       # outliers
+            sets_true.append(a)
+            sets_model.append(b)
+            acc.add(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV))
+        ht, hm = omet.hist_sum(sets_true, bins, ranges), omet.hist_sum(sets_model, bins, ranges)
+        if not (np.array_equal(acc.hist_true.cpu().numpy(), ht.astype(np.int64))
+                and np.array_equal(acc.hist_model.cpu().numpy(), hm.astype(np.int64))):
+            return 1.0, 0.0, {}
+        for rev in (False, True):
+            ref = omet.kl2(hm, ht) if rev else omet.kl2(ht, hm)
+            worst = max(worst, abs(acc.kl(reverse=rev) - ref))
+    return worst, 1e-12, {}

@@ -55,6 +55,7 @@ CASES = [
     ("edge_shapes", "case_edge_shapes()"),
     ("train_dsm", "case_train_epoch('DSM')"),
     ("train_pinn", "case_train_epoch('PINN')"),
+    ("hist_kl", "case_histogram_kl()"),
 ]
 
 TEMPLATE = """

@@ -27,3 +27,7 @@ def test_surrogate_energy_and_score():
 
 def test_surrogate_likelihood_vjp():
     _ok(gc.case_surrogate_vjp())
+
+
+def test_histogram_kl_matches_numpy_bit_for_bit():
+    _ok(gc.case_histogram_kl())

@@ -185,3 +185,18 @@ def test_sampler_trained_cde_linear_philox_noise():
     # score-MSE metric of main_diffusion_linear.py:78-83 on the stored probe points
     s0 = on.mlp(trained_cde_linear_params(), fx["score_x"], fx["score_y"], torch.zeros(256, 1)) / 0.1 ** 0.5
     assert torch.allclose(s0, fx["score_net"], rtol=1e-4, atol=1e-4)
+
+
+def test_metrics_oracle_kl_properties():
+    """oracle.metrics restates main_diffusion_linear.py:84-117: identical sample sets give KL 0; a shifted set a positive
+    KL; the sum over repeats equals the histogram of the concatenated repeats."""
+    import numpy as np
+    from oracle import metrics as omet
+    rng = np.random.default_rng(1)
+    a = [rng.standard_normal((5000, 2)).astype(np.float32) for _ in range(3)]
+    b = [x + 0.5 for x in a]
+    bins, ranges = (75, 75), ((-3.5, 3.5), (-3.5, 3.5))
+    ha, hb = omet.hist_sum(a, bins, ranges), omet.hist_sum(b, bins, ranges)
+    assert omet.kl2(ha, ha) == 0.0
+    assert omet.kl2(ha, hb) > 0.05
+    assert np.array_equal(ha, np.histogramdd(np.concatenate(a), bins=bins, range=ranges)[0])
