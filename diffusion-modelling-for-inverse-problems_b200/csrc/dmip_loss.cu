@@ -35,13 +35,19 @@ struct LossDev {
   float bmin, bmax, lam, lam2;
   int pde_loss, pde_metric, ic_metric;
   int has_I, has_T, has_S, has_Q;     // stream groups present
-  int post;                           // 0: CDE/CDiffE losses; 1: DPS prior net pass; 2: DPS likelihood net pass
+  int post;                           // 0: CDE/CDiffE losses; 1: DPS prior net pass; 2: DPS likelihood net pass;
+                                      // 3: grad_x pass of the adjoint Score-FPE route (streams P | S_k, no loss)
   float* aux_s;                       // post=1 out: s_prior (B,d);  post=2 in: target (B,d)
   float* aux_J;                       // post=1 out: J_s (B,d,d) row-major [i][k] = d s_i / d x_k
   float* aux_x0;                      // post=1 out: Tweedie mean x0_hat (B,d)
   float* aux_xt;                      // post=1 out: x_t (B,d)
   int n_streams, spt;                 // streams per sample, samples per tile
   int n_adj;                          // adjoint streams per sample: P [, I] [, T]
+  int n_tan;                          // spatial tangent streams: d (directions e_k) or 1 (Hutchinson probe v)
+  int gx;                             // 1: Score-FPE grad_x is read from `gradx` (adjoint route) instead of the Q streams
+  const float* hutch_v;               // post=3, Hutchinson: probe v (B,d); NULL = exact (e_k)
+  float* gradx;                       // post=3 out / gx=1 in: grad_x [div s + |s|^2 + x.s]  (B,d)
+  float* tan_z[DMIP_MAX_LAYERS];      // post=3: TAN_l [B][n_tan][N_l] pre-activation spatial tangents of hidden layer l
   const float* x;
   const float* y;
   const float* t;
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
   __shared__ float red[4];
   const int t = threadIdx.x;
   const int ns = P.n_streams, spt = P.spt, d = P.d;
-  const int sI = 1, sT = 1 + P.has_I, sS = sT + P.has_T, sQ = sS + (P.has_S ? d : 0);
+  const int sI = 1, sT = 1 + P.has_I, sS = sT + P.has_T, sQ = sS + (P.has_S ? P.n_tan : 0);
   (void)sQ;
   const long long n_tiles = (P.B + spt - 1) / spt;
 
@@ -125,7 +131,8 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
           else if (k < d + P.cdim) v = 0.f;
           else v = 1.f;
         } else if (P.has_S && st >= sS && st < sQ) {
-          v = (k == st - sS) ? 1.f : 0.f;    // S_k: e_k
+          if (P.hutch_v) v = (k < d) ? P.hutch_v[smp * d + k] : 0.f;   // Hutchinson probe   (losses.py:28-40)
+          else v = (k == st - sS) ? 1.f : 0.f;                          // S_k: e_k
         }                                    // Q: zero input
         // inputs of layer 0 for the adjoint streams (wgrad operands)
         const int aidx = (st == 0) ? 0 : (P.has_I && st == sI) ? 1 : (P.has_T && st == sT) ? (1 + P.has_I) : -1;
@@ -169,7 +176,13 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
               P.in_rows[l + 1][(smp * P.n_adj + 1 + P.has_I) * N + n] = hd;
             }
           }
-          if (P.has_S) {
+          if (P.post == 3) {
+            for (int k = 0; k < P.n_tan; ++k) {
+              const float zs = col[sS + k];
+              if (live) P.tan_z[l][(smp * P.n_tan + k) * N + n] = zs;
+              col[sS + k] = p1 * zs;
+            }
+          } else if (P.has_S) {
             float zs[kMaxD];
 #pragma unroll
             for (int k = 0; k < kMaxD; ++k)
@@ -197,6 +210,34 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
       K = N;
     }
 
+    if (P.post == 3) {
+      // ---- grad_x pass: seeds of the reverse sweep for phi = div s + |s|^2 + x.s  (losses.py:88-90), with
+      // div s = sum_k (S_k)_k / sqrt(beta) (exact) or v.(J v) / sqrt(beta) (Hutchinson):
+      //   abar_P[j] = 2 a_j / beta + z_t[j] / sqrt(beta),  abar_Sk[j] = dir_k[j] / sqrt(beta);  direct term a_k / sqrt(beta)
+      const int L = P.n_layers - 1, od = P.out_dim, na = 1 + P.n_tan;
+      for (int idx = t; idx < spt * na * od; idx += kThreadsL) {
+        const int j = idx % od, st = (idx / od) % na, sl = idx / (od * na);
+        const long long smp = s0 + sl;
+        if (smp >= P.B) continue;
+        float beta, alpha, var;
+        vp_terms(P.t[smp], P.bmin, P.bmax, beta, alpha, var);
+        const float sb = sqrtf(beta);
+        float v;
+        if (st == 0) {
+          const float a = in[j * kLd + sl * ns] + P.b[L][j];
+          const float z0 = (j < P.xdim) ? P.x[smp * P.xdim + j] : P.y[smp * P.ydim + (j - P.xdim)];
+          const float zt = P.eps[smp * d + j] * sqrtf(var) + alpha * z0;
+          v = 2.f * a / beta + zt / sb;
+          P.gradx[smp * d + j] = a / sb;
+        } else {
+          const float dir = P.hutch_v ? P.hutch_v[smp * d + j] : (j == st - 1 ? 1.f : 0.f);
+          v = dir / sb;
+        }
+        P.abar[(smp * na + st) * od + j] = v;
+      }
+      __syncthreads();
+      continue;
+    }
     // ---- per-sample loss terms and output adjoints (one thread per sample; `in` holds the raw last-layer rows)
     if (t < spt && s0 + t < P.B) {
       const long long smp = s0 + t;
@@ -255,7 +296,21 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
       }
       if (P.has_T) {
         float* abarT = P.abar + (smp * P.n_adj + 1 + P.has_I) * od;
-        if (P.pde_loss == 0) {
+        if (P.pde_loss == 0 && P.gx) {
+          // Score-FPE residual with grad_x from the adjoint route (k_gradx_bwd), any d
+          for (int k = 0; k < d; ++k) {
+            const float a = o[k * kLd + 0] + P.b[L][k];
+            const float ds_dt = o[k * kLd + sT] / sb - a * db / (2.f * beta * sb);
+            const float R = ds_dt - 0.5f * beta * P.gradx[smp * d + k];
+            float g;
+            if (P.pde_metric == 1) { l_pde += fabsf(R); g = (R > 0.f) - (R < 0.f); }
+            else { l_pde += R * R; g = 2.f * R; }
+            g *= P.lam / d * P.inv_B;
+            abarT[k] = g / sb;
+            abarP[k] += -g * db / (2.f * beta * sb);
+          }
+          l_pde *= P.lam / d;
+        } else if (P.pde_loss == 0) {
           // Score-FPE residual R = ds/dt - beta/2 grad_x[div s + |s|^2 + x.s], grad_x constant (losses.py:88-95, Q9)
           float a[kMaxD], zt[kMaxD], J[kMaxD][kMaxD], gtr[kMaxD];
 #pragma unroll
@@ -411,6 +466,75 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_bwd(const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------ grad_x (adjoint route)
+// Reverse sweep through the (primal, spatial tangents) jet of the post=3 forward pass; rows = (sample, P | S_k).
+// With hbar the adjoint of h and hdbar_k those of the tangents hd_k = phi'(z) zd_k:
+//     zbar = phi' hbar + phi'' sum_k zd_k hdbar_k,     zdbar_k = phi' hdbar_k,
+// and the gradient w.r.t. the diffused state is the first d columns of zbar_0 W_0.  Cost (2 + n_tan) net passes instead of
+// the d(d+1)/2 second-order streams of the forward-only route: this is what makes d = 26 (CDiffE, scatterometry) and the
+// Hutchinson estimator (n_tan = 1) affordable.  Nothing here carries a parameter gradient (grad_x is detached, Q9).
+__global__ void __launch_bounds__(kThreadsL, 1) k_gradx_bwd(const __grid_constant__ LossDev P) {
+  extern __shared__ __align__(16) float smem[];
+  float* buf0 = smem;
+  float* buf1 = smem + kMaxW * kLd;
+  float* wbuf = buf1 + kMaxW * kLd;
+  const int t = threadIdx.x;
+  const int nt = P.n_tan, na = 1 + nt, d = P.d;
+  const int spt = kRows / na;
+  const long long n_tiles = (P.B + spt - 1) / spt;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long s0 = tile * spt;
+    const int L = P.n_layers - 1;
+    for (int idx = t; idx < kRows * P.out_dim; idx += kThreadsL) {
+      const int n = idx / kRows, r = idx % kRows;
+      const int sl = r / na, st = r % na;
+      const long long smp = s0 + sl;
+      buf0[n * kLd + r] = (sl < spt && smp < P.B) ? P.abar[(smp * na + st) * P.out_dim + n] : 0.f;
+    }
+    __syncthreads();
+    float* in = buf0;
+    float* out = buf1;
+    for (int l = L; l >= 1; --l) {
+      const int N = P.width[l], Kp = P.width[l - 1];
+      tile_gemm(in, out, P.W[l], N, Kp, wbuf);
+      for (int idx = t; idx < Kp * spt; idx += kThreadsL) {
+        const int k = idx % Kp, sl = idx / Kp;
+        const long long smp = s0 + sl;
+        if (smp >= P.B) continue;
+        float* col = out + k * kLd + sl * na;
+        const float h = P.in_rows[l][smp * Kp + k];
+        float p1, p2;
+        if (l - 1 == 0) {
+          const float u = atanhf(h);
+          p1 = (1.f - h * h) * (1.f - u * u);
+          p2 = p1 * (-2.f * h * (1.f - u * u) - 2.f * u);
+        } else {
+          p1 = 1.f - h * h;
+          p2 = -2.f * h * p1;
+        }
+        float cross = 0.f;
+        for (int j = 0; j < nt; ++j) {
+          const float hdbar = col[1 + j];
+          cross = fmaf(P.tan_z[l - 1][(smp * nt + j) * Kp + k], hdbar, cross);
+          col[1 + j] = p1 * hdbar;
+        }
+        col[0] = p1 * col[0] + p2 * cross;
+      }
+      __syncthreads();
+      float* tmp = in;
+      in = out;
+      out = tmp;
+    }
+    tile_gemm(in, out, P.W[0], P.width[0], P.in_dim, wbuf);   // xbar[k] = sum_n zbar_0[n] W_0[n][k]
+    for (int idx = t; idx < d * spt; idx += kThreadsL) {
+      const int k = idx % d, sl = idx / d;
+      const long long smp = s0 + sl;
+      if (smp < P.B) P.gradx[smp * d + k] += out[k * kLd + sl * na];
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradients
 // dW[n][k] += sum_r ADJ[r][n] * IN[r][k]   (r over B*n_adj rows), db[n] += sum_{r: stream is P or I} ADJ[r][n].
 // 128 x 128 output tile per CTA (256 threads, 8 x 8 outputs each, operands staged through double-buffered shared
@@ -512,6 +636,9 @@ struct PassCfg {
   const DmipMlp* net;
   int xdim, ydim, d, cdim;
   int has_I, has_T, has_S, has_Q, post;
+  int n_tan, gx;               // spatial tangent streams (0 = d); gx: grad_x comes from `gradx`
+  const float* hutch_v;
+  float* gradx;
   int kind, model, pde_loss, pde_metric, ic_metric;
   long long batch, batch_global;
   float bmin, bmax, lam, lam2;
@@ -522,7 +649,9 @@ struct PassCfg {
 
 struct LossPlan {
   int n_streams, spt, n_adj;
+  int n_tan;
   size_t off_wt[DMIP_MAX_LAYERS], off_in[DMIP_MAX_LAYERS], off_adj[DMIP_MAX_LAYERS], off_zdt[DMIP_MAX_LAYERS], off_abar;
+  size_t off_tan[DMIP_MAX_LAYERS];
   size_t bytes;
 };
 
@@ -537,10 +666,14 @@ int check_net(const DmipMlp& net, int want_in, const char* what) {
 
 int plan_pass(const PassCfg& c, LossPlan* p) {
   const DmipMlp& net = *c.net;
-  p->n_streams = 1 + c.has_I + c.has_T + (c.has_S ? c.d : 0) + (c.has_Q ? c.d * (c.d + 1) / 2 : 0);
-  DMIP_REQUIRE(p->n_streams <= kRows, "too many jet streams (%d)", p->n_streams);
+  p->n_tan = c.has_S ? (c.n_tan > 0 ? c.n_tan : c.d) : 0;
+  p->n_streams = 1 + c.has_I + c.has_T + p->n_tan + (c.has_Q ? c.d * (c.d + 1) / 2 : 0);
+  DMIP_REQUIRE(p->n_streams <= kRows, "too many jet streams (%d > %d): the Score-FPE loss with exact divergence supports "
+               "d <= %d diffused dimensions; use divergence_method = 'hutchinson' or pde_loss = 'cScoreFPE'",
+               p->n_streams, kRows, kRows - 1);
   p->spt = kRows / p->n_streams;
   p->n_adj = 1 + c.has_I + c.has_T;
+  const bool gpass = c.post == 3;      // grad_x pass: no adjoint rows / wgrad operands, but the tangents are kept
   size_t off = 0;
   int k = net.in_dim;
   const size_t B = static_cast<size_t>(c.batch);
@@ -548,12 +681,13 @@ int plan_pass(const PassCfg& c, LossPlan* p) {
     const int n = net.width[l];
     p->off_wt[l] = off;  off += align_up(sizeof(float) * k * n);
     p->off_in[l] = off;  off += align_up(sizeof(float) * B * p->n_adj * k);
-    p->off_adj[l] = off; off += align_up(sizeof(float) * B * p->n_adj * n);
+    p->off_adj[l] = off; off += gpass ? 0 : align_up(sizeof(float) * B * p->n_adj * n);
     p->off_zdt[l] = off; off += (c.has_T && l < net.n_layers - 1) ? align_up(sizeof(float) * B * n) : 0;
+    p->off_tan[l] = off; off += (gpass && l < net.n_layers - 1) ? align_up(sizeof(float) * B * p->n_tan * n) : 0;
     k = n;
   }
   p->off_abar = off;
-  off += align_up(sizeof(float) * B * p->n_adj * net.out_dim);
+  off += align_up(sizeof(float) * B * (gpass ? 1 + p->n_tan : p->n_adj) * net.out_dim);
   p->bytes = off;
   return DMIP_OK;
 }
@@ -586,11 +720,19 @@ int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
   }
   c->has_I = q->kind == DMIP_LOSS_PINN;
   c->has_T = pde;
-  c->has_S = pde && q->pde_loss == DMIP_PDE_FPE;
+  const bool fpe = pde && q->pde_loss == DMIP_PDE_FPE;
+  if (fpe) {
+    DMIP_REQUIRE(q->divergence == DMIP_DIV_EXACT || q->divergence == DMIP_DIV_HUTCHINSON ||
+                 q->divergence == DMIP_DIV_EXACT_ADJOINT,
+                 "No valid value for divergence method specified. Need to be one of \"exact\",\"hutchinson\",\"approx\" or "
+                 "\"approximate\"");
+    DMIP_REQUIRE(q->divergence != DMIP_DIV_HUTCHINSON || q->hutch_v != nullptr || q->batch == 0,
+                 "divergence = hutchinson needs the probe vectors hutch_v (batch, d)");
+  }
+  // forward-only route (second-order streams) for small d, adjoint route (grad_x pass + reverse sweep) otherwise
+  c->gx = fpe && (q->divergence != DMIP_DIV_EXACT || c->d > kMaxD);
+  c->has_S = fpe && !c->gx;
   c->has_Q = c->has_S;
-  if (c->has_S)
-    DMIP_REQUIRE(c->d <= kMaxD, "exact Score-FPE divergence supports d <= %d diffused dimensions (got %d); "
-                 "use pde_loss = cScoreFPE", kMaxD, c->d);
   c->kind = q->kind; c->model = q->model;
   c->pde_loss = q->pde_loss; c->pde_metric = q->pde_metric; c->ic_metric = q->ic_metric;
   c->batch = q->batch; c->batch_global = q->batch_global;
@@ -612,6 +754,7 @@ int loss_init() {
     DMIP_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_jets_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_gradx_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
     g_loss_sm = n;
     if (dev >= 0 && dev < 64) g_loss_ready[dev] = true;
   }
@@ -634,6 +777,7 @@ int run_pass(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
   D.has_I = c.has_I; D.has_T = c.has_T; D.has_S = c.has_S; D.has_Q = c.has_Q; D.post = c.post;
   D.aux_s = c.aux_s; D.aux_J = c.aux_J; D.aux_x0 = c.aux_x0; D.aux_xt = c.aux_xt;
   D.n_streams = p.n_streams; D.spt = p.spt; D.n_adj = p.n_adj;
+  D.n_tan = p.n_tan; D.gx = c.gx; D.hutch_v = c.hutch_v; D.gradx = c.gradx;
   D.x = c.x; D.y = c.y; D.t = c.t; D.eps = c.eps; D.ic_target = c.ic_target;
   D.losses = c.losses;
   D.abar = reinterpret_cast<float*>(ws + p.off_abar);
@@ -648,19 +792,28 @@ int run_pass(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
     D.in_rows[l] = reinterpret_cast<float*>(ws + p.off_in[l]);
     D.adj_rows[l] = reinterpret_cast<float*>(ws + p.off_adj[l]);
     D.zdt[l] = reinterpret_cast<float*>(ws + p.off_zdt[l]);
+    D.tan_z[l] = reinterpret_cast<float*>(ws + p.off_tan[l]);
     dim3 grid(ceil_div(k, 32), ceil_div(n, 32)), block(32, 8);
     k_transpose_l<<<grid, block, 0, s>>>(net.W[l], wt, n, k);
     DMIP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     k = n;
   }
-  DMIP_CHECK_CUDA(cudaMemsetAsync(c.grad, 0, loss_grad_floats(&net) * sizeof(float), s));
+  if (c.post != 3) DMIP_CHECK_CUDA(cudaMemsetAsync(c.grad, 0, loss_grad_floats(&net) * sizeof(float), s));
   if (c.batch == 0) return DMIP_OK;
 
   const long long tiles_f = (c.batch + p.spt - 1) / p.spt;
   k_jets_fwd<<<static_cast<unsigned>(tiles_f < 4LL * n_sm ? tiles_f : 4LL * n_sm), kThreadsL, kLossSmem, s>>>(D);
   DMIP_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  if (c.post == 3) {   // grad_x pass: reverse sweep to the inputs only
+    const int spt_g = kRows / (1 + p.n_tan);
+    const long long tiles_g = (c.batch + spt_g - 1) / spt_g;
+    k_gradx_bwd<<<static_cast<unsigned>(tiles_g < 4LL * n_sm ? tiles_g : 4LL * n_sm), kThreadsL, kLossSmem, s>>>(D);
+    DMIP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return DMIP_OK;
+  }
   const int spt_b = kRows / p.n_adj;
   const long long tiles_b = (c.batch + spt_b - 1) / spt_b;
   k_jets_bwd<<<static_cast<unsigned>(tiles_b < 4LL * n_sm ? tiles_b : 4LL * n_sm), kThreadsL, kLossSmem, s>>>(D);
@@ -758,11 +911,43 @@ int plan_posterior(const DmipPosteriorLoss* q, PostPlan* P) {
 
 }  // namespace
 
+namespace {
+
+// main pass, preceded by the grad_x pass when the Score-FPE term takes the adjoint route
+struct FullPlan {
+  PassCfg c, cg;
+  LossPlan p, pg;
+  bool two;
+  size_t off_gradx, bytes;
+};
+
+int plan_loss(const DmipLoss* q, FullPlan* F) {
+  int rc = cfg_from_loss(q, &F->c);
+  if (rc) return rc;
+  if ((rc = plan_pass(F->c, &F->p))) return rc;
+  F->two = F->c.gx != 0;
+  F->off_gradx = 0;
+  F->bytes = F->p.bytes;
+  if (F->two) {
+    F->cg = F->c;
+    F->cg.has_I = 0; F->cg.has_T = 0; F->cg.has_S = 1; F->cg.has_Q = 0; F->cg.gx = 0; F->cg.post = 3;
+    F->cg.kind = DMIP_LOSS_DSM;
+    F->cg.n_tan = (q->divergence == DMIP_DIV_HUTCHINSON) ? 1 : F->c.d;
+    F->cg.hutch_v = (q->divergence == DMIP_DIV_HUTCHINSON) ? q->hutch_v : nullptr;
+    if ((rc = plan_pass(F->cg, &F->pg))) return rc;
+    const size_t pass = F->p.bytes > F->pg.bytes ? F->p.bytes : F->pg.bytes;   // the passes run one after the other
+    F->off_gradx = pass;
+    F->bytes = pass + align_up(sizeof(float) * static_cast<size_t>(q->batch) * F->c.d);
+  }
+  return DMIP_OK;
+}
+
+}  // namespace
+
 size_t loss_workspace(const DmipLoss* q) {
-  PassCfg c;
-  LossPlan p;
-  if (cfg_from_loss(q, &c) || plan_pass(c, &p)) return 0;
-  return p.bytes;
+  FullPlan F;
+  if (plan_loss(q, &F)) return 0;
+  return F.bytes > 16 ? F.bytes : 16;
 }
 
 size_t loss_grad_floats(const DmipMlp* net) {
@@ -776,19 +961,24 @@ size_t loss_grad_floats(const DmipMlp* net) {
 }
 
 int launch_loss(const DmipLoss* q, cudaStream_t s) {
-  PassCfg c;
-  LossPlan p;
-  int rc = cfg_from_loss(q, &c);
+  FullPlan F;
+  int rc = plan_loss(q, &F);
   if (rc) return rc;
-  if ((rc = plan_pass(c, &p))) return rc;
   DMIP_REQUIRE(q->out_losses && q->grad, "out_losses / grad is NULL");
   DMIP_REQUIRE(q->batch == 0 || (q->x && q->y && q->t && q->eps), "x / y / t / eps is NULL");
-  if (!q->workspace || q->workspace_bytes < p.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) {
-    set_error("workspace too small or misaligned: need %zu bytes", p.bytes);
+  if (!q->workspace || q->workspace_bytes < F.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 15)) {
+    set_error("workspace too small or misaligned: need %zu bytes", F.bytes);
     return DMIP_EWORKSPACE;
   }
+  uint8_t* ws = static_cast<uint8_t*>(q->workspace);
   DMIP_CHECK_CUDA(cudaMemsetAsync(q->out_losses, 0, 4 * sizeof(float), s));
-  return run_pass(c, p, static_cast<uint8_t*>(q->workspace), s);
+  if (F.two) {
+    float* gradx = reinterpret_cast<float*>(ws + F.off_gradx);
+    F.cg.gradx = gradx;
+    F.c.gradx = gradx;
+    if ((rc = run_pass(F.cg, F.pg, ws, s))) return rc;
+  }
+  return run_pass(F.c, F.p, ws, s);
 }
 
 size_t posterior_loss_workspace(const DmipPosteriorLoss* q) {

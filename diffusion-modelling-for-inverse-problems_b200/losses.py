@@ -22,15 +22,35 @@ from . import _lib
 
 _LOSS_DSM, _LOSS_DSM_PDE, _LOSS_PINN = 0, 1, 2
 _METRIC = {'L1': 1, 'L2': 2}
+_DIVERGENCE = {'exact': 0, 'hutchinson': 1, 'approx': 1, 'approximate': 1, 'exact_adjoint': 2}
+
+
+def rademacher_like(s):
+    """+-1 with probability 1/2 each (losses.py:7-11), drawn on the device of `s`."""
+    return torch.randint(0, 2, s.shape, device=s.device).to(s.dtype) * 2 - 1
+
+
+def _divergence(loss_fn, z):
+    """divergence_method of ScoreFPELoss.forward (losses.py:81-86) -> (code, probe or None).  The probe of the
+    Hutchinson estimator is drawn like div_estimator does (one Rademacher sample) unless `loss_fn.probe` injects one."""
+    m = getattr(loss_fn, 'divergence_method', 'exact')
+    if m not in _DIVERGENCE:
+        raise ValueError('No valid value for divergence method specified. Need to be one of "exact","hutchinson",'
+                         '"approx" or "approximate", but {} was given'.format(m))
+    code = _DIVERGENCE[m]
+    if code != 1 or loss_fn.pde_loss.name != 'FPELoss':
+        return code, None
+    v = getattr(loss_fn, 'probe', None)
+    return code, (rademacher_like(z) if v is None else v)
 
 
 class DmipLoss(C.Structure):
     _fields_ = [("kind", C.c_int32), ("model", C.c_int32), ("xdim", C.c_int32), ("ydim", C.c_int32),
                 ("batch", C.c_int64), ("batch_global", C.c_int64), ("net", _lib.DmipMlp),
                 ("beta_min", C.c_float), ("beta_max", C.c_float), ("lam", C.c_float), ("lam2", C.c_float),
-                ("pde_loss", C.c_int32), ("pde_metric", C.c_int32), ("ic_metric", C.c_int32),
+                ("pde_loss", C.c_int32), ("pde_metric", C.c_int32), ("ic_metric", C.c_int32), ("divergence", C.c_int32),
                 ("x", C.c_void_p), ("y", C.c_void_p), ("t", C.c_void_p), ("eps", C.c_void_p),
-                ("ic_target", C.c_void_p), ("out_losses", C.c_void_p), ("grad", C.c_void_p),
+                ("ic_target", C.c_void_p), ("hutch_v", C.c_void_p), ("out_losses", C.c_void_p), ("grad", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
@@ -70,8 +90,10 @@ class _FusedLoss(torch.autograd.Function):
         d.beta_min, d.beta_max = cfg['beta_min'], cfg['beta_max']
         d.lam, d.lam2 = cfg.get('lam', 0.0), cfg.get('lam2', 0.0)
         d.pde_loss, d.pde_metric, d.ic_metric = cfg.get('pde_loss', 0), cfg.get('pde_metric', 1), cfg.get('ic_metric', 1)
+        d.divergence = cfg.get('divergence', 0)
         tens = {}
-        for name, v in (('x', x), ('y', y), ('t', t.reshape(-1)), ('eps', eps), ('ic_target', ic_target)):
+        for name, v in (('x', x), ('y', y), ('t', t.reshape(-1)), ('eps', eps), ('ic_target', ic_target),
+                        ('hutch_v', cfg.get('hutch_v'))):
             if v is None:
                 continue
             v = v.detach().to(dev, torch.float32).contiguous()
@@ -158,17 +180,19 @@ def _model_kind(x, diffused_samples):
 class DSM_PDELoss(nn.Module):
     """DSM + lam * PDE residual (Lai et al. 2023)."""
 
-    def __init__(self, lam=1., pde_loss='FPE', pde_metric='L1'):
+    def __init__(self, lam=1., pde_loss='FPE', pde_metric='L1', *, divergence_method='exact'):
         super().__init__()
         self.lam = lam
         self.dsm_loss = DSMLoss()
         self.pde_loss = ScoreFPELoss(pde_metric) if pde_loss == 'FPE' else ConditionalScoreFPELoss(pde_metric)
         self.name = 'DSM_PDELoss'
+        self.divergence_method = divergence_method
 
     def forward(self, model, x, y, diffused_samples, t, target, std, g):
+        div, probe = _divergence(self, diffused_samples)
         cfg = dict(kind=_LOSS_DSM_PDE, model=_model_kind(x, diffused_samples), lam=float(self.lam),
                    pde_loss=0 if self.pde_loss.name == 'FPELoss' else 1, pde_metric=_metric(self.pde_loss.metric),
-                   batch_global=getattr(self, 'batch_global', 0))
+                   divergence=div, hutch_v=probe, batch_global=getattr(self, 'batch_global', 0))
         out, cfg = _fused(model, cfg, x, y, t, target)
         self.last_launch_count = cfg['launches']
         return out[0], {'PDE-Loss': out[3].detach(), 'DSM-Loss': out[1].detach()}
@@ -177,8 +201,10 @@ class DSM_PDELoss(nn.Module):
 class PINNLoss(nn.Module):
     """DSM + lam2 * initial condition at t=0 + lam * PDE residual (Raissi et al. 2019 style)."""
 
-    def __init__(self, initial_condition, lam=1., lam2=1., pde_loss='FPE', ic_metric='L1', pde_metric='L1'):
+    def __init__(self, initial_condition, lam=1., lam2=1., pde_loss='FPE', ic_metric='L1', pde_metric='L1', *,
+                 divergence_method='exact'):
         super().__init__()
+        self.divergence_method = divergence_method
         self.lam = lam
         self.lam2 = lam2
         self.initial_condition = initial_condition
@@ -188,9 +214,11 @@ class PINNLoss(nn.Module):
         self.ic_metric = ic_metric
 
     def forward(self, model, x, y, diffused_samples, t, target, std, g):
+        div, probe = _divergence(self, diffused_samples)
         cfg = dict(kind=_LOSS_PINN, model=_model_kind(x, diffused_samples), lam=float(self.lam), lam2=float(self.lam2),
                    pde_loss=0 if self.pde_loss.name == 'FPELoss' else 1, pde_metric=_metric(self.pde_loss.metric),
-                   ic_metric=_metric(self.ic_metric), batch_global=getattr(self, 'batch_global', 0))
+                   ic_metric=_metric(self.ic_metric), divergence=div, hutch_v=probe,
+                   batch_global=getattr(self, 'batch_global', 0))
         with torch.no_grad():
             ic_target = self.initial_condition(x, y)
         out, cfg = _fused(model, cfg, x, y, t, target, ic_target)

@@ -147,8 +147,14 @@ int dmip_mlp_forward(const DmipForward* d, void* stream);
 #define DMIP_LOSS_DSM 0     /* loss_fn.name == 'DSMLoss'                                   */
 #define DMIP_LOSS_DSM_PDE 1 /* DSM_PDELoss                                                 */
 #define DMIP_LOSS_PINN 2    /* PINNLoss                                                    */
-#define DMIP_PDE_FPE 0      /* pde_loss = 'FPE'  (needs xdim [+ydim for CDiffE] <= 4)      */
+#define DMIP_PDE_FPE 0      /* pde_loss = 'FPE'  (exact divergence: d = xdim [+ydim for CDiffE] <= 31) */
 #define DMIP_PDE_CFPE 1     /* pde_loss = 'cScoreFPE'                                      */
+/* divergence_method of ScoreFPELoss.forward (losses.py:81-86).  EXACT: d <= 4 runs forward-only (d + d(d+1)/2 tangent
+ * streams), larger d takes the adjoint route (d tangent streams forward, one reverse sweep for grad_x);
+ * EXACT_ADJOINT forces the adjoint route (same values; test hook); HUTCHINSON: v.(J v) with the caller's probe. */
+#define DMIP_DIV_EXACT 0
+#define DMIP_DIV_HUTCHINSON 1
+#define DMIP_DIV_EXACT_ADJOINT 2
 #define DMIP_L1 1
 #define DMIP_L2 2
 
@@ -162,11 +168,14 @@ typedef struct DmipLoss {
   float beta_min, beta_max;
   float lam, lam2;
   int32_t pde_loss, pde_metric, ic_metric;
+  int32_t divergence;     /* DMIP_DIV_*: ScoreFPELoss.forward's divergence_method (losses.py:77-86)                  */
   const float* x;         /* device (batch, xdim)                                           */
   const float* y;         /* device (batch, ydim)                                           */
   const float* t;         /* device (batch,)  from sample_t (models/diffusion.py:48-58)     */
   const float* eps;       /* device (batch, d) standard normals, d = xdim (CDE) | xdim+ydim */
   const float* ic_target; /* device (batch, xdim) = initial_condition(x, y); PINN only      */
+  const float* hutch_v;   /* device (batch, d) probe of div_estimator (losses.py:28-40): +-1 (rademacher_like) or
+                             Gaussian; DMIP_DIV_HUTCHINSON only                              */
   float* out_losses;      /* device float[4]                                                */
   float* grad;            /* device float[dmip_loss_grad_floats(net)]                       */
   void* workspace;        /* device, dmip_loss_workspace_bytes(), 16-byte aligned           */

@@ -31,12 +31,14 @@ def _xdot(t, x0, eps):
     return eps * b * (1 - v) / (2 * std) - 0.5 * b * alpha * x0
 
 
-def score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=True):
+def score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=True, probe=None):
     """Common jets for one batch.
 
     z_t  (B,d): diffused state fed to the net (x_t for CDE, [x_t,y_t] for CDiffE)
     cond (B,c) or None: undiffused conditioning columns (y for CDE, none for CDiffE)
     z0   (B,d): clean state the diffusion started from;  eps (B,d) its noise.
+    probe (B,d) or None: the vector v of div_estimator (losses.py:28-40); given, the divergence is the one-sample
+          Hutchinson estimate v.(J_s^T v) instead of tr J_s, as `divergence_method='hutchinson'` evaluates it.
     Returns dict with a, s, ds_dt (total), and if need_space: div_s, grad_x (detached).
     """
     B, d = z_t.shape
@@ -52,7 +54,11 @@ def score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=True):
             e = zeros.clone()
             e[:, k] = 1.0
             dirs.append(e)
-        pairs = [(1 + i, 1 + k) for i in range(d) for k in range(i, d)]
+        if probe is None:
+            pairs = [(1 + i, 1 + k) for i in range(d) for k in range(i, d)]
+        else:
+            dirs.append(torch.cat([probe, torch.zeros(B, nin - d, dtype=inp.dtype)], 1))   # index d + 1
+            pairs = [(d + 1, 1 + k) for k in range(d)]
     a, ad, add = onets.mlp_jets(params, inp, dirs, pairs)
     b = vp.beta(t)                       # (B,1)
     sb = b ** 0.5
@@ -61,15 +67,20 @@ def score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=True):
     out = {"a": a, "s": s, "beta": b,
            "ds_dt": ad[0] / sb - a * dbeta / (2 * b ** 1.5)}
     if need_space:
-        J = torch.stack(ad[1:], dim=2)                           # J[b,i,k] = d a_i / d x_k
-        out["div_s"] = torch.diagonal(J, dim1=1, dim2=2).sum(1, keepdim=True) / sb
-        gtr = torch.zeros(B, d, dtype=inp.dtype)                 # grad_x tr J
-        for idx, (i, k) in enumerate(pairs):
-            i -= 1
-            k -= 1
-            gtr[:, k] += add[idx][:, i]
-            if i != k:
-                gtr[:, i] += add[idx][:, k]
+        J = torch.stack(ad[1:1 + d], dim=2)                      # J[b,i,k] = d a_i / d x_k
+        gtr = torch.zeros(B, d, dtype=inp.dtype)                 # grad_x tr J   |   grad_x v.(J v)
+        if probe is None:
+            out["div_s"] = torch.diagonal(J, dim1=1, dim2=2).sum(1, keepdim=True) / sb
+            for idx, (i, k) in enumerate(pairs):
+                i -= 1
+                k -= 1
+                gtr[:, k] += add[idx][:, i]
+                if i != k:
+                    gtr[:, i] += add[idx][:, k]
+        else:
+            out["div_s"] = (probe * ad[1 + d]).sum(1, keepdim=True) / sb
+            for k in range(d):
+                gtr[:, k] = (probe * add[k]).sum(1)              # sum_j v_j d^2 a_j [v, e_k]
         JTa = torch.einsum("bik,bi->bk", J, a)
         JTx = torch.einsum("bik,bi->bk", J, z_t)
         out["grad_x"] = (gtr / sb + 2 * JTa / b + (a + JTx) / sb).detach()
@@ -121,10 +132,10 @@ def dsm_loss(params, model_kind, x, y, t, eps):
     return dsm(s, std, eps).mean()
 
 
-def dsm_pde_loss(params, model_kind, x, y, t, eps, lam=1.0, pde_loss="FPE", pde_metric="L1"):
+def dsm_pde_loss(params, model_kind, x, y, t, eps, lam=1.0, pde_loss="FPE", pde_metric="L1", probe=None):
     """DSM_PDELoss.forward (losses.py:143-164).  Returns (loss, info)."""
     z0, cond, z_t, std = _split(model_kind, x, y, t, eps)
-    terms = score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=(pde_loss != "cScoreFPE"))
+    terms = score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=(pde_loss != "cScoreFPE"), probe=probe)
     l_dsm = dsm(terms["s"], std, eps)
     l_pde = lam * _pde(terms, t, eps, std, pde_loss, pde_metric)
     loss = l_dsm.mean() + l_pde.mean()                                  # Q10
@@ -132,7 +143,7 @@ def dsm_pde_loss(params, model_kind, x, y, t, eps, lam=1.0, pde_loss="FPE", pde_
 
 
 def pinn_loss(params, model_kind, x, y, t, eps, ic_target, lam=1.0, lam2=1.0,
-              pde_loss="FPE", ic_metric="L1", pde_metric="L1"):
+              pde_loss="FPE", ic_metric="L1", pde_metric="L1", probe=None):
     """PINNLoss.forward (losses.py:214-242).  `ic_target` = initial_condition(x, y),
     (B,xdim) (analytic linear score, linear_problem.py:61-65, or the scatterometry
     score_posterior).  Returns (loss, info)."""
@@ -140,7 +151,7 @@ def pinn_loss(params, model_kind, x, y, t, eps, ic_target, lam=1.0, lam2=1.0,
     z0, cond, z_t, std = _split(model_kind, x, y, t, eps)
     t0 = torch.zeros_like(t)
     s0 = onets.mlp(params, x, y, t0) / vp.beta(t0) ** 0.5               # :221-223
-    terms = score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=(pde_loss != "cScoreFPE"))
+    terms = score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=(pde_loss != "cScoreFPE"), probe=probe)
     diff = s0[:, :xdim] - ic_target
     l_ic = lam2 * ((diff ** 2).mean(1, keepdim=True) if ic_metric == "L2" else diff.abs().mean(1, keepdim=True))
     l_dsm = dsm(terms["s"], std, eps)

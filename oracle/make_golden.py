@@ -1,7 +1,8 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference
 (/root/reference, imported through oracle/shims) on seeded inputs.
 
-Run in the authoring container only:   python oracle/make_golden.py
+Run in the authoring container only:   python oracle/make_golden.py [fixture-name ...]
+(no names = regenerate everything; with names only those fixtures are recomputed)
 (/root/reference does not exist on the GPU box; the fixtures travel instead.)
 
 Noise injection: torch.randn / torch.randn_like are replaced, for the duration
@@ -32,6 +33,13 @@ import utils_scatterometry as ref_scat  # noqa: E402
 from models.SNF import energy_grad   # noqa: E402
 
 from oracle.weights import make_params, state_dict_from_params  # noqa: E402
+
+ONLY = set(sys.argv[1:])
+
+
+def want(name):
+    return not ONLY or name in ONLY
+
 
 OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -85,7 +93,8 @@ def save(name, **arrs):
 # 0. surrogate checkpoint as a fixture (data, not source)
 # ---------------------------------------------------------------------------
 surr_model, surr_cfg = ref_scat.load_forward_model("/root/reference/trained_models/scatterometry")
-save("surrogate", **{k.replace(".", "_"): v for k, v in surr_model.state_dict().items()})
+if want("surrogate"):
+    save("surrogate", **{k.replace(".", "_"): v for k, v in surr_model.state_dict().items()})
 
 
 def scat_data(n, seed):
@@ -101,6 +110,8 @@ def scat_data(n, seed):
 # 1. net forward  a(x, y, t)  (nets.py:32-35) — double tanh pin (Q1)
 # ---------------------------------------------------------------------------
 def fx_mlp(name, xdim, ydim, out_dim, hidden, seed, B=64, cond=True):
+    if not want(name):
+        return
     m = CDE(xdim, ydim, list(hidden))
     net = m.sde.a
     if out_dim != xdim:
@@ -127,6 +138,8 @@ fx_mlp("mlp_small", 2, 2, 2, (64, 64), 14)
 # 2. samplers (models/diffusion.py:27-46, :158-180)
 # ---------------------------------------------------------------------------
 def fx_sampler_cde(name, xdim, ydim, hidden, seed, N, S, mean=0.0, std=1.0):
+    if not want(name):
+        return
     m = CDE(xdim, ydim, list(hidden))
     load(m.sde.a, make_params(seed, xdim + ydim + 1, xdim, hidden))
     g = gen(seed + 1)
@@ -140,6 +153,8 @@ def fx_sampler_cde(name, xdim, ydim, hidden, seed, N, S, mean=0.0, std=1.0):
 
 
 def fx_sampler_cdiffe(name, xdim, ydim, hidden, seed, N, S):
+    if not want(name):
+        return
     m = CDiffE(xdim, ydim, list(hidden))
     load(m.sde.a, make_params(seed, xdim + ydim + 1, xdim + ydim, hidden))
     orig_mu = m.sde.mu
@@ -159,6 +174,8 @@ def fx_sampler_cdiffe(name, xdim, ydim, hidden, seed, N, S):
 
 
 def fx_sampler_dps(name, xdim, ydim, hidden, seed, N, S):
+    if not want(name):
+        return
     m = PosteriorDiffusionEstimator(xdim, ydim, list(hidden))
     load(m.sde.a.prior_net, make_params(seed, xdim + 1, xdim, hidden))
     load(m.sde.a.likelihood_net, make_params(seed + 100, xdim + ydim + 1, xdim, hidden))
@@ -213,6 +230,8 @@ def lin_data(B, seed):
 
 
 def fx_loss(name, model_kind, problem, loss_kind, hidden, seed, B, full_grads=False, **kw):
+    if not want(name):
+        return
     xdim, ydim = (2, 2) if problem == "linear" else (3, 23)
     cls = CDE if model_kind == "CDE" else CDiffE
     m = cls(xdim, ydim, list(hidden))
@@ -223,6 +242,8 @@ def fx_loss(name, model_kind, problem, loss_kind, hidden, seed, B, full_grads=Fa
     t = (torch.rand(B, 1, generator=g) * (1 - 2e-4) + 1e-4)
     d = out_dim
     eps = torch.randn(B, d, generator=g)
+    div_method = kw.pop("divergence_method", "exact")
+    probe = (torch.randint(0, 2, (B, d), generator=g) * 2 - 1).float() if div_method != "exact" else None
     if problem == "linear":
         ic_fn = lin.score_posterior
     else:
@@ -235,6 +256,12 @@ def fx_loss(name, model_kind, problem, loss_kind, hidden, seed, B, full_grads=Fa
         loss_fn = ref_losses.PINNLoss(ic_fn, **kw)
     elif loss_kind == "DSM_PDE":
         loss_fn = ref_losses.DSM_PDELoss(**kw)
+    if probe is not None:
+        # ScoreFPELoss.forward(..., divergence_method=...) is the reference's own argument (losses.py:77-86); the
+        # composite losses never pass it, so it is bound here; rademacher_like (losses.py:7-11) hands out the stored probe
+        import functools
+        loss_fn.pde_loss.forward = functools.partial(loss_fn.pde_loss.forward, divergence_method=div_method)
+        ref_losses.rademacher_like = lambda s_: probe.clone()
     t_leaf = t.clone().requires_grad_(True)
     z = x if model_kind == "CDE" else torch.cat([x, y], 1)
     with feed([eps]):
@@ -254,6 +281,8 @@ def fx_loss(name, model_kind, problem, loss_kind, hidden, seed, B, full_grads=Fa
                 meta=np.array([seed, xdim, ydim, B] + list(hidden)))
     if loss_kind == "PINN":
         arrs["ic_target"] = ic_fn(x, y)
+    if probe is not None:
+        arrs["probe"] = probe
     for k, v in info.items():
         arrs["info_" + k.replace(" ", "_").replace("-", "_")] = v.detach()
     arrs.update(grad_summary("", grads_of(m.sde.a), full_grads))
@@ -280,9 +309,18 @@ fx_loss("loss_dsmpde_cde_linear_cfpe", "CDE", "linear", "DSM_PDE", H, 41, 128, l
 fx_loss("loss_pinn_small", "CDE", "linear", "PINN", (64, 64), 42, 64, full_grads=True,
         lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
 fx_loss("loss_dsm_small", "CDE", "linear", "DSM", (64, 64), 43, 64, full_grads=True)
+# d = 26 (CDiffE on scatterometry): exact divergence = 53 double-backward passes upstream; and the Hutchinson estimator
+fx_loss("loss_pinn_cdiffe_scat", "CDiffE", "scat", "PINN", H, 44, 48,
+        lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+fx_loss("loss_pinn_cde_scat_hutch", "CDE", "scat", "PINN", H, 45, 128, divergence_method="hutchinson",
+        lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+fx_loss("loss_dsmpde_cdiffe_scat_hutch", "CDiffE", "scat", "DSM_PDE", H, 46, 64, divergence_method="approx",
+        lam=0.05, pde_loss="FPE", pde_metric="L2")
 
 
 def fx_posterior(name, hidden, seed, B, lam, full_grads=False):
+    if not want(name):
+        return
     m = PosteriorDiffusionEstimator(3, 23, list(hidden))
     load(m.sde.a.prior_net, make_params(seed, 4, 3, hidden))
     load(m.sde.a.likelihood_net, make_params(seed + 100, 27, 3, hidden))
@@ -310,28 +348,30 @@ fx_posterior("loss_posterior_small", (64, 64), 52, 64, lam=0.1, full_grads=True)
 # ---------------------------------------------------------------------------
 # 4. scatterometry energy and its gradient (utils_scatterometry.py:30-38, SNF.py:234-237)
 # ---------------------------------------------------------------------------
-g = gen(61)
-x = torch.rand(512, 3, generator=g) * 2.4 - 1.2          # straddles the +-1 boundary penalty
-_, y = scat_data(512, 62)
-e = lambda z: ref_scat.get_log_posterior(z, surr_model, 0.2, 0.01, y, 1000)
-gx, E = energy_grad(x.clone(), e)
-with torch.no_grad():
-    fx = surr_model(x)
-save("scat_energy", x=x, y=y, E=E.detach(), grad=gx.detach(), fx=fx)
+if want("scat_energy"):
+    g = gen(61)
+    x = torch.rand(512, 3, generator=g) * 2.4 - 1.2          # straddles the +-1 boundary penalty
+    _, y = scat_data(512, 62)
+    e = lambda z: ref_scat.get_log_posterior(z, surr_model, 0.2, 0.01, y, 1000)
+    gx, E = energy_grad(x.clone(), e)
+    with torch.no_grad():
+        fx = surr_model(x)
+    save("scat_energy", x=x, y=y, E=E.detach(), grad=gx.detach(), fx=fx)
 
 # ---------------------------------------------------------------------------
 # 5. VP closed forms + analytic linear score (sdes.py:21-49, linear_problem.py:61-65)
 # ---------------------------------------------------------------------------
-sde = ref_sdes.VariancePreservingSDE()
-t = torch.linspace(0, 1, 101).view(-1, 1)
-y0 = torch.randn(101, 3, generator=gen(71))
-eps = torch.randn(101, 3, generator=gen(72))
-with feed([eps]):
-    yt, e2, std, gg = sde.sample(t, y0, return_noise=True)
-x, y = lin_data(64, 73)
-save("vp_closed_forms", t=t, beta=sde.beta(t), alpha=sde.mean_weight(t), var=sde.var(t), y0=y0, eps=eps,
-     yt=yt, std=std, g=gg, f=sde.f(t, y0), lin_x=x, lin_y=y, lin_score=lin.score_posterior(x, y))
-print("done")
+if want("vp_closed_forms"):
+    sde = ref_sdes.VariancePreservingSDE()
+    t = torch.linspace(0, 1, 101).view(-1, 1)
+    y0 = torch.randn(101, 3, generator=gen(71))
+    eps = torch.randn(101, 3, generator=gen(72))
+    with feed([eps]):
+        yt, e2, std, gg = sde.sample(t, y0, return_noise=True)
+    x, y = lin_data(64, 73)
+    save("vp_closed_forms", t=t, beta=sde.beta(t), alpha=sde.mean_weight(t), var=sde.var(t), y0=y0, eps=eps,
+         yt=yt, std=std, g=gg, f=sde.f(t, y0), lin_x=x, lin_y=y, lin_score=lin.score_posterior(x, y))
+    print("done")
 
 # ---------------------------------------------------------------------------
 # 6. A *trained* linear CDE (contractive reverse dynamics, O(1) samples): the
@@ -342,41 +382,42 @@ print("done")
 #    although its analytic posterior treats `scale` as a variance (linear_problem.py:17) — with
 #    sqrt(scale) the trained model targets the analytic posterior stored in the fixture.
 # ---------------------------------------------------------------------------
-from datasets import generate_dataset_linear, get_dataloader_linear  # noqa: E402
-from oracle import philox  # noqa: E402
+if want("trained_cde_linear") or want("sampler_trained_cde_linear"):
+    from datasets import generate_dataset_linear, get_dataloader_linear  # noqa: E402
+    from oracle import philox  # noqa: E402
 
-torch.manual_seed(1234)
-np.random.seed(1234)
-m = CDE(2, 2, [512, 512, 512])
-opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3)
-xs, ys = generate_dataset_linear(2, lin, 20000)
-loss_fn = ref_losses.DSMLoss()
-m.sde.train()
-for ep in range(240):
-    if ep in (120, 200):
-        for gp in opt.param_groups:
-            gp["lr"] *= 0.3
-    loss, _ = m.train_epoch(opt, loss_fn, get_dataloader_linear(xs, ys.clone(), lin.scale ** 0.5, 500))
-    if ep % 20 == 0:
-        print("epoch", ep, float(loss.detach()))
-m.sde.eval()
-sd = m.sde.a.state_dict()
-save("trained_cde_linear", **{k.replace(".", "_"): v for k, v in sd.items()})
-N, S, seed = 512, 200, 777
-y = torch.tensor([0.4, -0.7])
-gidx = np.arange(N)
-x0 = torch.from_numpy(philox.normals(gidx, philox.STEP_INIT, 0, 2, seed))
-noise = torch.from_numpy(np.stack([philox.normals(gidx, i, 0, 2, seed) for i in range(S)]))
-with feed([x0] + list(noise)):
-    out = m(y, num_samples=N, num_steps=S)
-post = lin.get_posterior(y, device="cpu")
-with torch.no_grad():
-    xg = torch.randn(256, 2, generator=gen(5))
-    yg = lin(xg)
-    s0 = m.sde.a(xg, yg, torch.zeros(256, 1)) / 0.1 ** 0.5
-save("sampler_trained_cde_linear", y=y, out=out, philox=np.array([N, S, seed]),
-     post_mean=post.mean, post_cov=post.covariance_matrix,
-     score_x=xg, score_y=yg, score_net=s0, score_true=lin.score_posterior(xg, yg))
-print("sample mean", out.mean(0), "posterior mean", post.mean)
-print("sample cov", np.cov(out.T), "posterior cov", post.covariance_matrix)
-print("done6")
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    m = CDE(2, 2, [512, 512, 512])
+    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3)
+    xs, ys = generate_dataset_linear(2, lin, 20000)
+    loss_fn = ref_losses.DSMLoss()
+    m.sde.train()
+    for ep in range(240):
+        if ep in (120, 200):
+            for gp in opt.param_groups:
+                gp["lr"] *= 0.3
+        loss, _ = m.train_epoch(opt, loss_fn, get_dataloader_linear(xs, ys.clone(), lin.scale ** 0.5, 500))
+        if ep % 20 == 0:
+            print("epoch", ep, float(loss.detach()))
+    m.sde.eval()
+    sd = m.sde.a.state_dict()
+    save("trained_cde_linear", **{k.replace(".", "_"): v for k, v in sd.items()})
+    N, S, seed = 512, 200, 777
+    y = torch.tensor([0.4, -0.7])
+    gidx = np.arange(N)
+    x0 = torch.from_numpy(philox.normals(gidx, philox.STEP_INIT, 0, 2, seed))
+    noise = torch.from_numpy(np.stack([philox.normals(gidx, i, 0, 2, seed) for i in range(S)]))
+    with feed([x0] + list(noise)):
+        out = m(y, num_samples=N, num_steps=S)
+    post = lin.get_posterior(y, device="cpu")
+    with torch.no_grad():
+        xg = torch.randn(256, 2, generator=gen(5))
+        yg = lin(xg)
+        s0 = m.sde.a(xg, yg, torch.zeros(256, 1)) / 0.1 ** 0.5
+    save("sampler_trained_cde_linear", y=y, out=out, philox=np.array([N, S, seed]),
+         post_mean=post.mean, post_cov=post.covariance_matrix,
+         score_x=xg, score_y=yg, score_net=s0, score_true=lin.score_posterior(xg, yg))
+    print("sample mean", out.mean(0), "posterior mean", post.mean)
+    print("sample cov", np.cov(out.T), "posterior cov", post.covariance_matrix)
+    print("done6")

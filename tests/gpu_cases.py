@@ -217,16 +217,23 @@ LOSS_CASES = {
     "loss_pinn_small": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="FPE", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear_cfpe": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="cScoreFPE", pde_metric="L1"), 1.0),
+    "loss_pinn_cdiffe_scat": ("CDiffE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_cde_scat_hutch": ("CDE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1",
+                                                     divergence_method="hutchinson"), 1.0),
+    "loss_dsmpde_cdiffe_scat_hutch": ("CDiffE", "DSM_PDE", dict(lam=0.05, pde_loss="FPE", pde_metric="L2",
+                                                                divergence_method="approx"), 1.0),
 }
 
 
-def case_loss(name):
+def case_loss(name, route=None):
     """Fused loss forward+backward (fp32 kernels) vs the reference's autograd result stored in the fixture:
     loss and every info-dict entry within 3e-4 relative; every parameter gradient within 3e-3 of its scale
     (atomics make the fp32 summation order of the batch reductions non-deterministic)."""
     from dmip import losses as dl
     from util import check_grads
     model_kind, kind, kw, gain = LOSS_CASES[name]
+    if route is not None:       # 'exact_adjoint': the exact divergence through the grad_x reverse sweep instead of Q streams
+        kw = dict(kw, divergence_method=route)
     fx = load_golden(name)
     seed, xdim, ydim, B = (int(v) for v in fx["meta"][:4])
     hidden = meta_hidden(fx, 4)
@@ -245,6 +252,8 @@ def case_loss(name):
             loss_fn = dl.PINNLoss(lambda xx, yy: ic, **kw)
         else:
             loss_fn = dl.DSM_PDELoss(**kw)
+        if "probe" in fx:
+            loss_fn.probe = fx["probe"].to(DEV)
         z = x if model_kind == "CDE" else torch.cat([x, y], 1)
         loss, info = loss_fn(m.sde, x, y, z, t, eps, None, None)
     m.sde.a.zero_grad()

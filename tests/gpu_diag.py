@@ -43,7 +43,11 @@ CASES = [
     "loss_dsm_small", "loss_dsm_cde_linear", "loss_dsm_cdiffe_linear", "loss_dsm_cde_scat",
     "loss_pinn_small", "loss_pinn_cde_linear", "loss_pinn_cde_linear_g3", "loss_pinn_cde_linear_l2l1",
     "loss_pinn_cde_linear_cfpe", "loss_pinn_cde_scat", "loss_pinn_cdiffe_linear",
-    "loss_dsmpde_cde_linear", "loss_dsmpde_cde_linear_cfpe"]] + [
+    "loss_dsmpde_cde_linear", "loss_dsmpde_cde_linear_cfpe",
+    "loss_pinn_cdiffe_scat", "loss_pinn_cde_scat_hutch", "loss_dsmpde_cdiffe_scat_hutch"]] + [
+    ("loss_adj_" + n[5:], f"case_loss('{n}', 'exact_adjoint')") for n in [
+        "loss_pinn_small", "loss_pinn_cde_linear_g3", "loss_pinn_cde_scat", "loss_pinn_cdiffe_linear",
+        "loss_dsmpde_cde_linear"]] + [
     ("surr_energy", "case_surrogate_energy()"),
     ("surr_vjp", "case_surrogate_vjp()"),
     ("loss_posterior_scat", "case_posterior_loss('loss_posterior_scat')"),

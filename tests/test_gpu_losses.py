@@ -16,6 +16,13 @@ def test_fused_loss(name):
     _ok(gc.case_loss(name))
 
 
+@pytest.mark.parametrize("name", ["loss_pinn_small", "loss_pinn_cde_linear_g3", "loss_pinn_cde_scat",
+                                  "loss_pinn_cdiffe_linear", "loss_dsmpde_cde_linear"])
+def test_fused_loss_exact_divergence_adjoint_route(name):
+    """d <= 4 runs forward-only by default; the adjoint route (what d = 26 uses) must give the same reference values"""
+    _ok(gc.case_loss(name, "exact_adjoint"))
+
+
 @pytest.mark.parametrize("name", ["loss_posterior_scat", "loss_posterior_small"])
 def test_posterior_loss(name):
     _ok(gc.case_posterior_loss(name))

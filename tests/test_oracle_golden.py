@@ -81,6 +81,11 @@ LOSS_CASES = {
     "loss_pinn_small": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="FPE", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear_cfpe": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="cScoreFPE", pde_metric="L1"), 1.0),
+    "loss_pinn_cdiffe_scat": ("CDiffE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
+    "loss_pinn_cde_scat_hutch": ("CDE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1",
+                                                     divergence_method="hutchinson"), 1.0),
+    "loss_dsmpde_cdiffe_scat_hutch": ("CDiffE", "DSM_PDE", dict(lam=0.05, pde_loss="FPE", pde_metric="L2",
+                                                                divergence_method="approx"), 1.0),
 }
 
 
@@ -93,6 +98,9 @@ def test_losses(name):
     # fp64 oracle vs fp32 reference: removes the oracle's own round-off from the comparison
     params = _leaf(make_params(seed, xdim + ydim + 1, out_dim, meta_hidden(fx, 4), gain=gain, dtype=torch.float64))
     x, y, t, eps = fx["x"], fx["y"], fx["t"], fx["eps"]
+    kw = dict(kw)
+    if kw.pop("divergence_method", "exact") != "exact":
+        kw["probe"] = fx["probe"]                      # the v of div_estimator (losses.py:28-40) stored with the fixture
     if kind == "DSM":
         loss, info = ol.dsm_loss(params, model, x, y, t, eps), {}
     elif kind == "PINN":
