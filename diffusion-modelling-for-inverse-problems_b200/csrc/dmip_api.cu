@@ -167,6 +167,16 @@ int dmip_surrogate_score(const DmipSurrogate* d, void* stream) {
   return launch_surrogate(d, static_cast<cudaStream_t>(stream));
 }
 
+size_t dmip_metropolis_workspace_bytes(const DmipMetropolis* d) { return d ? metropolis_workspace(d) : 0; }
+
+int dmip_metropolis(const DmipMetropolis* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  return launch_metropolis(d, static_cast<cudaStream_t>(stream));
+}
+
 size_t dmip_posterior_loss_workspace_bytes(const DmipPosteriorLoss* d) { return d ? posterior_loss_workspace(d) : 0; }
 
 int dmip_posterior_loss_fwd_bwd(const DmipPosteriorLoss* d, void* stream) {

@@ -71,6 +71,8 @@ int launch_histogramdd(const DmipHistogram* d, cudaStream_t s);
 int launch_hist_kl(const void* hp, const void* hq, long long m, double epsilon, double* out, cudaStream_t s);
 size_t surrogate_workspace(const DmipSurrogate* d);
 int launch_surrogate(const DmipSurrogate* d, cudaStream_t s);
+size_t metropolis_workspace(const DmipMetropolis* d);
+int launch_metropolis(const DmipMetropolis* d, cudaStream_t s);
 size_t sampler_tc_workspace();
 void debug_set_timeline(unsigned long long* buf, int cap);
 int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s);

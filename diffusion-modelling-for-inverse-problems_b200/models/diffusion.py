@@ -119,14 +119,28 @@ class BaseClassDiffusionModel():
             out = out.view(n_obs, num_samples, self.xdim)
         if return_tensor:
             return out
-        # the reference's single device->host crossing (models/diffusion.py:44), through a cached pinned staging buffer
-        # (a pageable .cpu() of 1M x 100 samples costs 0.2 s; pinned DMA + one host memcpy 0.06 s)
-        n = out.numel()
-        if self._stage is None or self._stage.numel() < n:
-            self._stage = torch.empty(n, dtype=torch.float32, pin_memory=True)
-        self._stage[:n].copy_(out.reshape(-1), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return self._stage[:n].view(out.shape).numpy().copy()
+        # the reference's single device->host crossing (models/diffusion.py:44): pinned DMA in 32 MB chunks through two
+        # cached staging buffers, each chunk copied into the result array (multi-threaded torch CPU copy) while the next
+        # one is in flight.  A pageable .cpu() of 1M x 100 samples costs 0.2 s, one big pinned copy + numpy copy 0.1 s.
+        flat = out.reshape(-1)
+        n = flat.numel()
+        chunk = 8 << 20
+        if self._stage is None:
+            self._stage = [torch.empty(chunk, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            self._stage_ev = [torch.cuda.Event() for _ in range(2)]
+        host = torch.empty(n, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev)
+        n_chunks = (n + chunk - 1) // chunk
+        for c in range(n_chunks + 1):
+            if c < n_chunks:
+                lo, hi = c * chunk, min(n, (c + 1) * chunk)
+                self._stage[c & 1][:hi - lo].copy_(flat[lo:hi], non_blocking=True)
+                self._stage_ev[c & 1].record(stream)
+            if c >= 1:
+                lo, hi = (c - 1) * chunk, min(n, c * chunk)
+                self._stage_ev[(c - 1) & 1].synchronize()
+                host[lo:hi].copy_(self._stage[(c - 1) & 1][:hi - lo])
+        return host.view(out.shape).numpy()
 
     # ------------------------------------------------------------------ training
     def sample_t(self, x, eps=1e-4):

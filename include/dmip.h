@@ -216,6 +216,35 @@ typedef struct DmipSurrogate {
 size_t dmip_surrogate_workspace_bytes(const DmipSurrogate* d);
 int dmip_surrogate_score(const DmipSurrogate* d, void* stream);
 
+/* ---- Metropolis ground-truth chains on the scatterometry posterior ---------------------------------------------
+ * Replaces anneal_to_energy (models/SNF.py:250-275, langevin_prop=False) as generate_gt_samples calls it
+ * (generate_scatterometry_ground_truth.py:26-29): `steps` random-walk Metropolis steps on E = get_log_posterior,
+ * proposal x + noise_std * N(0, I), accept when u < exp(E(x) - E(x')).  n_obs * n_per_obs independent chains, chain i
+ * targets observation y[i / n_per_obs]; x holds the start points on entry (upstream: U(-1,1)^3) and the final points on
+ * return; de (optional) = E(final) - E(start), the second return value of anneal_to_energy.  One launch runs all steps.
+ * rng_mode DMIP_RNG_PHILOX: in-kernel Philox keyed by (seed, gidx_base + chain, step); DMIP_RNG_INJECTED: the caller's
+ * normals noise (steps, n, xdim) and uniforms unif (steps, n), in the order the reference draws them. */
+typedef struct DmipMetropolis {
+  DmipMlp net;             /* the surrogate (ReLU MLP), in_dim = xdim <= 8, out_dim = ydim */
+  float a, b, lambd_bd;
+  float noise_std;         /* NOISE_STD_MCMC */
+  int32_t n_obs;
+  int64_t n_per_obs;
+  int32_t steps;           /* METR_STEPS */
+  const float* y;          /* device (n_obs, ydim) */
+  float* x;                /* device (n_obs * n_per_obs, xdim), in/out */
+  float* de;               /* device (n_obs * n_per_obs,) or NULL */
+  int32_t rng_mode;
+  uint64_t seed, gidx_base;
+  const float* noise;
+  const float* unif;
+  void* workspace;         /* device, dmip_metropolis_workspace_bytes() */
+  size_t workspace_bytes;
+} DmipMetropolis;
+
+size_t dmip_metropolis_workspace_bytes(const DmipMetropolis* d);
+int dmip_metropolis(const DmipMetropolis* d, void* stream);
+
 /* ---- PosteriorLoss (DPS joint loss), forward + backward -------------------------------------------------------
  * Replaces PosteriorLoss.forward + likelihood_target (losses.py:349-386) and the loss.backward() of
  * PosteriorDiffusionEstimator.train_epoch (models/diffusion.py:204-229):

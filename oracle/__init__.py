@@ -23,4 +23,4 @@ Two boundaries stay "parity unpinned": the training-time sampler of `t`
 the VE-SDE / MMD items of BASELINE.json that have no reference counterpart.
 """
 
-from . import vp, nets, sampler, losses, scatterometry, philox, metrics  # noqa: F401
+from . import vp, nets, sampler, losses, scatterometry, philox, metrics, mcmc  # noqa: F401

@@ -359,6 +359,36 @@ if want("scat_energy"):
     save("scat_energy", x=x, y=y, E=E.detach(), grad=gx.detach(), fx=fx)
 
 # ---------------------------------------------------------------------------
+# 4b. Metropolis ground-truth chains (models/SNF.py:250-275 as called by generate_scatterometry_ground_truth.py:26-29)
+# ---------------------------------------------------------------------------
+if want("mcmc_scat"):
+    from models.SNF import anneal_to_energy
+    n_obs, n_per, S, noise_std = 2, 128, 40, 0.05
+    g = gen(81)
+    _, ys = scat_data(n_obs, 82)
+    x0 = torch.rand(n_obs * n_per, 3, generator=g) * 2 - 1
+    x0[:4] *= 1.3                                       # a few starts outside the +-1 box (boundary penalty active)
+    noise = torch.randn(S, n_obs * n_per, 3, generator=g)
+    unif = torch.rand(S, n_obs * n_per, generator=g)
+    outs, des = [], []
+    for i in range(n_obs):
+        sl = slice(i * n_per, (i + 1) * n_per)
+        inflated = ys[i][None, :].repeat(n_per, 1)
+        energy = lambda x: ref_scat.get_log_posterior(x, surr_model, 0.2, 0.01, inflated, 1000)
+        uq = [u for u in unif[:, sl]]
+        o_rand_like = torch.rand_like
+        torch.rand_like = lambda t_, **kw: uq.pop(0).reshape(t_.shape).clone()
+        try:
+            with feed([z for z in noise[:, sl]]):
+                xf, de = anneal_to_energy(x0[sl].clone(), energy, S, noise_std=noise_std)
+        finally:
+            torch.rand_like = o_rand_like
+        outs.append(xf.detach())
+        des.append(de.detach())
+    save("mcmc_scat", y=ys, x0=x0, noise=noise, unif=unif, out=torch.cat(outs), de=torch.cat(des),
+         meta=np.array([n_obs, n_per, S]), noise_std=np.float32(noise_std))
+
+# ---------------------------------------------------------------------------
 # 5. VP closed forms + analytic linear score (sdes.py:21-49, linear_problem.py:61-65)
 # ---------------------------------------------------------------------------
 if want("vp_closed_forms"):

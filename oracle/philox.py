@@ -8,7 +8,8 @@ counter = (gidx_lo, gidx_hi, step, (stream << 16) | quad)   key = (seed_lo, seed
   gidx   : global particle index (obs * n_per_obs + n) — results are independent of
            how particles are split over CTAs or GPUs
   step   : SDE step index; 0xFFFFFFFF for the initial draw x0
-  stream : 0 = state noise, 1 = CDiffE observation re-diffusion noise
+  stream : 0 = state noise, 1 = CDiffE observation re-diffusion noise,
+           2 = Metropolis proposal noise, 3 = Metropolis acceptance uniform (first output word, quad 0)
   quad   : element index // 4; the four 32-bit outputs give elements 4q..4q+3
 Box–Muller on (u1,u2) = ((r>>8)+0.5)/2^24:  n0 = R cos(th), n1 = R sin(th).
 """
@@ -62,3 +63,13 @@ def normals(gidx, step, stream, dim, seed):
         out[:, :, 2 * j] = R * np.cos(th)
         out[:, :, 2 * j + 1] = R * np.sin(th)
     return out.reshape(len(gidx), nq * 4)[:, :dim]
+
+
+def uniforms(gidx, step, stream, seed):
+    """(len(gidx),) float32 uniforms in (0,1): the first output word of the (gidx, step, stream, quad 0) block."""
+    gidx = np.asarray(gidx, dtype=np.uint64)
+    c0 = (gidx & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    c1 = (gidx >> np.uint64(32)).astype(np.uint32)
+    r0, _, _, _ = philox4x32_10(c0, c1, np.uint32(step), np.uint32(stream) << np.uint32(16),
+                                seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return _u01(r0)

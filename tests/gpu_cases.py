@@ -538,3 +538,80 @@ def case_histogram_kl():
             ref = omet.kl2(hm, ht) if rev else omet.kl2(ht, hm)
             worst = max(worst, abs(acc.kl(reverse=rev) - ref))
     return worst, 1e-12, {}
+
+
+# ------------------------------------------------------------------------------------------- Metropolis chains (N3)
+def _chains_match(x, ref, de, de_ref):
+    """fraction of chains that differ from the reference (an accept decision on a near-tie may flip in fp32) and the
+    energy-difference error of the matching ones"""
+    same = (x - ref).abs().max(1).values <= 2e-5
+    bad_de = ((de[same] - de_ref[same]).abs() > 1e-3 * de_ref[same].abs() + 5e-2).float().mean().item()
+    return 1.0 - same.float().mean().item() + bad_de
+
+
+def case_metropolis(mode):
+    """dmip.mcmc.anneal_to_energy vs the reference's anneal_to_energy (models/SNF.py:250-275) on the stored random
+    stream (fixture mcmc_scat, 2 observations x 128 chains x 40 steps): >= 98 % of the chains end on the same point to
+    2e-5 with the same energy difference.  mode 'philox': the in-kernel Philox stream must reproduce, bit for bit, the
+    run fed with the numpy mirror of that stream."""
+    from dmip import mcmc
+    fm, _ = _surrogate_module()
+    fx = load_golden("mcmc_scat")
+    n_obs, n_per, S = (int(v) for v in fx["meta"])
+    x0, ys = fx["x0"].to(DEV), fx["y"].to(DEV)
+    std = float(fx["noise_std"])
+    if mode == "injected":
+        x, de = mcmc.anneal_to_energy(x0, fm, 0.2, 0.01, ys, 1000, S, std, injected=dict(noise=fx["noise"], unif=fx["unif"]))
+        return _chains_match(x.cpu(), fx["out"], de.cpu(), fx["de"]), 0.02, {}
+    seed, base = 4321, 1000
+    gidx = np.arange(n_obs * n_per) + base
+    noise = torch.from_numpy(np.stack([oracle.philox.normals(gidx, i, 2, 3, seed) for i in range(S)]))
+    unif = torch.from_numpy(np.stack([oracle.philox.uniforms(gidx, i, 3, seed) for i in range(S)]))
+    xa, dea = mcmc.anneal_to_energy(x0, fm, 0.2, 0.01, ys, 1000, S, std, seed=seed, gidx_base=base)
+    xb, deb = mcmc.anneal_to_energy(x0, fm, 0.2, 0.01, ys, 1000, S, std, injected=dict(noise=noise, unif=unif))
+    moved = ((xa - x0).abs().max(1).values > 0).float().mean().item()
+    err = _chains_match(xa.cpu(), xb.cpu(), dea.cpu(), deb.cpu()) + (0.0 if moved > 0.5 else 1.0)
+    return err, 0.02, dict(moved=moved)
+
+
+def case_evaluate():
+    """dmip.evaluation on the trained linear CDE: all observations in one sampler launch per repeat, histograms / KL /
+    NLL / score MSE on the GPU.  The KL column must equal scipy's on the same accumulated counts (checked inside
+    case_histogram_kl); here: the trained model is close to the analytic posterior (KL2 < 0.5 with 2 x 5000 samples in
+    75 x 75 bins, |NLL gap| < 0.1) and the scatterometry variant runs end to end on generated ground truth."""
+    from dmip import evaluation, mcmc
+    from dmip.linear_problem import LinearForwardProblem
+    from dmip.models.diffusion import CDE
+    from dmip.utils_scatterometry import make_score_posterior
+    m = trained_model()
+    lin = LinearForwardProblem()
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randn(6, 2, generator=g)
+    ys = lin(xs) + 0.3 ** 0.5 * torch.randn(6, 2, generator=g)
+    kl, nlpd, mse, table = evaluation.evaluate_linear(m, ys, lin, n_samples_x=5000, n_repeats=2)
+    ok = kl < 0.5 and nlpd < 0.1 and np.isfinite(mse) and table['KL2'].shape == (6,)
+    fm, _ = _surrogate_module()
+    params = {'a': 0.2, 'b': 0.01, 'lambd_bd': 1000, 'xdim': 3, 'ydim': 23}
+    xt = torch.rand(3, 3, generator=g) * 1.6 - 0.8
+    with torch.no_grad():
+        ysc = fm(xt.to(DEV))
+    gt = mcmc.generate_gt_samples(fm, params, ysc, 2048, 60, 0.02, n_repeats=2, seed=11)
+    torch.manual_seed(0)
+    ms = CDE(3, 23, [512, 512, 512])
+    ms.sde.to(DEV)
+    # a short DSM fit so that the reverse SDE contracts (an untrained net sends every sample out of the histogram range
+    # and the KL is 0/0, upstream too)
+    from dmip import losses as dl
+    X = torch.rand(8000, 3, device=DEV) * 2 - 1
+    with torch.no_grad():
+        fX = fm(X)
+        Y = fX + 0.01 * torch.randn_like(fX) + 0.2 * fX * torch.randn_like(fX)
+    opt = torch.optim.Adam(ms.sde.a.parameters(), lr=1e-3)
+    for _ in range(25):
+        ms.train_epoch(opt, dl.DSMLoss(), lambda: ((X[i:i + 1000], Y[i:i + 1000]) for i in range(0, 8000, 1000)))
+    kl2, nlpd2, mse2, table2 = evaluation.evaluate_scatterometry(
+        ms, ysc, fm, lambda i, j: gt[i, j], 2048, make_score_posterior(fm, params), 0.2, 0.01, 1000, n_repeats=2,
+        num_steps=20)
+    ok = ok and all(np.isfinite(v).all() for v in table2.values()) and set(table2) == {
+        'KL2', 'KL_reverse', 'NLL_mcmc', 'NLL_diffusion', 'MSE'}
+    return (0.0 if ok else 1.0), 0.5, dict(kl=float(kl), nlpd=float(nlpd), mse=float(mse), kl_scat=float(kl2))

@@ -60,6 +60,9 @@ CASES = [
     ("train_dsm", "case_train_epoch('DSM')"),
     ("train_pinn", "case_train_epoch('PINN')"),
     ("hist_kl", "case_histogram_kl()"),
+    ("mcmc_injected", "case_metropolis('injected')"),
+    ("mcmc_philox", "case_metropolis('philox')"),
+    ("evaluate", "case_evaluate()"),
 ]
 
 TEMPLATE = """

@@ -65,10 +65,11 @@ def _sizeof_from_c(struct_names):
 
 def test_ctypes_struct_layouts_match_the_header():
     """The header is plain C (compiles with gcc -std=c99) and the Python mirrors have identical sizes."""
-    from dmip import _lib, losses, metrics, posterior, utils_scatterometry
+    from dmip import _lib, losses, mcmc, metrics, posterior, utils_scatterometry
     mirrors = {"DmipMlp": _lib.DmipMlp, "DmipSampler": _lib.DmipSampler, "DmipForward": _lib.DmipForward,
                "DmipLoss": losses.DmipLoss, "DmipPosteriorLoss": posterior.DmipPosteriorLoss,
-               "DmipSurrogate": utils_scatterometry.DmipSurrogate, "DmipHistogram": metrics.DmipHistogram}
+               "DmipSurrogate": utils_scatterometry.DmipSurrogate, "DmipHistogram": metrics.DmipHistogram,
+               "DmipMetropolis": mcmc.DmipMetropolis}
     sizes = _sizeof_from_c(list(mirrors))
     for name, cls in mirrors.items():
         assert C.sizeof(cls) == sizes[name], (name, C.sizeof(cls), sizes[name])

@@ -38,3 +38,12 @@ def test_surrogate_likelihood_vjp():
 
 def test_histogram_kl_matches_numpy_bit_for_bit():
     _ok(gc.case_histogram_kl())
+
+
+@pytest.mark.parametrize("mode", ["injected", "philox"])
+def test_metropolis_chains_match_reference(mode):
+    _ok(gc.case_metropolis(mode))
+
+
+def test_evaluate_loops_run_on_gpu():
+    _ok(gc.case_evaluate())

@@ -208,3 +208,19 @@ def test_metrics_oracle_kl_properties():
     assert omet.kl2(ha, ha) == 0.0
     assert omet.kl2(ha, hb) > 0.05
     assert np.array_equal(ha, np.histogramdd(np.concatenate(a), bins=bins, range=ranges)[0])
+
+
+def test_metropolis_oracle_matches_reference_chains():
+    """oracle.mcmc.anneal_to_energy vs the reference's anneal_to_energy run on the stored normals / uniforms
+    (fixture mcmc_scat): identical accept decisions, final points and energy differences."""
+    from oracle import mcmc as omc
+    fx = load_golden("mcmc_scat")
+    n_obs, n_per, S = (int(v) for v in fx["meta"])
+    sp = surrogate_params()
+    y = fx["y"].repeat_interleave(n_per, 0)
+    x, de = omc.anneal_to_energy(sp, fx["x0"], y, fx["noise"], fx["unif"], float(fx["noise_std"]))
+    moved = ((fx["out"] - fx["x0"]).abs().max(1).values > 0).float().mean().item()
+    assert moved > 0.5, moved                                      # the chains did move
+    same = ((x - fx["out"]).abs().max(1).values <= 1e-6)
+    assert same.float().mean().item() >= 0.99                      # a near-tie may flip an accept in fp32
+    assert torch.allclose(de[same], fx["de"][same], rtol=1e-4, atol=2e-2)
