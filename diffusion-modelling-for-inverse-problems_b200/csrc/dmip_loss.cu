@@ -238,141 +238,110 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
       __syncthreads();
       continue;
     }
-    // ---- per-sample loss terms and output adjoints (one thread per sample; `in` holds the raw last-layer rows)
-    if (t < spt && s0 + t < P.B) {
-      const long long smp = s0 + t;
-      const float* o = in + t * ns;            // o[j*kLd + stream]
-      const int L = P.n_layers - 1;
-      const int od = P.out_dim;
-      const float tt = P.t[smp];
-      float beta, alpha, var;
-      vp_terms(tt, P.bmin, P.bmax, beta, alpha, var);
-      const float sd = sqrtf(var), sb = sqrtf(beta), db = P.bmax - P.bmin;
-      float* abarP = P.abar + (smp * P.n_adj + 0) * od;
-      float l_dsm = 0.f, l_ic = 0.f, l_pde = 0.f;
-      if (P.post == 1) {
-        // DPS prior net: s_prior = prior_net(x_t, t) IS the score (no 1/g); DSM on it; Tweedie mean and Jacobian
-        // for the likelihood target                                                   (losses.py:374-381)
-        for (int j = 0; j < od; ++j) {
-          const float sp = o[j * kLd + 0] + P.b[L][j];
-          const float xt = P.eps[smp * d + j] * sd + alpha * P.x[smp * P.xdim + j];
-          const float r = sp * sd + P.eps[smp * d + j];
-          l_dsm += 0.5f * r * r;
-          abarP[j] = P.inv_B * r * sd;
-          P.aux_s[smp * d + j] = sp;
-          P.aux_xt[smp * d + j] = xt;
-          P.aux_x0[smp * d + j] = (xt + var * sp) / alpha;
-          for (int k = 0; k < d; ++k) P.aux_J[(smp * d + j) * d + k] = o[j * kLd + sS + k];
-        }
-      } else if (P.post == 2) {
-        // DPS likelihood net: sum_j (alpha s_lik - target)^2, target detached           (losses.py:382)
-        for (int j = 0; j < od; ++j) {
-          const float r = alpha * (o[j * kLd + 0] + P.b[L][j]) - P.aux_s[smp * d + j];
-          l_ic += P.lam * r * r;
-          abarP[j] = P.inv_B * P.lam * 2.f * r * alpha;
-        }
-      } else
-      // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                            (losses.py:49-52, Q3)
-      for (int j = 0; j < od; ++j) {
-        const float a = o[j * kLd + 0] + P.b[L][j];
-        const float r = a / sb * sd + P.eps[smp * d + j];
-        l_dsm += 0.5f * r * r;
-        abarP[j] = P.inv_B * r * sd / sb;
-      }
-      if (P.has_I) {                           // initial condition at t = 0          (losses.py:221-230)
-        float* abarI = P.abar + (smp * P.n_adj + 1) * od;
-        const float g0 = sqrtf(P.bmin);
-        for (int j = 0; j < od; ++j) {
-          float g = 0.f;
-          if (j < P.xdim) {
-            const float diff = (o[j * kLd + sI] + P.b[L][j]) / g0 - P.ic_target[smp * P.xdim + j];
-            if (P.ic_metric == 2) { l_ic += diff * diff; g = 2.f * diff; }
-            else { l_ic += fabsf(diff); g = (diff > 0.f) - (diff < 0.f); }
-            g *= P.lam2 / (P.xdim * g0);
+    // ---- loss terms and output adjoints, one (sample, output component) item per thread (`in` holds the raw
+    // last-layer rows); partial sums meet in red[] through warp shuffles
+    {
+      const int L = P.n_layers - 1, od = P.out_dim;
+      const float db = P.bmax - P.bmin;
+      const int n_items = spt * od;
+      for (int base = 0; base < n_items; base += kThreadsL) {
+        const int idx = base + t;
+        const int sl = idx / od, j = idx - sl * od;
+        const long long smp = s0 + sl;
+        float l_dsm = 0.f, l_ic = 0.f, l_pde = 0.f;
+        if (idx < n_items && smp < P.B) {
+          const float* o = in + sl * ns;           // o[c*kLd + stream]
+          float beta, alpha, var;
+          vp_terms(P.t[smp], P.bmin, P.bmax, beta, alpha, var);
+          const float sd = sqrtf(var), sb = sqrtf(beta);
+          const float aj = o[j * kLd + 0] + P.b[L][j];
+          const float epsj = P.eps[smp * d + j];
+          float abP;                               // adjoint of the primal output j
+          if (P.post == 1) {
+            // DPS prior net: s_prior = prior_net(x_t, t) IS the score (no 1/g); DSM on it; Tweedie mean and Jacobian
+            // for the likelihood target                                                   (losses.py:374-381)
+            const float xt = epsj * sd + alpha * P.x[smp * P.xdim + j];
+            const float r = aj * sd + epsj;
+            l_dsm = 0.5f * r * r;
+            abP = P.inv_B * r * sd;
+            P.aux_s[smp * d + j] = aj;
+            P.aux_xt[smp * d + j] = xt;
+            P.aux_x0[smp * d + j] = (xt + var * aj) / alpha;
+            for (int k = 0; k < d; ++k) P.aux_J[(smp * d + j) * d + k] = o[j * kLd + sS + k];
+          } else if (P.post == 2) {
+            // DPS likelihood net: sum_j (alpha s_lik - target)^2, target detached           (losses.py:382)
+            const float r = alpha * aj - P.aux_s[smp * d + j];
+            l_ic = P.lam * r * r;
+            abP = P.inv_B * P.lam * 2.f * r * alpha;
+          } else {
+            // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                            (losses.py:49-52, Q3)
+            const float r = aj / sb * sd + epsj;
+            l_dsm = 0.5f * r * r;
+            abP = P.inv_B * r * sd / sb;
           }
-          abarI[j] = P.inv_B * g;
-        }
-        l_ic *= P.lam2 / P.xdim;
-      }
-      if (P.has_T) {
-        float* abarT = P.abar + (smp * P.n_adj + 1 + P.has_I) * od;
-        if (P.pde_loss == 0 && P.gx) {
-          // Score-FPE residual with grad_x from the adjoint route (k_gradx_bwd), any d
-          for (int k = 0; k < d; ++k) {
-            const float a = o[k * kLd + 0] + P.b[L][k];
-            const float ds_dt = o[k * kLd + sT] / sb - a * db / (2.f * beta * sb);
-            const float R = ds_dt - 0.5f * beta * P.gradx[smp * d + k];
-            float g;
-            if (P.pde_metric == 1) { l_pde += fabsf(R); g = (R > 0.f) - (R < 0.f); }
-            else { l_pde += R * R; g = 2.f * R; }
-            g *= P.lam / d * P.inv_B;
-            abarT[k] = g / sb;
-            abarP[k] += -g * db / (2.f * beta * sb);
-          }
-          l_pde *= P.lam / d;
-        } else if (P.pde_loss == 0) {
-          // Score-FPE residual R = ds/dt - beta/2 grad_x[div s + |s|^2 + x.s], grad_x constant (losses.py:88-95, Q9)
-          float a[kMaxD], zt[kMaxD], J[kMaxD][kMaxD], gtr[kMaxD];
-#pragma unroll
-          for (int i = 0; i < kMaxD; ++i) {
-            a[i] = 0.f; zt[i] = 0.f; gtr[i] = 0.f;
-#pragma unroll
-            for (int k = 0; k < kMaxD; ++k) J[i][k] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < kMaxD; ++i)
-            if (i < d) {
-              a[i] = o[i * kLd + 0] + P.b[L][i];
-              const float z0 = (i < P.xdim) ? P.x[smp * P.xdim + i] : P.y[smp * P.ydim + (i - P.xdim)];
-              zt[i] = P.eps[smp * d + i] * sd + alpha * z0;
-#pragma unroll
-              for (int k = 0; k < kMaxD; ++k)
-                if (k < d) J[i][k] = o[i * kLd + 1 + P.has_I + P.has_T + k];     // d a_i / d x_k
+          if (P.has_I) {                           // initial condition at t = 0          (losses.py:221-230)
+            const float g0 = sqrtf(P.bmin);
+            float g = 0.f;
+            if (j < P.xdim) {
+              const float diff = (o[j * kLd + sI] + P.b[L][j]) / g0 - P.ic_target[smp * P.xdim + j];
+              if (P.ic_metric == 2) { l_ic = diff * diff; g = 2.f * diff; }
+              else { l_ic = fabsf(diff); g = (diff > 0.f) - (diff < 0.f); }
+              l_ic *= P.lam2 / P.xdim;
+              g *= P.lam2 / (P.xdim * g0);
             }
-#pragma unroll
-          for (int i = 0; i < kMaxD; ++i)
-#pragma unroll
-            for (int k = i; k < kMaxD; ++k)
-              if (k < d) {
-                const int q = 1 + P.has_I + P.has_T + d + q_index(i, k, d);
-                gtr[k] += o[i * kLd + q];                    // d^2 a_i / dx_i dx_k
-                if (i != k) gtr[i] += o[k * kLd + q];        // d^2 a_k / dx_k dx_i
+            P.abar[(smp * P.n_adj + 1) * od + j] = P.inv_B * g;
+          }
+          if (P.has_T) {
+            const float ds_dt = o[j * kLd + sT] / sb - aj * db / (2.f * beta * sb);
+            float g;                               // d loss / d ds_dt[j]
+            if (P.pde_loss == 0) {
+              // Score-FPE residual R = ds/dt - beta/2 grad_x[div s + |s|^2 + x.s], grad_x constant (losses.py:88-95, Q9)
+              float grad_x;
+              if (P.gx) {
+                grad_x = P.gradx[smp * d + j];     // adjoint route (k_gradx_bwd), any d
+              } else {
+                float JTa = 0.f, JTx = 0.f, gtr = 0.f;
+                for (int i = 0; i < d; ++i) {
+                  const float ai = o[i * kLd + 0] + P.b[L][i];
+                  const float z0 = (i < P.xdim) ? P.x[smp * P.xdim + i] : P.y[smp * P.ydim + (i - P.xdim)];
+                  const float zti = P.eps[smp * d + i] * sd + alpha * z0;
+                  const float Jij = o[i * kLd + sS + j];                        // d a_i / d x_j
+                  JTa = fmaf(Jij, ai, JTa);
+                  JTx = fmaf(Jij, zti, JTx);
+                  gtr += o[i * kLd + sQ + q_index(min(i, j), max(i, j), d)];    // d^2 a_i / dx_i dx_j
+                }
+                grad_x = gtr / sb + 2.f * JTa / beta + (aj + JTx) / sb;
               }
-          for (int k = 0; k < d; ++k) {
-            float JTa = 0.f, JTx = 0.f;
+              const float R = ds_dt - 0.5f * beta * grad_x;
+              if (P.pde_metric == 1) { l_pde = fabsf(R); g = (R > 0.f) - (R < 0.f); }
+              else { l_pde = R * R; g = 2.f * R; }
+              l_pde *= P.lam / d;
+              g *= P.lam / d * P.inv_B;
+            } else {
+              // cScoreFPE: sum_j (std^3 ds/dt - eps beta alpha^2 / 2)^2                  (losses.py:116-124)
+              const float r = sd * sd * sd * ds_dt - 0.5f * epsj * beta * alpha * alpha;
+              if (P.pde_metric == 2) { l_pde = r * r; g = 2.f * r; }
+              else { l_pde = fabsf(r); g = (r > 0.f) - (r < 0.f); }
+              l_pde *= P.lam;
+              g *= P.lam * sd * sd * sd * P.inv_B;
+            }
+            P.abar[(smp * P.n_adj + 1 + P.has_I) * od + j] = g / sb;
+            abP += -g * db / (2.f * beta * sb);
+          }
+          P.abar[(smp * P.n_adj + 0) * od + j] = abP;
+        }
 #pragma unroll
-            for (int i = 0; i < kMaxD; ++i)
-              if (i < d) { JTa += J[i][k] * a[i]; JTx += J[i][k] * zt[i]; }
-            const float grad_x = gtr[k] / sb + 2.f * JTa / beta + (a[k] + JTx) / sb;
-            const float ds_dt = o[k * kLd + sT] / sb - a[k] * db / (2.f * beta * sb);
-            const float R = ds_dt - 0.5f * beta * grad_x;
-            float g;
-            if (P.pde_metric == 1) { l_pde += fabsf(R); g = (R > 0.f) - (R < 0.f); }
-            else { l_pde += R * R; g = 2.f * R; }
-            g *= P.lam / d * P.inv_B;
-            abarT[k] = g / sb;
-            abarP[k] += -g * db / (2.f * beta * sb);
-          }
-          l_pde *= P.lam / d;
-        } else {
-          // cScoreFPE: sum_j (std^3 ds/dt - eps beta alpha^2 / 2)^2                  (losses.py:116-124)
-          for (int j = 0; j < od; ++j) {
-            const float a = o[j * kLd + 0] + P.b[L][j];
-            const float ds_dt = o[j * kLd + sT] / sb - a * db / (2.f * beta * sb);
-            const float r = sd * sd * sd * ds_dt - 0.5f * P.eps[smp * d + j] * beta * alpha * alpha;
-            float g;
-            if (P.pde_metric == 2) { l_pde += r * r; g = 2.f * r; }
-            else { l_pde += fabsf(r); g = (r > 0.f) - (r < 0.f); }
-            g *= P.lam * sd * sd * sd * P.inv_B;
-            abarT[j] = g / sb;
-            abarP[j] += -g * db / (2.f * beta * sb);
-          }
-          l_pde *= P.lam;
+        for (int off = 16; off > 0; off >>= 1) {
+          l_dsm += __shfl_xor_sync(0xffffffffu, l_dsm, off);
+          l_ic += __shfl_xor_sync(0xffffffffu, l_ic, off);
+          l_pde += __shfl_xor_sync(0xffffffffu, l_pde, off);
+        }
+        if ((t & 31) == 0) {
+          atomicAdd(&red[1], l_dsm);
+          atomicAdd(&red[2], l_ic);
+          atomicAdd(&red[3], l_pde);
         }
       }
-      atomicAdd(&red[1], l_dsm);
-      atomicAdd(&red[2], l_ic);
-      atomicAdd(&red[3], l_pde);
     }
     __syncthreads();
     if (t == 0) {

@@ -66,7 +66,9 @@ __device__ void tile_gemm_direct(const float* in, float* out, const float* __res
 
 // ---- staged variant: the weights stream through shared memory in 16-k slabs (cp.async, double buffered), so their L2
 // latency is paid one slab (16 k-steps) ahead instead of one k-step ahead, and every thread reads its four weights with
-// one conflict-free LDS.128.  Thread (rg, ng) owns R rows and columns 4 ng .. 4 ng + 3; N = 64 R (512 or 256).
+// one conflict-free LDS.128.  Thread (rg, ng) owns R rows and columns 4 ng .. 4 ng + 3; N = 64 R (512 or 256).  A warp
+// covers ALL 32 rows x 4 R columns (lane = row group x column group), so per k-step it touches 128 B of activations
+// and 16 R B of weights: 3 shared-memory wavefronts per 32 FFMA instead of 6 with one row group per warp.
 constexpr int kSlabK = 16;
 constexpr int kWbufFloats = 2 * kSlabK * kMaxW;   // 64 KB
 
@@ -84,7 +86,8 @@ __device__ void tile_gemm_staged(const float* in, float* out, const float* __res
   constexpr int N = 64 * R;              // 512 threads x (4 columns x R rows) = 32 rows x N columns
   constexpr int kGroups = N / 4;         // column groups
   const int t = threadIdx.x;
-  const int rg = t / kGroups, ng = t % kGroups;
+  const int rg = (t & 31) / R, ng = (t >> 5) * R + (t & 31) % R;   // 32 / R row groups x R column groups per warp
+  static_assert(kGroups == (kThreadsL / 32) * R, "16 warps x R column groups cover the N / 4 groups");
   float acc[R][4];
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -145,8 +148,42 @@ __device__ void tile_gemm_staged(const float* in, float* out, const float* __res
   __syncthreads();
 }
 
-// out[n*kLd + r] = sum_k in[k*kLd + r] * Wt[k*N + n]: staged path for the big square layers, direct path otherwise
+// ---- skinny outputs (N <= 32 with a long contraction: the nets' last layer, the first layer of a reverse sweep).  The
+// direct path would leave all but 4 N threads idle and walk K serially behind one global load per step (ncu: 30 % of
+// k_jets_fwd's warp samples sat at its closing barrier).  Here a row's contraction is cut into 16 k-slices held by one
+// half-warp and summed with shuffles; the weights (<= 64 KB) are L1 hits.
+__device__ void tile_gemm_skinny(const float* in, float* out, const float* __restrict__ Wt, int K, int N) {
+  const int t = threadIdx.x;
+  const int r = t >> 4, ks = t & 15;   // 32 rows x 16 k-slices
+  for (int nb = 0; nb < N; nb += 8) {
+    const int nn = N - nb < 8 ? N - nb : 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = ks; k < K; k += 16) {
+      const float a = in[k * kLd + r];
+      const float* w = Wt + static_cast<size_t>(k) * N + nb;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nn) acc[i] = fmaf(a, __ldg(w + i), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if (ks == 0 && i < nn) out[(nb + i) * kLd + r] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// out[n*kLd + r] = sum_k in[k*kLd + r] * Wt[k*N + n]: staged path for the big square layers, skinny path for few
+// outputs behind a long contraction, direct path otherwise
 __device__ void tile_gemm(const float* in, float* out, const float* __restrict__ Wt, int K, int N, float* wbuf) {
+  if (N <= 32 && K >= 64) { tile_gemm_skinny(in, out, Wt, K, N); return; }
   if ((K % kSlabK) == 0 && K >= 64 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0) {
     if (N == 512) { tile_gemm_staged<8>(in, out, Wt, K, wbuf); return; }
     if (N == 256) { tile_gemm_staged<4>(in, out, Wt, K, wbuf); return; }
