@@ -796,7 +796,7 @@ int run_pass(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
   for (int l = 0; l < net.n_layers; ++l) {
     const int n = net.width[l];
     const int tiles = ceil_div(n, kWgT) * ceil_div(k, kWgT);
-    int split = (2 * n_sm + tiles - 1) / tiles;
+    int split = (2 * n_sm) / tiles;   // two CTAs are resident per SM: one full wave, never a nearly empty second one
     const long long max_split = (rows + 255) / 256;
     if (split > max_split) split = static_cast<int>(max_split);
     if (split < 1) split = 1;
