@@ -459,6 +459,45 @@ __global__ void __launch_bounds__(512, 1) k_xu_rate(int iters, long long* out, f
   if (a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7] + __uint_as_float(pk) == 123.f) sink[0] = a[0];
 }
 
+// legacy warp-level tensor path: issue rate of mma.sync with 16 warps x 8 independent accumulator tiles
+template <int kKind>
+__device__ long long mmasync_loop(int iters, float (&c)[8][4], uint32_t a0, uint32_t b0) {
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (kKind == 0) {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                     : "r"(a0), "r"(a0 + j), "r"(a0 ^ 5u), "r"(a0 + 3u), "r"(b0), "r"(b0 + j));
+      } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                     : "r"(a0), "r"(a0 + j), "r"(a0 ^ 5u), "r"(a0 + 3u), "r"(b0), "r"(b0 + j));
+      }
+    }
+  }
+  __syncthreads();
+  return clock64() - t0;
+}
+
+__global__ void __launch_bounds__(512, 1) k_mmasync_rate(int iters, long long* out, float* sink) {
+  float c[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[j][e] = 0.f;
+  const uint32_t a0 = 0x3c003c00u + threadIdx.x, b0 = 0x3c003c00u ^ threadIdx.x;
+  const long long t0 = mmasync_loop<0>(iters, c, a0 & 0x3fffe000u, b0 & 0x3fffe000u);
+  const long long t1 = mmasync_loop<1>(iters, c, a0, b0);
+  if (threadIdx.x == 0) { out[0] = t0; out[1] = t1; }
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc += c[j][0] + c[j][1] + c[j][2] + c[j][3];
+  if (acc == 123.f) sink[0] = acc;
+}
+
 }  // namespace
 
 int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int stream_bytes, int grid, const void* gsrc,
@@ -515,7 +554,9 @@ int launch_debug_prim_bench(int iters, long long* out, cudaStream_t s) {
   DMIP_CHECK_CUDA(cudaGetLastError());
   k_xu_rate<<<1, 512, 0, s>>>(iters, out, reinterpret_cast<float*>(out + 60));
   DMIP_CHECK_CUDA(cudaGetLastError());
-  count_launch(4);
+  k_mmasync_rate<<<1, 512, 0, s>>>(iters, out + 53, reinterpret_cast<float*>(out + 61));
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch(5);
   return DMIP_OK;
 }
 

@@ -615,3 +615,22 @@ def case_evaluate():
     ok = ok and all(np.isfinite(v).all() for v in table2.values()) and set(table2) == {
         'KL2', 'KL_reverse', 'NLL_mcmc', 'NLL_diffusion', 'MSE'}
     return (0.0 if ok else 1.0), 0.5, dict(kl=float(kl), nlpd=float(nlpd), mse=float(mse), kl_scat=float(kl2))
+
+
+def case_host_results_do_not_alias():
+    """model(y) returns numpy arrays that live in pooled pinned buffers: an array the caller still holds must never be
+    overwritten by a later call; a dropped one is recycled (no new pinned allocation)."""
+    m = trained_model()
+    y = torch.tensor([0.4, -0.7])
+    x1 = m(y, num_samples=4096, num_steps=10, seed=1)
+    keep = x1.copy()
+    x2 = m(y, num_samples=4096, num_steps=10, seed=2)
+    row = x2[5]                                   # a derived view keeps its parent buffer busy
+    ok = np.array_equal(x1, keep) and not np.array_equal(x1, x2) and len(m._stage['pool']) == 2
+    del x2
+    x3 = m(y, num_samples=4096, num_steps=10, seed=3)
+    ok = ok and len(m._stage['pool']) == 3 and np.array_equal(x1, keep)
+    del x3, row
+    x4 = m(y, num_samples=4096, num_steps=10, seed=1)
+    ok = ok and len(m._stage['pool']) == 3 and np.array_equal(x4, keep) and np.array_equal(x1, keep)
+    return (0.0 if ok else 1.0), 0.5, {}

@@ -63,6 +63,7 @@ CASES = [
     ("mcmc_injected", "case_metropolis('injected')"),
     ("mcmc_philox", "case_metropolis('philox')"),
     ("evaluate", "case_evaluate()"),
+    ("host_alias", "case_host_results_do_not_alias()"),
 ]
 
 TEMPLATE = """

@@ -31,3 +31,7 @@ for i, n in enumerate(["MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "F2FP.BF16 pack", "F
                        "tanh.approx.f16x2 (2 per instr)", "tanh.approx.bf16x2 (2 per instr)", "cvt.rn.f16x2.f32 pack"]):
     cyc = r[40 + i]
     print(f"  {n:28s} {cyc / (iters * 8):7.2f} cycles per warp-instruction per scheduler x4 warps -> {512 * iters * 8 / cyc:6.1f} lanes/clk/SM")
+print("mma.sync (legacy warp-level tensor path), 16 warps x 8 independent accumulator tiles:")
+for i, (n, fl) in enumerate([("m16n8k8 tf32", 2 * 16 * 8 * 8), ("m16n8k16 bf16", 2 * 16 * 8 * 16)]):
+    cyc = r[53 + i]
+    print(f"  {n:16s} {cyc / (iters * 8 * 4):7.2f} cycles per mma per scheduler -> {16 * 8 * iters * fl / cyc:8.0f} FLOP/clk/SM")

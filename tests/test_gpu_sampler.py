@@ -64,3 +64,7 @@ def test_posterior_statistics_preserved_at_64k_particles():
 
 def test_edge_shapes_and_invalid_arguments():
     _ok(gc.case_edge_shapes())
+
+
+def test_returned_host_arrays_are_never_overwritten():
+    _ok(gc.case_host_results_do_not_alias())
