@@ -70,7 +70,8 @@ __device__ void tile_gemm_direct(const float* in, float* out, const float* __res
 // covers ALL 32 rows x 4 R columns (lane = row group x column group), so per k-step it touches 128 B of activations
 // and 16 R B of weights: 3 shared-memory wavefronts per 32 FFMA instead of 6 with one row group per warp.
 constexpr int kSlabK = 16;
-constexpr int kWbufFloats = 2 * kSlabK * kMaxW;   // 64 KB
+constexpr int kSlabPad = 8;                                   // slab row stride N + 8: conflict-free fragment loads
+constexpr int kWbufFloats = 2 * kSlabK * (kMaxW + kSlabPad);  // 65 KB
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
@@ -180,13 +181,121 @@ __device__ void tile_gemm_skinny(const float* in, float* out, const float* __res
   __syncthreads();
 }
 
+// ---- tensor-core variant of the staged GEMM: warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, both TF32; acc += a_lo b_hi + a_hi b_lo + a_hi b_hi), which keeps fp32-level accuracy (~2^-21 per
+// product) at 3 MMAs per tile.  Measured mma.sync rate on B200 (tests/prim_bench.py): 811 FLOP/clk/SM for TF32 = 3.2x
+// the FFMA rate, so the split GEMM has ~1.06x the FFMA peak.  MEASURED (config 2, PINN step): FFMA engine 32.8 ms, 3xTF32
+// 32.5 ms, plain TF32 25.7 ms with loss errors up to 1.3e-3 -> the FFMA engine stays the default (fp32 like the
+// reference); these variants build with DMIP_TILE=MMA3 / DMIP_TILE=TF32X1 (csrc/build.sh) for experiments.
+// Orientation: the WEIGHT slab is the A operand (M = output features, row stride N + 8), the 32 activation rows are B
+// (four n-tiles of 8): a warp owns 2 R features x 32 rows; C fragments store as float2 along the row index.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int R, bool kSplit>
+__device__ void tile_gemm_mma(const float* in, float* out, const float* __restrict__ Wt, int K, float* wbuf) {
+  constexpr int N = 64 * R;              // 512 or 256
+  constexpr int kMT = R / 4;             // m-tiles (16 features) per warp: 2 or 1
+  constexpr int kLdW = N + kSlabPad;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n0 = warp * (16 * kMT);
+  float acc[kMT][4][4];
+#pragma unroll
+  for (int m = 0; m < kMT; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
+  const int n_slabs = K / kSlabK;
+  constexpr int kChunksRow = N / 4;                 // 16-byte chunks per slab row
+  constexpr int kChunks = kSlabK * kChunksRow;
+  auto issue = [&](int s) {
+    const float* src = Wt + static_cast<size_t>(s) * kSlabK * N;
+    float* dst = wbuf + (s & 1) * kSlabK * kLdW;
+    for (int c = t; c < kChunks; c += kThreadsL) {
+      const int row = c / kChunksRow, col = c - row * kChunksRow;
+      cp_async16(dst + row * kLdW + col * 4, src + c * 4);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int s = 0; s < n_slabs; ++s) {
+    if (s + 1 < n_slabs) {
+      issue(s + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* w = wbuf + (s & 1) * kSlabK * kLdW + n0 + g;
+    const float* a = in + s * kSlabK * kLd + g;
+#pragma unroll
+    for (int kk = 0; kk < kSlabK; kk += 8) {
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float x = a[(kk + t4 + 4 * e) * kLd + n * 8];
+          bh[n][e] = to_tf32(x);
+          if (kSplit) bl[n][e] = to_tf32(x - __uint_as_float(bh[n][e]));
+        }
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x = w[(kk + t4 + 4 * (e >> 1)) * kLdW + m * 16 + 8 * (e & 1)];
+          ah[e] = to_tf32(x);
+          if (kSplit) al[e] = to_tf32(x - __uint_as_float(ah[e]));
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          if (kSplit) {
+            mma_tf32(acc[m][n], al, bh[n][0], bh[n][1]);
+            mma_tf32(acc[m][n], ah, bl[n][0], bl[n][1]);
+          }
+          mma_tf32(acc[m][n], ah, bh[n][0], bh[n][1]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int m = 0; m < kMT; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      float* o = out + (n0 + m * 16 + g) * kLd + n * 8 + 2 * t4;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[m][n][0], acc[m][n][1]);
+      *reinterpret_cast<float2*>(o + 8 * kLd) = make_float2(acc[m][n][2], acc[m][n][3]);
+    }
+  __syncthreads();
+}
+
 // out[n*kLd + r] = sum_k in[k*kLd + r] * Wt[k*N + n]: staged path for the big square layers, skinny path for few
 // outputs behind a long contraction, direct path otherwise
 __device__ void tile_gemm(const float* in, float* out, const float* __restrict__ Wt, int K, int N, float* wbuf) {
   if (N <= 32 && K >= 64) { tile_gemm_skinny(in, out, Wt, K, N); return; }
   if ((K % kSlabK) == 0 && K >= 64 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0) {
+#if defined(DMIP_TILE_TF32X1)      // experiment: plain TF32 (errors up to 1.3e-3 on the loss fixtures, PINN step 25.7 ms)
+    if (N == 512) { tile_gemm_mma<8, false>(in, out, Wt, K, wbuf); return; }
+    if (N == 256) { tile_gemm_mma<4, false>(in, out, Wt, K, wbuf); return; }
+#elif defined(DMIP_TILE_MMA3)      // experiment: 3xTF32 (fp32-level accuracy, PINN step 32.5 ms = the FFMA engine's)
+    if (N == 512) { tile_gemm_mma<8, true>(in, out, Wt, K, wbuf); return; }
+    if (N == 256) { tile_gemm_mma<4, true>(in, out, Wt, K, wbuf); return; }
+#else
     if (N == 512) { tile_gemm_staged<8>(in, out, Wt, K, wbuf); return; }
     if (N == 256) { tile_gemm_staged<4>(in, out, Wt, K, wbuf); return; }
+#endif
   }
   tile_gemm_direct(in, out, Wt, K, N);
 }
