@@ -1,5 +1,5 @@
 // dmip_pack.cu — re-tile an nn.Linear MLP ([in] -> 512 -> 512 -> 512 -> [out]) into the operand images the
-// tcgen05 kernels stream: bf16, K-major, 128-byte swizzle, one 16 KB stage = 128 out-features x 64 k, stored in
+// tcgen05 kernels stream: 16-bit (layer 0 bf16, layers 1-3 f16), K-major, 128-byte swizzle, one 16 KB stage = 128 out-features x 64 k, stored in
 // the exact order the MMA warp consumes them (layer 0: chunk-major, then layers 1, 2, output layer), followed by
 // an fp32 tail (biases and the row-constant columns of W0).  Source layout: state_dict keys 0/3/5/7.
 #include "dmip_common.h"
@@ -72,7 +72,14 @@ __global__ void k_pack(const PackParams p) {
       } else if (r < p.out_rows) {
         v = p.W[3][static_cast<size_t>(r) * 512 + kg];
       }
+#ifndef DMIP_H_F16
       const unsigned short h = static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xFFFFu);
+#else
+      // layers 1-3 multiply f16 activations (tanh values): their weights are f16 too (kind::f16 wants one format for
+      // both operands; 11 mantissa bits instead of 8, |w| clamped to the f16 range); layer 0 meets the bf16 hi/lo state
+      const unsigned short h = static_cast<unsigned short>(
+          (l == 0 ? pack_bf16x2(v, 0.f) : pack_f16x2(fminf(fmaxf(v, -65504.f), 65504.f), 0.f)) & 0xFFFFu);
+#endif
       *reinterpret_cast<unsigned short*>(img + sw128_offset(r, k, 16384)) = h;
     }
   } else {

@@ -208,6 +208,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// same with A = B = f16 (format 0).  Mixing f16 activations with bf16 weights in one instruction traps on B200.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T      (issued by ONE thread)
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -287,6 +291,37 @@ __device__ __forceinline__ float tanh_unit_poly(float u) {
   p = fmaf(p, t, -0.3288920521736145f);
   p = fmaf(p, t, 0.999693751335144f);
   return u * p;
+}
+// ---- packed f16x2 epilogue math: the hidden activations are tanh values in (-1, 1), where f16 carries 11 mantissa
+// bits against bf16's 8, and every instruction below handles two elements (half the issue slots of the f32 versions)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {   // element with the lower index in bits [0,16)
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {           // MUFU.TANH.F16x2
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+// tanh_unit_poly on a packed pair, coefficients rounded to f16: max abs error 5.9e-4 over |u| <= tanh(1)... (the bf16
+// rounding this replaces had 2.0e-3)
+__device__ __forceinline__ uint32_t tanh_unit_poly_f16x2(uint32_t u) {
+  const uint32_t t = hmul2(u, u);
+  uint32_t p = hfma2(0xa650a650u, t, 0x2f632f63u);   // -0.024658, 0.115417
+  p = hfma2(p, t, 0xb543b543u);                      // -0.328857
+  p = hfma2(p, t, 0x3bff3bffu);                      //  0.999512
+  return hmul2(u, p);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {  // element with the lower index in bits [0,16)
   uint32_t r;
