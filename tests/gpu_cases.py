@@ -401,7 +401,8 @@ def case_posterior_statistics():
     (linear_problem.py:41-46).  Tolerances: |mean shift| <= 3e-3 and |std ratio - 1| <= 5e-3 vs fp32 (SURVEY.md §8d);
     the reference's own quality metric — histogram KL with 75 bins on [-3.5, 3.5]^2 (main_diffusion_linear.py:86-117) —
     between the two precisions <= 2e-3 (two independent fp32 runs of this size differ by ~3e-2: sampling noise);
-    mean / covariance vs the analytic posterior within the trained model's own error (0.08 / 0.05)."""
+    mean / covariance vs the analytic posterior within the trained model's own error (0.08 / 0.05); and, on independent
+    noise streams, KL(fp32 || bf16) <= 1.5 x KL(fp32 || fp32') at 131,072 particles (the SURVEY's statistical bar)."""
     import numpy as np
     fx = load_golden("sampler_trained_cde_linear")
     m = trained_model()
@@ -421,8 +422,18 @@ def case_posterior_statistics():
     post_mean, post_cov = fx["post_mean"].numpy(), fx["post_cov"].numpy()
     emean = float(np.abs(lo.mean(0) - post_mean).max())
     ecov = float(np.abs(np.cov(lo.T) - post_cov).max())
-    err = max(dmean / 3e-3, rstd / 5e-3, kl / 2e-3, emean / 0.08, ecov / 0.05)
-    return err, 1.0, dict(dmean=dmean, rstd=rstd, kl=kl, emean=emean, ecov=ecov)
+    # SURVEY.md §8d, statistical tolerance: on INDEPENDENT noise streams the histogram KL between the new path and the
+    # fp32 path must not exceed 1.5 x the KL between two independent fp32 runs (GPU-side histograms, dmip.metrics)
+    from dmip import metrics as dmet
+    bins, rng = (75, 75), ((-3.5, 3.5), (-3.5, 3.5))
+    N2 = 131072
+    sets = [m(fx["y"], num_samples=N2, num_steps=S, precision=prec, seed=sd, return_tensor=True)
+            for prec, sd in (("bf16", 31), ("fp32", 32), ("fp32", 33))]
+    h_new, h_ref, h_ref2 = (dmet.histogramdd(x, bins, rng) for x in sets)
+    kl_new = float(dmet.hist_kl(h_ref, h_new))
+    kl_ref = float(dmet.hist_kl(h_ref, h_ref2))
+    err = max(dmean / 3e-3, rstd / 5e-3, kl / 2e-3, emean / 0.08, ecov / 0.05, kl_new / (1.5 * kl_ref))
+    return err, 1.0, dict(dmean=dmean, rstd=rstd, kl=kl, emean=emean, ecov=ecov, kl_new=kl_new, kl_ref=kl_ref)
 
 
 def case_edge_shapes():
