@@ -269,7 +269,9 @@ def run_sampler(args, rank, world):
     ach_tf = (float(per_rank) * S / (kernel_ms * 1e-3)) * F / 1e12      # per GPU, from the kernel's own launch duration
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_tc_mlp_dram_bytes_per_launch")
+        # measured for the default launch of a workload only (ncu capture of that exact command); null otherwise
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_tc_mlp_dram_bytes_per_launch", {})
+        traffic = tr.get(args.workload) if (not args.particles and not args.sde_steps) else None
     except Exception:
         pass
     cfg_names = {"synthetic": "configs[4]: synthetic CDE", "cdiffe_scat": "configs[2]: scatterometry CDiffE",
