@@ -143,6 +143,18 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+CFG_NAMES = {"synthetic": "configs[4]: synthetic CDE", "cdiffe_scat": "configs[2]: scatterometry CDiffE",
+             "dps_scat": "configs[3] (per-GPU share): scatterometry DPS"}
+
+
+def workload_name(args):
+    """`config.workload` of the sampler workloads — the same string on our arm and on the reference arm"""
+    kind, xdim, ydim, n_obs, n_def, s_def = WORKLOADS[args.workload]
+    N, S = args.particles or n_def, args.sde_steps or s_def
+    return (f"{CFG_NAMES[args.workload]} xdim={xdim} ydim={ydim} hidden=512x3, {n_obs} observation(s) x "
+            f"{N} particles per GPU x {S} SDE steps per bench step, Philox noise in-kernel")
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -160,8 +172,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "score-net evals/sec (posterior sampler)", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[4]: synthetic CDE xdim=100 ydim=27 hidden=512x3; CPU sample "
-                               f"{n} particles x {s} SDE steps per bench step (rate is linear in N*S, SURVEY.md App. B)"},
+        "config": {"workload": workload_name(args) if args.workload in WORKLOADS else args.workload,
+                   "sample": f"CPU step = {n} particles x {s} SDE steps of the synthetic CDE net (xdim 100, ydim 27); the "
+                             "rate is linear in particles x steps (SURVEY.md App. B)"},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": f"{n} particles x {s} steps, torch CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -274,15 +287,12 @@ def run_sampler(args, rank, world):
         traffic = tr.get(args.workload) if (not args.particles and not args.sde_steps) else None
     except Exception:
         pass
-    cfg_names = {"synthetic": "configs[4]: synthetic CDE", "cdiffe_scat": "configs[2]: scatterometry CDiffE",
-                 "dps_scat": "configs[3] (per-GPU share): scatterometry DPS"}
     line = {
         "metric": "score-net evals/sec (posterior sampler)", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg_names[args.workload]} xdim={xdim} ydim={ydim} hidden=512x3, {n_obs} observation(s) x "
-                               f"{N} particles per GPU x {S} SDE steps per bench step, Philox noise in-kernel",
+        "config": {"workload": workload_name(args),
                    "samples_per_sec": value / S, "l2": "256 MB buffer zeroed between timed iterations",
                    "finite": finite, "gaps_ms": [round(g, 2) for g in gaps_ms]},
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
