@@ -85,8 +85,6 @@ def lib():
         L.dmip_forward_workspace_bytes.argtypes = [C.POINTER(DmipForward)]
         L.dmip_mlp_forward.restype = C.c_int
         L.dmip_mlp_forward.argtypes = [C.POINTER(DmipForward), C.c_void_p]
-        L.dmip_debug_umma.restype = C.c_int
-        L.dmip_debug_umma.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -156,11 +154,19 @@ def mlp_desc(net, keep):
 
 
 class PackedNet:
-    """Cache of the tcgen05 operand image of one net; re-packed when a parameter changes."""
+    """Cache of the tcgen05 operand image of one net; re-packed when a parameter changes.
+
+    "Changes" are detected through (data_ptr, tensor version): optimizer steps, `load_state_dict`, `copy_` and every
+    other in-place op on the parameter bump the version.  Writes THROUGH `p.data` (EMA, manual clipping) do not — call
+    `invalidate()` (or `model.invalidate_packed()`) after such an update."""
 
     def __init__(self):
         self.key = None
         self.buf = None
+
+    def invalidate(self):
+        """Force a re-pack at the next use."""
+        self.key = None
 
     def get(self, net, n_varying, out_rows, split):
         L = require_gpu()
@@ -181,6 +187,12 @@ class PackedNet:
         return self.buf
 
 
-def tc_supported(net):
+def tc_supported(net, n_varying=None, split=2):
+    """True when the tcgen05 kernels can run this net: [in] -> 512 -> 512 -> 512 -> [out <= 128] and a layer-0 GEMM depth
+    (the row-varying input columns, split `split` ways) of at most 512 — the conditions of tc_net_geom (csrc/dmip_pack.cu)."""
     layers = linear_layers(net)
-    return len(layers) == 4 and all(l.out_features == 512 for l in layers[:3]) and layers[-1].out_features <= 128
+    if not (len(layers) == 4 and all(l.out_features == 512 for l in layers[:3]) and layers[-1].out_features <= 128):
+        return False
+    dv = layers[0].in_features if n_varying is None else n_varying
+    k0 = (split - 1) * ((dv + 7) // 8 * 8) + dv
+    return (k0 + 15) // 16 * 16 <= 512

@@ -202,39 +202,10 @@ int dmip_hist_kl(const void* hist_p, const void* hist_q, int64_t n_bins_total, d
   return launch_hist_kl(hist_p, hist_q, n_bins_total, epsilon, out, static_cast<cudaStream_t>(stream));
 }
 
-int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream) {
-  reset_launch_count();
-  int rc = require_device();
-  if (rc) return rc;
-  return launch_debug_mma_bench(mode, n, k, iters, grid, static_cast<long long*>(cycles), static_cast<cudaStream_t>(stream));
-}
-
-int dmip_debug_mma_bench2(int32_t cg, int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t stream_bytes, int32_t grid,
-                          const void* gsrc, void* cycles, void* stream) {
-  reset_launch_count();
-  int rc = require_device();
-  if (rc) return rc;
-  return launch_debug_mma_bench2(cg, mode, n, k, iters, stream_bytes, grid, gsrc, static_cast<long long*>(cycles),
-                                 static_cast<cudaStream_t>(stream));
-}
-
-int dmip_debug_prim_bench(int32_t iters, void* out, void* stream) {
-  reset_launch_count();
-  int rc = require_device();
-  if (rc) return rc;
-  return launch_debug_prim_bench(iters, static_cast<long long*>(out), static_cast<cudaStream_t>(stream));
-}
-
+#if defined(DMIP_DEBUG) || defined(DMIP_JOBMARKS)
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity) {
   debug_set_timeline(static_cast<unsigned long long*>(device_buf), capacity);
 }
-
-int dmip_debug_umma(int32_t mode, const float* a, const float* w, float* d, int32_t n, int32_t k, void* stream) {
-  reset_launch_count();
-  int rc = require_device();
-  if (rc) return rc;
-  DMIP_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (A in smem) or 1 (A in tmem)");
-  return launch_debug_umma(mode, a, w, d, n, k, static_cast<cudaStream_t>(stream));
-}
+#endif
 
 }  // extern "C"

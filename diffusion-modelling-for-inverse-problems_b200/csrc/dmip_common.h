@@ -75,10 +75,4 @@ size_t metropolis_workspace(const DmipMetropolis* d);
 int launch_metropolis(const DmipMetropolis* d, cudaStream_t s);
 size_t sampler_tc_workspace();
 void debug_set_timeline(unsigned long long* buf, int cap);
-int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s);
-int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int stream_bytes, int grid, const void* gsrc,
-                            long long* cycles, cudaStream_t s);
-int launch_debug_prim_bench(int iters, long long* out, cudaStream_t s);
-int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s);
-
 }  // namespace dmip

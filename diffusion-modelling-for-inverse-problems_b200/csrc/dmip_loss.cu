@@ -15,7 +15,11 @@
 //
 // Three kernels: k_jets_fwd (one CTA = 32 stream-rows: GEMM per layer + jet activation in shared memory, per-sample
 // loss and top adjoints), k_jets_bwd (adjoint rows back through the layers), k_wgrad (dW_l = ADJ_l^T IN_l, split-K).
+#include <stdlib.h>
+#include <string.h>
+
 #include "dmip_common.h"
+#include "dmip_tcl.h"
 #include "dmip_tile.cuh"
 
 namespace dmip {
@@ -680,13 +684,53 @@ struct PassCfg {
   float *aux_s, *aux_J, *aux_x0, *aux_xt;
 };
 
+// workspace map of the tcgen05 path (dmip_tcl.cu): packed weight images, stash images, phi'' zd, output adjoints
+struct TclPlan {
+  bool use;
+  TclStreams st;
+  long long n_tiles_fwd, n_tiles_bwd;
+  size_t off_stages_fwd, off_stages_bwd, off_in[4][2], off_adj[4][2], off_ct[3], off_abar, bytes;
+};
+
 struct LossPlan {
   int n_streams, spt, n_adj;
   int n_tan;
   size_t off_wt[DMIP_MAX_LAYERS], off_in[DMIP_MAX_LAYERS], off_adj[DMIP_MAX_LAYERS], off_zdt[DMIP_MAX_LAYERS], off_abar;
   size_t off_tan[DMIP_MAX_LAYERS];
   size_t bytes;
+  TclPlan tcl;
 };
+
+inline size_t align_1k(size_t v) { return (v + 1023) & ~size_t(1023); }
+
+// The tensor-core path serves [in <= 64] -> 512 -> 512 -> 512 -> [out <= 64] nets (every score net of the reference's
+// configs) for the compiled stream sets; everything else — other widths, the grad_x pass of the adjoint Score-FPE route —
+// runs the fp32 FFMA kernels of this file.  DMIP_LOSS_PATH=ffma forces the FFMA kernels (A/B measurements, tests).
+void plan_tcl(const PassCfg& c, int n_tan, TclPlan* t) {
+  const DmipMlp& net = *c.net;
+  *t = TclPlan{};
+  t->st.has_I = c.has_I; t->st.has_T = c.has_T; t->st.n_tan = n_tan; t->st.has_Q = c.has_Q;
+  const char* force = getenv("DMIP_LOSS_PATH");
+  const bool shape_ok = net.n_layers == 4 && net.width[0] == 512 && net.width[1] == 512 && net.width[2] == 512 &&
+                        net.out_dim <= kTclSmallF && net.in_dim <= kTclSmallF;
+  t->use = shape_ok && c.post != 3 && c.batch > 0 && tcl_streams_supported(t->st) && !(force && strcmp(force, "ffma") == 0);
+  if (!t->use) return;
+  const long long B = c.batch;
+  t->n_tiles_fwd = (B + t->st.spt_fwd() - 1) / t->st.spt_fwd();
+  t->n_tiles_bwd = (B + t->st.spt_bwd() - 1) / t->st.spt_bwd();
+  const size_t big = static_cast<size_t>(t->n_tiles_bwd) * 512 * 128, small = static_cast<size_t>(t->n_tiles_bwd) * kTclSmallF * 128;
+  size_t off = 0;
+  t->off_stages_fwd = off; off += align_1k(static_cast<size_t>(kTclFwdStages) * kTclStage);
+  t->off_stages_bwd = off; off += align_1k(static_cast<size_t>(kTclBwdStages) * kTclStage);
+  for (int l = 0; l < 4; ++l)
+    for (int h = 0; h < 2; ++h) {
+      t->off_in[l][h] = off;  off += align_1k(l == 0 ? small : big);
+      t->off_adj[l][h] = off; off += align_1k(l == 3 ? small : big);
+    }
+  for (int l = 0; l < 3; ++l) { t->off_ct[l] = off; off += c.has_T ? align_1k(static_cast<size_t>(B) * 512 * sizeof(float)) : 0; }
+  t->off_abar = off; off += align_1k(static_cast<size_t>(B) * t->st.n_adj() * net.out_dim * sizeof(float));
+  t->bytes = off;
+}
 
 int check_net(const DmipMlp& net, int want_in, const char* what) {
   DMIP_REQUIRE(net.n_layers >= 2 && net.n_layers <= DMIP_MAX_LAYERS, "%s: n_layers out of range", what);
@@ -722,6 +766,8 @@ int plan_pass(const PassCfg& c, LossPlan* p) {
   p->off_abar = off;
   off += align_up(sizeof(float) * B * (gpass ? 1 + p->n_tan : p->n_adj) * net.out_dim);
   p->bytes = off;
+  plan_tcl(c, p->n_tan, &p->tcl);
+  if (p->tcl.use) p->bytes = p->tcl.bytes;
   return DMIP_OK;
 }
 
@@ -794,8 +840,55 @@ int loss_init() {
   return DMIP_OK;
 }
 
+// One pass on the tcgen05 kernels: weight images, forward (loss terms, output adjoints, stashes), backward, four
+// weight-gradient GEMMs.
+int run_pass_tcl(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
+  const DmipMlp& net = *c.net;
+  const TclPlan& t = p.tcl;
+  TclDev D = {};
+  D.stages_fwd = ws + t.off_stages_fwd;
+  D.stages_bwd = ws + t.off_stages_bwd;
+  long long off = 0;
+  int k = net.in_dim;
+  for (int l = 0; l < 4; ++l) {
+    D.W[l] = net.W[l];
+    D.b[l] = net.b[l];
+    off += static_cast<long long>(net.width[l]) * k;
+    D.off_b[l] = off;
+    off += net.width[l];
+    k = net.width[l];
+    for (int h = 0; h < 2; ++h) {
+      D.in_img[l][h] = ws + t.off_in[l][h];
+      D.adj_img[l][h] = ws + t.off_adj[l][h];
+    }
+    if (l < 3) D.ct[l] = reinterpret_cast<float*>(ws + t.off_ct[l]);
+  }
+  D.in_dim = net.in_dim; D.out_dim = net.out_dim;
+  D.k0steps_fwd = (net.in_dim + 15) / 16;
+  D.k0steps_bwd = (net.out_dim + 15) / 16;
+  D.kind = c.kind; D.model = c.model; D.xdim = c.xdim; D.ydim = c.ydim; D.d = c.d; D.cdim = c.cdim; D.post = c.post;
+  D.pde_loss = c.pde_loss; D.pde_metric = c.pde_metric; D.ic_metric = c.ic_metric; D.gx = c.gx;
+  D.has_I = t.st.has_I; D.has_T = t.st.has_T; D.n_tan = t.st.n_tan; D.has_Q = t.st.has_Q;
+  D.B = c.batch;
+  D.inv_B = 1.0f / static_cast<float>(c.batch_global > 0 ? c.batch_global : c.batch);
+  D.bmin = c.bmin; D.bmax = c.bmax; D.lam = c.lam; D.lam2 = c.lam2;
+  D.x = c.x; D.y = c.y; D.t = c.t; D.eps = c.eps; D.ic_target = c.ic_target; D.gradx = c.gradx;
+  D.aux_s = c.aux_s; D.aux_J = c.aux_J; D.aux_x0 = c.aux_x0; D.aux_xt = c.aux_xt;
+  D.losses = c.losses;
+  D.abar = reinterpret_cast<float*>(ws + t.off_abar);
+  D.grad = c.grad;
+  D.n_tiles_fwd = t.n_tiles_fwd; D.n_tiles_bwd = t.n_tiles_bwd;
+  int rc;
+  if ((rc = tcl_launch_pack(D, s))) return rc;
+  DMIP_CHECK_CUDA(cudaMemsetAsync(c.grad, 0, loss_grad_floats(&net) * sizeof(float), s));
+  if ((rc = tcl_launch_fwd(D, s))) return rc;
+  if ((rc = tcl_launch_bwd(D, s))) return rc;
+  return tcl_launch_wgrad(D, s);
+}
+
 // Enqueue one pass.  `ws` must hold p.bytes; c.grad is zeroed here, c.losses is NOT (the caller owns it).
 int run_pass(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t s) {
+  if (p.tcl.use) return run_pass_tcl(c, p, ws, s);
   int rc = loss_init();
   if (rc) return rc;
   const int n_sm = g_loss_sm;

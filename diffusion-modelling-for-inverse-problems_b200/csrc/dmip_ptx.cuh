@@ -213,6 +213,31 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// General form of the two above: operand formats bf16, D = fp32; a_mn / b_mn = 1 selects the MN-major ("transposed")
+// shared-memory layout of that operand (bit 15 / bit 16).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_major(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Shared-memory operand descriptor, 128-byte swizzle, with explicit leading / stride byte offsets.
+//   K-major : rows of 64 k (128 B); 8 rows = one 1024 B atom; SBO = distance between 8-row groups; LBO unused (16 B).
+//   MN-major: lines of 64 MN elements (128 B); 8 consecutive k = one 1024 B atom; LBO = distance between 64-element
+//             MN groups, SBO = distance between 8-k groups (CUTLASS canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16 B units).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Byte offset of element (mn, k) of an MN-major SWIZZLE_128B bf16 image (see umma_smem_desc): the 16-byte chunk
+// holding MN elements 8c .. 8c+7 of line k sits at chunk position c ^ (k & 7).
+__host__ __device__ __forceinline__ uint32_t mn128_offset(uint32_t mn, uint32_t k, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t line = k & 7u, c = (mn & 63u) >> 3;
+  return (mn >> 6) * lbo_bytes + (k >> 3) * sbo_bytes + line * 128u + ((c ^ line) << 4) + (mn & 7u) * 2u;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T      (issued by ONE thread)
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -245,6 +270,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* gptr, float v) {   // fire-and-forget fp32 atomic add (SASS: RED)
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gptr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(

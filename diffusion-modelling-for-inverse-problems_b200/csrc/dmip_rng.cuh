@@ -39,7 +39,9 @@ __device__ __forceinline__ void philox_normal4(uint64_t gidx, uint32_t step, uin
   for (int j = 0; j < 2; ++j) {
     const float u1 = u01(r[2 * j]), u2 = u01(r[2 * j + 1]);
     float R;   // sqrt.approx (1 ulp, branch-free): keeps the draw one straight-line block the scheduler can interleave
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(-2.0f * __logf(u1)));
+    // u01 can round to exactly 1 and __logf is only specified to an ABSOLUTE error there: clamp the radicand so a
+    // slightly positive log can never turn into NaN (one FMNMX)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(fmaxf(-2.0f * __logf(u1), 0.0f)));
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
     z[2 * j] = R * c;

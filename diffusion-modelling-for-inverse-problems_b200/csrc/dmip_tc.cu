@@ -964,146 +964,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
   }
 }
 
-// ------------------------------------------------------------------------------------------------ self-test kernel
-// D(128 x n) = A(128 x k) W(n x k)^T through the same descriptors / layouts / TMEM access as the sampler.
-__global__ void __launch_bounds__(128, 1) k_debug_umma(int mode, const float* __restrict__ a, const float* __restrict__ w,
-                                                        float* __restrict__ d, int n, int k) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                       // up to 4 K-blocks
-  uint8_t* sW = smem + 4 * kStageBytes;     // up to 4 K-blocks
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * kStageBytes);
-  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 8 * kStageBytes + 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = threadIdx.x;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(holder);
-  for (int i = threadIdx.x; i < 8 * kStageBytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  // operand images
-  for (int kk = 0; kk < k; ++kk) {
-    const unsigned short ha = static_cast<unsigned short>(pack_bf16x2(a[row * k + kk], 0.f) & 0xFFFFu);
-    *reinterpret_cast<unsigned short*>(sA + sw128_offset(row, kk, kStageBytes)) = ha;
-    if (row < n) {
-      const unsigned short hw = static_cast<unsigned short>(pack_bf16x2(w[row * k + kk], 0.f) & 0xFFFFu);
-      *reinterpret_cast<unsigned short*>(sW + sw128_offset(row, kk, kStageBytes)) = hw;
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *holder;
-  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  if (mode == 1) {
-    // A into tensor memory: lane = row, 32-bit column c = elements (2c, 2c+1)
-    for (int c0 = 0; c0 < k / 2; c0 += 16) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(a[row * k + 2 * (c0 + j)], a[row * k + 2 * (c0 + j) + 1]);
-      tmem_st16(lane_taddr + kTmemH + c0, pk);
-    }
-    tc_wait_st();
-    tc_fence_before();
-  }
-  __syncthreads();
-  tc_fence_after();
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(n));
-    const uint32_t d_tmem = tmem_base + kTmemAcc;
-    for (int kb = 0; kb < k / 64; ++kb)
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sW) + kb * kStageBytes + kk * 32);
-        const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-        if (mode == 0)
-          umma_ss(d_tmem, umma_smem_desc_sw128(smem_u32(sA) + kb * kStageBytes + kk * 32), bdesc, idesc, acc);
-        else
-          umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, acc);
-      }
-    tc_commit(bar);
-  }
-  mbar_wait(bar, 0, 0x900);
-  tc_fence_after();
-  for (int pc = 0; pc < n / 8; ++pc) {
-    uint32_t v[8];
-    tmem_ld8(lane_taddr + kTmemAcc + pc * 8, v);
-    tc_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 8; ++e) d[row * n + pc * 8 + e] = __uint_as_float(v[e]);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-  (void)lane;
-}
-
-// ------------------------------------------------------------------------------------------------ MMA micro-benchmark
-// Issues `iters` x (k/16) back-to-back tcgen05.mma (M=128, N=n, K=16) from one elected lane and reports the
-// cycles from first issue to completion.  mode 0: A in shared memory, 1: A in tensor memory.  Operands are whatever
-// is in shared / tensor memory (zeros): only the timing matters.
-__global__ void __launch_bounds__(128, 1) k_debug_mma_bench(int mode, int n, int k, int iters, long long* cycles) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sW = smem + 4 * kStageBytes;   // up to 256 rows x 4 K-blocks
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * kStageBytes);
-  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 12 * kStageBytes + 8);
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<512>(holder);
-  for (int i = threadIdx.x; i < 12 * kStageBytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *holder, 0);
-  if (warp == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(n));
-    const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
-    const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(sW) & 0x3FFFFu) >> 4;
-    const uint32_t wkb = static_cast<uint32_t>(n) * 128u;   // bytes per K-block of the B image
-    const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      for (int kb = 0; kb < k / 64; ++kb) {
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bdesc = desc_hi | (b_lo0 + ((kb * wkb) >> 4) + kk * 2);
-            const uint32_t d_tmem = tmem_base + kTmemAcc + (it & 1) * 0;   // same accumulator: worst-case dependence
-            if (mode == 0) umma_ss(d_tmem, desc_hi | (a_lo0 + ((kb * kStageBytes) >> 4) + kk * 2), bdesc, idesc, 1u);
-            else umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, 1u);
-          }
-        }
-        __syncwarp();
-      }
-    }
-    if (elect_one()) tc_commit(bar);
-    __syncwarp();
-    const long long t1 = clock64();
-    mbar_wait(bar, 0, 0x901);
-    const long long t2 = clock64();
-    if (threadIdx.x == 0) {
-      cycles[blockIdx.x * 2] = t1 - t0;
-      cycles[blockIdx.x * 2 + 1] = t2 - t0;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
 int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows, int split, TcNetDev* o) {
   TcNetGeom g;
   int rc = tc_net_geom(net, n_varying, out_rows, split, &g);
@@ -1274,27 +1134,6 @@ int launch_forward_tc(const DmipForward* d, cudaStream_t s) {
   P.fcond_dim = d->cond_dim;
   P.out_dim = d->net.out_dim;
   return launch(P, s);
-}
-
-int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s) {
-  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256 && n % 16 == 0 && n >= 16 && n <= 256 && grid >= 1, "bad bench shape");
-  const int smem = 12 * kStageBytes + 64 + 1024;
-  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_debug_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_debug_mma_bench<<<grid, 128, smem, s>>>(mode, n, k, iters, cycles);
-  DMIP_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return DMIP_OK;
-}
-
-int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s) {
-  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256, "debug_umma: k must be 64, 128, 192 or 256");
-  DMIP_REQUIRE(n % 16 == 0 && n >= 16 && n <= 128, "debug_umma: n must be a multiple of 16 in [16,128]");
-  const int smem = 8 * kStageBytes + 64 + 1024;
-  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_debug_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_debug_umma<<<1, 128, smem, s>>>(mode, a, w, d, n, k);
-  DMIP_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return DMIP_OK;
 }
 
 }  // namespace dmip

@@ -83,22 +83,82 @@ def allreduce_gradients(params, extra=None, group=None):
     return None
 
 
-def train_step_data_parallel(model, optimizer, loss_fn, x, y, t=None, group=None):
+class GradBucket:
+    """One persistent flat fp32 buffer  [gradients of every parameter, in the kernels' flat order | 8 scalar slots]  whose
+    slices ARE the parameters' `.grad`: the fused loss kernels write the gradient straight into it (`grad_out`), one
+    `all_reduce` sums gradients and loss scalars of all ranks in place, and `optimizer.step()` reads the same memory —
+    the 2-4 MB are touched once per step, with no concatenation, no copy back and no host synchronisation."""
+
+    N_SCALARS = 8
+
+    def __init__(self, nets):
+        from ._lib import linear_layers
+        self.params = [p for net in nets for lin in linear_layers(net) for p in (lin.weight, lin.bias)]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n + self.N_SCALARS, device=dev, dtype=torch.float32)
+        self.n_grad = n
+        self.bind()
+
+    def bind(self):
+        """(Re-)attach the parameters' .grad to the bucket (e.g. after `optimizer.zero_grad(set_to_none=True)`)."""
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def grads(self):
+        return self.flat[:self.n_grad]
+
+    @property
+    def scalars(self):
+        return self.flat[self.n_grad:]
+
+    def all_reduce(self, group=None):
+        rank, ws = world()
+        if ws > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def _bucket_nets(model):
+    a = model.sde.a
+    if hasattr(a, 'prior_net'):                       # PosteriorScore: flat order [prior | likelihood] (posterior.py)
+        return [a.prior_net, a.likelihood_net]
+    return [a]
+
+
+def train_step_data_parallel(model, optimizer, loss_fn, x, y, t=None, group=None, batch_global=None):
     """One optimisation step of CDE/CDiffE/PosteriorDiffusionEstimator.train_epoch (models/diffusion.py:80-102) with the
-    batch split across ranks: x, y are THIS rank's rows; the loss means run over the global batch."""
+    batch split across ranks: x, y are THIS rank's rows; the loss means run over the global batch.
+
+    `batch_global`: rows of the whole batch over all ranks.  Default: this rank's rows x world size (equal shards — what
+    `shard_range` gives when the batch divides evenly); pass it explicitly for ragged shards.  It is a host integer: no
+    collective and no device->host read is spent on it.  The step: fused loss kernels write the gradient into the
+    model's GradBucket, ONE all-reduce (gradients + loss scalars), optimizer.step()."""
     from .losses import fused_train_step
     rank, ws = world()
-    n_local = torch.tensor([x.shape[0]], device=x.device, dtype=torch.int64)
-    if ws > 1:
-        dist.all_reduce(n_local, group=group)
-    loss_fn.batch_global = int(n_local.item())
+    bucket = getattr(model, '_grad_bucket', None)
+    if bucket is None:
+        bucket = model._grad_bucket = GradBucket(_bucket_nets(model))
+    bucket.bind()                                     # cheap: re-points .grad at the bucket if something dropped it
     if t is None:
         t = model.sample_t(x)
-    loss, info = fused_train_step(model, loss_fn, x, y, t)
-    optimizer.zero_grad()
-    loss.backward()
+    loss_fn.batch_global = int(batch_global) if batch_global else x.shape[0] * ws
+    loss_fn.grad_out = bucket.grads
+    try:
+        with torch.no_grad():
+            loss, info = fused_train_step(model, loss_fn, x, y, t)
+    finally:                                          # module state must not leak into a later single-process train_epoch
+        loss_fn.batch_global = 0
+        loss_fn.grad_out = None
     keys = sorted(info)
-    scalars = torch.stack([loss.detach()] + [info[k] for k in keys])
-    scalars = allreduce_gradients(model.sde.a.parameters(), scalars, group)
+    sc = bucket.scalars
+    sc.zero_()
+    sc[0] = loss
+    for i, k in enumerate(keys):
+        sc[1 + i] = info[k]
+    bucket.all_reduce(group)
     optimizer.step()
-    return scalars[0], {k: scalars[1 + i] for i, k in enumerate(keys)}
+    out = bucket.scalars.clone()
+    return out[0], {k: out[1 + i] for i, k in enumerate(keys)}

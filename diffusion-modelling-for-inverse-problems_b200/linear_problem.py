@@ -52,8 +52,13 @@ class LinearForwardProblem:
         return MultivariateNormal(self.posterior_mean(y).to(device), self.posterior_cov().to(device))
 
     def log_posterior(self, xs, ys, epsilon=1e-6):
-        """the quadratic form 1/2 (x - m)^T C^-1 (x - m) the reference returns under this name (:48-58), (n, 1)"""
-        x_res = xs - self.posterior_mean(ys)
+        """1/2 (x - m)^T C^-1 (x - m), (n, 1) — the value the reference returns under this name (linear_problem.py:48-58),
+        reproduced expression by expression: its batch mean is  y_res @ (A^T Sigma_y^-1)  (NOT the posterior mean of
+        `get_posterior`, which is y_res @ (Sigma_y^-1 A): an upstream quirk; the only caller is the SNF baseline,
+        main_baselines_linear.py:210) and its covariance is  Lam - A^T Sigma_y^-1 A.  Golden: tests/golden/linear_log_posterior.npz."""
+        y_res = ys - (self.A @ self.mu + self.b).to(ys)
+        mean = y_res @ (self.A.T @ self.Sigma_y_inv).to(ys)
+        x_res = xs - mean
         cov = (self.Lam - self.A.T @ self.Sigma_y_inv @ self.A).to(xs)
         cov_inv = torch.linalg.inv(cov + epsilon * torch.eye(self.xdim).to(xs))
         return (0.5 * (x_res @ cov_inv) * x_res).sum(1, keepdim=True)

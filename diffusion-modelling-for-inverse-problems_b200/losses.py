@@ -73,43 +73,55 @@ def _metric(m):
     return _METRIC[m]
 
 
+def _launch_fused(net, cfg, x, y, t, eps, ic_target, grad_out=None):
+    """One dmip_loss_fwd_bwd call.  Returns (losses[4], flat gradient, kernel launches).  `grad_out`: a caller-owned flat
+    fp32 buffer (dmip_loss_grad_floats(net) elements) the kernels write the gradient into — the data-parallel step hands
+    in its all-reduce bucket, whose slices ARE the parameters' .grad (dmip.distributed.GradBucket)."""
+    L = _bind()
+    dev = x.device
+    keep = []
+    d = DmipLoss()
+    d.kind, d.model = cfg['kind'], cfg['model']
+    d.xdim, d.ydim = x.shape[1], y.shape[1]
+    d.batch = x.shape[0]
+    d.batch_global = cfg.get('batch_global', 0) or x.shape[0]
+    d.net = _lib.mlp_desc(net, keep)
+    d.beta_min, d.beta_max = cfg['beta_min'], cfg['beta_max']
+    d.lam, d.lam2 = cfg.get('lam', 0.0), cfg.get('lam2', 0.0)
+    d.pde_loss, d.pde_metric, d.ic_metric = cfg.get('pde_loss', 0), cfg.get('pde_metric', 1), cfg.get('ic_metric', 1)
+    d.divergence = cfg.get('divergence', 0)
+    tens = {}
+    for name, v in (('x', x), ('y', y), ('t', t.reshape(-1)), ('eps', eps), ('ic_target', ic_target),
+                    ('hutch_v', cfg.get('hutch_v'))):
+        if v is None:
+            continue
+        v = v.detach().to(dev, torch.float32).contiguous()
+        tens[name] = v
+        setattr(d, name, v.data_ptr())
+    losses = torch.empty(4, device=dev, dtype=torch.float32)
+    n_grad = L.dmip_loss_grad_floats(C.byref(d.net))
+    if grad_out is None:
+        grad = torch.empty(n_grad, device=dev, dtype=torch.float32)
+    else:
+        grad = grad_out
+        assert grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == n_grad
+    d.out_losses, d.grad = losses.data_ptr(), grad.data_ptr()
+    nbytes = L.dmip_loss_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        _lib.check(-1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
+    with torch.cuda.device(dev):
+        _lib.check(L.dmip_loss_fwd_bwd(C.byref(d), _lib.stream_ptr()))
+    return losses, grad, L.dmip_last_launch_count()
+
+
 class _FusedLoss(torch.autograd.Function):
     """forward: one dmip_loss_fwd_bwd call -> losses[4]; backward: hands the flat gradient to the parameters."""
 
     @staticmethod
     def forward(ctx, net, cfg, x, y, t, eps, ic_target, *params):
-        L = _bind()
-        dev = x.device
-        keep = []
-        d = DmipLoss()
-        d.kind, d.model = cfg['kind'], cfg['model']
-        d.xdim, d.ydim = x.shape[1], y.shape[1]
-        d.batch = x.shape[0]
-        d.batch_global = cfg.get('batch_global', 0) or x.shape[0]
-        d.net = _lib.mlp_desc(net, keep)
-        d.beta_min, d.beta_max = cfg['beta_min'], cfg['beta_max']
-        d.lam, d.lam2 = cfg.get('lam', 0.0), cfg.get('lam2', 0.0)
-        d.pde_loss, d.pde_metric, d.ic_metric = cfg.get('pde_loss', 0), cfg.get('pde_metric', 1), cfg.get('ic_metric', 1)
-        d.divergence = cfg.get('divergence', 0)
-        tens = {}
-        for name, v in (('x', x), ('y', y), ('t', t.reshape(-1)), ('eps', eps), ('ic_target', ic_target),
-                        ('hutch_v', cfg.get('hutch_v'))):
-            if v is None:
-                continue
-            v = v.detach().to(dev, torch.float32).contiguous()
-            tens[name] = v
-            setattr(d, name, v.data_ptr())
-        losses = torch.empty(4, device=dev, dtype=torch.float32)
-        grad = torch.empty(L.dmip_loss_grad_floats(C.byref(d.net)), device=dev, dtype=torch.float32)
-        d.out_losses, d.grad = losses.data_ptr(), grad.data_ptr()
-        nbytes = L.dmip_loss_workspace_bytes(C.byref(d))
-        if nbytes == 0:
-            _lib.check(-1)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
-        with torch.cuda.device(dev):
-            _lib.check(L.dmip_loss_fwd_bwd(C.byref(d), _lib.stream_ptr()))
-        cfg['launches'] = L.dmip_last_launch_count()
+        losses, grad, cfg['launches'] = _launch_fused(net, cfg, x, y, t, eps, ic_target)
         ctx.flat = grad
         ctx.shapes = [p.shape for p in params]
         return losses
@@ -131,8 +143,26 @@ def _fused(sde, cfg, x, y, t, eps, ic_target=None):
     if not x.is_cuda:
         raise RuntimeError("dmip fused losses run on CUDA (sm_100a) only: there is no CPU fallback")
     cfg = dict(cfg, beta_min=float(sde.base_sde.beta_min), beta_max=float(sde.base_sde.beta_max))
+    grad_out = cfg.pop('grad_out', None)
+    if grad_out is not None:                  # raw mode (data-parallel step): no autograd edge, gradient lands in grad_out
+        out, _, cfg['launches'] = _launch_fused(net, cfg, x, y, t, eps, ic_target, grad_out)
+        return out, cfg
     params = [p for lin in _lib.linear_layers(net) for p in (lin.weight, lin.bias)]
     return _FusedLoss.apply(net, cfg, x, y, t, eps, ic_target, *params), cfg
+
+
+def _check_diffused(model, x, y, diffused_samples, t, target, std):
+    """The fused kernels re-derive x_t = alpha(t) z_0 + std(t) eps from (x, y, t, eps) in-kernel.  A caller that hands in the
+    reference's full argument list (std is a tensor) gets it validated: a different x_t would silently give a different
+    loss than the reference.  The internal train loop passes std=None and skips this (no host sync on the hot path)."""
+    if std is None or not torch.is_tensor(diffused_samples):
+        return
+    z0 = x if diffused_samples.shape[1] == x.shape[1] else torch.cat([x, y], dim=1)
+    tt = t.detach().reshape(-1, 1)
+    want = model.base_sde.mean_weight(tt) * z0 + model.base_sde.var(tt) ** 0.5 * target
+    if not torch.allclose(diffused_samples.detach(), want, rtol=1e-4, atol=1e-5):
+        raise ValueError("diffused_samples is not alpha(t) * [x(,y)] + std(t) * target: the fused loss kernels re-derive "
+                         "x_t from (x, y, t, target) and cannot take an arbitrary x_t (INTEGRATION.md, deviations)")
 
 
 class DSMLoss(nn.Module):
@@ -190,9 +220,11 @@ class DSM_PDELoss(nn.Module):
 
     def forward(self, model, x, y, diffused_samples, t, target, std, g):
         div, probe = _divergence(self, diffused_samples)
+        _check_diffused(model, x, y, diffused_samples, t, target, std)
         cfg = dict(kind=_LOSS_DSM_PDE, model=_model_kind(x, diffused_samples), lam=float(self.lam),
                    pde_loss=0 if self.pde_loss.name == 'FPELoss' else 1, pde_metric=_metric(self.pde_loss.metric),
-                   divergence=div, hutch_v=probe, batch_global=getattr(self, 'batch_global', 0))
+                   divergence=div, hutch_v=probe, batch_global=getattr(self, 'batch_global', 0),
+                   grad_out=getattr(self, 'grad_out', None))
         out, cfg = _fused(model, cfg, x, y, t, target)
         self.last_launch_count = cfg['launches']
         return out[0], {'PDE-Loss': out[3].detach(), 'DSM-Loss': out[1].detach()}
@@ -218,7 +250,8 @@ class PINNLoss(nn.Module):
         cfg = dict(kind=_LOSS_PINN, model=_model_kind(x, diffused_samples), lam=float(self.lam), lam2=float(self.lam2),
                    pde_loss=0 if self.pde_loss.name == 'FPELoss' else 1, pde_metric=_metric(self.pde_loss.metric),
                    ic_metric=_metric(self.ic_metric), divergence=div, hutch_v=probe,
-                   batch_global=getattr(self, 'batch_global', 0))
+                   batch_global=getattr(self, 'batch_global', 0), grad_out=getattr(self, 'grad_out', None))
+        _check_diffused(model, x, y, diffused_samples, t, target, std)
         with torch.no_grad():
             ic_target = self.initial_condition(x, y)
         out, cfg = _fused(model, cfg, x, y, t, target, ic_target)
@@ -244,10 +277,11 @@ class PosteriorLoss(nn.Module):
         return posterior_loss_fused(self, model, x, y, t, eps)
 
 
-def dsm_fused(model, x, y, t, eps, batch_global=0):
+def dsm_fused(model, x, y, t, eps, batch_global=0, grad_out=None):
     """mean_B DSMLoss(a(x_t, y, t)/g, std, eps) with its parameter gradient — the `loss_fn.name == 'DSMLoss'` branch of
     CDE/CDiffE.train_epoch (models/diffusion.py:83-85, :134-137) as one fused call.  Returns (loss, launches)."""
-    cfg = dict(kind=_LOSS_DSM, model=_lib.CDE if model.variant == 'CDE' else _lib.CDIFFE, batch_global=batch_global)
+    cfg = dict(kind=_LOSS_DSM, model=_lib.CDE if model.variant == 'CDE' else _lib.CDIFFE, batch_global=batch_global,
+               grad_out=grad_out)
     out, cfg = _fused(model.sde, cfg, x, y, t, eps)
     return out[0], cfg['launches']
 
@@ -260,7 +294,8 @@ def fused_train_step(model, loss_fn, x, y, t):
     z = x if model.variant == 'CDE' else torch.cat([x, y], dim=1)
     eps = torch.randn_like(z)                                   # VariancePreservingSDE.sample's draw (sdes.py:45)
     if loss_fn.name == 'DSMLoss':
-        loss, loss_fn.last_launch_count = dsm_fused(model, x, y, t, eps, getattr(loss_fn, 'batch_global', 0))
+        loss, loss_fn.last_launch_count = dsm_fused(model, x, y, t, eps, getattr(loss_fn, 'batch_global', 0),
+                                                    getattr(loss_fn, 'grad_out', None))
         return loss, {}
     # composite losses take the reference's argument list; the diffused samples are re-derived in-kernel from
     # (x, y, t, eps), so only their width (CDE vs CDiffE) is read from the tensor passed here

@@ -72,11 +72,14 @@ class BaseClassDiffusionModel():
         d = _lib.DmipSampler()
         d.variant = _VARIANT[self.variant]
         prec = _lib.precision_code(self.precision if precision is None else precision)
-        if prec == _lib.PREC_BF16 and not (_lib.tc_supported(net) and (net2 is None or _lib.tc_supported(net2))
+        dv = self.xdim + self.ydim if self.variant == 'CDiffE' else self.xdim
+        if prec == _lib.PREC_BF16 and not (_lib.tc_supported(net, dv, self.l0_split)
+                                            and (net2 is None or _lib.tc_supported(net2, self.xdim, self.l0_split))
                                             and (net2 is None or self.xdim <= 8) and self.xdim <= 104
                                             and (self.variant != 'CDiffE' or (self.xdim <= 32 and self.ydim <= 24))):
             prec = _lib.PREC_F32             # other layer widths / state sizes: fp32 FFMA kernels (still CUDA, never CPU)
         d.precision = prec
+        self.last_precision = 'bf16' if prec == _lib.PREC_BF16 else 'fp32'   # the path that actually ran (bench.py's dtype)
         d.xdim, d.ydim = self.xdim, self.ydim
         d.n_obs, d.n_per_obs, d.num_steps = n_obs, num_samples, num_steps
         d.T = float(self.sde.T)
@@ -106,7 +109,6 @@ class BaseClassDiffusionModel():
         d.gidx_base = int(gidx_base)
         with torch.cuda.device(dev):
             if prec == _lib.PREC_BF16:
-                dv = self.xdim + self.ydim if self.variant == 'CDiffE' else self.xdim
                 d.packed = self._packed[0].get(net, dv, self.xdim, self.l0_split).data_ptr()
                 if net2 is not None:
                     d.packed2 = self._packed[1].get(net2, self.xdim, self.xdim, self.l0_split).data_ptr()
@@ -164,6 +166,11 @@ class BaseClassDiffusionModel():
                 evs[(c - 1) & 1].synchronize()
                 host[lo:hi].copy_(bufs[(c - 1) & 1][:hi - lo])
         return host.view(out.shape).numpy()
+
+    def invalidate_packed(self):
+        """Drop the cached tcgen05 weight images (needed only after writes through `p.data`, see _lib.PackedNet)."""
+        for p in self._packed:
+            p.invalidate()
 
     # ------------------------------------------------------------------ training
     def sample_t(self, x, eps=1e-4):

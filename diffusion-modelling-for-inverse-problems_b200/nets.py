@@ -44,8 +44,9 @@ class _ScoreMLP(nn.Sequential):
         d = _lib.DmipForward()
         d.net = _lib.mlp_desc(self, keep)
         prec = _lib.precision_code(self.precision)
-        if prec == _lib.PREC_BF16 and not _lib.tc_supported(self):
-            prec = _lib.PREC_F32                     # other widths: the fp32 FFMA kernels (still CUDA, never CPU)
+        if prec == _lib.PREC_BF16 and not _lib.tc_supported(self, None, self.l0_split):
+            prec = _lib.PREC_F32                     # other widths / too deep a layer 0: fp32 FFMA kernels (still CUDA, never CPU)
+        self.last_precision = 'bf16' if prec == _lib.PREC_BF16 else 'fp32'   # the path that actually ran
         d.precision = prec
         d.l0_split = self.l0_split
         d.n = n
@@ -61,15 +62,20 @@ class _ScoreMLP(nn.Sequential):
             d.cond = cond.data_ptr()
         out = torch.empty(n, self.output_dim, device=x.device, dtype=torch.float32)
         d.out = out.data_ptr()
-        if prec == _lib.PREC_BF16:
-            d.packed = self._packed.get(self, d.net.in_dim, self.output_dim, self.l0_split).data_ptr()
-        else:
-            ws = torch.empty(max(L.dmip_forward_workspace_bytes(C.byref(d)), 16), dtype=torch.uint8, device=x.device)
-            keep.append(ws)
-            d.workspace = ws.data_ptr()
-            d.workspace_bytes = ws.numel()
-        _lib.check(L.dmip_mlp_forward(C.byref(d), _lib.stream_ptr()))
+        with torch.cuda.device(x.device):            # launch on the tensors' device and its current stream
+            if prec == _lib.PREC_BF16:
+                d.packed = self._packed.get(self, d.net.in_dim, self.output_dim, self.l0_split).data_ptr()
+            else:
+                ws = torch.empty(max(L.dmip_forward_workspace_bytes(C.byref(d)), 16), dtype=torch.uint8, device=x.device)
+                keep.append(ws)
+                d.workspace = ws.data_ptr()
+                d.workspace_bytes = ws.numel()
+            _lib.check(L.dmip_mlp_forward(C.byref(d), _lib.stream_ptr()))
         return out
+
+    def invalidate_packed(self):
+        """Drop the cached tcgen05 weight image (needed only after writes through `p.data`, see _lib.PackedNet)."""
+        self._packed.invalidate()
 
     def _dispatch(self, x, cond, t):
         params_need_grad = torch.is_grad_enabled() and (

@@ -53,8 +53,13 @@ class _FusedPosteriorLoss(torch.autograd.Function):
         losses = torch.empty(4, device=dev, dtype=torch.float32)
         n1 = L.dmip_loss_grad_floats(C.byref(d.prior_net))
         n2 = L.dmip_loss_grad_floats(C.byref(d.lik_net))
-        g1 = torch.empty(n1, device=dev, dtype=torch.float32)
-        g2 = torch.empty(n2, device=dev, dtype=torch.float32)
+        go = cfg.get('grad_out')     # data-parallel step: one flat bucket [prior | likelihood] (dmip.distributed.GradBucket)
+        if go is not None:
+            assert go.is_cuda and go.dtype == torch.float32 and go.is_contiguous() and go.numel() == n1 + n2
+            g1, g2 = go[:n1], go[n1:]
+        else:
+            g1 = torch.empty(n1, device=dev, dtype=torch.float32)
+            g2 = torch.empty(n2, device=dev, dtype=torch.float32)
         d.out_losses, d.grad_prior, d.grad_lik = losses.data_ptr(), g1.data_ptr(), g2.data_ptr()
         nbytes = L.dmip_posterior_loss_workspace_bytes(C.byref(d))
         if nbytes == 0:
@@ -81,6 +86,10 @@ class _FusedPosteriorLoss(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
+class _NoCtx:
+    """stand-in for the autograd context when the kernel is called without an autograd edge"""
+
+
 def posterior_loss_fused(loss_mod, model, x, y, t, eps=None):
     """loss_mod: PosteriorLoss; model: PluginReverseSDE whose drift `a` is a PosteriorScore.  `eps` (optional) injects
     the forward-SDE draw that `base_sde.sample` would make (losses.py:374)."""
@@ -94,8 +103,11 @@ def posterior_loss_fused(loss_mod, model, x, y, t, eps=None):
     cfg = dict(prior_net=prior, lik_net=lik, forward_model=loss_mod.forward_model,
                beta_min=float(model.base_sde.beta_min), beta_max=float(model.base_sde.beta_max),
                a=float(loss_mod.a), b=float(loss_mod.b), lam=float(loss_mod.lam),
-               batch_global=getattr(loss_mod, 'batch_global', 0),
+               batch_global=getattr(loss_mod, 'batch_global', 0), grad_out=getattr(loss_mod, 'grad_out', None),
                shapes=([p.shape for p in p1], [p.shape for p in p2]))
-    out = _FusedPosteriorLoss.apply(cfg, x, y, t, eps, *p1, *p2)
+    if cfg['grad_out'] is not None:      # raw mode: no autograd edge, the gradients land in the caller's bucket
+        out = _FusedPosteriorLoss.forward(_NoCtx(), cfg, x, y, t, eps, *p1, *p2)
+    else:
+        out = _FusedPosteriorLoss.apply(cfg, x, y, t, eps, *p1, *p2)
     loss_mod.last_launch_count = cfg['launches']
     return out[0], {'PriorLoss': out[1].detach(), 'LikelihoodLoss': out[2].detach()}

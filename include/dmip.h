@@ -296,24 +296,13 @@ typedef struct DmipHistogram {
 int dmip_histogramdd(const DmipHistogram* d, void* stream);
 int dmip_hist_kl(const void* hist_p, const void* hist_q, int64_t n_bins_total, double epsilon, double* out, void* stream);
 
-/* ---- debug / self-test hooks (used by tests/ only) ------------------------------------------------------
- * One 128 x n x k bf16 GEMM through the library's own tcgen05 helpers.  mode 0: A from shared memory,
- * mode 1: A from tensor memory.  a: device (128,k) fp32, w: device (n,k) fp32, d: device (128,n) fp32.
- * k multiple of 64 (<=512), n multiple of 16 (<=128). */
-/* tcgen05.mma issue-rate micro-benchmark: `iters` x (k/16) MMAs of shape 128 x n x 16 per CTA on `grid` CTAs;
- * cycles: device int64[2*grid] = (issue cycles, completion cycles) per CTA. */
-int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream);
-/* Same probe for CTA-pair instructions and with a concurrent bulk-TMA stream: cg = CTAs per MMA (1|2; M = 128*cg),
- * mode bit 0: A from tensor memory, bit 1: alternate accumulators; stream_bytes copied global->shared per K-block by a
- * second warp (gsrc: device buffer >= 8 MB + 64 KB).  cycles: device int64[4*grid] = (issue, complete, producer, -). */
-int dmip_debug_mma_bench2(int32_t cg, int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t stream_bytes, int32_t grid,
-                          const void* gsrc, void* cycles, void* stream);
-/* Cost of the synchronisation primitives (cycles for `iters` iterations of ten small sequences; out: device int64[32]). */
-int dmip_debug_prim_bench(int32_t iters, void* out, void* stream);
-/* Timeline hook: when set, CTA 0 of the tcgen05 kernels records (clock64 << 16 | event code) entries into
+/* ---- debug hook (exists only in -DDMIP_DEBUG / -DDMIP_JOBMARKS builds of the library; the tcgen05 building-block
+ * self-tests and micro-benchmarks live in tools/probe/, outside the product) ------------------------------------------
+ * Timeline: when set, CTA 0 of the tcgen05 sampler records (clock64 << 16 | event code) entries into
  * device_buf[1..capacity) and the entry count into device_buf[0] (uint64).  Pass NULL to switch off. */
+#if defined(DMIP_DEBUG) || defined(DMIP_JOBMARKS)
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity);
-int dmip_debug_umma(int32_t mode, const float* a, const float* w, float* d, int32_t n, int32_t k, void* stream);
+#endif
 
 #ifdef __cplusplus
 }

@@ -404,6 +404,15 @@ if want("vp_closed_forms"):
     print("done")
 
 # ---------------------------------------------------------------------------
+# 5b. LinearForwardProblem.log_posterior / get_posterior (linear_problem.py:41-58) on a seeded batch
+# ---------------------------------------------------------------------------
+if want("linear_log_posterior"):
+    x, y = lin_data(32, 74)
+    post = lin.get_posterior(y[0], device="cpu")
+    save("linear_log_posterior", x=x, y=y, log_posterior=lin.log_posterior(x, y), post_mean0=post.mean,
+         post_cov=post.covariance_matrix, score=lin.score_posterior(x, y), fwd=lin(x))
+
+# ---------------------------------------------------------------------------
 # 6. A *trained* linear CDE (contractive reverse dynamics, O(1) samples): the
 #    fixture for bf16-path sample parity and for posterior statistics.
 #    Trained with the reference's own CDE.train_epoch + DSMLoss + data loader

@@ -58,7 +58,7 @@ def normals(gidx, step, stream, dim, seed):
     for j, (ra, rb) in enumerate(((r0, r1), (r2, r3))):
         u1 = _u01(ra)
         u2 = _u01(rb)
-        R = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
+        R = np.sqrt(np.maximum(np.float32(-2.0) * np.log(u1), np.float32(0.0))).astype(np.float32)   # clamp as dmip_rng.cuh
         th = np.float32(2.0 * np.pi) * u2
         out[:, :, 2 * j] = R * np.cos(th)
         out[:, :, 2 * j + 1] = R * np.sin(th)

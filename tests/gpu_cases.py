@@ -22,17 +22,19 @@ def _dmip():
 
 # ------------------------------------------------------------------------------------------- tcgen05 building block
 def case_umma(mode, n, k, seed=0):
-    """128 x n x k bf16 GEMM via dmip_debug_umma.  bf16 products are exact in fp32, so only the summation order
+    """128 x n x k bf16 GEMM via dmip_debug_umma (tools/probe).  bf16 products are exact in fp32, so only the summation order
     differs from the fp64 reference on bf16-rounded operands: tolerance 1e-4 * sqrt(k)."""
     _, _lib = _dmip()
-    L = _lib.require_gpu()
+    _lib.require_gpu()
+    from tools.probe import probe     # building-block self-tests live outside the product library
+    L = probe.lib()
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(128, k, generator=g)
     w = torch.randn(n, k, generator=g)
     ref = (a.bfloat16().double() @ w.bfloat16().double().T).float()
     ad, wd = a.to(DEV), w.to(DEV)
     d = torch.full((128, n), float("nan"), device=DEV)
-    _lib.check(L.dmip_debug_umma(mode, ad.data_ptr(), wd.data_ptr(), d.data_ptr(), n, k, _lib.stream_ptr()))
+    probe.check(L.dmip_debug_umma(mode, ad.data_ptr(), wd.data_ptr(), d.data_ptr(), n, k, _lib.stream_ptr()))
     torch.cuda.synchronize()
     err = (d.cpu() - ref).abs().max().item()
     tol = 1e-4 * k ** 0.5
@@ -271,6 +273,27 @@ def case_loss(name, route=None):
         print("  grad mismatch:", str(e)[:300])
         err = max(err, 1.0)
     return err, 3e-4, dict(loss=loss.item(), ref=ref)
+
+
+def case_loss_path_taken():
+    """kernel launches per fused PINN call on the linear CDE: tcgen05 path = pack + fwd + bwd + 4 wgrad = 7;
+    FFMA path = 4 transposes + fwd + bwd + 4 wgrad (+ memset not counted) = 10."""
+    import os
+    from dmip import losses as dl
+    from dmip.models.diffusion import CDE
+    torch.manual_seed(0)
+    m = CDE(2, 2, [512, 512, 512])
+    m.sde.to(DEV)
+    x, y, t = _dp_problem(512)
+    counts = {}
+    for path in ("tc", "ffma"):
+        os.environ["DMIP_LOSS_PATH"] = path
+        loss_fn = dl.PINNLoss(lambda xx, yy: -xx, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+        loss_fn(m.sde, x.to(DEV), y.to(DEV), x.to(DEV), t.to(DEV), torch.randn(512, 2, device=DEV), None, None)
+        counts[path] = loss_fn.last_launch_count
+    os.environ.pop("DMIP_LOSS_PATH", None)
+    ok = counts["tc"] == 7 and counts["ffma"] == 10
+    return (0.0 if ok else 1.0), 0.5, {k: float(v) for k, v in counts.items()}
 
 
 # ------------------------------------------------------------------------------------------- scatterometry surrogate (K4)
@@ -645,3 +668,148 @@ def case_host_results_do_not_alias():
     x4 = m(y, num_samples=4096, num_steps=10, seed=1)
     ok = ok and len(m._stage['pool']) == 3 and np.array_equal(x4, keep) and np.array_equal(x1, keep)
     return (0.0 if ok else 1.0), 0.5, {}
+
+
+# ------------------------------------------------------------------------------------------- data-parallel training (e2)
+def _dp_problem(B=4096, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 2, generator=g)
+    A = torch.tensor([[1.0, 0.5], [0.0, 1.0]])
+    y = x @ A.T + torch.tensor([0.3, 0.5]) + 0.3 ** 0.5 * torch.randn(B, 2, generator=g)
+    t = torch.rand(B, 1, generator=g) * 0.98 + 0.01
+    return x, y, t
+
+
+def _dp_model_and_loss(kind):
+    from dmip import losses as dl
+    from dmip.models.diffusion import CDE
+    torch.manual_seed(0)
+    m = CDE(2, 2, [512, 512, 512])
+    if kind == "DSM":
+        loss_fn = dl.DSMLoss()
+    else:
+        loss_fn = dl.PINNLoss(lambda xx, yy: -xx, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+    return m, loss_fn
+
+
+def _dp_single_process_reference(kind, x, y, t, eps_seed):
+    """loss and flat gradient of ONE process on the whole batch (the autograd route of train_epoch)"""
+    from dmip.losses import fused_train_step
+    m, loss_fn = _dp_model_and_loss(kind)
+    torch.manual_seed(eps_seed)
+    loss, info = fused_train_step(m, loss_fn, x.to(DEV), y.to(DEV), t.to(DEV))
+    m.sde.a.zero_grad()
+    loss.backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in m.sde.a.parameters()])
+    return loss.detach(), flat
+
+
+def case_data_parallel_emulated(kind):
+    """Two data-parallel ranks emulated on ONE GPU: each shard is evaluated with batch_global = B into its own flat
+    gradient bucket, the buckets are summed (what the all-reduce does) and compared with the single-process step on the
+    concatenated batch: gradients within 2e-5 of their scale (+ the reduction-order noise of fp32 atomics), loss 1e-5.
+    The forward-SDE noise is injected so both arrangements see identical eps."""
+    from dmip import distributed as dd
+    from dmip import losses as dl
+    x, y, t = _dp_problem()
+    B = x.shape[0]
+    eps = torch.randn(B, 2, generator=torch.Generator().manual_seed(9))
+    m, loss_fn = _dp_model_and_loss(kind)
+    m.sde.to(DEV)
+
+    def run(sl, bg, grad_out=None):
+        xs, ys, ts, es = (v[sl].to(DEV) for v in (x, y, t, eps))
+        if kind == "DSM":
+            loss, _ = dl.dsm_fused(m, xs, ys, ts, es, batch_global=bg, grad_out=grad_out)
+            return loss
+        loss_fn.batch_global, loss_fn.grad_out = bg, grad_out
+        try:
+            loss, _ = loss_fn(m.sde, xs, ys, xs, ts, es, None, None)
+        finally:
+            loss_fn.batch_global, loss_fn.grad_out = 0, None
+        return loss
+
+    full = run(slice(0, B), 0)
+    m.sde.a.zero_grad()
+    full.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in m.sde.a.parameters()]).clone()
+    buckets, losses = [], []
+    for r in range(2):
+        s, c = dd.shard_range(B, r, 2)
+        b = dd.GradBucket([m.sde.a])
+        with torch.no_grad():
+            losses.append(run(slice(s, s + c), B, b.grads).detach())
+        buckets.append(b.grads.clone())
+    got = buckets[0] + buckets[1]
+    e_g = ((got - ref).abs().max() / ref.abs().max()).item()
+    e_l = abs((losses[0] + losses[1]).item() - full.item()) / abs(full.item())
+    return max(e_g / 2e-4, e_l / 1e-5), 1.0, dict(e_g=e_g, e_l=e_l)
+
+
+def _dp_nccl_worker(rank, world, port, kind, ret):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        from dmip import distributed as dd
+        x, y, t = _dp_problem()
+        B = x.shape[0]
+        m, loss_fn = _dp_model_and_loss(kind)          # same seed on every rank: identical weights
+        m.sde.to(f"cuda:{rank}")
+        opt = torch.optim.SGD(m.sde.a.parameters(), lr=0.0)     # lr 0: the step leaves the weights, the grads stay readable
+        s, c = dd.shard_range(B, rank, world)
+        dev = f"cuda:{rank}"
+        torch.manual_seed(1234 + rank)
+        loss, info = dd.train_step_data_parallel(m, opt, loss_fn, x[s:s + c].to(dev), y[s:s + c].to(dev), t[s:s + c].to(dev),
+                                                 batch_global=B)
+        flat = torch.cat([p.grad.reshape(-1) for p in m.sde.a.parameters()])
+        ret[rank] = (loss.item(), flat.cpu(), {k: v.item() for k, v in info.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def case_data_parallel_nccl(kind="DSM"):
+    """Two real ranks (NCCL, one process per GPU; needs >= 2 GPUs): after train_step_data_parallel both ranks hold the SAME
+    all-reduced gradient, and it equals the emulated sum of the two shards' gradients evaluated in this process on the
+    same eps (seed 1234 + rank per shard) — the collective adds nothing but the sum."""
+    import socket
+    import torch.multiprocessing as mp
+    from dmip import distributed as dd
+    s_ = socket.socket()
+    s_.bind(("127.0.0.1", 0))
+    port = s_.getsockname()[1]
+    s_.close()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_dp_nccl_worker, args=(r, 2, port, kind, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0, p.exitcode
+        res = dict(ret)
+    # the same two shards in this process, summed by hand
+    from dmip.losses import fused_train_step
+    x, y, t = _dp_problem()
+    B = x.shape[0]
+    m, loss_fn = _dp_model_and_loss(kind)
+    m.sde.to(DEV)
+    total, loss_sum = None, 0.0
+    for r in range(2):
+        s, c = dd.shard_range(B, r, 2)
+        b = dd.GradBucket([m.sde.a])
+        loss_fn.batch_global, loss_fn.grad_out = B, b.grads
+        torch.manual_seed(1234 + r)
+        with torch.no_grad():
+            loss, _ = fused_train_step(m, loss_fn, x[s:s + c].to(DEV), y[s:s + c].to(DEV), t[s:s + c].to(DEV))
+        loss_fn.batch_global, loss_fn.grad_out = 0, None
+        total = b.grads.clone() if total is None else total + b.grads
+        loss_sum += loss.item()
+    total = total.cpu()
+    e_same = (res[0][1] - res[1][1]).abs().max().item()
+    e_g = ((res[0][1] - total).abs().max() / total.abs().max()).item()
+    e_l = abs(res[0][0] - loss_sum) / abs(loss_sum)
+    return max(e_same / 1e-12 if e_same > 0 else 0.0, e_g / 2e-4, e_l / 1e-5), 1.0, dict(e_same=e_same, e_g=e_g, e_l=e_l)

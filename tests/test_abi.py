@@ -15,6 +15,7 @@ HEADER = os.path.join(ROOT, "include", "dmip.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#if defined\(DMIP_DEBUG\).*?#endif", "", src, flags=re.S)      # debug-build-only hooks
     return sorted(set(re.findall(r"\b(dmip_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -42,6 +43,8 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, missing
     for s in declared_symbols():
         getattr(lib, s)                        # dlsym
+    # probes, self-tests and micro-benchmarks are not part of the product library (they live in tools/probe)
+    assert not [s for s in exported if s.startswith("dmip_debug")], "debug entry points leaked into the product"
 
 
 def test_version_and_error_string(lib):

@@ -132,3 +132,34 @@ def _dp_loss_case(rank, world):
 def test_data_parallel_loss_equals_single_process():
     res = _run(_dp_loss_case)
     assert max(res.values()) < 1e-5
+
+
+def _bucket_case(rank, world):
+    """GradBucket: the parameters' .grad alias one flat buffer; one all_reduce sums gradients and scalars in place."""
+    from dmip.distributed import GradBucket
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2))
+    b = GradBucket([net])
+    assert b.flat.numel() == 5 * 16 + 16 + 16 * 2 + 2 + GradBucket.N_SCALARS
+    g = torch.Generator().manual_seed(100 + rank)
+    b.grads.copy_(torch.randn(b.n_grad, generator=g))          # what the fused kernel does through grad_out
+    b.scalars[0] = 1.0 + rank
+    b.all_reduce()
+    lin0 = net[0]
+    aliased = lin0.weight.grad.data_ptr() == b.flat.data_ptr()
+    for p in net.parameters():
+        p.grad = None                                           # optimizer.zero_grad(set_to_none=True)
+    b.bind()
+    aliased = aliased and lin0.weight.grad.data_ptr() == b.flat.data_ptr()
+    return b.flat.clone(), aliased
+
+
+def test_grad_bucket_allreduce_gloo():
+    res = _run(_bucket_case)
+    n = 5 * 16 + 16 + 16 * 2 + 2
+    want = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    for r in range(2):
+        flat, aliased = res[r]
+        assert aliased
+        assert torch.allclose(flat[:n], want)
+        assert float(flat[n]) == 3.0

@@ -11,21 +11,35 @@ def _ok(res):
     assert err <= tol, (err, tol, {k: v for k, v in extra.items() if isinstance(v, float)})
 
 
+@pytest.fixture(params=["tc", "ffma"])
+def loss_path(request, monkeypatch):
+    """Both kernel families against the same reference fixtures: 'tc' = the tcgen05 kernels wherever they apply
+    (csrc/dmip_tcl.cu; the default), 'ffma' = the fp32 FFMA kernels of csrc/dmip_loss.cu forced for every pass."""
+    monkeypatch.setenv("DMIP_LOSS_PATH", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", sorted(gc.LOSS_CASES))
-def test_fused_loss(name):
+def test_fused_loss(name, loss_path):
     _ok(gc.case_loss(name))
 
 
 @pytest.mark.parametrize("name", ["loss_pinn_small", "loss_pinn_cde_linear_g3", "loss_pinn_cde_scat",
                                   "loss_pinn_cdiffe_linear", "loss_dsmpde_cde_linear"])
-def test_fused_loss_exact_divergence_adjoint_route(name):
+def test_fused_loss_exact_divergence_adjoint_route(name, loss_path):
     """d <= 4 runs forward-only by default; the adjoint route (what d = 26 uses) must give the same reference values"""
     _ok(gc.case_loss(name, "exact_adjoint"))
 
 
 @pytest.mark.parametrize("name", ["loss_posterior_scat", "loss_posterior_small"])
-def test_posterior_loss(name):
+def test_posterior_loss(name, loss_path):
     _ok(gc.case_posterior_loss(name))
+
+
+def test_tensor_core_loss_path_is_the_one_that_runs():
+    """The [512,512,512] fixtures must take the tcgen05 kernels (5 launches: pack, forward, backward, 4 weight-gradient
+    GEMMs = 7) — not silently the FFMA kernels (11 launches for the same pass)."""
+    _ok(gc.case_loss_path_taken())
 
 
 def test_surrogate_energy_and_score():

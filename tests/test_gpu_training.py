@@ -10,3 +10,19 @@ pytestmark = pytest.mark.gpu
 def test_train_epoch_reduces_the_loss_and_learns_the_posterior(loss_name):
     err, tol, extra = gc.case_train_epoch(loss_name)
     assert err <= tol, extra
+
+
+@pytest.mark.parametrize("kind", ["DSM", "PINN"])
+def test_data_parallel_shards_sum_to_the_single_process_gradient(kind):
+    """per-rank gradients with means over the GLOBAL batch, summed, equal the one-process step."""
+    err, tol, extra = gc.case_data_parallel_emulated(kind)
+    assert err <= tol, extra
+
+
+@pytest.mark.parametrize("kind", ["DSM", "PINN"])
+def test_data_parallel_two_ranks_nccl(kind):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    err, tol, extra = gc.case_data_parallel_nccl(kind)
+    assert err <= tol, extra

@@ -1,11 +1,11 @@
 """Staged GPU diagnostic: runs each parity case in its own subprocess (a device trap poisons the CUDA context of
-the process that hit it) with a timeout, prints one line per case.  Usage:  python tests/gpu_diag.py [filter]"""
+the process that hit it) with a timeout, prints one line per case.  Usage:  python tools/gpu_diag.py [filter]"""
 import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "tests")     # gpu_cases.py lives with the tests
 
 CASES = [
     ("umma_ss_n128_k64", "case_umma(0, 128, 64)"),

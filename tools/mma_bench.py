@@ -7,8 +7,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dmip import _lib
 
-L = _lib.require_gpu()
-L.dmip_debug_mma_bench.argtypes = [C.c_int32] * 5 + [C.c_void_p, C.c_void_p]
+_lib.require_gpu()
+from tools.probe import probe
+L = probe.lib()
 for grid in (1, 148):
     for mode in (0, 1):
         for n in (64, 128, 256):

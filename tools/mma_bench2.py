@@ -9,8 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dmip import _lib
 
-L = _lib.require_gpu()
-L.dmip_debug_mma_bench2.argtypes = [C.c_int32] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p]
+_lib.require_gpu()
+from tools.probe import probe
+L = probe.lib()
 src = torch.zeros((8 << 20) + (64 << 10), dtype=torch.uint8, device="cuda")
 grid = 148
 iters, k = 256, 256

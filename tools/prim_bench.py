@@ -7,8 +7,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dmip import _lib
 
-L = _lib.require_gpu()
-L.dmip_debug_prim_bench.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+_lib.require_gpu()
+from tools.probe import probe
+L = probe.lib()
 names = ["try_wait (completed phase)", "elect + arrive", "arrive + wait for it", "clock64", "tcgen05.commit (idle)",
          "commit + wait for it", "tcgen05.fence::after", "3 constant-bank loads", "issuer skeleton (wait+fence+commit)",
          "producer skeleton (wait+expect_tx)"]

@@ -1,8 +1,26 @@
-// dmip_debug.cu — tcgen05 design probes (tests/ only): MMA issue rate for single-CTA and CTA-pair instructions, A from
-// shared or tensor memory, with an optional concurrent bulk-TMA weight stream into the same shared memory.  The
-// numbers these print decide the sampler's tiling (DESIGN.md "K1 tiling").
-#include "dmip_common.h"
-#include "dmip_ptx.cuh"
+// dmip_probe.cu — tcgen05 design probes and building-block self-tests.  NOT part of the product: builds into
+// tools/probe/libdmip_probe.so (tools/probe/build.sh), loaded only by tests/ and tools/.  MMA issue rate for single-CTA
+// and CTA-pair instructions, A from shared or tensor memory, with an optional concurrent bulk-TMA weight stream; the
+// cost of the synchronisation primitives; small GEMMs through the library's own descriptor / layout helpers
+// (K-major and MN-major operands, bf16 hi/lo split).  The numbers these print decide the kernels' tiling.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../diffusion-modelling-for-inverse-problems_b200/csrc/dmip_common.h"
+#include "../../diffusion-modelling-for-inverse-problems_b200/csrc/dmip_ptx.cuh"
+
+namespace dmip {
+// the product's error / launch-count plumbing lives in dmip_api.cu; the probe library carries its own
+static thread_local char g_probe_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_probe_err, sizeof(g_probe_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int) {}
+void reset_launch_count() {}
+}  // namespace dmip
 
 namespace dmip {
 
@@ -498,7 +516,281 @@ __global__ void __launch_bounds__(512, 1) k_mmasync_rate(int iters, long long* o
   if (acc == 123.f) sink[0] = acc;
 }
 
+
+// ---- constants of the sampler's tile geometry the self-test kernels reuse
+constexpr int kStageBytes = 16384;
+constexpr uint32_t kTmemH = 0;
+constexpr uint32_t kTmemAcc = 256;
+
+// ------------------------------------------------------------------------------------------------ self-test kernel
+// D(128 x n) = A(128 x k) W(n x k)^T through the same descriptors / layouts / TMEM access as the sampler.
+__global__ void __launch_bounds__(128, 1) k_debug_umma(int mode, const float* __restrict__ a, const float* __restrict__ w,
+                                                        float* __restrict__ d, int n, int k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                       // up to 4 K-blocks
+  uint8_t* sW = smem + 4 * kStageBytes;     // up to 4 K-blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * kStageBytes);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 8 * kStageBytes + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(holder);
+  for (int i = threadIdx.x; i < 8 * kStageBytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // operand images
+  for (int kk = 0; kk < k; ++kk) {
+    const unsigned short ha = static_cast<unsigned short>(pack_bf16x2(a[row * k + kk], 0.f) & 0xFFFFu);
+    *reinterpret_cast<unsigned short*>(sA + sw128_offset(row, kk, kStageBytes)) = ha;
+    if (row < n) {
+      const unsigned short hw = static_cast<unsigned short>(pack_bf16x2(w[row * k + kk], 0.f) & 0xFFFFu);
+      *reinterpret_cast<unsigned short*>(sW + sw128_offset(row, kk, kStageBytes)) = hw;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  if (mode == 1) {
+    // A into tensor memory: lane = row, 32-bit column c = elements (2c, 2c+1)
+    for (int c0 = 0; c0 < k / 2; c0 += 16) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(a[row * k + 2 * (c0 + j)], a[row * k + 2 * (c0 + j) + 1]);
+      tmem_st16(lane_taddr + kTmemH + c0, pk);
+    }
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(n));
+    const uint32_t d_tmem = tmem_base + kTmemAcc;
+    for (int kb = 0; kb < k / 64; ++kb)
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sW) + kb * kStageBytes + kk * 32);
+        const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+        if (mode == 0)
+          umma_ss(d_tmem, umma_smem_desc_sw128(smem_u32(sA) + kb * kStageBytes + kk * 32), bdesc, idesc, acc);
+        else
+          umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, acc);
+      }
+    tc_commit(bar);
+  }
+  mbar_wait(bar, 0, 0x900);
+  tc_fence_after();
+  for (int pc = 0; pc < n / 8; ++pc) {
+    uint32_t v[8];
+    tmem_ld8(lane_taddr + kTmemAcc + pc * 8, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[row * n + pc * 8 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+  (void)lane;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA micro-benchmark
+// Issues `iters` x (k/16) back-to-back tcgen05.mma (M=128, N=n, K=16) from one elected lane and reports the
+// cycles from first issue to completion.  mode 0: A in shared memory, 1: A in tensor memory.  Operands are whatever
+// is in shared / tensor memory (zeros): only the timing matters.
+__global__ void __launch_bounds__(128, 1) k_debug_mma_bench(int mode, int n, int k, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + 4 * kStageBytes;   // up to 256 rows x 4 K-blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * kStageBytes);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 12 * kStageBytes + 8);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(holder);
+  for (int i = threadIdx.x; i < 12 * kStageBytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *holder, 0);
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(n));
+    const uint64_t desc_hi = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+    const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(sW) & 0x3FFFFu) >> 4;
+    const uint32_t wkb = static_cast<uint32_t>(n) * 128u;   // bytes per K-block of the B image
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int kb = 0; kb < k / 64; ++kb) {
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = desc_hi | (b_lo0 + ((kb * wkb) >> 4) + kk * 2);
+            const uint32_t d_tmem = tmem_base + kTmemAcc + (it & 1) * 0;   // same accumulator: worst-case dependence
+            if (mode == 0) umma_ss(d_tmem, desc_hi | (a_lo0 + ((kb * kStageBytes) >> 4) + kk * 2), bdesc, idesc, 1u);
+            else umma_ts(d_tmem, tmem_base + kTmemH + kb * 32 + kk * 8, bdesc, idesc, 1u);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit(bar);
+    __syncwarp();
+    const long long t1 = clock64();
+    mbar_wait(bar, 0, 0x901);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      cycles[blockIdx.x * 2] = t1 - t0;
+      cycles[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+
+// ------------------------------------------------------------------------------------------------ general GEMM self-test
+// D(128 x n) = A(128 x k) B(n x k)^T with either operand K-major or MN-major in shared memory, optionally as the bf16x3
+// split product  A_hi B_hi + A_hi B_lo + A_lo B_hi  (what the fused loss kernels run), through umma_smem_desc /
+// mn128_offset / sw128_offset.  The image strides and the descriptor fields are passed separately so the host can
+// probe the meaning of LBO / SBO for MN-major operands.
+struct Umma2Params {
+  int a_mn, b_mn, n, k, split, iters;
+  uint32_t a_img_lbo, a_img_sbo, b_img_lbo, b_img_sbo;   // MN-major image strides (bytes)
+  uint32_t a_fld_lbo, a_fld_sbo, b_fld_lbo, b_fld_sbo;   // descriptor fields (bytes)
+  const float* a;
+  const float* b;
+  float* d;
+  long long* cycles;
+};
+
+constexpr int kU2A = 32768, kU2B = 65536;   // bytes per image: A hi | A lo | B hi | B lo
+
+__global__ void __launch_bounds__(128, 1) k_umma2(const __grid_constant__ Umma2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA[2] = {smem, smem + kU2A};
+  uint8_t* sB[2] = {smem + 2 * kU2A, smem + 2 * kU2A + kU2B};
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kU2A + 2 * kU2B);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(smem + 2 * kU2A + 2 * kU2B + 8);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(holder);
+  for (int i = threadIdx.x; i < (2 * kU2A + 2 * kU2B) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const int n = P.n, k = P.k;
+  auto put = [&](uint8_t* const (&img)[2], uint32_t off, float v) {
+    const float hi = bf16_round(v);
+    *reinterpret_cast<unsigned short*>(img[0] + off) = static_cast<unsigned short>(pack_bf16x2(hi, 0.f) & 0xFFFFu);
+    *reinterpret_cast<unsigned short*>(img[1] + off) = static_cast<unsigned short>(pack_bf16x2(v - hi, 0.f) & 0xFFFFu);
+  };
+  for (int kk = 0; kk < k; ++kk) {
+    const int m = threadIdx.x;
+    put(sA, P.a_mn ? mn128_offset(m, kk, P.a_img_lbo, P.a_img_sbo) : sw128_offset(m, kk, 128 * 128), P.a[m * k + kk]);
+    for (int r = threadIdx.x; r < n; r += 128)
+      put(sB, P.b_mn ? mn128_offset(r, kk, P.b_img_lbo, P.b_img_sbo) : sw128_offset(r, kk, n * 128), P.b[r * k + kk]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  long long t0 = 0, t1 = 0;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16_major(128, static_cast<uint32_t>(n), P.a_mn, P.b_mn);
+    t0 = clock64();
+    for (int it = 0; it < P.iters; ++it) {
+      for (int j = 0; j < k / 16; ++j) {
+        // start address of K-slice j of each image
+        const uint32_t a_off = P.a_mn ? j * 2 * P.a_img_sbo : (j >> 2) * (128 * 128) + (j & 3) * 32;
+        const uint32_t b_off = P.b_mn ? j * 2 * P.b_img_sbo : (j >> 2) * (n * 128) + (j & 3) * 32;
+        const uint32_t al = P.a_mn ? P.a_fld_lbo : 16, as = P.a_mn ? P.a_fld_sbo : 1024;
+        const uint32_t bl = P.b_mn ? P.b_fld_lbo : 16, bs = P.b_mn ? P.b_fld_sbo : 1024;
+        const uint64_t ah = umma_smem_desc(smem_u32(sA[0]) + a_off, al, as), alo = umma_smem_desc(smem_u32(sA[1]) + a_off, al, as);
+        const uint64_t bh = umma_smem_desc(smem_u32(sB[0]) + b_off, bl, bs), blo = umma_smem_desc(smem_u32(sB[1]) + b_off, bl, bs);
+        umma_ss(tmem_base, ah, bh, idesc, (it | j) != 0 ? 1u : 0u);
+        if (P.split) {
+          umma_ss(tmem_base, ah, blo, idesc, 1u);
+          umma_ss(tmem_base, alo, bh, idesc, 1u);
+        }
+      }
+    }
+    tc_commit(bar);
+    t1 = clock64();
+  }
+  mbar_wait(bar, 0, 0x902);
+  tc_fence_after();
+  if (threadIdx.x == 0 && P.cycles) {
+    P.cycles[0] = t1 - t0;
+    P.cycles[1] = clock64() - t0;
+  }
+  for (int pc = 0; pc < n / 8; ++pc) {
+    uint32_t v[8];
+    tmem_ld8(lane_taddr + pc * 8, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) P.d[threadIdx.x * n + pc * 8 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
+
+int launch_debug_mma_bench(int mode, int n, int k, int iters, int grid, long long* cycles, cudaStream_t s) {
+  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256 && n % 16 == 0 && n >= 16 && n <= 256 && grid >= 1, "bad bench shape");
+  const int smem = 12 * kStageBytes + 64 + 1024;
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_debug_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_debug_mma_bench<<<grid, 128, smem, s>>>(mode, n, k, iters, cycles);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
+}
+
+int launch_debug_umma(int mode, const float* a, const float* w, float* d, int n, int k, cudaStream_t s) {
+  DMIP_REQUIRE(k % 64 == 0 && k >= 64 && k <= 256, "debug_umma: k must be 64, 128, 192 or 256");
+  DMIP_REQUIRE(n % 16 == 0 && n >= 16 && n <= 128, "debug_umma: n must be a multiple of 16 in [16,128]");
+  const int smem = 8 * kStageBytes + 64 + 1024;
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_debug_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_debug_umma<<<1, 128, smem, s>>>(mode, a, w, d, n, k);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMIP_OK;
+}
+
+
+int launch_debug_umma2(const Umma2Params& P, cudaStream_t s) {
+  DMIP_REQUIRE(P.k % 16 == 0 && P.k >= 16 && P.k <= 128, "umma2: k must be a multiple of 16 in [16,128]");
+  DMIP_REQUIRE(P.n % 8 == 0 && P.n >= 8 && P.n <= 256, "umma2: n must be a multiple of 8 in [8,256]");
+  const int smem = 2 * kU2A + 2 * kU2B + 64 + 1024;
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_umma2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma2<<<1, 128, smem, s>>>(P);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  return DMIP_OK;
+}
 
 int launch_debug_mma_bench2(int cg, int mode, int n, int k, int iters, int stream_bytes, int grid, const void* gsrc,
                             long long* cycles, cudaStream_t s) {
@@ -561,3 +853,42 @@ int launch_debug_prim_bench(int iters, long long* out, cudaStream_t s) {
 }
 
 }  // namespace dmip
+
+using namespace dmip;
+
+extern "C" {
+
+const char* dmip_probe_last_error(void) { return g_probe_err; }
+
+int dmip_debug_mma_bench(int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t grid, void* cycles, void* stream) {
+  return launch_debug_mma_bench(mode, n, k, iters, grid, static_cast<long long*>(cycles), static_cast<cudaStream_t>(stream));
+}
+
+int dmip_debug_mma_bench2(int32_t cg, int32_t mode, int32_t n, int32_t k, int32_t iters, int32_t stream_bytes, int32_t grid,
+                          const void* gsrc, void* cycles, void* stream) {
+  return launch_debug_mma_bench2(cg, mode, n, k, iters, stream_bytes, grid, gsrc, static_cast<long long*>(cycles),
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int dmip_debug_prim_bench(int32_t iters, void* out, void* stream) {
+  return launch_debug_prim_bench(iters, static_cast<long long*>(out), static_cast<cudaStream_t>(stream));
+}
+
+int dmip_debug_umma(int32_t mode, const float* a, const float* w, float* d, int32_t n, int32_t k, void* stream) {
+  DMIP_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (A in smem) or 1 (A in tmem)");
+  return launch_debug_umma(mode, a, w, d, n, k, static_cast<cudaStream_t>(stream));
+}
+
+/* general GEMM self-test: majors[2] = {a_mn, b_mn}; img[4] = {a_lbo, a_sbo, b_lbo, b_sbo} image strides and
+ * fld[4] the descriptor fields (bytes); cycles: device int64[2] or NULL */
+int dmip_debug_umma2(const int32_t* majors, int32_t n, int32_t k, int32_t split, int32_t iters, const uint32_t* img,
+                     const uint32_t* fld, const float* a, const float* b, float* d, void* cycles, void* stream) {
+  Umma2Params P = {};
+  P.a_mn = majors[0]; P.b_mn = majors[1]; P.n = n; P.k = k; P.split = split; P.iters = iters;
+  P.a_img_lbo = img[0]; P.a_img_sbo = img[1]; P.b_img_lbo = img[2]; P.b_img_sbo = img[3];
+  P.a_fld_lbo = fld[0]; P.a_fld_sbo = fld[1]; P.b_fld_lbo = fld[2]; P.b_fld_sbo = fld[3];
+  P.a = a; P.b = b; P.d = d; P.cycles = static_cast<long long*>(cycles);
+  return launch_debug_umma2(P, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
