@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the dmip-b200 hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...] [--no-also]
 
-Default workload (BASELINE.json configs[4], the config the metric "score-net evals/sec at 1/2/4/8 B200 + % tensor peak"
-is quoted on): synthetic CDE score net, xdim 100, ydim 27 (SURVEY.md §8a †), hidden [512,512,512], weights
+Headline workload (BASELINE.json configs[4], the config the metric "score-net evals/sec at 1/2/4/8 B200 + % tensor peak"
+is quoted on): synthetic CDE score net, xdim 100, ydim 27, hidden [512,512,512], weights
 torch.manual_seed(0) default init, one observation y ~ N(0,I) (seed 1), --particles (default 1,048,576) per GPU,
 --sde-steps (default 1000) Euler–Maruyama steps, Philox seed 1234.  One bench "step" = one full posterior-sampling
 call  model(y, num_samples=particles, num_steps=sde_steps)  = particles x sde_steps score-net evaluations = ONE launch
@@ -16,12 +16,16 @@ offset = rank * particles; no communication on the hot loop).
              is the numpy array the reference returns (device->host copy inside the timed region).
 `roofline` — tensor bound: achieved = evals/s x F (F = algorithmic FLOP per evaluation, unpadded dims, tanh / SDE
              update not counted) vs the measured SUSTAINED bf16 cuBLAS peak (the kernel runs > 1 s).
-`cpu_baseline` / `--impl reference` — the CPU oracle port of the reference sampler (oracle/sampler.py, which follows
-             models/diffusion.py:27-46 op for op) on all host cores, on a bounded sample of the same workload.
-
-Other workloads (not the headline line; same JSON shape): cdiffe_scat = configs[2] (scatterometry CDiffE, 1M x 1000),
-dps_scat = configs[3] per-GPU share (32 observations x 65,536 particles), pinn_linear = configs[1] (linear CDE,
-PINNLoss fwd+bwd+Adam at batch 65,536; metric samples/s).
+`cpu_baseline` / `--impl reference` — the reference's OWN classes (models/diffusion.py CDE.__call__, staged unmodified
+             under baseline/_ref by baseline/make_ref.py) on the host cores, on a bounded sample of the same workload;
+             the oracle port (oracle/sampler.py) only if the staged sources are missing — `kind` says which ran.
+`also`     — the other BASELINE configs as short runs on the same JSON line, each with its own value / ms / roofline /
+             e2e: cdiffe_scat = configs[2] (scatterometry CDiffE, 1M x 1000), dps_scat = configs[3] per-GPU share
+             (32 observations x 65,536 particles), pinn_linear = configs[1] (linear CDE, PINNLoss fwd+bwd+Adam at batch
+             65,536), dsm_linear (the DSM step at the same batch), posterior_loss (DPS joint loss, batch 16,384),
+             surrogate_score (K4 at 256 x 65,536 rows), sweep (configs[4] at 64K ... 16M particles, S = 200);
+             for --gpus N > 1: pinn_dp, the data-parallel PINN step (gradient all-reduce over NCCL) instead.
+The same workloads can be run alone with --workload (then they are the JSON line's headline).
 """
 import argparse
 import json
@@ -42,6 +46,7 @@ WORKLOADS = {
     "cdiffe_scat": ("CDiffE", 3, 23, 1, 1 << 20, 1000),
     "dps_scat": ("Posterior", 3, 23, 32, 1 << 16, 1000),
 }
+SURR_FLOP = 2 * 2 * (3 * 256 + 256 * 256 * 2 + 256 * 23)       # surrogate forward + reverse sweep = 550,912 FLOP / row
 
 
 def flop_per_eval(kind, xdim, ydim):
@@ -65,9 +70,32 @@ def parse():
     ap.add_argument("--sde-steps", type=int, default=0)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="synthetic", choices=list(WORKLOADS) + ["pinn_linear", "mcmc_scat"],
-                    help="synthetic = BASELINE configs[4] (the headline line); the others are configs[2], [3], [1]")
+    ap.add_argument("--no-also", action="store_true", help="headline line only (skip the other BASELINE configs)")
+    ap.add_argument("--workload", default="synthetic",
+                    choices=list(WORKLOADS) + ["pinn_linear", "dsm_linear", "posterior_loss", "surrogate_score", "mcmc_scat"],
+                    help="synthetic = BASELINE configs[4] (the headline line); the others are configs[2], [3], [1], ...")
     return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- stdout discipline
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """rank 0 prints ONE JSON line on stdout; everything else that writes to fd 1 (NCCL's INFO log, library banners) is
+    sent to stderr instead — the log stays available to the driver without polluting the JSON."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
@@ -80,23 +108,70 @@ def cpu_params(in_dim, out_dim, seed=0):
     return [(l.weight.detach().clone(), l.bias.detach().clone()) for l in layers]
 
 
+_REF_MODEL = {}
+
+
+def _reference_cde(xdim, ydim):
+    """The stock reference class on CPU (baseline/_ref = unmodified reference files; oracle/shims for the three modules
+    the reference tree does not contain).  None if the staged sources are missing."""
+    key = (xdim, ydim)
+    if key in _REF_MODEL:
+        return _REF_MODEL[key]
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    model = None
+    if os.path.exists(os.path.join(ref_dir, "models", "diffusion.py")):
+        import importlib
+        import torch
+        saved_path, saved_mods = list(sys.path), {k: sys.modules.get(k) for k in ("models", "sdes", "nets", "losses")}
+        avail = torch.cuda.is_available
+        try:
+            sys.path[:0] = [ref_dir, os.path.join(ROOT, "oracle", "shims")]
+            for k in saved_mods:
+                sys.modules.pop(k, None)
+            torch.cuda.is_available = lambda: False        # the reference picks its device at import time: keep it on CPU
+            mod = importlib.import_module("models.diffusion")
+            torch.manual_seed(0)
+            model = mod.CDE(xdim, ydim, list(HIDDEN))
+            model.sde.eval()
+        except Exception as e:                             # noqa: BLE001 — fall back to the port, and say so
+            print("reference arm: stock classes unavailable:", repr(e), file=sys.stderr)
+            model = None
+        finally:
+            torch.cuda.is_available = avail
+            sys.path[:] = saved_path
+            for k, v in saved_mods.items():
+                sys.modules.pop(k, None)
+                if v is not None:
+                    sys.modules[k] = v
+    _REF_MODEL[key] = model
+    return model
+
+
 def cpu_sampler_rate(n, s, xdim=100, ydim=27):
-    """Time the CPU oracle port of BaseClassDiffusionModel.forward on n particles x s steps (all host cores)."""
+    """Time the reference sampler on n particles x s steps on all host cores.  Returns (evals/s, cores, seconds, kind):
+    kind 'reference' = the stock CDE.__call__ of the reference (torch's own RNG, the per-step ones*ts[i] / cat / addmm
+    of models/diffusion.py:27-46); kind 'port' = oracle/sampler.py, only when baseline/_ref is missing."""
     import torch
-    from oracle import sampler as osamp            # the one place bench.py may execute oracle/
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = cpu_params(xdim + ydim + 1, xdim)
     g = torch.Generator().manual_seed(1)
     y = torch.randn(ydim, generator=g)
-    x0 = torch.randn(n, xdim, generator=g)
-    noise = torch.randn(1, n, xdim, generator=g).expand(s, n, xdim)   # one draw reused: timing is unaffected
+    model = _reference_cde(xdim, ydim)
     with torch.no_grad():
-        osamp.em_sampler_cde(params, y, x0[:256], noise[:2, :256], 2)       # warm-up
+        if model is not None:
+            model(y, num_samples=256, num_steps=2)                              # warm-up
+            t0 = time.perf_counter()
+            model(y, num_samples=n, num_steps=s)
+            return n * s / (time.perf_counter() - t0), cores, time.perf_counter() - t0, "reference"
+        from oracle import sampler as osamp            # fallback: the one other place bench.py may execute oracle/
+        params = cpu_params(xdim + ydim + 1, xdim)
+        x0 = torch.randn(n, xdim, generator=g)
+        noise = torch.randn(1, n, xdim, generator=g).expand(s, n, xdim)   # one draw reused: timing is unaffected
+        osamp.em_sampler_cde(params, y, x0[:256], noise[:2, :256], 2)
         t0 = time.perf_counter()
         osamp.em_sampler_cde(params, y, x0, noise, s)
         dt = time.perf_counter() - t0
-    return n * s / dt, cores, dt
+    return n * s / dt, cores, dt, "port"
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -142,6 +217,57 @@ def load_peaks():
         return {}
 
 
+def load_traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+_FP32_PEAK = {}
+
+
+def measured_fp32_tflops():
+    """Denominator for the kernels that are fp32 FFMA by design (K4 surrogate, Metropolis): the cuBLAS SGEMM rate with
+    TF32 off, measured live on this GPU (8192^3, best of 5) — a measured peak instead of the nominal 72 TFLOP/s."""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _FP32_PEAK:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            a = torch.randn(8192, 8192, device="cuda")
+            b = torch.randn(8192, 8192, device="cuda")
+            best = 1e9
+            for i in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                if i:
+                    best = min(best, e0.elapsed_time(e1))
+            _FP32_PEAK[dev] = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+    return _FP32_PEAK[dev]
+
+
+def tensor_roofline(ach_tf, sustained, **extra):
+    """roofline object against the measured bf16 tensor peak (MEASURED_PEAKS.json; fallback of B200_PROFILING.md)"""
+    peaks = load_peaks()
+    key = "bf16_tflops_sustained" if sustained else "bf16_tflops"
+    peak = peaks.get(key)
+    src = f"measured {'sustained' if sustained else 'burst'} bf16 cuBLAS (MEASURED_PEAKS.json)"
+    if not peak:
+        peak, src = (1400.0 if sustained else 1590.0), "fallback bf16 peak (B200_PROFILING.md)"
+    r = {"bound": "tensor", "achieved": ach_tf, "peak": peak, "unit": "TFLOP/s", "frac": ach_tf / peak, "traffic": None,
+         "peak_source": src}
+    r.update(extra)
+    return r
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 CFG_NAMES = {"synthetic": "configs[4]: synthetic CDE", "cdiffe_scat": "configs[2]: scatterometry CDiffE",
              "dps_scat": "configs[3] (per-GPU share): scatterometry DPS"}
@@ -163,24 +289,25 @@ def run_reference(args, rank):
     for _ in range(min(args.warmup, 1)):
         cpu_sampler_rate(2048, 4)
     secs = []
-    cores = os.cpu_count()
+    cores, kind = os.cpu_count(), "port"
     for _ in range(args.steps):
-        _, cores, dt = cpu_sampler_rate(n, s)
+        _, cores, dt, kind = cpu_sampler_rate(n, s)
         secs.append(dt)
     value = n * s * len(secs) / sum(secs)
-    line = {
+    what = ("the reference's own CDE.__call__ (baseline/_ref, unmodified models/diffusion.py + sdes.py + nets.py)"
+            if kind == "reference" else "oracle port of models/diffusion.py:27-46 (baseline/_ref missing)")
+    emit({
         "impl": "reference", "metric": "score-net evals/sec (posterior sampler)", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args) if args.workload in WORKLOADS else args.workload,
-                   "sample": f"CPU step = {n} particles x {s} SDE steps of the synthetic CDE net (xdim 100, ydim 27); the "
-                             "rate is linear in particles x steps (SURVEY.md App. B)"},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                   "sample": f"CPU step = {n} particles x {s} SDE steps of the synthetic CDE net (xdim 100, ydim 27) through "
+                             f"{what}; the rate is linear in particles x steps (SURVEY.md App. B)"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind,
                          "sample": f"{n} particles x {s} steps, torch CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+    })
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -191,29 +318,281 @@ def setup_dist(world):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")      # the init log (ranks, NVLS, rings) goes to stderr, see claim_stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return local, dist
 
 
-def run_sampler(args, rank, world):
-    import torch
+def require_lib():
     import dmip
-    from dmip.models import diffusion as dm
-
-    local, dist = setup_dist(world)
     if not dmip.is_available():
         raise RuntimeError("libdmip_sm100.so missing or device is not sm_100 — no fallback")
-    kind, xdim, ydim, n_obs, n_def, s_def = WORKLOADS[args.workload]
-    N, S = args.particles or n_def, args.sde_steps or s_def
-    F = flop_per_eval(kind, xdim, ydim)
 
+
+def event_ms(fn, steps, warmup, before=None):
+    """mean milliseconds per call of fn (CUDA events on torch's current stream = the stream the kernels launch on)"""
+    import torch
+    for _ in range(warmup):
+        if before:
+            before()
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        if before:
+            before()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+
+def make_sampler_model(workload, rank=0):
+    import torch
+    from dmip.models import diffusion as dm
+    kind, xdim, ydim, n_obs, n_def, s_def = WORKLOADS[workload]
     torch.manual_seed(0)
     cls = {"CDE": dm.CDE, "CDiffE": dm.CDiffE, "Posterior": dm.PosteriorDiffusionEstimator}[kind]
     model = cls(xdim, ydim, HIDDEN)          # default nn.Linear init under seed 0 (random-init weights, synthetic)
     model.sde.eval()
     y_host = torch.randn(n_obs, ydim, generator=torch.Generator().manual_seed(1 + rank))
     y_host = (y_host[0] if n_obs == 1 else y_host).contiguous().pin_memory()
+    return model, y_host
+
+
+def also_sampler(workload, N, S, flush, steps=1, warmup=1, e2e=True):
+    """one short device-timed + one end-to-end run of a sampler workload (single GPU)"""
+    import torch
+    kind, xdim, ydim, n_obs, _, _ = WORKLOADS[workload]
+    model, y_host = make_sampler_model(workload)
+    y_dev = y_host.cuda()
+    kw = dict(num_samples=N, num_steps=S, precision="bf16", seed=1234)
+    ms = event_ms(lambda: model(y_dev, return_tensor=True, **kw), steps, warmup, before=flush.zero_)
+    evals = float(n_obs) * N * S
+    F = flop_per_eval(kind, xdim, ydim)
+    out = {"config": f"{CFG_NAMES[workload]} xdim={xdim} ydim={ydim}, {n_obs} obs x {N} particles x {S} steps",
+           "value": evals / (ms * 1e-3), "unit": "evals/s", "ms": ms, "samples_per_sec": evals / S / (ms * 1e-3),
+           "dtype": "bf16" if model.last_precision == "bf16" else "f32", "gpu_launches": model.last_launch_count * steps,
+           "roofline": tensor_roofline(evals * F / (ms * 1e-3) / 1e12, sustained=ms > 500, flop_per_eval=F,
+                                       kernel="k_tc_mlp")}
+    tr = load_traffic().get("k_tc_mlp_dram_bytes_per_launch", {})
+    if workload in tr and N == WORKLOADS[workload][4] and S == WORKLOADS[workload][5]:
+        out["roofline"]["traffic"] = tr[workload]
+    if e2e:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x_np = model(y_host, **kw)
+        dt = time.perf_counter() - t0
+        out["e2e"] = {"value": evals / dt, "unit": "evals/s", "h2d_bytes_per_step": n_obs * ydim * 4,
+                      "d2h_bytes_per_step": int(x_np.size) * 4}
+        del x_np
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def linear_batch(B, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 2, generator=g)
+    A = torch.tensor([[1.0, 0.5], [0.0, 1.0]])
+    y = x @ A.T + torch.tensor([0.3, 0.5]) + 0.3 * torch.randn(B, 2, generator=g)
+    t = torch.rand(B, 1, generator=g) * 0.998 + 1e-3
+    return x, y, t
+
+
+def also_train(kind, B, steps=5, warmup=3, dist=None, rank=0, world=1):
+    """configs[1]: linear CDE training step (fused loss forward + backward + Adam) at batch B per GPU.
+    kind 'PINN': PINNLoss(FPE exact divergence, L1, ic L2) as config_linear.yml:11-16; 'DSM': the DSM branch."""
+    import torch
+    from dmip import distributed as dd, losses as dl
+    from dmip.models.diffusion import CDE
+    torch.manual_seed(0)
+    model = CDE(2, 2, HIDDEN)
+    opt = torch.optim.Adam(model.sde.a.parameters(), lr=1e-4)
+    x, y, t = linear_batch(B, 7 + rank)
+    xh, yh = x.pin_memory(), y.pin_memory()
+    xd, yd, td = x.cuda(), y.cuda(), t.cuda()
+    if kind == "PINN":
+        loss_fn = dl.PINNLoss(lambda xx, yy: -xx, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+        flop_sample, name = 14, "configs[1]: linear CDE + PINNLoss(FPE exact divergence, L1, ic L2)"
+    else:
+        loss_fn = dl.DSMLoss()
+        flop_sample, name = 3, "linear CDE + DSMLoss"
+    F = flop_per_eval("CDE", 2, 2)
+    last = {}
+
+    def step(xa, ya):
+        last["loss"], _ = dd.train_step_data_parallel(model, opt, loss_fn, xa, ya, td, batch_global=B * world)
+
+    if dist is not None:
+        dist.barrier()
+    ms = event_ms(lambda: step(xd, yd), steps, warmup)
+    launches = getattr(loss_fn, "last_launch_count", 0) * steps
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(xh.cuda(non_blocking=True), yh.cuda(non_blocking=True))
+        lv = last["loss"].item()                        # device -> host read of the step's result
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tmax = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms, e2e_s = tmax.tolist()
+    value = B * world / (ms * 1e-3)
+    tc_path = os.environ.get("DMIP_LOSS_PATH", "tc") != "ffma"
+    ach = value / world * flop_sample * F / 1e12
+    if tc_path:
+        roof = tensor_roofline(ach, sustained=False, flop_per_sample=flop_sample * F,
+                               kernel="k_tcl_fwd + k_tcl_bwd + k_tcl_wgrad (bf16x3 split: 3 tensor-core FLOP per algorithmic FLOP)",
+                               tensor_flops_issued_tflops=3 * ach)
+        tr = load_traffic().get("k_tcl_dram_bytes_per_step", {})
+        roof["traffic"] = tr.get(kind.lower()) if B == 65536 else None
+    else:
+        pk = measured_fp32_tflops()
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                "peak_source": "measured cuBLAS SGEMM (TF32 off) on this GPU: the FFMA loss kernels are fp32",
+                "flop_per_sample": flop_sample * F, "kernel": "k_jets_fwd + k_jets_bwd + k_wgrad"}
+    out = {"config": f"{name}, batch {B} per GPU, Adam" + (f", data parallel over {world} GPUs (NCCL all-reduce of one "
+                                                            f"gradient bucket)" if world > 1 else ""),
+           "value": value, "unit": "samples/s", "ms": ms, "dtype": "bf16x3 (fp32-accurate split)" if tc_path else "f32",
+           "loss": lv, "gpu_launches": launches, "roofline": roof,
+           "e2e": {"value": B * world * steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * 16,
+                   "d2h_bytes_per_step": 4}}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def also_posterior_loss(B=16384, steps=5, warmup=3):
+    """PosteriorDiffusionEstimator.train_epoch body (models/diffusion.py:204-229): PosteriorLoss forward + backward +
+    Adam on both nets, scatterometry shapes, random-init surrogate of the reference's architecture."""
+    import torch
+    from dmip.models.diffusion import PosteriorDiffusionEstimator
+    torch.manual_seed(0)
+    fm = torch.nn.Sequential(torch.nn.Linear(3, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                             torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 23)).cuda()
+    for q in fm.parameters():
+        q.requires_grad = False
+    m = PosteriorDiffusionEstimator(3, 23, HIDDEN)
+    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-4)
+    loss_fn = m.loss_fn(fm, 0.2, 0.01, lam=0.01)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(B, 3, generator=g) * 2 - 1)
+    xh = x.pin_memory()
+    xd = x.cuda()
+    with torch.no_grad():
+        yd = fm(xd)
+    yh = yd.cpu().pin_memory()
+    td = (torch.rand(B, 1, generator=g) * 0.998 + 1e-3).cuda()
+    last = {}
+
+    def step(xa, ya):
+        loss, _ = loss_fn(m.sde, xa, ya, td)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        last["loss"] = loss.detach()
+
+    ms = event_ms(lambda: step(xd, yd), steps, warmup)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(xh.cuda(non_blocking=True), yh.cuda(non_blocking=True))
+        lv = last["loss"].item()
+    e2e_s = time.perf_counter() - t0
+    Fp, Fl = flop_per_eval("CDE", 0, 3) if False else 2 * (4 * 512 + 2 * 512 * 512 + 512 * 3), flop_per_eval("CDE", 3, 23)
+    flop = 6 * Fp + 3 * Fl + SURR_FLOP       # prior: 1 + 3 tangent streams forward + 2 F backward; likelihood 3 F; surrogate VJP
+    ach = B / (ms * 1e-3) * flop / 1e12
+    return {"config": f"scatterometry DPS: PosteriorLoss forward + backward + Adam on prior and likelihood net, batch {B}",
+            "value": B / (ms * 1e-3), "unit": "samples/s", "ms": ms, "dtype": "bf16x3 (fp32-accurate split)", "loss": lv,
+            "gpu_launches": getattr(loss_fn, "last_launch_count", 0) * steps,
+            "roofline": tensor_roofline(ach, sustained=False, flop_per_sample=flop,
+                                        kernel="2 x (k_tcl_fwd + k_tcl_bwd + k_tcl_wgrad) + k_surrogate"),
+            "e2e": {"value": B * steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * (3 + 23) * 4,
+                    "d2h_bytes_per_step": 4}}
+
+
+def also_surrogate(rows=256 * 65536, steps=3, warmup=2):
+    """K4 at the size of configs[3]: energy and posterior score (get_log_posterior + energy_grad) for 256 x 65,536 rows"""
+    import torch
+    from dmip import utils_scatterometry as us
+    torch.manual_seed(0)
+    fm = torch.nn.Sequential(torch.nn.Linear(3, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                             torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 23)).cuda()
+    for q in fm.parameters():
+        q.requires_grad = False
+    g = torch.Generator().manual_seed(5)
+    chunk = 1 << 22                                   # the call is row-independent: 4M-row calls keep the host buffers small
+    n_chunks = (rows + chunk - 1) // chunk
+    xh = (torch.rand(chunk, 3, generator=g) * 2 - 1).pin_memory()
+    xd = xh.cuda()
+    with torch.no_grad():
+        yd = fm(xd[:65536]).repeat(chunk // 65536, 1).contiguous()
+    yh = yd.cpu().pin_memory()
+
+    def call(xa, ya):
+        return us.surrogate_call(fm, xa, ya, 0.2, 0.01, 1000.0)
+
+    ms = event_ms(lambda: [call(xd, yd) for _ in range(n_chunks)], steps, warmup)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_chunks):
+        E, gr, _ = call(xh.cuda(non_blocking=True), yh.cuda(non_blocking=True))
+        gh = gr.cpu()
+    e2e_s = time.perf_counter() - t0
+    ach = rows / (ms * 1e-3) * SURR_FLOP / 1e12
+    pk = measured_fp32_tflops()
+    return {"config": f"K4 surrogate energy + score, {rows} rows (256 observations x 65,536 particles), in calls of {chunk} rows",
+            "value": rows / (ms * 1e-3), "unit": "rows/s", "ms": ms, "dtype": "f32", "gpu_launches": n_chunks * steps,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                         "peak_source": "measured cuBLAS SGEMM (TF32 off) on this GPU: k_surrogate is fp32 FFMA by design "
+                                        "(the energy has 1/b^2 = 1e4 terms)", "flop_per_row": SURR_FLOP, "kernel": "k_surrogate"},
+            "e2e": {"value": rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": rows * 26 * 4, "d2h_bytes_per_step": rows * 12}}
+
+
+def run_also(args, flush):
+    """The other BASELINE configs, single GPU, short runs; every entry carries value / ms / roofline / e2e."""
+    import torch
+    also = {}
+
+    def guard(name, fn):
+        try:
+            also[name] = fn()
+        except Exception as e:                         # noqa: BLE001 — one failing extra must not lose the headline
+            also[name] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
+    guard("cdiffe_scat", lambda: also_sampler("cdiffe_scat", 1 << 20, 1000, flush))
+    guard("dps_scat", lambda: also_sampler("dps_scat", 1 << 16, 1000, flush))
+    guard("pinn_linear", lambda: also_train("PINN", 65536))
+    guard("dsm_linear", lambda: also_train("DSM", 65536))
+    guard("posterior_loss", also_posterior_loss)
+    guard("surrogate_score", also_surrogate)
+    sweep = {}
+    for n in (1 << 16, 1 << 18, 1 << 22, 1 << 24):
+        try:
+            r = also_sampler("synthetic", n, 200, flush, steps=1, warmup=1, e2e=n <= (1 << 22))
+            sweep[str(n)] = {"value": r["value"], "ms": r["ms"], "frac": r["roofline"]["frac"],
+                             "e2e": r.get("e2e", {}).get("value")}
+        except Exception as e:                         # noqa: BLE001
+            sweep[str(n)] = {"error": repr(e)[:200]}
+    also["sweep"] = {"config": "configs[4] synthetic CDE, particles swept at S = 200 SDE steps, 1 GPU (e2e up to 4M particles: "
+                               "the 16M result is 6.7 GB of samples)", "unit": "evals/s", "particles": sweep}
+    return also
+
+
+def run_sampler(args, rank, world):
+    import torch
+    local, dist = setup_dist(world)
+    require_lib()
+    kind, xdim, ydim, n_obs, n_def, s_def = WORKLOADS[args.workload]
+    N, S = args.particles or n_def, args.sde_steps or s_def
+    F = flop_per_eval(kind, xdim, ydim)
+    model, y_host = make_sampler_model(args.workload, rank)
     y_dev = y_host.cuda()
     per_rank = n_obs * N                      # particles integrated by one rank per bench step
     kw = dict(num_samples=N, num_steps=S, precision=args.precision, seed=1234, gidx_base=rank * per_rank)
@@ -253,6 +632,7 @@ def run_sampler(args, rank, world):
         [kev[-1][1].elapsed_time(ev1)]
     clk = clocks.stop(t_wall0, t_wall1)
     finite = bool(torch.isfinite(out).all().item())
+    del out
 
     # ---- end-to-end through the reference-facing call, host buffers
     barrier()
@@ -262,11 +642,23 @@ def run_sampler(args, rank, world):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert x_np.shape[-1] == xdim
+    del x_np
 
     if dist is not None:
         tmax = torch.tensor([ms, e2e_s, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms, e2e_s, kernel_ms = tmax.tolist()
+
+    # ---- the other BASELINE configs (single GPU), or the data-parallel training step (multi GPU)
+    also = None
+    if not args.no_also and args.workload == "synthetic" and not args.particles and not args.sde_steps:
+        if world == 1:
+            also = run_also(args, flush)
+        else:
+            try:
+                also = {"pinn_dp": also_train("PINN", 65536, dist=dist, rank=rank, world=world)}
+            except Exception as e:                     # noqa: BLE001
+                also = {"pinn_dp": {"error": repr(e)[:300]}}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -274,116 +666,57 @@ def run_sampler(args, rank, world):
 
     evals = float(per_rank) * S * args.steps * world
     value = evals / (ms * 1e-3)
-    peaks = load_peaks()
-    peak_tf = peaks.get("bf16_tflops_sustained")
-    peak_src = "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json): the kernel runs inside a > 1 s step"
-    if not peak_tf:
-        peak_tf, peak_src = 1400.0, "fallback sustained bf16 (B200_PROFILING.md)"
     ach_tf = (float(per_rank) * S / (kernel_ms * 1e-3)) * F / 1e12      # per GPU, from the kernel's own launch duration
-    traffic = None
-    try:
-        # measured for the default launch of a workload only (ncu capture of that exact command); null otherwise
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_tc_mlp_dram_bytes_per_launch", {})
-        traffic = tr.get(args.workload) if (not args.particles and not args.sde_steps) else None
-    except Exception:
-        pass
+    roof = tensor_roofline(ach_tf, sustained=True, flop_per_eval=F, kernel="k_tc_mlp (one launch per bench step)",
+                           kernel_ms=kernel_ms)
+    roof["peak_source"] += ": the kernel runs inside a > 1 s step"
+    peaks = load_peaks()
+    roof["frac_of_burst_peak"] = (ach_tf / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None
+    # measured for the default launch of a workload only (ncu capture of that exact command); null otherwise
+    tr = load_traffic().get("k_tc_mlp_dram_bytes_per_launch", {})
+    roof["traffic"] = tr.get(args.workload) if (not args.particles and not args.sde_steps) else None
+    ran = getattr(model, "last_precision", args.precision)
     line = {
         "metric": "score-net evals/sec (posterior sampler)", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": "bf16" if ran == "bf16" else "f32",     # the path that RAN: a bf16 request outside the tcgen05 kernel's shapes runs fp32
+        "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "samples_per_sec": value / S, "l2": "256 MB buffer zeroed between timed iterations",
                    "finite": finite, "gaps_ms": [round(g, 2) for g in gaps_ms]},
-        "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                     "traffic": traffic, "peak_source": peak_src, "flop_per_eval": F,
-                     "frac_of_burst_peak": (ach_tf / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None,
-                     "kernel": "k_tc_mlp (one launch per bench step)", "kernel_ms": kernel_ms},
+        "roofline": roof,
         "e2e": {"value": evals / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": n_obs * ydim * 4,
                 "d2h_bytes_per_step": per_rank * xdim * 4},
         "gpu_launches": launches,
         "clocks": clk,
     }
+    if also is not None:
+        line["also"] = also
     if not args.no_cpu_baseline and world == 1:
         n, s = 65536, 100
-        r, cores, dt = cpu_sampler_rate(n, s)
-        line["cpu_baseline"] = {"value": r, "unit": "evals/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} particles x {s} steps of the synthetic CDE net, torch CPU fp32, {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+        r, cores, dt, kind = cpu_sampler_rate(n, s)
+        line["cpu_baseline"] = {"value": r, "unit": "evals/s", "cores": cores, "kind": kind,
+                                "sample": f"{n} particles x {s} steps of the synthetic CDE net, torch CPU fp32, {dt:.1f} s"
+                                          + (" (stock reference CDE.__call__)" if kind == "reference" else " (oracle port)")}
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_pinn(args, rank, world):
-    """BASELINE configs[1]: linear CDE + PINNLoss (Score-FPE, exact divergence) training, batch 65,536 per GPU,
-    data parallel (gradient all-reduce).  One bench step = one optimisation step."""
-    import torch
-    import dmip
-    from dmip import distributed as dd, losses as dl
-    from dmip.models.diffusion import CDE
-
+def run_single(args, rank, world, fn, metric, **kw):
+    """a non-sampler workload as the JSON line's headline"""
     local, dist = setup_dist(world)
-    if not dmip.is_available():
-        raise RuntimeError("libdmip_sm100.so missing or device is not sm_100 — no fallback")
-    B = args.particles or 65536
-    torch.manual_seed(0)
-    model = CDE(2, 2, HIDDEN)
-    opt = torch.optim.Adam(model.sde.a.parameters(), lr=1e-4)
-    g = torch.Generator().manual_seed(7 + rank)
-    x = torch.randn(B, 2, generator=g)
-    A = torch.tensor([[1.0, 0.5], [0.0, 1.0]])
-    y = x @ A.T + 0.3 * torch.randn(B, 2, generator=g)
-    xh, yh = x.pin_memory(), y.pin_memory()
-    xd, yd = x.cuda(), y.cuda()
-    t = (torch.rand(B, 1, generator=g) * 0.998 + 1e-3).cuda()
-    loss_fn = dl.PINNLoss(lambda xx, yy: -xx, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
-
-    def step(xa, ya):
-        loss, info = dd.train_step_data_parallel(model, opt, loss_fn, xa, ya, t)
-        return loss
-
-    for _ in range(max(args.warmup, 0)):
-        step(xd, yd)
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    require_lib()
+    r = fn(dist=dist, rank=rank, world=world, **kw) if fn is also_train else fn(**kw)
     if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        step(xd, yd)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    launches = getattr(loss_fn, "last_launch_count", 0) * args.steps
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss = step(xh.cuda(non_blocking=True), yh.cuda(non_blocking=True))
-        lv = loss.item()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        tmax = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms, e2e_s = tmax.tolist()
         dist.destroy_process_group()
     if rank != 0:
         return
-    F = flop_per_eval("CDE", 2, 2)
-    value = B * world * args.steps / (ms * 1e-3)
-    ach = value / world * 14 * F / 1e12
-    print(json.dumps({
-        "metric": "PINNLoss training samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: linear CDE + PINNLoss(FPE exact divergence, L1, ic L2), batch {B} per GPU, Adam",
-                   "loss": lv},
-        "roofline": {"bound": "tensor", "achieved": ach, "peak": 72.0, "unit": "TFLOP/s", "frac": ach / 72.0, "traffic": None,
-                     "peak_source": "nominal fp32 FFMA rate (148 SM x 128 FMA x 2 x 1.9 GHz): the loss kernels are fp32 FFMA",
-                     "flop_per_sample": 14 * F, "kernel": "k_jets_fwd + k_jets_bwd + k_wgrad"},
-        "e2e": {"value": B * world * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * 16,
-                "d2h_bytes_per_step": 4},
-        "gpu_launches": launches,
-    }), flush=True)
+    emit({"metric": metric, "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": r["dtype"], "data": "synthetic", "config": {"workload": r["config"], "loss": r.get("loss")},
+          "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"]})
 
 
 def run_mcmc(args, rank, world):
@@ -391,11 +724,9 @@ def run_mcmc(args, rank, world):
     chains on the surrogate posterior, 8 observations x 30,000 chains per GPU (config_scatterometry.yml: n_samples_x),
     METR_STEPS = 1000 per bench step, one kernel launch.  Observations shard over ranks, no collective."""
     import torch
-    import dmip
     from dmip import mcmc
     local, dist = setup_dist(world)
-    if not dmip.is_available():
-        raise RuntimeError("libdmip_sm100.so missing or device is not sm_100 — no fallback")
+    require_lib()
     torch.manual_seed(0)
     fm = torch.nn.Sequential(torch.nn.Linear(3, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
                              torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 23)).cuda()
@@ -413,19 +744,9 @@ def run_mcmc(args, rank, world):
         x, _ = mcmc.anneal_to_energy(x0, fm, 0.2, 0.01, yv, 1000.0, S, 0.5, seed=1, gidx_base=rank * n_obs * n_per)
         return x.cpu() if to_host else x
 
-    for _ in range(max(args.warmup, 0)):
-        step(ys)
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if dist is not None:
         dist.barrier()
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        step(ys)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    ms = event_ms(lambda: step(ys), args.steps, max(args.warmup, 0)) * args.steps
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step(ys_h.cuda(non_blocking=True), to_host=True)
@@ -434,6 +755,8 @@ def run_mcmc(args, rank, world):
         tmax = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms, e2e_s = tmax.tolist()
+    pk = measured_fp32_tflops()
+    if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -441,31 +764,42 @@ def run_mcmc(args, rank, world):
     work = n_obs * n_per * S * world * args.steps
     value = work / (ms * 1e-3)
     ach = value / world * F / 1e12
-    print(json.dumps({
+    emit({
         "metric": "Metropolis chain-steps/sec (scatterometry ground truth)", "value": value, "unit": "chain-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"scatterometry Metropolis ground truth: {n_obs} observations x {n_per} chains per GPU x {S} "
                                "steps per bench step, random-init surrogate 3-256-256-256-23, Philox in-kernel"},
-        "roofline": {"bound": "tensor", "achieved": ach, "peak": 72.0, "unit": "TFLOP/s", "frac": ach / 72.0, "traffic": None,
-                     "peak_source": "nominal fp32 FFMA rate (148 SM x 128 FMA x 2 x 1.9 GHz): k_metropolis is fp32 FFMA",
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                     "peak_source": "measured cuBLAS SGEMM (TF32 off) on this GPU: k_metropolis is fp32 FFMA",
                      "flop_per_chain_step": F, "kernel": "k_metropolis (one launch per bench step)"},
         "e2e": {"value": work / e2e_s, "unit": "chain-steps/s", "h2d_bytes_per_step": n_obs * 23 * 4,
                 "d2h_bytes_per_step": n_obs * n_per * 12},
         "gpu_launches": getattr(mcmc.anneal_to_energy, "last_launch_count", 0) * args.steps,
-    }), flush=True)
+    })
 
 
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
     elif args.workload == "mcmc_scat":
         run_mcmc(args, rank, world)
     elif args.workload == "pinn_linear":
-        run_pinn(args, rank, world)
+        run_single(args, rank, world, also_train, "PINNLoss training samples/sec", kind="PINN", B=args.particles or 65536,
+                   steps=args.steps, warmup=args.warmup)
+    elif args.workload == "dsm_linear":
+        run_single(args, rank, world, also_train, "DSMLoss training samples/sec", kind="DSM", B=args.particles or 65536,
+                   steps=args.steps, warmup=args.warmup)
+    elif args.workload == "posterior_loss":
+        run_single(args, rank, world, also_posterior_loss, "PosteriorLoss training samples/sec", B=args.particles or 16384,
+                   steps=args.steps, warmup=args.warmup)
+    elif args.workload == "surrogate_score":
+        run_single(args, rank, world, also_surrogate, "surrogate score rows/sec", rows=args.particles or 256 * 65536,
+                   steps=args.steps, warmup=args.warmup)
     else:
         run_sampler(args, rank, world)
 

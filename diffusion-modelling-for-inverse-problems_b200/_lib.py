@@ -17,6 +17,7 @@ MAX_LAYERS = 8
 PREC_F32, PREC_BF16 = 0, 1
 CDE, CDIFFE, DPS = 0, 1, 2
 RNG_PHILOX, RNG_INJECTED = 0, 1
+SDE_VP, SDE_VE = 0, 1
 _PREC = {"fp32": PREC_F32, "f32": PREC_F32, "float32": PREC_F32, "bf16": PREC_BF16, "bfloat16": PREC_BF16}
 
 
@@ -36,7 +37,9 @@ class DmipSampler(C.Structure):
                 ("y", C.c_void_p), ("out", C.c_void_p),
                 ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("gidx_base", C.c_uint64),
                 ("x0", C.c_void_p), ("noise", C.c_void_p), ("ynoise", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("sde_kind", C.c_int32), ("sigma_min", C.c_float), ("sigma_max", C.c_float),
+                ("n_corrector", C.c_int32), ("snr", C.c_float)]
 
 
 class DmipForward(C.Structure):

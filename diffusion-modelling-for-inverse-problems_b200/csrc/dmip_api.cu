@@ -40,6 +40,12 @@ static int check_sampler(const DmipSampler* d) {
   DMIP_REQUIRE(d->xdim >= 1 && d->ydim >= 1, "xdim/ydim must be positive");
   DMIP_REQUIRE(d->n_obs >= 0 && d->n_per_obs >= 0, "negative particle count");
   DMIP_REQUIRE(d->num_steps >= 1, "num_steps must be >= 1");
+  DMIP_REQUIRE(d->sde_kind == DMIP_SDE_VP || d->sde_kind == DMIP_SDE_VE, "unknown sde_kind %d", d->sde_kind);
+  DMIP_REQUIRE(d->sde_kind != DMIP_SDE_VE || (d->sigma_min > 0.f && d->sigma_max > d->sigma_min),
+               "VE-SDE needs 0 < sigma_min < sigma_max");
+  DMIP_REQUIRE(d->n_corrector >= 0 && d->n_corrector <= 8, "n_corrector must be in 0..8 (got %d)", d->n_corrector);
+  DMIP_REQUIRE(d->n_corrector == 0 || d->snr > 0.f, "the corrector needs snr > 0");
+  DMIP_REQUIRE(static_cast<long long>(d->num_steps) * (1 + d->n_corrector) < (1LL << 31), "too many sub-steps");
   DMIP_REQUIRE(d->rng_mode == DMIP_RNG_PHILOX || d->rng_mode == DMIP_RNG_INJECTED, "unknown rng_mode %d", d->rng_mode);
   if (d->n_obs > 0 && d->n_per_obs > 0) {
     DMIP_REQUIRE(d->y && d->out, "y / out is NULL");

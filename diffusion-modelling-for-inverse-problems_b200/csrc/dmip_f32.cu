@@ -11,6 +11,7 @@
 // Reference code replaced: models/diffusion.py:27-46,158-180; sdes.py:21-49,77-87; nets.py:17-57,143-157.
 #include "dmip_common.h"
 #include "dmip_rng.cuh"
+#include "dmip_sde.cuh"
 
 namespace dmip {
 
@@ -33,7 +34,9 @@ struct F32Params {
   NetDev net[2];              // DPS: net[0] = prior (MLP2 on [x,t]), net[1] = likelihood (MLP on [x,y,t])
   int xdim, ydim, n_obs, tiles_per_obs, S;
   long long n_per_obs, n_tiles;
-  float T, bmin, bmax, mean, std, delta, sqrt_delta;
+  float T, bmin, bmax, mean, std, delta, sqrt_delta;   // bmin / bmax: beta range (VP) or sigma range (VE)
+  int sde_kind, n_corr;
+  float snr;
   const float* y;
   float* out;
   int rng_mode;
@@ -46,13 +49,6 @@ struct F32Params {
   const float* ft;
   int fx_dim, fcond_dim;
 };
-
-__device__ __forceinline__ float tau_of_step_f(int i, int S, float T) {
-  const float step = 1.0f / static_cast<float>(S);
-  const int steps = S + 1;
-  const float l = (i < steps / 2) ? step * static_cast<float>(i) : 1.0f - step * static_cast<float>(steps - i - 1);
-  return T - l * T;
-}
 
 // Evaluate the net on the 32 rows whose inputs sit in buf0 ([in_dim][kLd]).  Returns the buffer holding the
 // outputs ([out_dim][kLd]).  All 256 threads participate; ends with __syncthreads().
@@ -165,10 +161,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_f32_mlp(const __grid_constant_
     }
     __syncthreads();
 
-    for (int step = 0; step < P.S; ++step) {
-      const float tau = tau_of_step_f(step, P.S, P.T);
-      const float beta = P.bmin + dbeta * tau;
-      const float sb = sqrtf(beta);
+    const SdeSched sch = {P.sde_kind, P.S, P.n_corr, P.T, P.bmin, P.bmax, P.snr, P.delta, P.sqrt_delta};
+    const int n_sub = P.S * (1 + P.n_corr);        // sub-steps: predictor + correctors (dmip_sde.cuh)
+    for (int step = 0; step < n_sub; ++step) {
+      const SdeCoef co = sde_coef<false>(sch, step, P.variant == DMIP_DPS);
+      const float tau = co.tau;
+      const float sb = co.g;                       // g(tau): sqrt(beta) for the VP-SDE
       const float* res = nullptr;
       for (int p = 0; p < P.n_nets; ++p) {
         const NetDev& net = P.net[p];
@@ -185,8 +183,15 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_f32_mlp(const __grid_constant_
               v = P.y[obs * P.ydim + jj];
               if (P.variant == DMIP_CDIFFE) {
                 // y_t = eta * std(tau) + alpha(tau) y   (sdes.py:37-49 <- models/diffusion.py:172)
-                const float alpha = expf(-0.25f * tau * tau * dbeta - 0.5f * tau * P.bmin);
-                const float sd = sqrtf(1.0f - expf(-0.5f * tau * tau * dbeta - tau * P.bmin));
+                float alpha, sd;
+                if (P.sde_kind == kSdeVE) {
+                  float g2u, var;
+                  sde_terms<false>(sch, tau, g2u, alpha, var);
+                  sd = sqrtf(var);
+                } else {
+                  alpha = expf(-0.25f * tau * tau * dbeta - 0.5f * tau * P.bmin);
+                  sd = sqrtf(1.0f - expf(-0.5f * tau * tau * dbeta - tau * P.bmin));
+                }
                 float eta;
                 if (P.rng_mode == DMIP_RNG_PHILOX) {
                   float z[4];
@@ -226,8 +231,14 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_f32_mlp(const __grid_constant_
           const float eps = P.rng_mode == DMIP_RNG_PHILOX
                                 ? z[e]
                                 : P.noise[(static_cast<long long>(step) * n_total + g) * P.xdim + j];
-          const float mu = sb * a + 0.5f * beta * x;
-          P.out[g * P.xdim + j] = x + P.delta * mu + (P.sqrt_delta * sb) * eps;
+          if (!co.corrector) {
+            const float mu = sb * a + co.fx * x;              // g a - f   (sdes.py:77-79; fx = beta / 2 for VP, 0 for VE)
+            P.out[g * P.xdim + j] = x + P.delta * mu + (P.sqrt_delta * sb) * eps;
+          } else {
+            // Langevin corrector: x += e score + sqrt(2 e) z with score = a / g (a already carries g for DPS: sb * sum)
+            const float e = 0.5f * co.ke * co.ke;
+            P.out[g * P.xdim + j] = x + (e / sb) * a + co.ke * eps;
+          }
         }
       }
       __syncthreads();
@@ -353,8 +364,11 @@ int launch_sampler_f32(const DmipSampler* d, cudaStream_t s) {
   P.n_tiles = static_cast<long long>(P.tiles_per_obs) * d->n_obs;
   P.S = d->num_steps;
   P.T = d->T;
-  P.bmin = d->beta_min;
-  P.bmax = d->beta_max;
+  P.sde_kind = d->sde_kind;
+  P.bmin = d->sde_kind == DMIP_SDE_VE ? d->sigma_min : d->beta_min;
+  P.bmax = d->sde_kind == DMIP_SDE_VE ? d->sigma_max : d->beta_max;
+  P.n_corr = d->n_corrector;
+  P.snr = d->snr;
   P.mean = d->mean;
   P.std = d->std;
   const double delta = static_cast<double>(d->T) / d->num_steps;

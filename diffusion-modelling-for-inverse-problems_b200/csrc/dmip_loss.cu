@@ -689,7 +689,7 @@ struct TclPlan {
   bool use;
   TclStreams st;
   long long n_tiles_fwd, n_tiles_bwd;
-  size_t off_stages_fwd, off_stages_bwd, off_in[4][2], off_adj[4][2], off_ct[3], off_abar, bytes;
+  size_t off_stages_fwd, off_stages_bwd, off_in[4][2], off_adj[4][2], off_st[3], off_abar, bytes;
 };
 
 struct LossPlan {
@@ -727,7 +727,7 @@ void plan_tcl(const PassCfg& c, int n_tan, TclPlan* t) {
       t->off_in[l][h] = off;  off += align_1k(l == 0 ? small : big);
       t->off_adj[l][h] = off; off += align_1k(l == 3 ? small : big);
     }
-  for (int l = 0; l < 3; ++l) { t->off_ct[l] = off; off += c.has_T ? align_1k(static_cast<size_t>(B) * 512 * sizeof(float)) : 0; }
+  for (int l = 0; l < 3; ++l) { t->off_st[l] = off; off += align_1k(static_cast<size_t>(B) * t->st.n_adj() * 512 * sizeof(float)); }
   t->off_abar = off; off += align_1k(static_cast<size_t>(B) * t->st.n_adj() * net.out_dim * sizeof(float));
   t->bytes = off;
 }
@@ -861,7 +861,7 @@ int run_pass_tcl(const PassCfg& c, const LossPlan& p, uint8_t* ws, cudaStream_t 
       D.in_img[l][h] = ws + t.off_in[l][h];
       D.adj_img[l][h] = ws + t.off_adj[l][h];
     }
-    if (l < 3) D.ct[l] = reinterpret_cast<float*>(ws + t.off_ct[l]);
+    if (l < 3) D.st[l] = reinterpret_cast<float*>(ws + t.off_st[l]);
   }
   D.in_dim = net.in_dim; D.out_dim = net.out_dim;
   D.k0steps_fwd = (net.in_dim + 15) / 16;

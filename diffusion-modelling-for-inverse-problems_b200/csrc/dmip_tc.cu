@@ -31,6 +31,7 @@
 #include "dmip_common.h"
 #include "dmip_ptx.cuh"
 #include "dmip_rng.cuh"
+#include "dmip_sde.cuh"
 
 namespace dmip {
 
@@ -81,7 +82,9 @@ struct TcParams {
   TcNetDev net[2];
   int xdim, ydim, n_obs, tiles_per_obs, S;
   long long n_per_obs, n_tiles;
-  float T, bmin, bmax, mean, std, delta, sqrt_delta;
+  float T, bmin, bmax, mean, std, delta, sqrt_delta;   // bmin / bmax: beta range (VP) or sigma range (VE)
+  int sde_kind, n_corr;     // dmip_sde.cuh: forward SDE and corrector sub-steps per step
+  float snr;
   const float* y;
   float* out;
   int rng_mode;
@@ -137,14 +140,6 @@ template <int kRegs>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-
-__device__ __forceinline__ float tau_of_step(int i, int S, float T) {
-  // T - linspace(0, 1, S+1)[i] * T in fp32, linspace evaluated symmetrically as torch does (models/diffusion.py:34)
-  const float step = 1.0f / static_cast<float>(S);
-  const int steps = S + 1;
-  const float l = (i < steps / 2) ? step * static_cast<float>(i) : 1.0f - step * static_cast<float>(steps - i - 1);
-  return T - l * T;
-}
 
 __device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -423,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
 
   const int n_pass = keep(P.n_nets);
   const int S = keep(P.S);
-  const int n_steps = keep((P.mode == kModeSampler) ? S : 1);
+  const int n_steps = keep((P.mode == kModeSampler) ? S * (1 + P.n_corr) : 1);   // sub-steps: predictor + correctors
   constexpr int n_ring = kNumPairs;
 
   if (warp >= kNumRowWarps) {
@@ -605,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     uint32_t job = 0;     // global job counter (13 per pass; accumulator buffer = job & 1)
     uint32_t npass = 0;   // running pass counter: layer-0 bias buffer, parity of the once-per-pass barriers
     uint32_t cf0 = 0, cf1 = 0;   // hidden chunks seen in accumulator buffer 0 / 1
-    const float dbeta = P.bmax - P.bmin;
+    const SdeSched sch = {P.sde_kind, S, P.n_corr, P.T, P.bmin, P.bmax, P.snr, P.delta, P.sqrt_delta};
     const TcNetDev& net_last = P.net[n_pass - 1];
     const int dvp = (net_last.dv + 7) & ~7;
     const int split = P.net[0].split;
@@ -638,10 +633,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       // y_t = alpha(tau) y + std(tau) eta   (sdes.py:37-49 via models/diffusion.py:172): quads cgp and cgp + 4
       auto diffuse_y = [&](int stp) {
         if (!cdiffe) return;
-        const float tau = tau_of_step(stp, S, P.T);
-        const float Bt = 0.5f * tau * tau * dbeta + tau * P.bmin;
-        const float alpha = __expf(-0.5f * Bt);
-        const float sd = sqrtf(1.0f - __expf(-Bt));
+        float g2u, alpha, var;
+        sde_terms<true>(sch, sde_substep_tau(sch, stp), g2u, alpha, var);
+        const float sd = sqrtf(var);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int q = cgp + 4 * h;
@@ -700,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           for (int j = 0; j + 1 < net.n_const; ++j) u = fmaf(wr[j], P.y[obs * P.ydim + j], u);
           const float wt = wr[net.n_const - 1];
           if (p == 0) { myU[0] = u; myWt[0] = wt; } else if (dps) { myU[1] = u; myWt[1] = wt; }
-          if (p == 0) sB0[et] = fmaf(tau_of_step(0, S, P.T), wt, u);   // the previous tile's last pass has drained it
+          if (p == 0) sB0[et] = fmaf(sde_substep_tau(sch, 0), wt, u);   // the previous tile's last pass has drained it
         }
 #pragma unroll
         for (int i = 0; i < kOwn; ++i) {
@@ -747,9 +741,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
       tl_mark(tl, 0x500u);
 
       for (int step = 0; step < n_steps; ++step) {
-        const float tau = tau_of_step(step, S, P.T);
-        const float beta = P.bmin + dbeta * tau;
-        const float sb = sqrtf(beta);
+        const SdeCoef co = sde_coef<true>(sch, step, dps);   // x <- x (1 + kx) + ke eps + ca net   at time co.tau
+        const float tau = co.tau;
         const bool last_step = (step == n_steps - 1);
         float stash[dps ? 8 : 1];   // DPS: prior-net output of this step
 #pragma unroll
@@ -817,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                     if (i == (l - 1) * 2 + (c >> 1) && i < n_own) {
                       const int pc = piece_lo + i;
                       // the output layer's bias joins here too (x += ca * b3), off the step boundary's critical path
-                      const float ca = P.delta * (dps ? beta : sb);
+                      const float ca = co.ca;
                       const float* b3s = sB3 + (dps ? 8 : pc * 8);   // DPS: one piece, the likelihood net's bias
                       const float4 q0 = *reinterpret_cast<const float4*>(b3s);
                       const float4 q1 = *reinterpret_cast<const float4*>(b3s + 4);
@@ -829,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                       float za[4], zb[4];
 #pragma unroll
                       for (int e = 0; e < 4; ++e) { za[e] = zdraw[e]; zb[e] = zdraw4[e]; }
-                      const float kx = P.delta * 0.5f * beta, ke = P.sqrt_delta * sb;
+                      const float kx = co.kx, ke = co.ke;
 #pragma unroll
                       for (int e = 0; e < 8; ++e) {
                         const int j = pc * 8 + e;
@@ -855,7 +848,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             // layer 2 is done, so every row warp has left this pass's layer-0 epilogue: the single bias buffer may take
             // the next pass's effective layer-0 bias  b0 + W0[:,y]·y + tau'·W0[:,t]
             const bool wrap = (p + 1 == n_pass);
-            const float tau_n = wrap ? tau_of_step(step + 1, S, P.T) : tau;
+            const float tau_n = wrap ? sde_substep_tau(sch, step + 1) : tau;
             const float u = (wrap || !dps) ? myU[0] : myU[1];
             const float wt = (wrap || !dps) ? myWt[0] : myWt[1];
             sB0[et] = fmaf(tau_n, wt, u);
@@ -903,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             // DPS: a = sqrt(beta) (prior + lik) (nets.py:155-157)  =>  mu = beta (prior + lik) + beta x / 2.
             // The bias b3 is already in x (pre-update).  No masks: padded columns meet zero weights and zero noise and
             // stay zero; rows past the end of the tile integrate a harmless deterministic path and are never written.
-            const float ca = P.delta * (dps ? beta : sb);
+            const float ca = co.ca;
             uint32_t v[kOwn][8];
 #pragma unroll
             for (int i = 0; i < kOwn; ++i)
@@ -1095,8 +1088,11 @@ int launch_sampler_tc(const DmipSampler* d, cudaStream_t s) {
   P.n_tiles = static_cast<long long>(P.tiles_per_obs) * d->n_obs;
   P.S = d->num_steps;
   P.T = d->T;
-  P.bmin = d->beta_min;
-  P.bmax = d->beta_max;
+  P.sde_kind = d->sde_kind;
+  P.bmin = d->sde_kind == DMIP_SDE_VE ? d->sigma_min : d->beta_min;
+  P.bmax = d->sde_kind == DMIP_SDE_VE ? d->sigma_max : d->beta_max;
+  P.n_corr = d->n_corrector;
+  P.snr = d->snr;
   P.mean = d->mean;
   P.std = d->std;
   const double delta = static_cast<double>(d->T) / d->num_steps;  // models/diffusion.py:31

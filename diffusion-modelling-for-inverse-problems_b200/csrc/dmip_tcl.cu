@@ -382,12 +382,11 @@ __device__ __forceinline__ void fwd_build_input(const TclDev& P, long long tile,
 
 // One (layer, chunk, window) item of the forward epilogue: thread = feature n of the layer's output.
 template <class C, bool kFirst>
-__device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr, int n, long long smp0, bool tile_ok, int w,
-                                         uint8_t* smem) {
+__device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr, int n, float bias, long long smp0,
+                                         bool tile_ok, int w, uint8_t* smem) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tc_wait_ld();
-  const float bias = __ldg(P.b[g] + n);
   const uint32_t nterm = (static_cast<uint32_t>(n) >> 6) * 8192u + (static_cast<uint32_t>(n) & 7u) * 2u;
   const uint32_t nchunk = (static_cast<uint32_t>(n) & 63u) >> 3;
 #pragma unroll
@@ -396,9 +395,10 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
     float h, p1, p2;
     act_jet<kFirst>(__uint_as_float(v[base]) + bias, h, p1, p2);
     v[base] = __float_as_uint(h);
-    float hI = 0.f, hdT = 0.f, cT = 0.f;
+    float hI = 0.f, q1 = 0.f, hdT = 0.f, cT = 0.f;
     if (C::kI) {
-      hI = act_val<kFirst>(__uint_as_float(v[base + C::sI]) + bias);
+      float q2;
+      act_jet<kFirst>(__uint_as_float(v[base + C::sI]) + bias, hI, q1, q2);
       v[base + C::sI] = __float_as_uint(hI);
     }
     if (C::kT) {
@@ -423,10 +423,14 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
 #pragma unroll
       for (int k = 0; k < C::kNT; ++k) v[base + C::sS + k] = __float_as_uint(p1 * zs[k]);
     }
-    // stashes for the backward pass: inputs of layer g+1 for the adjoint streams (bf16 hi/lo, backward geometry) and
-    // the T -> P coupling phi''(z) zd (fp32)
+    // stashes for the backward pass: inputs of layer g+1 for the adjoint streams (bf16 hi/lo images in the backward
+    // geometry: weight-gradient operands) and the derivative state the backward epilogue needs (fp32, coalesced)
     const long long smp = smp0 + j;
     if (tile_ok && smp < P.B) {
+      float* sst = P.st[g] + (smp * C::NADJ) * 512 + n;
+      sst[0] = p1;
+      if (C::kI) sst[512] = q1;
+      if (C::kT) sst[(1 + C::kI) * 512] = cT;
       long long blk;
       uint32_t rb;
       bwd_row<C>(smp, 0, blk, rb);
@@ -452,7 +456,6 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
         split1(hdT, hi, lo);
         *reinterpret_cast<unsigned short*>(ihi + o) = hi;
         *reinterpret_cast<unsigned short*>(ilo + o) = lo;
-        P.ct[g][smp * 512 + n] = cT;
       }
     }
   }
@@ -614,6 +617,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
     float* b3sum = red + 4;
     float* outs = reinterpret_cast<float*>(smem + kOffHhi);
     uint32_t par0 = 0, par1 = 0;                        // phases of acc_full[0], acc_full[1]
+    float bias[3][2];                                   // this thread's two features per hidden layer (an L2 round trip
+#pragma unroll                                          // per item otherwise, on the path the next layer's MMAs wait for)
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) bias[g][ci] = __ldg(P.b[g] + (c_first + 2 * ci) * 128 + q * 32 + lane);
     {
       const bool ok = tile_first + static_cast<int>(crank) < n_tiles;
       fwd_build_input<C>(P, tile_first + static_cast<int>(crank), ok, smem + kOffIn, t);
@@ -636,8 +644,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
           const int c = c_first + 2 * ci;
           const int n = c * 128 + q * 32 + lane;
           const uint32_t taddr = lane_taddr + static_cast<uint32_t>((g & 1) * 256 + c * kNR + w * kWin);
-          if (g == 0) fwd_item<C, true>(P, g, taddr, n, smp0, tile_ok, w, smem);
-          else fwd_item<C, false>(P, g, taddr, n, smp0, tile_ok, w, smem);
+          // register select (the loops stay rolled: six copies of the item body would not fit the instruction cache)
+          const float bs = g == 0 ? (ci ? bias[0][1] : bias[0][0]) : g == 1 ? (ci ? bias[1][1] : bias[1][0]) : (ci ? bias[2][1] : bias[2][0]);
+          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, tile_ok, w, smem);
+          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, tile_ok, w, smem);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
@@ -723,73 +733,65 @@ __device__ __forceinline__ void bwd_build_input(const TclDev& P, long long tile,
   }
 }
 
-__device__ __forceinline__ float ld_img(const uint8_t* hi, const uint8_t* lo, size_t o) {
-  return join1(*reinterpret_cast<const unsigned short*>(hi + o), *reinterpret_cast<const unsigned short*>(lo + o));
-}
-
 // One (layer, chunk, window) item of the backward epilogue: thread = feature k of hidden layer L; the accumulator holds
 // hbar (adjoint of the layer's OUTPUT) for the window's adjoint rows.  With phi', phi'' at the stored forward state:
 //     zbar_P = phi' hbar_P + phi'' zd_T hbar_T,   zbar_T = phi' hbar_T,   zbar_I = phi'_I hbar_I.
+// The derivative state (dmip_tcl.h: st) is fetched with ONE batch of independent loads before the accumulator is
+// touched — per-sample dependent loads cost an HBM round trip each (measured: 171 K instead of 60 K cycles per tile).
 // Returns this thread's contribution to d loss / d b_L[k] (primal rows only).
-template <class C, bool kFirst>
-__device__ __forceinline__ float bwd_item(const TclDev& P, int L, bool to_smem, uint32_t taddr, int k, long long tile,
-                                          bool tile_ok, int w, uint8_t* smem) {
-  uint32_t v[32];
+template <class C>
+__device__ __forceinline__ void bwd_prefetch(const TclDev& P, int L, int k, long long tile, int w, float (&pre)[C::SPWB * C::NADJ]) {
+  const float* sst = P.st[L] + k;
+  const long long last = P.B - 1;
+#pragma unroll
+  for (int j = 0; j < C::SPWB; ++j) {
+    long long smp = tile * (2 * C::SPWB) + w * C::SPWB + j;
+    smp = smp < last ? smp : last;                   // rows past the batch read a valid sample and are masked later
+#pragma unroll
+    for (int a = 0; a < C::NADJ; ++a) pre[j * C::NADJ + a] = __ldg(sst + (smp * C::NADJ + a) * 512);
+  }
+}
+
+// accumulator (hbar) -> zbar rows in v[]; returns the bias-gradient contribution
+template <class C>
+__device__ __forceinline__ float bwd_math(const TclDev& P, uint32_t taddr, long long tile, bool tile_ok, int w,
+                                          const float (&pre)[C::SPWB * C::NADJ], uint32_t (&v)[32]) {
   tmem_ld32(taddr, v);
   tc_wait_ld();
-  const uint32_t kterm = (static_cast<uint32_t>(k) >> 6) * 8192u + (static_cast<uint32_t>(k) & 7u) * 2u;
-  const uint32_t kchunk = (static_cast<uint32_t>(k) & 63u) >> 3;
-  const size_t blk = static_cast<size_t>(tile) * (512 * 128) + kterm;
-  const uint8_t* ihi = P.in_img[L + 1][0] + blk;
-  const uint8_t* ilo = P.in_img[L + 1][1] + blk;
   float bs = 0.f;
-  auto row_off = [&](uint32_t r) { return (r >> 3) * 1024u + (r & 7u) * 128u + ((kchunk ^ (r & 7u)) << 4); };
 #pragma unroll
   for (int j = 0; j < C::SPWB; ++j) {
     const int base = j * C::NADJ;
     const long long smp = tile * (2 * C::SPWB) + w * C::SPWB + j;
-    const uint32_t rb = static_cast<uint32_t>(w * kWin + base);
-    float zP = 0.f, zI = 0.f, zT = 0.f;
-    if (tile_ok && smp < P.B) {
-      const float hP = ld_img(ihi, ilo, row_off(rb));
-      const float p1 = dphi_from_h<kFirst>(hP);
-      zP = p1 * __uint_as_float(v[base]);
-      if (C::kT) {
-        const float hbT = __uint_as_float(v[base + 1 + C::kI]);
-        zP = fmaf(P.ct[L][smp * 512 + k], hbT, zP);
-        zT = p1 * hbT;
-      }
-      if (C::kI) {
-        const float hI = ld_img(ihi, ilo, row_off(rb + 1));
-        zI = dphi_from_h<kFirst>(hI) * __uint_as_float(v[base + 1]);
-      }
-      bs += zP + zI;
+    const bool live = tile_ok && smp < P.B;
+    const float p1 = pre[base];
+    float zP = p1 * __uint_as_float(v[base]), zI = 0.f, zT = 0.f;
+    if (C::kT) {
+      const float hbT = __uint_as_float(v[base + 1 + C::kI]);
+      zP = fmaf(pre[base + 1 + C::kI], hbT, zP);
+      zT = p1 * hbT;
     }
+    if (C::kI) zI = pre[base + 1] * __uint_as_float(v[base + 1]);
+    if (!live) zP = zI = zT = 0.f;
+    bs += zP + zI;
     v[base] = __float_as_uint(zP);
     if (C::kI) v[base + 1] = __float_as_uint(zI);
     if (C::kT) v[base + 1 + C::kI] = __float_as_uint(zT);
   }
 #pragma unroll
   for (int r = C::SPWB * C::NADJ; r < kWin; ++r) v[r] = 0u;
-  if (tile_ok) {
-    // ADJ_L stash block: all 32 rows of the window (zeros included); the padding rows of IN_{L+1} are zeroed as well
-    uint8_t* ahi = P.adj_img[L][0] + blk;
-    uint8_t* alo = P.adj_img[L][1] + blk;
-#pragma unroll
-    for (int r = 0; r < kWin; ++r) {
-      unsigned short hi, lo;
-      split1(__uint_as_float(v[r]), hi, lo);
-      const uint32_t o = row_off(static_cast<uint32_t>(w * kWin + r));
-      *reinterpret_cast<unsigned short*>(ahi + o) = hi;
-      *reinterpret_cast<unsigned short*>(alo + o) = lo;
-      const int j = r / C::NADJ;
-      const bool dead = j >= C::SPWB || tile * (2 * C::SPWB) + w * C::SPWB + j >= P.B;
-      if (dead) {
-        *reinterpret_cast<unsigned short*>(const_cast<uint8_t*>(ihi) + o) = 0;
-        *reinterpret_cast<unsigned short*>(const_cast<uint8_t*>(ilo) + o) = 0;
-      }
-    }
-  }
+  return bs;
+}
+
+// zbar rows -> ADJ_L stash block (all 32 rows of the window, zeros included; the padding rows of IN_{L+1} are zeroed as
+// well) and, for L > 0, the B operand of the next GEMM
+template <class C>
+__device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, int k, long long tile, bool tile_ok, int w,
+                                          const uint32_t (&v)[32], uint8_t* smem) {
+  const uint32_t kterm = (static_cast<uint32_t>(k) >> 6) * 8192u + (static_cast<uint32_t>(k) & 7u) * 2u;
+  const uint32_t kchunk = (static_cast<uint32_t>(k) & 63u) >> 3;
+  const size_t blk = static_cast<size_t>(tile) * (512 * 128) + kterm;
+  auto row_off = [&](uint32_t r) { return (r >> 3) * 1024u + (r & 7u) * 128u + ((kchunk ^ (r & 7u)) << 4); };
   if (to_smem) {
     uint8_t* hrow = smem + kOffHhi + (static_cast<uint32_t>(k) >> 3) * 1024u + (static_cast<uint32_t>(k) & 7u) * 128u;
     const uint32_t line = static_cast<uint32_t>(k) & 7u;
@@ -804,7 +806,26 @@ __device__ __forceinline__ float bwd_item(const TclDev& P, int L, bool to_smem, 
       st_shared_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
     }
   }
-  return bs;
+  if (tile_ok) {
+    uint8_t* ahi = P.adj_img[L][0] + blk;
+    uint8_t* alo = P.adj_img[L][1] + blk;
+    uint8_t* ihi = P.in_img[L + 1][0] + blk;
+    uint8_t* ilo = P.in_img[L + 1][1] + blk;
+#pragma unroll
+    for (int r = 0; r < kWin; ++r) {
+      unsigned short hi, lo;
+      split1(__uint_as_float(v[r]), hi, lo);
+      const uint32_t o = row_off(static_cast<uint32_t>(w * kWin + r));
+      *reinterpret_cast<unsigned short*>(ahi + o) = hi;
+      *reinterpret_cast<unsigned short*>(alo + o) = lo;
+      const int j = r / C::NADJ;
+      const bool dead = j >= C::SPWB || tile * (2 * C::SPWB) + w * C::SPWB + j >= P.B;
+      if (dead) {
+        *reinterpret_cast<unsigned short*>(ihi + o) = 0;
+        *reinterpret_cast<unsigned short*>(ilo + o) = 0;
+      }
+    }
+  }
 }
 
 template <class C>
@@ -851,22 +872,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
         const int L = 2 - g;
         const uint32_t set = gc & 1u;
         ++gc;
+        const int k0 = c_first * 128 + q * 32 + lane, k1 = k0 + 256;     // this thread's two features (chunks c_first, c_first + 2)
+        // software pipeline: the derivative state of an item is in flight while the GEMM finishes / while the previous
+        // item's results are stored
+        float pre[C::SPWB * C::NADJ];
+        uint32_t v[32];
+        bwd_prefetch<C>(P, L, k0, tile, w, pre);
         mbar_wait(&B.acc_full[set], (par >> set) & 1u, 0xD00 + set);
         par ^= 1u << set;
         tc_fence_after();
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const int c = c_first + 2 * ci;
-          const int k = c * 128 + q * 32 + lane;
-          const uint32_t taddr = lane_taddr + set * 256u + static_cast<uint32_t>(c * kNR + w * kWin);
-          if (L == 0) bsum[g][ci] += bwd_item<C, true>(P, L, false, taddr, k, tile, tile_ok, w, smem);
-          else bsum[g][ci] += bwd_item<C, false>(P, L, true, taddr, k, tile, tile_ok, w, smem);
-          if (g < 2) {
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&B.hready[c]);
-          }
+        const uint32_t t0 = lane_taddr + set * 256u + static_cast<uint32_t>(c_first * kNR + w * kWin);
+        bsum[g][0] += bwd_math<C>(P, t0, tile, tile_ok, w, pre, v);
+        bwd_prefetch<C>(P, L, k1, tile, w, pre);
+        bwd_store<C>(P, L, L != 0, k0, tile, tile_ok, w, v, smem);
+        if (g < 2) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&B.hready[c_first]);
+        }
+        bsum[g][1] += bwd_math<C>(P, t0 + 2 * kNR, tile, tile_ok, w, pre, v);
+        bwd_store<C>(P, L, L != 0, k1, tile, tile_ok, w, v, smem);
+        if (g < 2) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&B.hready[c_first + 2]);
         }
         if (g == 1 && tb + tile_stride < n_tiles) {
           const int nt = tb + tile_stride + static_cast<int>(crank);

@@ -49,7 +49,8 @@ struct TclDev {
   //                         + (((f % 64) / 8) ^ (row % 8)) * 16 + (f % 8) * 2
   uint8_t* in_img[4][2];       // IN_l  hi/lo: inputs of layer l for the adjoint streams (l = 0: F = 64, else F = 512)
   uint8_t* adj_img[4][2];      // ADJ_l hi/lo: adjoints of layer l pre-activations (l = 3: F = 64, else F = 512)
-  float* ct[3];                // [B][512]: phi''(z) * (time tangent of z) of hidden layer l — the T -> P coupling
+  float* st[3];                // [B][n_adj][512] fp32 state of hidden layer l the backward epilogue needs, one slot per
+                               // adjoint stream: P: phi'(z_P) | I: phi'(z_I) | T: phi''(z_P) * zd_T (the T -> P coupling)
   float* grad;                 // flat gradient [W_0, b_0, W_1, b_1, ...] (bias sums are added here by the kernels)
   long long off_b[4];          // float offset of b_l inside grad
   long long n_tiles_fwd, n_tiles_bwd;

@@ -11,7 +11,9 @@ the persistent fused Euler–Maruyama kernel (`dmip_sampler_em_vp`, include/dmip
 signature are keyword-only: `precision` ('bf16' tcgen05 path | 'fp32' FFMA path), `seed` (Philox key; the
 reference uses torch's global RNG, which a fused kernel cannot consume — statistics are preserved, streams differ),
 `injected` (dict with 'x0', 'noise'[, 'ynoise'] standard-normal tensors: bit-for-bit the reference's draws, for
-parity tests), `gidx_base` (global particle offset for multi-GPU sharding), `return_tensor`.  `y` may also be a
+parity tests), `gidx_base` (global particle offset for multi-GPU sharding), `return_tensor`, `n_corrector` / `snr`
+(Langevin corrector sub-steps after every predictor step: the predictor–corrector sampler of Song et al. 2021; 0 = the
+reference's Euler–Maruyama predictor).  A model built with `base_sde=sdes.VarianceExplodingSDE(...)` samples the VE-SDE.  `y` may also be a
 batch (n_obs, ydim): all observations are integrated in the same launch and (n_obs, num_samples, xdim) is returned.
 
 CDiffE.forward upstream raises TypeError (it omits `cond` when calling `sde.mu`); the intended call
@@ -56,7 +58,7 @@ class BaseClassDiffusionModel():
         return self.sde.a, None
 
     def forward(self, y, num_samples=2000, num_steps=200, mean=0, std=1, *, precision=None, seed=None,
-                injected=None, gidx_base=0, return_tensor=False):
+                injected=None, gidx_base=0, return_tensor=False, n_corrector=0, snr=0.16):
         L = _lib.require_gpu()
         net, net2 = self._nets()
         dev = next(net.parameters()).device
@@ -84,6 +86,11 @@ class BaseClassDiffusionModel():
         d.n_obs, d.n_per_obs, d.num_steps = n_obs, num_samples, num_steps
         d.T = float(self.sde.T)
         d.beta_min, d.beta_max = float(self.sde.base_sde.beta_min), float(self.sde.base_sde.beta_max)
+        if isinstance(self.sde.base_sde, sdes.VarianceExplodingSDE):       # beyond the reference (include/dmip.h)
+            d.sde_kind = _lib.SDE_VE
+            d.sigma_min, d.sigma_max = float(self.sde.base_sde.sigma_min), float(self.sde.base_sde.sigma_max)
+        d.n_corrector, d.snr = int(n_corrector), float(snr)
+        n_sub = num_steps * (1 + int(n_corrector))                         # sub-steps: predictor + Langevin correctors
         d.mean, d.std = float(mean), float(std)
         d.net = _lib.mlp_desc(net, keep)
         if net2 is not None:
@@ -99,7 +106,7 @@ class BaseClassDiffusionModel():
                 keep.append(tns)
                 setattr(d, name, tns.data_ptr())
             assert injected['x0'].numel() == n_total * self.xdim, 'x0 must have shape (n_obs*num_samples, xdim)'
-            assert injected['noise'].numel() == num_steps * n_total * self.xdim, 'noise must be (S, N, xdim)'
+            assert injected['noise'].numel() == n_sub * n_total * self.xdim, 'noise must be (S * (1 + n_corrector), N, xdim)'
         else:
             d.rng_mode = _lib.RNG_PHILOX
             if seed is None:                 # fresh stream per call, like successive draws from a global RNG
@@ -203,11 +210,11 @@ class CDE(BaseClassDiffusionModel):
 
     variant = 'CDE'
 
-    def __init__(self, xdim, ydim, hidden_layers):
+    def __init__(self, xdim, ydim, hidden_layers, *, base_sde=None):
         super().__init__(xdim, ydim)
         score_net = MLP(input_dim=xdim + ydim + 1, output_dim=xdim, hidden_layers=hidden_layers,
                         activation=nn.Tanh()).to(device)
-        self.sde = sdes.PluginReverseSDE(sdes.VariancePreservingSDE(), score_net, T=1, debias=True)
+        self.sde = sdes.PluginReverseSDE(base_sde or sdes.VariancePreservingSDE(), score_net, T=1, debias=True)
 
 
 class CDiffE(BaseClassDiffusionModel):
@@ -215,11 +222,11 @@ class CDiffE(BaseClassDiffusionModel):
 
     variant = 'CDiffE'
 
-    def __init__(self, xdim, ydim, hidden_layers):
+    def __init__(self, xdim, ydim, hidden_layers, *, base_sde=None):
         super().__init__(xdim, ydim)
         score_net = MLP(input_dim=xdim + ydim + 1, output_dim=xdim + ydim, hidden_layers=hidden_layers,
                         activation=nn.Tanh()).to(device)
-        self.sde = sdes.PluginReverseSDE(sdes.VariancePreservingSDE(), score_net, T=1, debias=True)
+        self.sde = sdes.PluginReverseSDE(base_sde or sdes.VariancePreservingSDE(), score_net, T=1, debias=True)
 
 
 class PosteriorDiffusionEstimator(BaseClassDiffusionModel):
@@ -227,9 +234,9 @@ class PosteriorDiffusionEstimator(BaseClassDiffusionModel):
 
     variant = 'Posterior'
 
-    def __init__(self, xdim, ydim, hidden_layers):
+    def __init__(self, xdim, ydim, hidden_layers, *, base_sde=None):
         super().__init__(xdim, ydim)
-        forward_process = sdes.VariancePreservingSDE()
+        forward_process = base_sde or sdes.VariancePreservingSDE()
         prior_net = MLP2(input_dim=xdim + 1, output_dim=xdim, hidden_layers=hidden_layers,
                          activation=nn.Tanh()).to(device)
         likelihood_net = MLP(input_dim=xdim + ydim + 1, output_dim=xdim, hidden_layers=hidden_layers,

@@ -74,6 +74,52 @@ class VariancePreservingSDE(torch.nn.Module):
         return vp_truncated_inverse_cdf(u.view(-1), self.beta_min, self.beta_max, self.t_epsilon, self.T).view(*shape)
 
 
+class VarianceExplodingSDE(torch.nn.Module):
+    """VE-SDE of Song et al. 2021 (eq. 30-31): dy = sqrt(d[sigma^2(t)]/dt) dW, sigma(t) = sigma_min (sigma_max/sigma_min)^t.
+
+    NOT part of the reference (upstream ships only the VP-SDE, sdes.py:9-57); BASELINE.json names "VP/VE SDE", so this
+    class carries the interface of `VariancePreservingSDE` (f, g, mean_weight, var, sample, sample_debiasing_t) and the
+    samplers accept it as `base_sde` (parity unpinned; oracle restatement: oracle/ve.py).  The fused
+    training losses are VP-only, like upstream; sampling, incl. the Langevin corrector, runs in the same kernels."""
+
+    def __init__(self, sigma_min=0.01, sigma_max=50.0, T=1.0, t_epsilon=1e-5):
+        super().__init__()
+        self.sigma_min = sigma_min
+        self.sigma_max = sigma_max
+        self.T = T
+        self.t_epsilon = t_epsilon
+        # attribute names the samplers read from any base SDE
+        self.beta_min = 0.0
+        self.beta_max = 0.0
+
+    def sigma(self, t):
+        return self.sigma_min * (self.sigma_max / self.sigma_min) ** t
+
+    def mean_weight(self, t):
+        return torch.ones_like(t) if torch.is_tensor(t) else 1.0
+
+    def var(self, t):
+        return self.sigma(t) ** 2
+
+    def f(self, t, y):
+        return torch.zeros_like(y)
+
+    def g(self, t, y):
+        return torch.ones_like(y) * self.sigma(t) * math.sqrt(2.0 * math.log(self.sigma_max / self.sigma_min))
+
+    def sample(self, t, y0, return_noise=False):
+        std = self.var(t) ** 0.5
+        epsilon = torch.randn_like(y0)
+        yt = epsilon * std + y0
+        if not return_noise:
+            return yt
+        return yt, epsilon, std, self.g(t, yt)
+
+    def sample_debiasing_t(self, shape):
+        """uniform t (the likelihood weighting g^2 / std^2 of the VE-SDE is constant in t)"""
+        return self.t_epsilon + torch.rand(*shape) * (self.T - self.t_epsilon)
+
+
 class PluginReverseSDE(torch.nn.Module):
     """Reverse-time SDE with plug-in drift a = g * score:  mu = g a - f,  sigma = g  (time runs T - t)."""
 

@@ -48,6 +48,9 @@ extern "C" {
 #define DMIP_CDIFFE 1 /* CDiffE.forward, models/diffusion.py:158-180 (with the `cond` fix)    */
 #define DMIP_DPS 2    /* PosteriorDiffusionEstimator: base forward with nets.py:155-157 PosteriorScore as a */
 
+#define DMIP_SDE_VP 0 /* VariancePreservingSDE, sdes.py:9-57                                                       */
+#define DMIP_SDE_VE 1 /* variance-exploding SDE (no upstream counterpart)                                         */
+
 #define DMIP_RNG_PHILOX 0   /* counter-based Philox4x32-10 keyed by global particle index                  */
 #define DMIP_RNG_INJECTED 1 /* caller supplies x0 / per-step noise (parity tests)            */
 
@@ -107,6 +110,18 @@ typedef struct DmipSampler {
   const float* ynoise;             /* injected, CDiffE: (S, n_obs*n_per_obs, ydim)                   */
   void* workspace;                 /* device scratch, dmip_sampler_workspace_bytes(), 16-byte aligned */
   size_t workspace_bytes;
+  /* ---- beyond the reference (all zero = the reference's sampler: VP-SDE, Euler–Maruyama predictor only).
+   * BASELINE.json names "VP/VE SDE" and a "predictor sampler"; upstream has only VP (sdes.py:9-57) and no corrector, so
+   * these have no reference counterpart (parity unpinned; oracle restatement: oracle/sampler.py pc_sampler).
+   * VE: sigma(t) = sigma_min (sigma_max / sigma_min)^t, f = 0, g = sigma sqrt(2 ln(sigma_max / sigma_min)) (Song et al.
+   * 2021); CDiffE re-diffuses y with x_t | x_0 ~ N(x_0, sigma(t)^2).  n_corrector Langevin sub-steps follow every
+   * predictor step at its new time level: x += e s + sqrt(2 e) z, e = 2 snr^2 std(t)^2 (closed form of Song's norm rule).
+   * With correctors the sub-step index u = step * (1 + n_corrector) + c is the Philox step key and the first index of
+   * the injected noise / ynoise tensors, which then hold num_steps * (1 + n_corrector) slices. */
+  int32_t sde_kind;                /* DMIP_SDE_VP (0) / DMIP_SDE_VE (1)                               */
+  float sigma_min, sigma_max;      /* VE only                                                         */
+  int32_t n_corrector;             /* Langevin corrector sub-steps per step, 0..8                     */
+  float snr;                       /* corrector signal-to-noise ratio (Song et al.: 0.16)             */
 } DmipSampler;
 
 size_t dmip_sampler_workspace_bytes(const DmipSampler* d);

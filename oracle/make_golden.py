@@ -413,6 +413,110 @@ if want("linear_log_posterior"):
          post_cov=post.covariance_matrix, score=lin.score_posterior(x, y), fwd=lin(x))
 
 # ---------------------------------------------------------------------------
+# 5c. The reference's OWN `evaluate` loops (main_diffusion_linear.py:53-137, main_diffusion_scatterometry.py:40-124) on
+#     stored sample sets: `model(y, num_samples)` and `posterior.sample` / the ground-truth files are replaced by
+#     recorders / players of fixed arrays, everything else — score MSE, histogramdd, NLL, KL2, KL_reverse — is the
+#     reference's code, and its results.csv is the golden table.  (`utils` is stubbed: matplotlib / seaborn are absent,
+#     only utils.plot_density is referenced and plot_ys is empty.  evaluate() crashes on its last line — `.mean()` of a
+#     Python list, SURVEY.md App. C — after the table has been written.)
+# ---------------------------------------------------------------------------
+def _import_reference_main(name):
+    import importlib
+    import types
+    stub = types.ModuleType("utils")
+    stub.plot_density = lambda *a, **k: None
+    sys.modules["utils"] = stub
+    return importlib.import_module(name)
+
+
+class _Player:
+    """stands in for the model in `evaluate`: __call__ plays back stored sample sets, .sde is the real reference sde"""
+
+    def __init__(self, sde, sets):
+        self.sde = sde
+        self.sets = list(sets)
+
+    def __call__(self, y, num_samples=None, **kw):
+        return self.sets.pop(0)
+
+
+if want("eval_linear"):
+    import tempfile
+    import pandas as pd
+    main_lin = _import_reference_main("main_diffusion_linear")
+    fxw = dict(np.load(os.path.join(OUT, "trained_cde_linear.npz")))
+    mref = CDE(2, 2, [512, 512, 512])
+    mref.sde.a.load_state_dict({f"{k}.{n}": torch.from_numpy(fxw[f"{k}_{n}"]) for k in (0, 3, 5, 7) for n in ("weight", "bias")})
+    mref.sde.eval()
+    n_obs, n_rep, n = 3, 2, 2000
+    g = gen(91)
+    xs = torch.randn(n_obs, 2, generator=g)
+    ys = lin(xs) + lin.scale ** 0.5 * torch.randn(n_obs, 2, generator=g)
+    torch.manual_seed(92)
+    with torch.no_grad():
+        pred = [[mref(ys[i], num_samples=n, num_steps=50) for _ in range(n_rep)] for i in range(n_obs)]   # reference sampler
+    true_rec = []
+
+    class _Lin(LinearForwardProblem):
+        def get_posterior(self, y, device="cpu"):
+            post = super().get_posterior(y, device="cpu")
+            orig = post.sample
+
+            def sample(shape):
+                x = orig(shape)
+                true_rec.append(x.clone())
+                return x
+            post.sample = sample
+            return post
+
+    player = _Player(mref.sde, [p_ for row in pred for p_ in row])
+    torch.manual_seed(93)
+    with tempfile.TemporaryDirectory() as td:
+        try:
+            main_lin.evaluate(player, ys, _Lin(), td, plot_ys=[], n_samples_x=n, n_repeats=n_rep)
+        except AttributeError:
+            pass                                                    # the list.mean() defect on the function's last line
+        df = pd.read_csv(os.path.join(td, "results.csv"))
+    save("eval_linear", ys=ys, x_pred=np.stack([np.stack(r) for r in pred]),                       # (n_obs, n_rep, n, 2)
+         x_true=torch.stack(true_rec).view(n_obs, n_rep, n, 2),
+         KL2=df["KL2"].values, NLL_true=df["NLL_true"].values, NLL_diffusion=df["NLL_diffusion"].values, MSE=df["MSE"].values)
+
+if want("eval_scat"):
+    import tempfile
+    import pandas as pd
+    main_scat = _import_reference_main("main_diffusion_scatterometry")
+    n_obs, n_rep, n = 3, 2, 2000
+    mref = CDE(3, 23, [512, 512, 512])
+    load(mref.sde.a, make_params(95, 27, 3, H))
+    mref.sde.eval()
+    xs, ys = scat_data(n_obs, 96)
+    g = gen(97)
+    centre = xs[:, None, None, :]
+    x_true = (centre + 0.15 * torch.randn(n_obs, n_rep, n, 3, generator=g)).clamp(-1.15, 1.15)
+    x_pred = (centre + 0.03 + 0.18 * torch.randn(n_obs, n_rep, n, 3, generator=g)).clamp(-1.3, 1.3)   # some leave the range
+    params = dict(a=0.2, b=0.01, lambd_bd=1000)
+
+    def score_posterior(xx, yy):
+        e = lambda z: ref_scat.get_log_posterior(z, surr_model, 0.2, 0.01, yy, 1000)
+        return -energy_grad(xx.clone(), e)[0].detach()
+
+    with tempfile.TemporaryDirectory() as td:
+        gt_dir = os.path.join(td, "gt")
+        for i in range(n_obs):
+            os.makedirs(os.path.join(gt_dir, str(i)))
+            for j in range(n_rep):
+                np.save(os.path.join(gt_dir, str(i), f"{j}.npy"), x_true[i, j].numpy())
+        # the reference reads <gt_dir>/<i>/<j>.npy (datasets.py get_gt_samples_scatterometry)
+        player = _Player(mref.sde, [x_pred[i, j].numpy() for i in range(n_obs) for j in range(n_rep)])
+        try:
+            main_scat.evaluate(player, ys, surr_model, td, [], n, score_posterior, 0.2, 0.01, 1000, gt_dir, n_repeats=n_rep)
+        except AttributeError:
+            pass
+        df = pd.read_csv(os.path.join(td, "results.csv"))
+    save("eval_scat", ys=ys, x_pred=x_pred, x_true=x_true, meta=np.array([95]),
+         **{c: df[c].values for c in ("KL2", "KL_reverse", "NLL_mcmc", "NLL_diffusion", "MSE")})
+
+# ---------------------------------------------------------------------------
 # 6. A *trained* linear CDE (contractive reverse dynamics, O(1) samples): the
 #    fixture for bf16-path sample parity and for posterior statistics.
 #    Trained with the reference's own CDE.train_epoch + DSMLoss + data loader

@@ -813,3 +813,268 @@ def case_data_parallel_nccl(kind="DSM"):
     e_g = ((res[0][1] - total).abs().max() / total.abs().max()).item()
     e_l = abs(res[0][0] - loss_sum) / abs(loss_sum)
     return max(e_same / 1e-12 if e_same > 0 else 0.0, e_g / 2e-4, e_l / 1e-5), 1.0, dict(e_same=e_same, e_g=e_g, e_l=e_l)
+
+
+# ------------------------------------------------------------------------------------------- parity at BASELINE sizes
+def case_loss_at_baseline_batch(kind, B=65536, chunk=4096):
+    """BASELINE configs[1] size: linear CDE, batch 65,536 (2048 forward tiles over 148 SMs, split-K atomics over 144 CTAs,
+    `batch_global` scaling), fused DSM / PINN(FPE exact, L1, ic L2) on the GPU against the CPU oracle in fp64, evaluated
+    in chunks of 4096 rows and combined with the sum-of-means identity: loss and every info mean within
+    3e-4 relative, every parameter gradient within 3e-3 of its scale — the tolerances of the small fixtures."""
+    from dmip import losses as dl
+    from dmip.linear_problem import LinearForwardProblem
+    from dmip.models.diffusion import CDE
+    from oracle import losses as ol
+    lin = LinearForwardProblem()
+    g = torch.Generator().manual_seed(7)                           # SURVEY.md §8d config 2: x ~ N(0, I), seed 7
+    x = torch.randn(B, 2, generator=g)
+    y = lin(x) + 0.3 * torch.randn(B, 2, generator=g)
+    t = torch.rand(B, 1, generator=g) * (1 - 2e-4) + 1e-4
+    eps = torch.randn(B, 2, generator=g)
+    ic = lin.score_posterior(x, y)
+    params = make_params(0, 5, 2)
+    m = CDE(2, 2, [512, 512, 512])
+    m.sde.a.load_state_dict(state_dict_from_params(params))
+    m.sde.to(DEV)
+    kw = dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")    # config_linear.yml:11-16
+    xd, yd, td, ed = (v.to(DEV) for v in (x, y, t, eps))
+    if kind == "DSM":
+        loss, _ = dl.dsm_fused(m, xd, yd, td, ed)
+        info = {}
+    else:
+        icd = ic.to(DEV)
+        loss_fn = dl.PINNLoss(lambda xx, yy: icd, **kw)
+        loss, info = loss_fn(m.sde, xd, yd, xd, td, ed, None, None)
+    m.sde.a.zero_grad()
+    loss.backward()
+    got = [p.grad.detach().cpu().double() for p in m.sde.a.parameters()]
+    # oracle: fp64, chunked
+    p64 = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in params]
+    tot, tinfo = 0.0, {}
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    for s in range(0, B, chunk):
+        sl = slice(s, s + chunk)
+        a = [v[sl].double() for v in (x, y, t, eps)]
+        if kind == "DSM":
+            lc, ic_info = ol.dsm_loss(p64, "CDE", *a), {}
+        else:
+            lc, ic_info = ol.pinn_loss(p64, "CDE", *a, ic[sl].double(), **kw)
+        w = (min(B, s + chunk) - s) / B
+        (lc * w).backward()
+        tot += lc.item() * w
+        for k, v in ic_info.items():
+            tinfo[k] = tinfo.get(k, 0.0) + v.item() * w
+    err = abs(loss.item() - tot) / abs(tot)
+    for k, v in info.items():
+        err = max(err, abs(v.item() - tinfo[k]) / max(abs(tinfo[k]), 1e-12))
+    ref = [q.grad for W, b in p64 for q in (W, b)]
+    e_g = 0.0
+    for a_, r_ in zip(got, ref):
+        scale = r_.norm().item() / max(r_.numel() ** 0.5, 1.0)
+        e_g = max(e_g, (a_ - r_).abs().max().item() / (3e-3 * scale + 3e-3 * r_.abs().max().item()))
+    return max(err / 3e-4, e_g), 1.0, dict(loss=loss.item(), ref=tot, e_loss=err, e_grad=e_g)
+
+
+def case_sampler_trained_1000_steps(precision):
+    """Trained linear CDE at S = 1000 steps (5x the reference default: bf16 rounding accumulates 5x longer), N = 512,
+    the keyed Philox stream injected, against the CPU oracle sampler on the same noise: fp32 5e-4, bf16 1e-2 max abs
+    with |mean shift| <= 3e-3 and |std ratio - 1| <= 5e-3."""
+    fx = load_golden("trained_cde_linear")
+    params = on.params_from_state_dict({f"{k}.{n}": fx[f"{k}_{n}"] for k in (0, 3, 5, 7) for n in ("weight", "bias")})
+    m = trained_model()
+    N, S, seed = 512, 1000, 4242
+    y = torch.tensor([0.4, -0.7])
+    gidx = np.arange(N)
+    x0 = torch.from_numpy(oracle.philox.normals(gidx, oracle.philox.STEP_INIT, 0, 2, seed))
+    noise = torch.from_numpy(np.stack([oracle.philox.normals(gidx, i, 0, 2, seed) for i in range(S)]))
+    with torch.no_grad():
+        ref = osamp.em_sampler_cde(params, y, x0, noise, S)
+    out = torch.from_numpy(m(y, num_samples=N, num_steps=S, precision=precision, injected=dict(x0=x0, noise=noise)))
+    out_p = torch.from_numpy(m(y, num_samples=N, num_steps=S, precision=precision, seed=seed))     # in-kernel Philox
+    err = max((out - ref).abs().max().item(), (out_p - ref).abs().max().item())
+    tol = 5e-4 if precision == "fp32" else 1e-2
+    dmean = (out.mean(0) - ref.mean(0)).abs().max().item()
+    rstd = (out.std(0) / ref.std(0) - 1).abs().max().item()
+    if precision == "bf16" and (dmean > 3e-3 or rstd > 5e-3):
+        err = max(err, 1.0)
+    return err, tol, dict(out=out, ref=ref, dmean=dmean, rstd=rstd)
+
+
+def case_philox_equals_injected(kind, precision):
+    """CDiffE (in-kernel re-diffusion stream of y, Philox stream 1) and DPS (two-net pass): the kernel's own Philox
+    draws must reproduce the run fed with the numpy mirror of the same keyed streams (oracle/philox.py), as the CDE
+    cases already check.  Scatterometry shapes (xdim 3, ydim 23), untrained nets, S = 10: relative to max|x|, fp32 1e-4
+    (transcendental intrinsics differ from numpy by ~1e-6 per draw and the untrained dynamics amplify), bf16 2e-3."""
+    xdim, ydim, N, S, seed, base = 3, 23, 300, 10, 991, 5000
+    m = _model(kind, xdim, ydim, (512, 512, 512), 61)
+    y = torch.randn(ydim, generator=torch.Generator().manual_seed(2))
+    gidx = np.arange(N) + base
+    inj = dict(x0=torch.from_numpy(oracle.philox.normals(gidx, oracle.philox.STEP_INIT, 0, xdim, seed)),
+               noise=torch.from_numpy(np.stack([oracle.philox.normals(gidx, i, 0, xdim, seed) for i in range(S)])))
+    if kind == "CDiffE":
+        inj["ynoise"] = torch.from_numpy(np.stack([oracle.philox.normals(gidx, i, 1, ydim, seed) for i in range(S)]))
+    a = m(y, num_samples=N, num_steps=S, precision=precision, seed=seed, gidx_base=base, return_tensor=True)
+    b = m(y, num_samples=N, num_steps=S, precision=precision, injected=inj, return_tensor=True)
+    err = ((a - b).abs().max() / b.abs().max()).item()
+    return err, (1e-4 if precision == "fp32" else 2e-3), dict(out=a.cpu(), ref=b.cpu())
+
+
+def case_batched_observations_variant(kind):
+    """y of shape (n_obs, ydim) for CDiffE and DPS: all observations in ONE launch == one call per observation with the
+    matching global-index offset, bit for bit (BASELINE configs[3]: observations are the sharded unit)."""
+    xdim, ydim = 3, 23
+    m = _model(kind, xdim, ydim, (512, 512, 512), 62)
+    ys = torch.randn(3, ydim, generator=torch.Generator().manual_seed(5))
+    N, S, seed = 200, 8, 7
+    batched = m(ys, num_samples=N, num_steps=S, seed=seed, return_tensor=True)
+    assert batched.shape == (3, N, xdim)
+    err = 0.0
+    for o in range(3):
+        single = m(ys[o], num_samples=N, num_steps=S, seed=seed, gidx_base=o * N, return_tensor=True)
+        err = max(err, (single - batched[o]).abs().max().item())
+    # and through the public sharding helper: observations split over ranks (world size 1 here -> all of them)
+    from dmip.distributed import sample_sharded
+    one = sample_sharded(m, ys, num_samples=N, num_steps=S, seed=seed, shard='observations')
+    err = max(err, (one.view(3, N, xdim) - batched).abs().max().item())
+    return err, 0.0, {}
+
+
+_SCAT_MODELS = {}
+
+
+def _trained_scat_model(kind):
+    """A briefly DSM-trained scatterometry model (CDiffE: joint score of [x, y]; DPS: PosteriorLoss on both nets), so
+    that the reverse SDE contracts and sample statistics are meaningful; cached per process."""
+    if kind in _SCAT_MODELS:
+        return _SCAT_MODELS[kind]
+    from dmip import losses as dl
+    from dmip.models.diffusion import CDiffE, PosteriorDiffusionEstimator
+    fm, _ = _surrogate_module()
+    torch.manual_seed(0)
+    X = torch.rand(8000, 3, device=DEV) * 2 - 1
+    with torch.no_grad():
+        fX = fm(X)
+        Y = fX + 0.01 * torch.randn_like(fX) + 0.2 * fX * torch.randn_like(fX)
+    loader = lambda: ((X[i:i + 1000], Y[i:i + 1000]) for i in range(0, 8000, 1000))
+    if kind == "CDiffE":
+        m = CDiffE(3, 23, [512, 512, 512])
+        m.sde.to(DEV)
+        opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3)
+        for _ in range(40):
+            m.train_epoch(opt, dl.DSMLoss(), loader)
+    else:
+        m = PosteriorDiffusionEstimator(3, 23, [512, 512, 512])
+        m.sde.to(DEV)
+        opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3)
+        loss_fn = m.loss_fn(fm, 0.2, 0.01, lam=1e-4)
+        for _ in range(40):
+            m.train_epoch(opt, loss_fn, loader)
+    m.sde.eval()
+    _SCAT_MODELS[kind] = (m, fm, Y)
+    return _SCAT_MODELS[kind]
+
+
+def case_scat_statistics(kind):
+    """Posterior statistics of the bf16 tensor-core sampler against the fp32 kernel for a trained scatterometry CDiffE /
+    DPS model (models/diffusion.py:158-180, nets.py:155-157): 65,536 particles, 200 steps, same Philox key.
+    |mean shift| <= 5e-3 and |std ratio - 1| <= 1e-2 per coordinate, and the reference's own metric — the 75-bin histogram
+    KL on [-1.2, 1.2]^3 (main_diffusion_scatterometry.py:72-101) — between the two precisions <= 1.5 x the KL between two
+    independent fp32 runs (SURVEY.md §8d statistical tolerance)."""
+    from dmip import metrics as dmet
+    m, fm, Y = _trained_scat_model(kind)
+    y = Y[17].cpu()
+    N, S = 65536, 200
+    sets = {k: m(y, num_samples=N, num_steps=S, precision=p, seed=s, return_tensor=True)
+            for k, (p, s) in dict(lo=("bf16", 31), hi=("fp32", 31), hi2=("fp32", 32), lo2=("bf16", 33)).items()}
+    finite = all(bool(torch.isfinite(v).all()) for v in sets.values())
+    dmean = (sets["lo"].mean(0) - sets["hi"].mean(0)).abs().max().item()
+    rstd = (sets["lo"].std(0) / sets["hi"].std(0) - 1).abs().max().item()
+    bins, rng = (75, 75, 75), ((-1.2, 1.2),) * 3
+    h = {k: dmet.histogramdd(v, bins, rng) for k, v in sets.items()}
+    kl_new = float(dmet.hist_kl(h["hi"], h["lo2"]))
+    kl_ref = float(dmet.hist_kl(h["hi"], h["hi2"]))
+    inside = float(h["hi"].sum().item()) / N
+    err = max(dmean / 5e-3, rstd / 1e-2, kl_new / (1.5 * kl_ref) if kl_ref > 0 else 0.0, 0.0 if finite else 2.0,
+              0.0 if inside > 0.5 else 2.0)
+    return err, 1.0, dict(dmean=dmean, rstd=rstd, kl_new=kl_new, kl_ref=kl_ref, inside=inside)
+
+
+# ------------------------------------------------------------------------------------------- VE-SDE / predictor–corrector (N4)
+def case_pc_sampler(kind, sde_kind, n_corr, precision):
+    """VE-SDE and Langevin-corrector modes of the fused sampler (no upstream counterpart: parity unpinned)
+    against the oracle restatement oracle/ve.py — which with the VP-SDE and no corrector IS the pinned reference sampler
+    (tests/test_oracle_golden.py).  Injected noise, scatterometry shapes, untrained nets, S = 8 steps (x (1 + n_corr)
+    sub-steps): relative to max|x|, fp32 2e-5, bf16 3e-3; and the in-kernel Philox stream keyed by the sub-step index must
+    reproduce the run fed with its numpy mirror (fp32 1e-4, bf16 2e-3)."""
+    from dmip import sdes
+    from dmip.models.diffusion import CDE, CDiffE, PosteriorDiffusionEstimator
+    from oracle import ve
+    xdim, ydim, N, S, seed, snr = 3, 23, 200, 8, 77, 0.16
+    hidden = (512, 512, 512)
+    base = sdes.VarianceExplodingSDE(sigma_min=0.05, sigma_max=4.0) if sde_kind == "VE" else None
+    osde = ve.VE(0.05, 4.0) if sde_kind == "VE" else ve.VP()
+    if kind == "CDE":
+        m = CDE(xdim, ydim, list(hidden), base_sde=base)
+        p = make_params(71, xdim + ydim + 1, xdim, hidden)
+        m.sde.a.load_state_dict(state_dict_from_params(p))
+        net, variant = ve.net_fn("CDE", p), "CDE"
+    elif kind == "CDiffE":
+        m = CDiffE(xdim, ydim, list(hidden), base_sde=base)
+        p = make_params(72, xdim + ydim + 1, xdim + ydim, hidden)
+        m.sde.a.load_state_dict(state_dict_from_params(p))
+        net, variant = ve.net_fn("CDiffE", p), "CDiffE"
+    else:
+        m = PosteriorDiffusionEstimator(xdim, ydim, list(hidden), base_sde=base)
+        p2, p = make_params(73, xdim + 1, xdim, hidden), make_params(173, xdim + ydim + 1, xdim, hidden)
+        m.sde.a.prior_net.load_state_dict(state_dict_from_params(p2))
+        m.sde.a.likelihood_net.load_state_dict(state_dict_from_params(p))
+        net, variant = ve.net_fn("DPS", p, p2), "DPS"
+    m.sde.to(DEV)
+    y = torch.randn(ydim, generator=torch.Generator().manual_seed(3))
+    std0 = 4.0 if sde_kind == "VE" else 1.0
+    n_sub = S * (1 + n_corr)
+    gidx = np.arange(N)
+    x0 = torch.from_numpy(oracle.philox.normals(gidx, oracle.philox.STEP_INIT, 0, xdim, seed))
+    noise = torch.from_numpy(np.stack([oracle.philox.normals(gidx, u, 0, xdim, seed) for u in range(n_sub)]))
+    inj = dict(x0=x0, noise=noise)
+    ynoise = None
+    if kind == "CDiffE":
+        ynoise = torch.from_numpy(np.stack([oracle.philox.normals(gidx, u, 1, ydim, seed) for u in range(n_sub)]))
+        inj["ynoise"] = ynoise
+    with torch.no_grad():
+        ref = ve.pc_sampler(net, variant, y, x0 * std0, noise, S, osde, n_corr=n_corr, snr=snr, ynoise=ynoise)
+    kw = dict(num_samples=N, num_steps=S, std=std0, precision=precision, n_corrector=n_corr, snr=snr)
+    out = torch.from_numpy(m(y, injected=inj, **kw))
+    out_p = torch.from_numpy(m(y, seed=seed, **kw))
+    scale = ref.abs().max().item()
+    e_inj = (out - ref).abs().max().item() / scale
+    e_phx = (out_p - out).abs().max().item() / scale
+    t_inj, t_phx = (2e-5, 1e-4) if precision == "fp32" else (3e-3, 2e-3)
+    return max(e_inj / t_inj, e_phx / t_phx), 1.0, dict(e_inj=e_inj, e_phx=e_phx, out=out, ref=ref)
+
+
+def case_ve_trained_posterior():
+    """A VE-SDE CDE trained on the linear problem with a host-side DSM loop cannot use the fused (VP-only) losses, so the
+    statistical check of the VE / corrector samplers uses the ANALYTIC score of the linear-Gaussian posterior instead:
+    the perturbed posterior N(m, C + sigma(t)^2 I) has score -(C + sigma^2 I)^-1 (x - m), which a [512,512,512] net
+    cannot represent exactly — so the check is self-consistency: bf16 vs fp32 kernels on the same Philox key, with and
+    without the corrector (mean shift <= 2e-2 sigma-units, std ratio within 2e-2), on an untrained net scaled down to a
+    contraction.  (Documented limitation: no trained VE model exists upstream or here.)"""
+    from dmip import sdes
+    from dmip.models.diffusion import CDE
+    torch.manual_seed(0)
+    m = CDE(2, 2, [512, 512, 512], base_sde=sdes.VarianceExplodingSDE(sigma_min=0.05, sigma_max=2.0))
+    with torch.no_grad():
+        for p in m.sde.a.parameters():
+            p.mul_(0.5)
+    m.sde.to(DEV)
+    y = torch.tensor([0.4, -0.7])
+    worst = 0.0
+    for nc in (0, 1):
+        lo = m(y, num_samples=32768, num_steps=100, std=2.0, precision="bf16", seed=5, n_corrector=nc)
+        hi = m(y, num_samples=32768, num_steps=100, std=2.0, precision="fp32", seed=5, n_corrector=nc)
+        assert np.isfinite(lo).all() and np.isfinite(hi).all()
+        dmean = float(np.abs(lo.mean(0) - hi.mean(0)).max() / hi.std(0).max())
+        rstd = float(np.abs(lo.std(0) / hi.std(0) - 1).max())
+        worst = max(worst, dmean / 2e-2, rstd / 2e-2)
+    return worst, 1.0, {}

@@ -61,3 +61,9 @@ def test_metropolis_chains_match_reference(mode):
 
 def test_evaluate_loops_run_on_gpu():
     _ok(gc.case_evaluate())
+
+
+@pytest.mark.parametrize("kind", ["DSM", "PINN"])
+def test_fused_loss_at_baseline_batch_65536(kind, loss_path):
+    """BASELINE configs[1] size against the chunked fp64 oracle (sum-of-means identity)"""
+    _ok(gc.case_loss_at_baseline_batch(kind))

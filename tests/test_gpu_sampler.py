@@ -68,3 +68,35 @@ def test_edge_shapes_and_invalid_arguments():
 
 def test_returned_host_arrays_are_never_overwritten():
     _ok(gc.case_host_results_do_not_alias())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sampler_trained_1000_steps(precision):
+    _ok(gc.case_sampler_trained_1000_steps(precision))
+
+
+@pytest.mark.parametrize("kind", ["CDiffE", "Posterior"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_philox_mode_equals_injected_mirror(kind, precision):
+    _ok(gc.case_philox_equals_injected(kind, precision))
+
+
+@pytest.mark.parametrize("kind", ["CDiffE", "Posterior"])
+def test_batched_observations_cdiffe_dps(kind):
+    _ok(gc.case_batched_observations_variant(kind))
+
+
+@pytest.mark.parametrize("kind", ["CDiffE", "Posterior"])
+def test_scatterometry_posterior_statistics_bf16_vs_fp32(kind):
+    _ok(gc.case_scat_statistics(kind))
+
+
+@pytest.mark.parametrize("kind", ["CDE", "CDiffE", "Posterior"])
+@pytest.mark.parametrize("sde_kind,n_corr", [("VE", 0), ("VE", 1), ("VP", 2)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ve_sde_and_predictor_corrector_modes(kind, sde_kind, n_corr, precision):
+    _ok(gc.case_pc_sampler(kind, sde_kind, n_corr, precision))
+
+
+def test_ve_sampler_bf16_statistics_match_fp32():
+    _ok(gc.case_ve_trained_posterior())

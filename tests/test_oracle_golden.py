@@ -224,3 +224,44 @@ def test_metropolis_oracle_matches_reference_chains():
     same = ((x - fx["out"]).abs().max(1).values <= 1e-6)
     assert same.float().mean().item() >= 0.99                      # a near-tie may flip an accept in fp32
     assert torch.allclose(de[same], fx["de"][same], rtol=1e-4, atol=2e-2)
+
+
+def test_predictor_corrector_oracle_reduces_to_the_pinned_reference_sampler():
+    """oracle/ve.py generalises the sampler to the VE-SDE and a Langevin corrector (no upstream counterpart).  With the
+    VP-SDE and no corrector it must be bit-identical to the restatement pinned against the reference fixtures."""
+    import torch
+    from oracle import sampler as osamp, ve
+    from oracle.weights import make_params
+    torch.manual_seed(0)
+    p, p2, pc = make_params(1, 27, 3, (64, 64)), make_params(2, 4, 3, (64, 64)), make_params(3, 27, 26, (64, 64))
+    y, x0, S = torch.randn(23), torch.randn(50, 3), 7
+    noise, yn = torch.randn(S, 50, 3), torch.randn(S, 50, 23)
+    a = osamp.em_sampler_cde(p, y, x0, noise, S)
+    assert torch.equal(a, ve.pc_sampler(ve.net_fn("CDE", p), "CDE", y, x0, noise, S, ve.VP()))
+    a = osamp.em_sampler_dps(p2, p, y, x0, noise, S)
+    assert torch.equal(a, ve.pc_sampler(ve.net_fn("DPS", p, p2), "DPS", y, x0, noise, S, ve.VP()))
+    a = osamp.em_sampler_cdiffe(pc, y, x0, yn, noise, S)
+    assert torch.equal(a, ve.pc_sampler(ve.net_fn("CDiffE", pc), "CDiffE", y, x0, noise, S, ve.VP(), ynoise=yn))
+    # the corrector changes the result and keeps it finite; VE closed forms
+    b = ve.pc_sampler(ve.net_fn("CDE", p), "CDE", y, x0, torch.randn(2 * S, 50, 3), S, ve.VP(), n_corr=1)
+    assert torch.isfinite(b).all() and not torch.allclose(a, b)
+    sde = ve.VE(0.01, 50.0)
+    t = torch.tensor([[0.0], [0.5], [1.0]])
+    assert torch.allclose(sde.var(t) ** 0.5, torch.tensor([[0.01], [0.01 * 5000 ** 0.5], [50.0]]), rtol=1e-5)
+    # g^2 = d sigma^2 / dt
+    h = 1e-3
+    num = (sde.var(t + h) - sde.var(t - h)) / (2 * h)
+    assert torch.allclose(sde.g(t, t) ** 2, num, rtol=2e-4)
+
+
+def test_ve_host_class_matches_the_oracle_closed_forms():
+    import torch
+    from dmip import sdes
+    from oracle import ve
+    a, b = sdes.VarianceExplodingSDE(0.02, 7.0), ve.VE(0.02, 7.0)
+    t = torch.rand(16, 1)
+    y = torch.randn(16, 3)
+    assert torch.allclose(a.var(t), b.var(t)) and torch.allclose(a.g(t, y), b.g(t, y)) and torch.equal(a.f(t, y), b.f(t, y))
+    assert torch.equal(a.mean_weight(t), torch.ones_like(t))
+    yt, eps, std, g = a.sample(t, y, return_noise=True)
+    assert torch.allclose(yt, y + std * eps)
