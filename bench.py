@@ -318,7 +318,6 @@ def setup_dist(world):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "INFO")      # the init log (ranks, NVLS, rings) goes to stderr, see claim_stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return local, dist
 
@@ -783,6 +782,8 @@ def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")      # before torch / NCCL load; the log goes to stderr (claim_stdout)
     claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)

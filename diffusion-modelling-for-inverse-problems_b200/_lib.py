@@ -190,6 +190,36 @@ class PackedNet:
         return self.buf
 
 
+class Guarded:
+    """Debug allocator for kernel outputs and scratch (DMIP_GUARD=1): every buffer gets 4 KB of 0xA5 canary bytes in front
+    and behind; `check()` synchronises and raises if a kernel wrote outside what it was given.  compute-sanitizer is
+    closed on the GPU pool this was developed on (profiles/r02_compute_sanitizer_closed.txt) — this is the bounds check
+    the test-suite runs instead (tests/gpu_cases.py case_guarded_buffers)."""
+    PAD = 4096
+
+    def __init__(self):
+        self.on = os.environ.get("DMIP_GUARD", "") not in ("", "0")
+        self.bufs = []
+
+    def empty(self, n, dtype, device):
+        if not self.on:
+            return torch.empty(n, dtype=dtype, device=device)
+        item = torch.empty(0, dtype=dtype).element_size()
+        raw = torch.full((2 * self.PAD + n * item,), 0xA5, dtype=torch.uint8, device=device)
+        self.bufs.append((raw, n * item))
+        return raw[self.PAD:self.PAD + n * item].view(dtype)
+
+    def check(self, what=""):
+        if not self.on:
+            return
+        torch.cuda.synchronize()
+        for raw, nbytes in self.bufs:
+            ok = bool((raw[:self.PAD] == 0xA5).all()) and bool((raw[self.PAD + nbytes:] == 0xA5).all())
+            if not ok:
+                raise RuntimeError(f"dmip guard: a kernel wrote outside a {nbytes}-byte buffer ({what})")
+        self.bufs = []
+
+
 def tc_supported(net, n_varying=None, split=2):
     """True when the tcgen05 kernels can run this net: [in] -> 512 -> 512 -> 512 -> [out <= 128] and a layer-0 GEMM depth
     (the row-varying input columns, split `split` ways) of at most 512 — the conditions of tc_net_geom (csrc/dmip_pack.cu)."""

@@ -124,23 +124,34 @@ __device__ __forceinline__ uint32_t bop_off(uint32_t k, uint32_t row) {
   return (k >> 3) * 1024u + (k & 7u) * 128u + (((row >> 3) ^ (k & 7u)) << 4) + (row & 7u) * 2u;
 }
 
+// tanh to fp32 accuracy without the branch of tanhf: 1 - 2 / (e^{2|x|} + 1) on the two MUFU ops (ex2, rcp; absolute
+// error ~3e-7, where the quotient cancels) and the odd Taylor polynomial below |x| = 0.04 (relative error < 1e-7 there).
+// The epilogue of a layer's first accumulator chunks is on the path the next layer's MMAs wait for.
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(ax * 2.8853900817779268f));
+  const float big = 1.0f - __fdividef(2.0f, t + 1.0f);
+  const float x2 = x * x;
+  const float small = ax * fmaf(x2, fmaf(x2, 0.13333333f, -0.33333334f), 1.0f);
+  return copysignf(ax < 0.04f ? small : big, x);
+}
+
 // activation jets: value h, first and second derivative of phi at pre-activation z (layer 0: tanh(tanh), else tanh)
 template <bool kFirst>
 __device__ __forceinline__ void act_jet(float z, float& h, float& p1, float& p2) {
   if (kFirst) {
-    const float u = tanhf(z);
-    h = tanhf(u);
+    const float u = tanh_acc(z);
+    h = tanh_acc(u);
     const float du = 1.f - u * u;
     p1 = (1.f - h * h) * du;
     p2 = p1 * (-2.f * h * du - 2.f * u);
   } else {
-    h = tanhf(z);
+    h = tanh_acc(z);
     p1 = 1.f - h * h;
     p2 = -2.f * h * p1;
   }
 }
-template <bool kFirst>
-__device__ __forceinline__ float act_val(float z) { return kFirst ? tanhf(tanhf(z)) : tanhf(z); }
 // phi' from the stored output h (layer 0: h = tanh(u), u = atanh(h), |h| < tanh(1))
 template <bool kFirst>
 __device__ __forceinline__ float dphi_from_h(float h) {
@@ -383,12 +394,9 @@ __device__ __forceinline__ void fwd_build_input(const TclDev& P, long long tile,
 // One (layer, chunk, window) item of the forward epilogue: thread = feature n of the layer's output.
 template <class C, bool kFirst>
 __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr, int n, float bias, long long smp0,
-                                         bool tile_ok, int w, uint8_t* smem) {
-  uint32_t v[32];
+                                         bool tile_ok, int w, uint8_t* smem, uint32_t (&v)[32]) {
   tmem_ld32(taddr, v);
   tc_wait_ld();
-  const uint32_t nterm = (static_cast<uint32_t>(n) >> 6) * 8192u + (static_cast<uint32_t>(n) & 7u) * 2u;
-  const uint32_t nchunk = (static_cast<uint32_t>(n) & 63u) >> 3;
 #pragma unroll
   for (int j = 0; j < C::SPW; ++j) {
     const int base = j * C::NS;
@@ -423,40 +431,13 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
 #pragma unroll
       for (int k = 0; k < C::kNT; ++k) v[base + C::sS + k] = __float_as_uint(p1 * zs[k]);
     }
-    // stashes for the backward pass: inputs of layer g+1 for the adjoint streams (bf16 hi/lo images in the backward
-    // geometry: weight-gradient operands) and the derivative state the backward epilogue needs (fp32, coalesced)
+    // derivative state the backward epilogue needs (fp32, coalesced; dmip_tcl.h: st)
     const long long smp = smp0 + j;
     if (tile_ok && smp < P.B) {
       float* sst = P.st[g] + (smp * C::NADJ) * 512 + n;
       sst[0] = p1;
       if (C::kI) sst[512] = q1;
       if (C::kT) sst[(1 + C::kI) * 512] = cT;
-      long long blk;
-      uint32_t rb;
-      bwd_row<C>(smp, 0, blk, rb);
-      uint8_t* ihi = P.in_img[g + 1][0] + static_cast<size_t>(blk) * (512 * 128) + nterm;
-      uint8_t* ilo = P.in_img[g + 1][1] + static_cast<size_t>(blk) * (512 * 128) + nterm;
-      unsigned short hi, lo;
-      {
-        const uint32_t o = (rb >> 3) * 1024u + (rb & 7u) * 128u + ((nchunk ^ (rb & 7u)) << 4);
-        split1(h, hi, lo);
-        *reinterpret_cast<unsigned short*>(ihi + o) = hi;
-        *reinterpret_cast<unsigned short*>(ilo + o) = lo;
-      }
-      if (C::kI) {
-        const uint32_t r2 = rb + 1;
-        const uint32_t o = (r2 >> 3) * 1024u + (r2 & 7u) * 128u + ((nchunk ^ (r2 & 7u)) << 4);
-        split1(hI, hi, lo);
-        *reinterpret_cast<unsigned short*>(ihi + o) = hi;
-        *reinterpret_cast<unsigned short*>(ilo + o) = lo;
-      }
-      if (C::kT) {
-        const uint32_t r2 = rb + 1 + C::kI;
-        const uint32_t o = (r2 >> 3) * 1024u + (r2 & 7u) * 128u + ((nchunk ^ (r2 & 7u)) << 4);
-        split1(hdT, hi, lo);
-        *reinterpret_cast<unsigned short*>(ihi + o) = hi;
-        *reinterpret_cast<unsigned short*>(ilo + o) = lo;
-      }
     }
   }
 #pragma unroll
@@ -473,6 +454,35 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
     const uint32_t co = ((static_cast<uint32_t>(w * 4 + i) ^ line) << 4);
     st_shared_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
     st_shared_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// Second half of an item, AFTER the next layer's MMAs were told the K-blocks are there: the outputs of the adjoint streams
+// P | I | T (still in v[]) go to the IN_{g+1} stash image (bf16 hi/lo, backward geometry: weight-gradient operand).
+template <class C>
+__device__ __forceinline__ void fwd_stash(const TclDev& P, int g, int n, long long smp0, bool tile_ok, const uint32_t (&v)[32]) {
+  const uint32_t nterm = (static_cast<uint32_t>(n) >> 6) * 8192u + (static_cast<uint32_t>(n) & 7u) * 2u;
+  const uint32_t nchunk = (static_cast<uint32_t>(n) & 63u) >> 3;
+#pragma unroll
+  for (int j = 0; j < C::SPW; ++j) {
+    const long long smp = smp0 + j;
+    if (tile_ok && smp < P.B) {
+      long long blk;
+      uint32_t rb;
+      bwd_row<C>(smp, 0, blk, rb);
+      uint8_t* ihi = P.in_img[g + 1][0] + static_cast<size_t>(blk) * (512 * 128) + nterm;
+      uint8_t* ilo = P.in_img[g + 1][1] + static_cast<size_t>(blk) * (512 * 128) + nterm;
+#pragma unroll
+      for (int a = 0; a < C::NADJ; ++a) {
+        const int st = a == 0 ? 0 : (C::kI && a == 1) ? C::sI : C::sT;
+        const uint32_t r2 = rb + a;
+        const uint32_t o = (r2 >> 3) * 1024u + (r2 & 7u) * 128u + ((nchunk ^ (r2 & 7u)) << 4);
+        unsigned short hi, lo;
+        split1(__uint_as_float(v[j * C::NS + st]), hi, lo);
+        *reinterpret_cast<unsigned short*>(ihi + o) = hi;
+        *reinterpret_cast<unsigned short*>(ilo + o) = lo;
+      }
+    }
   }
 }
 
@@ -646,12 +656,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
           const uint32_t taddr = lane_taddr + static_cast<uint32_t>((g & 1) * 256 + c * kNR + w * kWin);
           // register select (the loops stay rolled: six copies of the item body would not fit the instruction cache)
           const float bs = g == 0 ? (ci ? bias[0][1] : bias[0][0]) : g == 1 ? (ci ? bias[1][1] : bias[1][0]) : (ci ? bias[2][1] : bias[2][0]);
-          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, tile_ok, w, smem);
-          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, tile_ok, w, smem);
+          uint32_t v[32];
+          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, tile_ok, w, smem, v);
+          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, tile_ok, w, smem, v);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&B.hready[c]);
+          fwd_stash<C>(P, g, n, smp0, tile_ok, v);
         }
         if (g == 1 && tb + tile_stride < n_tiles) {
           // GEMM 0 of this tile has retired (acc_full[0] above): the small operand region takes the next tile's inputs
@@ -787,7 +799,7 @@ __device__ __forceinline__ float bwd_math(const TclDev& P, uint32_t taddr, long 
 // well) and, for L > 0, the B operand of the next GEMM
 template <class C>
 __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, int k, long long tile, bool tile_ok, int w,
-                                          const uint32_t (&v)[32], uint8_t* smem) {
+                                          const uint32_t (&v)[32], uint8_t* smem, uint64_t* hready, int lane) {
   const uint32_t kterm = (static_cast<uint32_t>(k) >> 6) * 8192u + (static_cast<uint32_t>(k) & 7u) * 2u;
   const uint32_t kchunk = (static_cast<uint32_t>(k) & 63u) >> 3;
   const size_t blk = static_cast<size_t>(tile) * (512 * 128) + kterm;
@@ -805,6 +817,11 @@ __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, 
       st_shared_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
       st_shared_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
     }
+    // the next GEMM may read these K-blocks now; the global stash stores below are off its critical path
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(hready);
   }
   if (tile_ok) {
     uint8_t* ahi = P.adj_img[L][0] + blk;
@@ -884,21 +901,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
         const uint32_t t0 = lane_taddr + set * 256u + static_cast<uint32_t>(c_first * kNR + w * kWin);
         bsum[g][0] += bwd_math<C>(P, t0, tile, tile_ok, w, pre, v);
         bwd_prefetch<C>(P, L, k1, tile, w, pre);
-        bwd_store<C>(P, L, L != 0, k0, tile, tile_ok, w, v, smem);
-        if (g < 2) {
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&B.hready[c_first]);
-        }
+        bwd_store<C>(P, L, L != 0, k0, tile, tile_ok, w, v, smem, &B.hready[c_first], lane);
         bsum[g][1] += bwd_math<C>(P, t0 + 2 * kNR, tile, tile_ok, w, pre, v);
-        bwd_store<C>(P, L, L != 0, k1, tile, tile_ok, w, v, smem);
-        if (g < 2) {
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&B.hready[c_first + 2]);
-        }
+        bwd_store<C>(P, L, L != 0, k1, tile, tile_ok, w, v, smem, &B.hready[c_first + 2], lane);
         if (g == 1 && tb + tile_stride < n_tiles) {
           const int nt = tb + tile_stride + static_cast<int>(crank);
           bwd_build_input<C>(P, nt, nt < n_tiles, smem + kOffIn, t);

@@ -98,10 +98,11 @@ def _launch_fused(net, cfg, x, y, t, eps, ic_target, grad_out=None):
         v = v.detach().to(dev, torch.float32).contiguous()
         tens[name] = v
         setattr(d, name, v.data_ptr())
-    losses = torch.empty(4, device=dev, dtype=torch.float32)
+    guard = _lib.Guarded()
+    losses = guard.empty(4, torch.float32, dev)
     n_grad = L.dmip_loss_grad_floats(C.byref(d.net))
     if grad_out is None:
-        grad = torch.empty(n_grad, device=dev, dtype=torch.float32)
+        grad = guard.empty(n_grad, torch.float32, dev)
     else:
         grad = grad_out
         assert grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == n_grad
@@ -109,10 +110,11 @@ def _launch_fused(net, cfg, x, y, t, eps, ic_target, grad_out=None):
     nbytes = L.dmip_loss_workspace_bytes(C.byref(d))
     if nbytes == 0:
         _lib.check(-1)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = guard.empty(nbytes, torch.uint8, dev)
     d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     with torch.cuda.device(dev):
         _lib.check(L.dmip_loss_fwd_bwd(C.byref(d), _lib.stream_ptr()))
+    guard.check("dmip_loss_fwd_bwd")
     return losses, grad, L.dmip_last_launch_count()
 
 

@@ -97,7 +97,8 @@ class BaseClassDiffusionModel():
             d.net2 = _lib.mlp_desc(net2, keep)
         d.l0_split = self.l0_split
         d.y = ys.data_ptr()
-        out = torch.empty(n_total, self.xdim, device=dev, dtype=torch.float32)
+        guard = _lib.Guarded()
+        out = guard.empty(n_total * self.xdim, torch.float32, dev).view(n_total, self.xdim)
         d.out = out.data_ptr()
         if injected is not None:
             d.rng_mode = _lib.RNG_INJECTED
@@ -125,6 +126,7 @@ class BaseClassDiffusionModel():
             d.workspace_bytes = ws.numel()
             _lib.check(L.dmip_sampler_em_vp(C.byref(d), _lib.stream_ptr()))
             self.last_launch_count = L.dmip_last_launch_count()
+            guard.check("dmip_sampler_em_vp")
         if batched:
             out = out.view(n_obs, num_samples, self.xdim)
         if return_tensor:

@@ -10,11 +10,14 @@ when autograd is recording it runs the plain module chain so `loss.backward()` o
 `GaussianFourierProjection` / `TemporalMLP*` of the reference are unused by every model (nets.py:62-63) and omitted.
 """
 import ctypes as C
+import warnings
 
 import torch
 from torch import nn
 
 from . import _lib
+
+_WARNED_EAGER = [False]
 
 
 class _ScoreMLP(nn.Sequential):
@@ -85,6 +88,13 @@ class _ScoreMLP(nn.Sequential):
             return self._fused(x, cond, t)
         if not x.is_cuda:
             raise RuntimeError("dmip score nets run on CUDA (sm_100a) only: there is no CPU fallback")
+        if not _WARNED_EAGER[0]:
+            _WARNED_EAGER[0] = True
+            warnings.warn("dmip: autograd is recording through MLP.forward — this call runs the plain torch module chain "
+                          "(cuBLAS addmm), not the fused sm_100a kernels.  The fused kernels serve the no-grad calls "
+                          "(sampler, evaluation) and the fused losses (DSMLoss via train_epoch, PINNLoss, DSM_PDELoss, "
+                          "PosteriorLoss), which carry their own backward; wrap inference in torch.no_grad().",
+                          RuntimeWarning, stacklevel=3)
         parts = [x] + ([cond] if cond is not None and cond.numel() > 0 else []) + [t.view(len(x), 1)]
         inp = torch.cat(parts, dim=1)
         assert inp.ndim == 2, 'Input Tensor is expected to be 2D with shape (batch_size, xdim+ydim+1)'

@@ -59,6 +59,11 @@ def test_metropolis_chains_match_reference(mode):
     _ok(gc.case_metropolis(mode))
 
 
+@pytest.mark.parametrize("problem", ["linear", "scat"])
+def test_evaluation_tables_match_the_reference_evaluate_loops(problem):
+    _ok(gc.case_evaluate_parity(problem))
+
+
 def test_evaluate_loops_run_on_gpu():
     _ok(gc.case_evaluate())
 
@@ -67,3 +72,12 @@ def test_evaluate_loops_run_on_gpu():
 def test_fused_loss_at_baseline_batch_65536(kind, loss_path):
     """BASELINE configs[1] size against the chunked fp64 oracle (sum-of-means identity)"""
     _ok(gc.case_loss_at_baseline_batch(kind))
+
+
+def test_kernels_stay_inside_their_buffers():
+    """canary-guarded outputs and workspaces over ragged sizes (the stand-in for compute-sanitizer, closed on this pool)"""
+    _ok(gc.case_guarded_buffers())
+
+
+def test_documented_boundary_deviations():
+    _ok(gc.case_boundary_deviations())

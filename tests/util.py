@@ -16,7 +16,8 @@ def load_golden(name, dtype=torch.float32):
         if k.startswith("gidx") or "_gidx_" in k or k == "meta":
             out[k] = torch.from_numpy(v.astype(np.int64))
         else:
-            out[k] = torch.from_numpy(np.asarray(v, dtype=np.float32)).to(dtype)
+            npd = np.float64 if dtype == torch.float64 else np.float32      # float64 tables keep their precision
+            out[k] = torch.from_numpy(np.asarray(v, dtype=npd)).to(dtype)
     return out
 
 
