@@ -782,8 +782,9 @@ def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")      # before torch / NCCL load; the log goes to stderr (claim_stdout)
+    if world > 1 and os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "INFO"                # before torch / NCCL load: the communicator log (ranks, rings, NVLS)
+                                                         # goes to stderr (claim_stdout), never into the JSON line
     claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
