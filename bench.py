@@ -411,7 +411,7 @@ def also_train(kind, B, steps=5, warmup=3, dist=None, rank=0, world=1):
     from dmip.models.diffusion import CDE
     torch.manual_seed(0)
     model = CDE(2, 2, HIDDEN)
-    opt = torch.optim.Adam(model.sde.a.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.sde.a.parameters(), lr=1e-4, fused=True)   # config_linear.yml: Adam, lr 1e-4 (one fused launch)
     x, y, t = linear_batch(B, 7 + rank)
     xh, yh = x.pin_memory(), y.pin_memory()
     xd, yd, td = x.cuda(), y.cuda(), t.cuda()
@@ -477,7 +477,7 @@ def also_posterior_loss(B=16384, steps=5, warmup=3):
     for q in fm.parameters():
         q.requires_grad = False
     m = PosteriorDiffusionEstimator(3, 23, HIDDEN)
-    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-4, fused=True)
     loss_fn = m.loss_fn(fm, 0.2, 0.01, lam=0.01)
     g = torch.Generator().manual_seed(3)
     x = (torch.rand(B, 3, generator=g) * 2 - 1)

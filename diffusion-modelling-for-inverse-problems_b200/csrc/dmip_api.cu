@@ -163,6 +163,24 @@ int dmip_loss_fwd_bwd(const DmipLoss* d, void* stream) {
   return launch_loss(d, static_cast<cudaStream_t>(stream));
 }
 
+size_t dmip_mlp_grad_workspace_bytes(const DmipMlpGrad* d) { return d ? mlp_grad_workspace(d) : 0; }
+
+int dmip_mlp_forward_stash(const DmipMlpGrad* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  return launch_mlp_forward_stash(d, static_cast<cudaStream_t>(stream));
+}
+
+int dmip_mlp_backward(const DmipMlpGrad* d, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  DMIP_REQUIRE(d != nullptr, "descriptor is NULL");
+  return launch_mlp_backward(d, static_cast<cudaStream_t>(stream));
+}
+
 size_t dmip_surrogate_workspace_bytes(const DmipSurrogate* d) { return d ? surrogate_workspace(d) : 0; }
 
 int dmip_surrogate_score(const DmipSurrogate* d, void* stream) {

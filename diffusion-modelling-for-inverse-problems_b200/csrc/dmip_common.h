@@ -65,6 +65,9 @@ size_t forward_f32_workspace(const DmipForward* d);
 size_t loss_workspace(const DmipLoss* q);
 size_t loss_grad_floats(const DmipMlp* net);
 int launch_loss(const DmipLoss* q, cudaStream_t s);
+size_t mlp_grad_workspace(const DmipMlpGrad* q);
+int launch_mlp_forward_stash(const DmipMlpGrad* q, cudaStream_t s);
+int launch_mlp_backward(const DmipMlpGrad* q, cudaStream_t s);
 size_t posterior_loss_workspace(const DmipPosteriorLoss* q);
 int launch_posterior_loss(const DmipPosteriorLoss* q, cudaStream_t s);
 int launch_histogramdd(const DmipHistogram* d, cudaStream_t s);

@@ -721,7 +721,7 @@ void plan_tcl(const PassCfg& c, int n_tan, TclPlan* t) {
   const size_t big = static_cast<size_t>(t->n_tiles_bwd) * 512 * 128, small = static_cast<size_t>(t->n_tiles_bwd) * kTclSmallF * 128;
   size_t off = 0;
   t->off_stages_fwd = off; off += align_1k(static_cast<size_t>(kTclFwdStages) * kTclStage);
-  t->off_stages_bwd = off; off += align_1k(static_cast<size_t>(kTclBwdStages) * kTclStage);
+  t->off_stages_bwd = off; off += align_1k(static_cast<size_t>(kTclBwdStagesIn) * kTclStage);
   for (int l = 0; l < 4; ++l)
     for (int h = 0; h < 2; ++h) {
       t->off_in[l][h] = off;  off += align_1k(l == 0 ? small : big);
@@ -818,6 +818,27 @@ int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
   c->bmin = q->beta_min; c->bmax = q->beta_max; c->lam = q->lam; c->lam2 = q->lam2;
   c->x = q->x; c->y = q->y; c->t = q->t; c->eps = q->eps; c->ic_target = q->ic_target;
   c->losses = q->out_losses; c->grad = q->grad;
+  return DMIP_OK;
+}
+
+// dst[j] += sum_r src[r][j]  (few columns: one block per 256-row slab, smem-free warp reductions)
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ src, float* dst, long long rows, int cols) {
+  for (int j = 0; j < cols; ++j) {
+    float acc = 0.f;
+    for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows;
+         r += static_cast<long long>(gridDim.x) * blockDim.x)
+      acc += src[r * cols + j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&dst[j], acc);
+  }
+}
+
+int launch_colsum(const float* src, float* dst, long long rows, int cols, cudaStream_t s) {
+  const long long blocks = (rows + 255) / 256;
+  k_colsum<<<static_cast<unsigned>(blocks < 592 ? blocks : 592), 256, 0, s>>>(src, dst, rows, cols);
+  DMIP_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return DMIP_OK;
 }
 
@@ -1126,6 +1147,118 @@ int launch_loss(const DmipLoss* q, cudaStream_t s) {
     if ((rc = run_pass(F.cg, F.pg, ws, s))) return rc;
   }
   return run_pass(F.c, F.p, ws, s);
+}
+
+// ------------------------------------------------------------------------------------------------ plain net forward / backward
+namespace {
+
+int mlp_grad_plan(const DmipMlpGrad* q, PassCfg* c, LossPlan* p) {
+  DMIP_REQUIRE(q != nullptr && q->n >= 0, "descriptor is NULL or n < 0");
+  DMIP_REQUIRE(q->x_dim >= 1 && q->cond_dim >= 0 && q->x_dim + q->cond_dim + 1 == q->net.in_dim,
+               "Input Tensor is expected to be 2D with x_dim+cond_dim+1 = %d columns (net.in_dim = %d)",
+               q->x_dim + q->cond_dim + 1, q->net.in_dim);
+  int rc = check_net(q->net, q->net.in_dim, "net");
+  if (rc) return rc;
+  *c = PassCfg{};
+  c->net = &q->net;
+  c->xdim = q->x_dim; c->ydim = q->cond_dim; c->d = q->x_dim; c->cdim = q->cond_dim;
+  c->post = 4;
+  c->kind = DMIP_LOSS_DSM; c->model = DMIP_CDE;
+  c->batch = q->n; c->batch_global = q->n;
+  c->x = q->x; c->y = q->cond; c->t = q->t;
+  if ((rc = plan_pass(*c, p))) return rc;
+  DMIP_REQUIRE(p->tcl.use || q->n == 0, "dmip_mlp_forward_stash serves [in <= 64] -> 512 -> 512 -> 512 -> [out <= 64] nets "
+               "(tcgen05 kernels); use the module's own autograd for other shapes");
+  return DMIP_OK;
+}
+
+void mlp_grad_dev(const DmipMlpGrad* q, const PassCfg& c, const LossPlan& p, TclDev* D) {
+  const TclPlan& t = p.tcl;
+  uint8_t* ws = static_cast<uint8_t*>(q->workspace);
+  const DmipMlp& net = q->net;
+  *D = TclDev{};
+  D->stages_fwd = ws + t.off_stages_fwd;
+  D->stages_bwd = ws + t.off_stages_bwd;
+  long long off = 0;
+  int k = net.in_dim;
+  for (int l = 0; l < 4; ++l) {
+    D->W[l] = net.W[l];
+    D->b[l] = net.b[l];
+    off += static_cast<long long>(net.width[l]) * k;
+    D->off_b[l] = off;
+    off += net.width[l];
+    k = net.width[l];
+    for (int h = 0; h < 2; ++h) {
+      D->in_img[l][h] = ws + t.off_in[l][h];
+      D->adj_img[l][h] = ws + t.off_adj[l][h];
+    }
+    if (l < 3) D->st[l] = reinterpret_cast<float*>(ws + t.off_st[l]);
+  }
+  D->in_dim = net.in_dim; D->out_dim = net.out_dim;
+  D->k0steps_fwd = (net.in_dim + 15) / 16;
+  D->k0steps_bwd = (net.out_dim + 15) / 16;
+  D->xdim = c.xdim; D->ydim = c.ydim; D->d = c.d; D->cdim = c.cdim; D->post = 4;
+  D->B = c.batch; D->inv_B = 1.f;
+  D->x = c.x; D->y = c.y; D->t = c.t;
+  D->n_tiles_fwd = t.n_tiles_fwd; D->n_tiles_bwd = t.n_tiles_bwd;
+}
+
+int mlp_grad_check_ws(const DmipMlpGrad* q, const LossPlan& p) {
+  if (!q->workspace || q->workspace_bytes < p.bytes || (reinterpret_cast<uintptr_t>(q->workspace) & 1023)) {
+    set_error("workspace too small or not 1024-byte aligned: need %zu bytes", p.bytes);
+    return DMIP_EWORKSPACE;
+  }
+  return DMIP_OK;
+}
+
+}  // namespace
+
+size_t mlp_grad_workspace(const DmipMlpGrad* q) {
+  PassCfg c;
+  LossPlan p;
+  if (mlp_grad_plan(q, &c, &p) || !p.tcl.use) return 0;
+  return p.bytes;
+}
+
+int launch_mlp_forward_stash(const DmipMlpGrad* q, cudaStream_t s) {
+  PassCfg c;
+  LossPlan p;
+  int rc = mlp_grad_plan(q, &c, &p);
+  if (rc) return rc;
+  if (q->n == 0) return DMIP_OK;
+  DMIP_REQUIRE(q->x && q->t && q->out && (q->cond || q->cond_dim == 0), "x / cond / t / out is NULL");
+  if ((rc = mlp_grad_check_ws(q, p))) return rc;
+  TclDev D;
+  mlp_grad_dev(q, c, p, &D);
+  D.net_out = q->out;
+  // the forward never touches grad / losses in this mode, but its epilogue addresses them unconditionally at the end:
+  // point them at scratch inside the (not yet used) adjoint image of the output layer
+  D.grad = reinterpret_cast<float*>(D.adj_img[0][0]);
+  D.losses = reinterpret_cast<float*>(D.adj_img[0][1]);
+  for (int l = 0; l < 4; ++l) D.off_b[l] = 0;
+  if ((rc = tcl_launch_pack(D, s))) return rc;      // both images: the backward must see the weights of THIS forward
+  return tcl_launch_fwd(D, s);
+}
+
+int launch_mlp_backward(const DmipMlpGrad* q, cudaStream_t s) {
+  PassCfg c;
+  LossPlan p;
+  int rc = mlp_grad_plan(q, &c, &p);
+  if (rc) return rc;
+  DMIP_REQUIRE(q->grad_params != nullptr, "grad_params is NULL");
+  DMIP_CHECK_CUDA(cudaMemsetAsync(q->grad_params, 0, loss_grad_floats(&q->net) * sizeof(float), s));
+  if (q->n == 0) return DMIP_OK;
+  DMIP_REQUIRE(q->grad_out != nullptr, "grad_out is NULL");
+  if ((rc = mlp_grad_check_ws(q, p))) return rc;
+  TclDev D;
+  mlp_grad_dev(q, c, p, &D);
+  D.abar = const_cast<float*>(q->grad_out);
+  D.grad = q->grad_params;
+  D.grad_in = q->grad_in;
+  if ((rc = tcl_launch_bwd(D, s))) return rc;
+  if ((rc = tcl_launch_wgrad(D, s))) return rc;
+  // d / d b_3 = column sums of grad_out (the loss kernels get it from their own loss stage): one small reduction
+  return launch_colsum(q->grad_out, q->grad_params + (loss_grad_floats(&q->net) - q->net.out_dim), q->n, q->net.out_dim, s);
 }
 
 size_t posterior_loss_workspace(const DmipPosteriorLoss* q) {

@@ -346,7 +346,12 @@ __device__ __forceinline__ void fwd_build_input(const TclDev& P, long long tile,
     const long long smp = tile * (2 * C::SPW) + w * C::SPW + j;
     float v = 0.f;
     const bool live = tile_ok && j < C::SPW && smp < P.B && k < P.in_dim;
-    if (live) {
+    if (live && P.post == 4) {
+      // plain net forward: cat[x, cond, t] as given (nets.py:32-35, :52-57)
+      if (k < P.xdim) v = P.x[smp * P.xdim + k];
+      else if (k < P.xdim + P.ydim) v = P.y[smp * P.ydim + (k - P.xdim)];
+      else v = P.t[smp];
+    } else if (live) {
       const float tt = P.t[smp];
       float beta, alpha, var;
       vp_terms(tt, P.bmin, P.bmax, beta, alpha, var);
@@ -500,7 +505,11 @@ __device__ __forceinline__ void fwd_loss_stage(const TclDev& P, long long s0, bo
     const int sl = idx / od, j = idx - sl * od;
     const long long smp = s0 + sl;
     float l_dsm = 0.f, l_ic = 0.f, l_pde = 0.f;
-    if (idx < n_items && tile_ok && smp < P.B) {
+    if (idx < n_items && tile_ok && smp < P.B && P.post == 4) {
+      // plain net forward (dmip_mlp_forward_stash): the staged outputs are the result
+      const int row0 = (sl / C::SPW) * kWin + (sl % C::SPW) * C::NS;
+      P.net_out[smp * od + j] = outs[row0 * od + j];
+    } else if (idx < n_items && tile_ok && smp < P.B) {
       const int row0 = (sl / C::SPW) * kWin + (sl % C::SPW) * C::NS;
       const float* o = outs + row0 * od;             // o[stream * od + component]
       float beta, alpha, var;
@@ -845,7 +854,9 @@ __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, 
   }
 }
 
-template <class C>
+// kGradIn: a fourth GEMM, xbar = zbar_0 W0 (A = W0^T, one 128-row chunk of input columns), gives the gradient w.r.t. the
+// net's inputs (dmip_mlp_backward; the losses do not need it: grad_x of the Score-FPE term is a constant).
+template <class C, bool kGradIn>
 __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__ TclDev P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Bars B = make_bars(smem);
@@ -861,9 +872,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
   if (warp >= kNumRowWarps) {
     reg_dealloc<kRegsSmall>();
     if (warp == kProducerWarp) {
-      tcl_producer(keep(P.stages_bwd), kTclBwdStages, tile_first, n_tiles, tile_stride, smem + kOffW, B, crank, cmask);
+      tcl_producer(keep(P.stages_bwd), kGradIn ? kTclBwdStagesIn : kTclBwdStages, tile_first, n_tiles, tile_stride,
+                   smem + kOffW, B, crank, cmask);
     } else if (warp == kMmaWarp) {
-      tcl_issuer<3, 4>(keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
+      if (kGradIn) tcl_issuer<4, 1>(keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
+      else tcl_issuer<3, 4>(keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
     }
   } else {
     reg_alloc<kRegsRow>();
@@ -901,9 +914,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
         const uint32_t t0 = lane_taddr + set * 256u + static_cast<uint32_t>(c_first * kNR + w * kWin);
         bsum[g][0] += bwd_math<C>(P, t0, tile, tile_ok, w, pre, v);
         bwd_prefetch<C>(P, L, k1, tile, w, pre);
-        bwd_store<C>(P, L, L != 0, k0, tile, tile_ok, w, v, smem, &B.hready[c_first], lane);
+        bwd_store<C>(P, L, L != 0 || kGradIn, k0, tile, tile_ok, w, v, smem, &B.hready[c_first], lane);
         bsum[g][1] += bwd_math<C>(P, t0 + 2 * kNR, tile, tile_ok, w, pre, v);
-        bwd_store<C>(P, L, L != 0, k1, tile, tile_ok, w, v, smem, &B.hready[c_first + 2], lane);
+        bwd_store<C>(P, L, L != 0 || kGradIn, k1, tile, tile_ok, w, v, smem, &B.hready[c_first + 2], lane);
         if (g == 1 && tb + tile_stride < n_tiles) {
           const int nt = tb + tile_stride + static_cast<int>(crank);
           bwd_build_input<C>(P, nt, nt < n_tiles, smem + kOffIn, t);
@@ -911,6 +924,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(B.in_ready);
         }
+      }
+      if (kGradIn) {
+        // ---- gradient w.r.t. the inputs: accumulator chunk 0 = (input column, row); rows are samples (one adjoint stream)
+        const uint32_t set = gc & 1u;
+        ++gc;
+        mbar_wait(&B.acc_full[set], (par >> set) & 1u, 0xD10 + set);
+        par ^= 1u << set;
+        tc_fence_after();
+        if (c_first == 0 && q * 32 < P.in_dim) {
+          uint32_t v[32];
+          tmem_ld32(lane_taddr + set * 256u + static_cast<uint32_t>(w * kWin), v);
+          tc_wait_ld();
+          const int k = q * 32 + lane;
+          if (k < P.in_dim && tile_ok) {
+#pragma unroll
+            for (int r = 0; r < kWin; ++r) {
+              const long long smp = tile * kNR + w * kWin + r;
+              if (smp < P.B) P.grad_in[smp * P.in_dim + k] = __uint_as_float(v[r]);
+            }
+          }
+        }
+        tc_fence_before();
+        // the next tile's first epilogue overwrites the activation region this GEMM read: it has retired (acc_full)
       }
     }
 #pragma unroll
@@ -1063,7 +1099,7 @@ __global__ void __launch_bounds__(256) k_tcl_pack(const __grid_constant__ TclDev
   if (st < 8) { g = 0; c = st >> 1; kb = 0; part = st & 1; }
   else if (st < 72) { g = 1; const int i = st - 8; kb = i >> 3; c = (i >> 1) & 3; part = i & 1; }
   else if (st < 136) { g = 2; const int i = st - 72; kb = i >> 3; c = (i >> 1) & 3; part = i & 1; }
-  else { g = 3; const int i = st - 136; kb = i >> 1; c = 0; part = i & 1; }
+  else { g = 3; const int i = st - 136; kb = i >> 1; c = 0; part = i & 1; }   // forward: W3; backward: W0^T (input gradient)
   for (int e = threadIdx.x; e < 128 * 64; e += 256) {
     const int r = e >> 6, kk = e & 63;
     const int m = c * 128 + r, k = kb * 64 + kk;
@@ -1076,6 +1112,7 @@ __global__ void __launch_bounds__(256) k_tcl_pack(const __grid_constant__ TclDev
     } else {
       // backward: A = W^T: M = input feature m of the layer, K = its output feature k (GEMM 0: W3^T, 1: W2^T, 2: W1^T)
       if (g == 0) { if (k < P.out_dim) v = P.W[3][static_cast<size_t>(k) * 512 + m]; }
+      else if (g == 3) { if (m < P.in_dim) v = P.W[0][static_cast<size_t>(k) * P.in_dim + m]; }   // W0^T: M = input column
       else v = P.W[3 - g][static_cast<size_t>(k) * 512 + m];
     }
     unsigned short hi, lo;
@@ -1090,7 +1127,7 @@ bool g_tcl_ready[64] = {};
 template <class C>
 int set_attr() {
   DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tcl_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tcl_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  DMIP_CHECK_CUDA(cudaFuncSetAttribute((k_tcl_bwd<C, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   return DMIP_OK;
 }
 
@@ -1110,6 +1147,7 @@ int tcl_init() {
 #define X(i, t, n, q) if ((rc = set_attr<Cfg<i, t, n, q>>())) return rc;
     DMIP_TCL_CONFIGS(X)
 #undef X
+    DMIP_CHECK_CUDA(cudaFuncSetAttribute((k_tcl_bwd<Cfg<0, 0, 0, 0>, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tcl_wgrad<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem(256)));
     DMIP_CHECK_CUDA(cudaFuncSetAttribute(k_tcl_wgrad<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem(64)));
     if (dev >= 0 && dev < 64) g_tcl_ready[dev] = true;
@@ -1150,10 +1188,10 @@ bool tcl_streams_supported(const TclStreams& s) {
   return false;
 }
 
-size_t tcl_image_bytes() { return static_cast<size_t>(kTclFwdStages + kTclBwdStages) * kStage; }
+size_t tcl_image_bytes() { return static_cast<size_t>(kTclFwdStages + kTclBwdStagesIn) * kStage; }
 
 int tcl_launch_pack(const TclDev& P, cudaStream_t s) {
-  k_tcl_pack<<<kTclFwdStages + kTclBwdStages, 256, 0, s>>>(P);
+  k_tcl_pack<<<kTclFwdStages + kTclBwdStagesIn, 256, 0, s>>>(P);
   DMIP_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DMIP_OK;
@@ -1173,8 +1211,13 @@ int tcl_launch_fwd(const TclDev& P, cudaStream_t s) {
 int tcl_launch_bwd(const TclDev& P, cudaStream_t s) {
   int rc = tcl_init();
   if (rc) return rc;
+  if (P.grad_in != nullptr) {
+    DMIP_REQUIRE(P.has_I == 0 && P.has_T == 0 && P.n_tan == 0, "input gradients are computed for the plain net pass only");
+    return launch_clustered(k_tcl_bwd<Cfg<0, 0, 0, 0>, true>, P.n_tiles_bwd, P, s);
+  }
 #define X(i, t, n, q) \
-  if (P.has_I == i && P.has_T == t && P.n_tan == n && P.has_Q == q) return launch_clustered(k_tcl_bwd<Cfg<i, t, n, q>>, P.n_tiles_bwd, P, s);
+  if (P.has_I == i && P.has_T == t && P.n_tan == n && P.has_Q == q) \
+    return launch_clustered(k_tcl_bwd<Cfg<i, t, n, q>, false>, P.n_tiles_bwd, P, s);
   DMIP_TCL_CONFIGS(X)
 #undef X
   set_error("tcgen05 loss path: stream configuration not compiled in");

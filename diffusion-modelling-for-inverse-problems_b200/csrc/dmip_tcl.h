@@ -15,6 +15,7 @@ constexpr int kTclWin = 32;         // rows per epilogue window (one tcgen05.ld 
 constexpr int kTclStage = 16384;    // one weight stage: 128 features x 64 k, bf16, K-major, 128-byte swizzle
 constexpr int kTclFwdStages = 8 + 64 + 64 + 16;   // hi/lo stages of W0 | W1 | W2 | W3 in consumption order
 constexpr int kTclBwdStages = 8 + 64 + 64;        // W3^T | W2^T | W1^T
+constexpr int kTclBwdStagesIn = kTclBwdStages + 16;   // ... | W0^T: the input-gradient GEMM of dmip_mlp_backward
 constexpr int kTclSmallF = 64;      // feature count of the narrow stash images (layer-0 inputs, output-layer adjoints)
 
 // stream configuration of one pass: which jets ride along with the primal P (dmip_loss.cu header)
@@ -29,7 +30,7 @@ struct TclStreams {
 struct TclDev {
   // ---- net: [in_dim] -> 512 -> 512 -> 512 -> [out_dim]
   const uint8_t* stages_fwd;   // kTclFwdStages x 16 KB
-  const uint8_t* stages_bwd;   // kTclBwdStages x 16 KB
+  const uint8_t* stages_bwd;   // kTclBwdStagesIn x 16 KB (the last 16 are consumed only when grad_in is set)
   const float* W[4];           // original fp32 weights (pack kernel input)
   const float* b[4];
   int in_dim, out_dim;
@@ -51,6 +52,9 @@ struct TclDev {
   uint8_t* adj_img[4][2];      // ADJ_l hi/lo: adjoints of layer l pre-activations (l = 3: F = 64, else F = 512)
   float* st[3];                // [B][n_adj][512] fp32 state of hidden layer l the backward epilogue needs, one slot per
                                // adjoint stream: P: phi'(z_P) | I: phi'(z_I) | T: phi''(z_P) * zd_T (the T -> P coupling)
+  // ---- plain net forward / backward (dmip_mlp_forward_stash / dmip_mlp_backward): post == 4
+  float* net_out;              // forward: (B, out_dim) net outputs; inputs are x (B, xdim) | y = cond (B, ydim) | t (B,) as they are
+  float* grad_in;              // backward: (B, in_dim) gradient w.r.t. the concatenated inputs, or NULL
   float* grad;                 // flat gradient [W_0, b_0, W_1, b_1, ...] (bias sums are added here by the kernels)
   long long off_b[4];          // float offset of b_l inside grad
   long long n_tiles_fwd, n_tiles_bwd;

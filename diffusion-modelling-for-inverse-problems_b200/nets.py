@@ -5,8 +5,10 @@ and its numerics: tanh is applied twice after the first Linear, because the refe
 second time under the name 'act' and `nn.Sequential.forward` walks every registered module.  That is
 reproduced here on purpose so reference checkpoints (`current_model.pt`, `diffusion.pt`) load and behave identically.
 
-`forward` on CUDA tensors without autograd runs the fused kernels of libdmip_sm100.so (`dmip_mlp_forward`);
-when autograd is recording it runs the plain module chain so `loss.backward()` of user-written losses keeps working.
+`forward` on CUDA tensors without autograd runs the fused kernels of libdmip_sm100.so (`dmip_mlp_forward`); when
+autograd is recording it runs `dmip_mlp_forward_stash` and registers `dmip_mlp_backward` as its backward (tcgen05 kernels,
+first-order: parameter and input gradients), so `loss.backward()` of user-written losses runs on the library too; nets
+outside the shapes those kernels serve fall back to the torch module chain with a RuntimeWarning.
 `GaussianFourierProjection` / `TemporalMLP*` of the reference are unused by every model (nets.py:62-63) and omitted.
 """
 import ctypes as C
@@ -18,6 +20,89 @@ from torch import nn
 from . import _lib
 
 _WARNED_EAGER = [False]
+
+
+class DmipMlpGrad(C.Structure):
+    _fields_ = [("net", _lib.DmipMlp), ("n", C.c_int64), ("x_dim", C.c_int32), ("cond_dim", C.c_int32),
+                ("x", C.c_void_p), ("cond", C.c_void_p), ("t", C.c_void_p), ("out", C.c_void_p),
+                ("grad_out", C.c_void_p), ("grad_params", C.c_void_p), ("grad_in", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+def _bind_grad():
+    L = _lib.require_gpu()
+    if not getattr(L, "_mlp_grad_bound", False):
+        L.dmip_mlp_grad_workspace_bytes.restype = C.c_size_t
+        L.dmip_mlp_grad_workspace_bytes.argtypes = [C.POINTER(DmipMlpGrad)]
+        L.dmip_mlp_forward_stash.restype = C.c_int
+        L.dmip_mlp_forward_stash.argtypes = [C.POINTER(DmipMlpGrad), C.c_void_p]
+        L.dmip_mlp_backward.restype = C.c_int
+        L.dmip_mlp_backward.argtypes = [C.POINTER(DmipMlpGrad), C.c_void_p]
+        L.dmip_loss_grad_floats.restype = C.c_size_t
+        L.dmip_loss_grad_floats.argtypes = [C.POINTER(_lib.DmipMlp)]
+        L._mlp_grad_bound = True
+    return L
+
+
+def _grad_desc(net, x, cond, t, keep):
+    d = DmipMlpGrad()
+    d.net = _lib.mlp_desc(net, keep)
+    d.n = x.shape[0]
+    d.x_dim = x.shape[1]
+    d.x, d.t = x.data_ptr(), t.data_ptr()
+    if cond is not None:
+        d.cond_dim = cond.shape[1]
+        d.cond = cond.data_ptr()
+    return d
+
+
+class _MlpFn(torch.autograd.Function):
+    """a(x, cond, t) with a backward on the library's own kernels (`dmip_mlp_forward_stash` / `dmip_mlp_backward`,
+    include/dmip.h): what `loss.backward()` of a user-written loss runs instead of torch's addmm / tanh chain.
+    First-order only — the reference's double-backward losses (losses.py:14-26) are the fused PINNLoss / DSM_PDELoss."""
+
+    @staticmethod
+    def forward(ctx, net, x, cond, t, *params):
+        L = _bind_grad()
+        keep = [x, cond, t]
+        d = _grad_desc(net, x, cond, t, keep)
+        out = torch.empty(x.shape[0], net.output_dim, device=x.device, dtype=torch.float32)
+        d.out = out.data_ptr()
+        nbytes = L.dmip_mlp_grad_workspace_bytes(C.byref(d))
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
+        d.workspace = (ws.data_ptr() + 1023) & ~1023
+        d.workspace_bytes = nbytes
+        with torch.cuda.device(x.device):
+            _lib.check(L.dmip_mlp_forward_stash(C.byref(d), _lib.stream_ptr()))
+        ctx.d, ctx.keep, ctx.ws = d, keep, ws
+        ctx.shapes = [p.shape for p in params]
+        ctx.dims = (x.shape[1], 0 if cond is None else cond.shape[1])
+        net.last_launch_count = L.dmip_last_launch_count()
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        L = _bind_grad()
+        d = ctx.d
+        gout = gout.contiguous().float()
+        dev = gout.device
+        flat = torch.empty(L.dmip_loss_grad_floats(C.byref(d.net)), device=dev, dtype=torch.float32)
+        need_in = any(ctx.needs_input_grad[1:4])
+        gin = torch.empty(gout.shape[0], d.net.in_dim, device=dev, dtype=torch.float32) if need_in else None
+        d.grad_out, d.grad_params = gout.data_ptr(), flat.data_ptr()
+        d.grad_in = gin.data_ptr() if need_in else None
+        with torch.cuda.device(dev):
+            _lib.check(L.dmip_mlp_backward(C.byref(d), _lib.stream_ptr()))
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            grads.append(flat[off:off + shp.numel()].view(shp))
+            off += shp.numel()
+        xd, cd = ctx.dims
+        gx = gin[:, :xd] if need_in and ctx.needs_input_grad[1] else None
+        gc = gin[:, xd:xd + cd] if need_in and cd and ctx.needs_input_grad[2] else None
+        gt = gin[:, xd + cd:].reshape(ctx.keep[2].shape) if need_in and ctx.needs_input_grad[3] else None
+        return (None, gx, gc, gt, *grads)
 
 
 class _ScoreMLP(nn.Sequential):
@@ -76,6 +161,22 @@ class _ScoreMLP(nn.Sequential):
             _lib.check(L.dmip_mlp_forward(C.byref(d), _lib.stream_ptr()))
         return out
 
+    def _autograd_fused(self, x, cond, t):
+        """Autograd through the library's own kernels (forward with stash + backward), or None when the net's shape is
+        outside what they serve."""
+        L = _bind_grad()
+        if x.shape[0] == 0:
+            return None
+        xx = x.float().contiguous()
+        cc = None if cond is None or cond.numel() == 0 else cond.float().contiguous()
+        tt = t.float().reshape(-1).contiguous()
+        assert tt.numel() == xx.shape[0], 'Input Tensor is expected to be 2D with shape (batch_size, xdim+ydim+1)'
+        probe = _grad_desc(self, xx.detach(), None if cc is None else cc.detach(), tt.detach(), [])
+        if L.dmip_mlp_grad_workspace_bytes(C.byref(probe)) == 0:
+            return None
+        params = [p for lin in _lib.linear_layers(self) for p in (lin.weight, lin.bias)]
+        return _MlpFn.apply(self, xx, cc, tt, *params)
+
     def invalidate_packed(self):
         """Drop the cached tcgen05 weight image (needed only after writes through `p.data`, see _lib.PackedNet)."""
         self._packed.invalidate()
@@ -88,13 +189,14 @@ class _ScoreMLP(nn.Sequential):
             return self._fused(x, cond, t)
         if not x.is_cuda:
             raise RuntimeError("dmip score nets run on CUDA (sm_100a) only: there is no CPU fallback")
+        fused = self._autograd_fused(x, cond, t)
+        if fused is not None:
+            return fused
         if not _WARNED_EAGER[0]:
             _WARNED_EAGER[0] = True
-            warnings.warn("dmip: autograd is recording through MLP.forward — this call runs the plain torch module chain "
-                          "(cuBLAS addmm), not the fused sm_100a kernels.  The fused kernels serve the no-grad calls "
-                          "(sampler, evaluation) and the fused losses (DSMLoss via train_epoch, PINNLoss, DSM_PDELoss, "
-                          "PosteriorLoss), which carry their own backward; wrap inference in torch.no_grad().",
-                          RuntimeWarning, stacklevel=3)
+            warnings.warn("dmip: autograd is recording through MLP.forward of a net the tcgen05 kernels do not serve (they take "
+                          "[in <= 64] -> 512 -> 512 -> 512 -> [out <= 64]) — this call runs the plain torch module chain "
+                          "(cuBLAS addmm), not the fused sm_100a kernels.", RuntimeWarning, stacklevel=3)
         parts = [x] + ([cond] if cond is not None and cond.numel() > 0 else []) + [t.view(len(x), 1)]
         inp = torch.cat(parts, dim=1)
         assert inp.ndim == 2, 'Input Tensor is expected to be 2D with shape (batch_size, xdim+ydim+1)'

@@ -150,6 +150,33 @@ typedef struct DmipForward {
 size_t dmip_forward_workspace_bytes(const DmipForward* d);
 int dmip_mlp_forward(const DmipForward* d, void* stream);
 
+/* ---- score-net forward WITH a backward: autograd support for user-written losses --------------------------------
+ * dmip_mlp_forward_stash evaluates a(x, cond, t) like dmip_mlp_forward and keeps, in the caller's workspace, what the
+ * backward needs; dmip_mlp_backward turns a gradient w.r.t. the outputs into the flat parameter gradient
+ * [W_0, b_0, W_1, b_1, ...] and (optionally) the gradient w.r.t. the concatenated inputs cat[x, cond, t] — what
+ * `out.backward()` does through nets.py:32-35 / :52-57 upstream.  tcgen05 kernels, bf16x3 split products (fp32-level
+ * accuracy); nets [in <= 64] -> 512 -> 512 -> 512 -> [out <= 64] only (dmip_mlp_grad_workspace_bytes returns 0 otherwise and
+ * the Python layer falls back to the plain torch module chain with a warning).  The same descriptor (same workspace,
+ * untouched in between) must be passed to both calls; first-order derivatives only. */
+typedef struct DmipMlpGrad {
+  DmipMlp net;
+  int64_t n;
+  int32_t x_dim, cond_dim;
+  const float* x;          /* device (n, x_dim)                       */
+  const float* cond;       /* device (n, cond_dim) or NULL            */
+  const float* t;          /* device (n,)                             */
+  float* out;              /* forward:  device (n, out_dim)           */
+  const float* grad_out;   /* backward: device (n, out_dim)           */
+  float* grad_params;      /* backward: device float[dmip_loss_grad_floats(net)], overwritten */
+  float* grad_in;          /* backward: device (n, in_dim) or NULL    */
+  void* workspace;         /* device, dmip_mlp_grad_workspace_bytes(), 1024-byte aligned; lives from forward to backward */
+  size_t workspace_bytes;
+} DmipMlpGrad;
+
+size_t dmip_mlp_grad_workspace_bytes(const DmipMlpGrad* d);
+int dmip_mlp_forward_stash(const DmipMlpGrad* d, void* stream);
+int dmip_mlp_backward(const DmipMlpGrad* d, void* stream);
+
 /* ---- fused score-training losses: forward + backward in one call -------------------------------------------
  * Replaces, per batch, the body of CDE/CDiffE.train_epoch (models/diffusion.py:80-88, :129-139) up to and including
  * loss.backward(): VariancePreservingSDE.sample with the Gaussian draw `eps` supplied by the caller, the net

@@ -1190,10 +1190,58 @@ def case_boundary_deviations():
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         tt = t.clone().requires_grad_(True)
-        out = m.sde.a(x, y, tt)
+        out = m.sde.a(x, y, tt)                     # [512,512,512]: autograd on the library's own kernels, no warning
         out.sum().backward()
-        ok = ok and any("autograd is recording" in str(i.message) for i in w) and tt.grad is not None
+        ok = ok and not w and tt.grad is not None
+        small = dnets.MLP(5, 2, [64, 64], torch.nn.Tanh()).to(DEV)      # other widths: torch module chain, says so
+        small(x, y, t.clone().requires_grad_(True)).sum().backward()
+        ok = ok and any("autograd is recording" in str(i.message) for i in w)
     opt = torch.optim.SGD(m.sde.a.parameters(), lr=0.0)
     dd.train_step_data_parallel(m, opt, loss_fn, x, y, t)
     ok = ok and getattr(loss_fn, "batch_global", 0) == 0 and getattr(loss_fn, "grad_out", None) is None
     return (0.0 if ok else 1.0), 0.5, {}
+
+
+# ------------------------------------------------------------------------------------------- autograd through the score net
+def case_mlp_autograd(which):
+    """`loss.backward()` of a user-written loss through MLP / MLP2.forward: the library's own forward-with-stash and
+    backward kernels (dmip_mlp_forward_stash / dmip_mlp_backward, tcgen05, bf16x3) against torch's autograd through the
+    plain module chain in fp64: outputs 2e-5 of their scale, every parameter gradient and the gradients w.r.t. x, y and t
+    3e-4 of theirs.  Ragged batch (tile tail + masked cluster CTA)."""
+    from dmip import nets as dnets
+    torch.manual_seed(1)
+    n = 333
+    if which == "cde_linear":
+        net, xd, cd = dnets.MLP(5, 2, [512, 512, 512], torch.nn.Tanh()), 2, 2
+    elif which == "cdiffe_scat":
+        net, xd, cd = dnets.MLP(27, 26, [512, 512, 512], torch.nn.Tanh()), 26, 0
+    else:
+        net, xd, cd = dnets.MLP2(4, 3, [512, 512, 512], torch.nn.Tanh()), 3, 0
+    net.to(DEV)
+    x = torch.randn(n, xd, device=DEV, requires_grad=True)
+    y = torch.randn(n, cd, device=DEV, requires_grad=True) if cd else None
+    t = torch.rand(n, 1, device=DEV, requires_grad=True)
+    wgt = torch.randn(n, net.output_dim, device=DEV)
+
+    def call(mod, xx, yy, ttt):
+        if which == "mlp2":
+            return mod(xx, ttt)
+        return mod(xx, yy if yy is not None else torch.Tensor([]).to(DEV), ttt)
+
+    out = call(net, x, y, t)
+    (out * wgt).sum().backward()
+    got = [out.detach()] + [p.grad.clone() for p in net.parameters()] + [v.grad.clone() for v in (x, y, t) if v is not None]
+    # fp64 reference through the plain module chain
+    import copy
+    ref_net = copy.deepcopy(net).double()
+    xr, tr = x.detach().double().requires_grad_(True), t.detach().double().requires_grad_(True)
+    yr = y.detach().double().requires_grad_(True) if cd else None
+    parts = [xr] + ([yr] if cd else []) + [tr]
+    ro = torch.nn.Sequential.forward(ref_net, torch.cat(parts, 1))
+    (ro * wgt.double()).sum().backward()
+    ref = [ro.detach()] + [p.grad for p in ref_net.parameters()] + [v.grad for v in (xr, yr, tr) if v is not None]
+    worst = 0.0
+    for i, (a, b) in enumerate(zip(got, ref)):
+        e = ((a.double() - b).abs().max() / b.abs().max()).item()
+        worst = max(worst, e / (2e-5 if i == 0 else 3e-4))
+    return worst, 1.0, {}

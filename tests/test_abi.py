@@ -68,8 +68,8 @@ def _sizeof_from_c(struct_names):
 
 def test_ctypes_struct_layouts_match_the_header():
     """The header is plain C (compiles with gcc -std=c99) and the Python mirrors have identical sizes."""
-    from dmip import _lib, losses, mcmc, metrics, posterior, utils_scatterometry
-    mirrors = {"DmipMlp": _lib.DmipMlp, "DmipSampler": _lib.DmipSampler, "DmipForward": _lib.DmipForward,
+    from dmip import _lib, losses, mcmc, metrics, nets, posterior, utils_scatterometry
+    mirrors = {"DmipMlpGrad": nets.DmipMlpGrad, "DmipMlp": _lib.DmipMlp, "DmipSampler": _lib.DmipSampler, "DmipForward": _lib.DmipForward,
                "DmipLoss": losses.DmipLoss, "DmipPosteriorLoss": posterior.DmipPosteriorLoss,
                "DmipSurrogate": utils_scatterometry.DmipSurrogate, "DmipHistogram": metrics.DmipHistogram,
                "DmipMetropolis": mcmc.DmipMetropolis}

@@ -81,3 +81,8 @@ def test_kernels_stay_inside_their_buffers():
 
 def test_documented_boundary_deviations():
     _ok(gc.case_boundary_deviations())
+
+
+@pytest.mark.parametrize("which", ["cde_linear", "cdiffe_scat", "mlp2"])
+def test_autograd_through_the_score_net_runs_on_the_library_kernels(which):
+    _ok(gc.case_mlp_autograd(which))
