@@ -227,5 +227,6 @@ def tc_supported(net, n_varying=None, split=2):
     if not (len(layers) == 4 and all(l.out_features == 512 for l in layers[:3]) and layers[-1].out_features <= 128):
         return False
     dv = layers[0].in_features if n_varying is None else n_varying
-    k0 = (split - 1) * ((dv + 7) // 8 * 8) + dv
+    parts = 1 if split == 4 else split               # l0_split = 4: one f16 part
+    k0 = (parts - 1) * ((dv + 7) // 8 * 8) + dv
     return (k0 + 15) // 16 * 16 <= 512

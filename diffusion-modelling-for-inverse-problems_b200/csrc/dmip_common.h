@@ -36,7 +36,8 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 // Geometry of the packed image of one [in]->512->512->512->[out] net for the tcgen05 path.
 struct TcNetGeom {
   int n_varying;   // dv: leading input columns that enter the layer-0 GEMM
-  int split;       // layer-0 operand split (1,2,3)
+  int split;       // layer-0 operand parts (1,2,3); l0_split = 4 (one part, f16 operands) is stored as split = 1, l0_f16 = 1
+  int l0_f16;      // layer 0 multiplies f16 x f16 (11 mantissa bits of the state for the MMA count of plain bf16)
   int dvp;         // part stride of the split operand: round_up(dv, 8)
   int k0;          // (split - 1) * dvp + dv
   int k0pad;       // k0 rounded up to 16

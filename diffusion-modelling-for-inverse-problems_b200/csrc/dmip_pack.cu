@@ -12,7 +12,9 @@ int tc_net_geom(const DmipMlp* net, int n_varying, int out_rows, int split, TcNe
   DMIP_REQUIRE(net->n_layers == 4 && net->width[0] == 512 && net->width[1] == 512 && net->width[2] == 512,
                "tcgen05 path needs hidden_layers == [512,512,512] (got %d layers, widths %d,%d,%d); use DMIP_PREC_F32",
                net->n_layers, net->width[0], net->width[1], net->width[2]);
-  DMIP_REQUIRE(split >= 1 && split <= 3, "l0_split must be 1, 2 or 3 (got %d)", split);
+  DMIP_REQUIRE(split >= 1 && split <= 4, "l0_split must be 1, 2, 3 or 4 (got %d)", split);
+  g->l0_f16 = split == 4 ? 1 : 0;
+  if (split == 4) split = 1;
   DMIP_REQUIRE(n_varying >= 1 && n_varying <= net->in_dim, "n_varying %d out of range (in_dim %d)", n_varying,
                net->in_dim);
   DMIP_REQUIRE(out_rows >= 1 && out_rows <= net->out_dim && out_rows <= 128,
@@ -36,7 +38,7 @@ namespace {
 struct PackParams {
   const float* W[4];
   const float* b[4];
-  int in_dim, dv, dvp, split, k0, kb0, out_rows, n_const, n_stages;
+  int in_dim, dv, dvp, split, l0_f16, k0, kb0, out_rows, n_const, n_stages;
   uint8_t* stages;
   float* tail;
 };
@@ -64,7 +66,7 @@ __global__ void k_pack(const PackParams p) {
         if (part < p.split && idx < p.dv) {
           // operand parts [x_hi | x_lo | x_hi] meet weight parts [W_hi | W_hi | W_lo]
           const float w = p.W[0][static_cast<size_t>(n) * p.in_dim + idx];
-          const float hi = bf16_round(w);
+          const float hi = p.l0_f16 ? w : bf16_round(w);
           v = (part == 2) ? (w - hi) : hi;
         }
       } else if (l < 3) {
@@ -73,7 +75,9 @@ __global__ void k_pack(const PackParams p) {
         v = p.W[3][static_cast<size_t>(r) * 512 + kg];
       }
 #ifndef DMIP_H_F16
-      const unsigned short h = static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xFFFFu);
+      // l0_split = 4: layer 0 is an f16 x f16 product (kind::f16 wants one format for both operands), |w| clamped to the f16 range
+      const unsigned short h = static_cast<unsigned short>(
+          ((l == 0 && p.l0_f16) ? pack_f16x2(fminf(fmaxf(v, -65504.f), 65504.f), 0.f) : pack_bf16x2(v, 0.f)) & 0xFFFFu);
 #else
       // layers 1-3 multiply f16 activations (tanh values): their weights are f16 too (kind::f16 wants one format for
       // both operands; 11 mantissa bits instead of 8, |w| clamped to the f16 range); layer 0 meets the bf16 hi/lo state
@@ -106,6 +110,7 @@ int launch_pack(const DmipMlp* net, const TcNetGeom& g, void* packed, cudaStream
   p.dv = g.n_varying;
   p.dvp = g.dvp;
   p.split = g.split;
+  p.l0_f16 = g.l0_f16;
   p.k0 = g.k0;
   p.kb0 = g.kb0;
   p.out_rows = g.out_rows;

@@ -54,6 +54,11 @@ constexpr int kCluster = 2;          // CTAs per cluster sharing one multicast w
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemH = 0;       // 256 columns: 128 x 512 bf16 activations (A operand)
 constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
+// l0_split = 4, CDE / DPS samplers: the f16 layer-0 operand (<= 128 k = 64 columns) sits in the LAST quarter of the
+// activation columns.  H1 / H3 chunk 3 overwrites them only after the layer's last MMA has retired, chunks 0-2 never touch
+// them, and the output layer (which reads all of H3) is complete before the next operand is written — so layer 0 runs
+// tensor-memory A operands (0.5 N + 13 cycles per instruction instead of 0.5 N + 46).
+constexpr uint32_t kTmemL0 = kTmemH + 192;
 
 // shared-memory map (offsets from the 1024-aligned dynamic shared memory base; 231.6 of the 232.4 KB a CTA may have)
 constexpr int kOffH = 0;
@@ -74,7 +79,8 @@ struct TcNetDev {
   const float* b2;
   const float* b3;
   const float* w0c;  // [512][n_const]
-  int kb0, ksteps0, dv, split, outpad, n_const, n_stages;
+  int kb0, ksteps0, dv, split, l0_f16, outpad, n_const, n_stages;
+  int l0_tmem;   // the (single f16 part) layer-0 operand lives in tensor memory, columns kTmemL0 .. (TS MMAs instead of SS)
 };
 
 struct TcParams {
@@ -265,9 +271,17 @@ __device__ __forceinline__ void a0_store(uint8_t* sH, int row, int k, float v) {
   const unsigned short h = static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xFFFFu);
   *reinterpret_cast<unsigned short*>(sH + off) = h;
 }
+// l0_split = 4: the layer-0 operand is ONE f16 part (11 mantissa bits; |x| clamped to the f16 range) — the MMA count of
+// plain bf16 with 8x its resolution of the state
+__device__ __forceinline__ float f16_clamp(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ void a0_store_f16(uint8_t* sH, int row, int k, float v) {
+  const uint32_t off = sw128_offset(static_cast<uint32_t>(row), static_cast<uint32_t>(k), kStageBytes);
+  *reinterpret_cast<unsigned short*>(sH + off) = static_cast<unsigned short>(pack_f16x2(f16_clamp(v), 0.f) & 0xFFFFu);
+}
 // element `idx` (of dv row-varying inputs) with value v, under the layer-0 split scheme; the parts of the split
 // operand start at multiples of dvp = round_up(dv, 8) so that 8 consecutive inputs are one 16-byte chunk
 __device__ __forceinline__ void a0_put(uint8_t* sH, int row, int idx, int dvp, int split, float v) {
+  if (split == 4) { a0_store_f16(sH, row, idx, v); return; }
   const float hi = bf16_round(v);
   a0_store(sH, row, idx, hi);
   if (split >= 2) a0_store(sH, row, dvp + idx, v - hi);
@@ -275,6 +289,13 @@ __device__ __forceinline__ void a0_put(uint8_t* sH, int row, int idx, int dvp, i
 }
 // eight consecutive inputs idx0 .. idx0+7 (idx0 % 8 == 0): one 16-byte swizzled store per split part
 __device__ __forceinline__ void a0_put8(uint8_t* sH, int row, int idx0, int dvp, int split, const float* v) {
+  uint8_t* rowp0 = sH + (row >> 3) * 1024 + (row & 7) * 128;
+  if (split == 4) {
+    st_shared_v4(rowp0 + (idx0 >> 6) * kStageBytes + ((((idx0 & 63) >> 3) ^ (row & 7)) << 4),
+                 pack_f16x2(f16_clamp(v[0]), f16_clamp(v[1])), pack_f16x2(f16_clamp(v[2]), f16_clamp(v[3])),
+                 pack_f16x2(f16_clamp(v[4]), f16_clamp(v[5])), pack_f16x2(f16_clamp(v[6]), f16_clamp(v[7])));
+    return;
+  }
   float hi[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) hi[e] = bf16_round(v[e]);
@@ -493,6 +514,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             const int net_kb0 = keep(P.net[p].kb0), net_ksteps0 = keep(P.net[p].ksteps0);
             const uint32_t idesc_out = umma_idesc_bf16(128, static_cast<uint32_t>(keep(P.net[p].outpad)));
             constexpr uint32_t idesc_hid = umma_idesc_bf16(128, 128);
+            const uint32_t idesc_l0 = keep(P.net[p].l0_f16) ? umma_idesc_f16(128, 128) : idesc_hid;
+            const bool net_l0_tmem = keep(P.net[p].l0_tmem) != 0;
             tl_mark(tl, 0xD00u);
             job_mark(tl, 0xD00u);
             mbar_wait(B.a0_ready, a0_par, 0x200);
@@ -516,10 +539,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                 const uint32_t a_lo = a_base + kb * kBlk16;
                 if (elect_one()) {
                   if (!(dbg & 2)) {
+                    if (net_l0_tmem) {
+                      const uint32_t a_tm = tmem_base + kTmemL0 + kb * 32;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                      if (kk < nk)
-                        umma_ss(d_tmem, desc_hi | (a_lo + kk * 2), desc_hi | (b_lo + kk * 2), idesc_hid, (kb | kk) != 0 ? 1u : 0u);
+                      for (int kk = 0; kk < 4; ++kk)
+                        if (kk < nk) umma_ts(d_tmem, a_tm + kk * 8, desc_hi | (b_lo + kk * 2), idesc_l0, (kb | kk) != 0 ? 1u : 0u);
+                    } else {
+#pragma unroll
+                      for (int kk = 0; kk < 4; ++kk)
+                        if (kk < nk)
+                          umma_ss(d_tmem, desc_hi | (a_lo + kk * 2), desc_hi | (b_lo + kk * 2), idesc_l0, (kb | kk) != 0 ? 1u : 0u);
+                    }
                   }
                   if (half == 1u) tc_commit_multicast(&B.empty[s], cmask);
                   if (kb == net_kb0 - 1) tc_commit(&B.acc_full[buf]);
@@ -596,6 +626,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x;    // 0..511: owner of hidden unit `et` of the effective layer-0 bias
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    if (P.net[0].l0_tmem && cgp == 0) {
+      // K padding of the tensor-memory layer-0 operand must be finite from the first step on (it meets zero weights)
+      const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) tmem_st16(lane_taddr + kTmemL0 + c0, z);
+      tc_wait_st();
+    }
+    asm volatile("bar.sync 2, 512;" ::: "memory");   // row warps only: zeros before any operand piece is written
     TlRole tl = tl_role(P, dbg, warp == 0 ? 2 : 3, lane == 0 && (warp == 0 || warp == 12));
     uint32_t job = 0;     // global job counter (13 per pass; accumulator buffer = job & 1)
     uint32_t npass = 0;   // running pass counter: layer-0 bias buffer, parity of the once-per-pass barriers
@@ -603,7 +641,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
     const SdeSched sch = {P.sde_kind, S, P.n_corr, P.T, P.bmin, P.bmax, P.snr, P.delta, P.sqrt_delta};
     const TcNetDev& net_last = P.net[n_pass - 1];
     const int dvp = (net_last.dv + 7) & ~7;
-    const int split = P.net[0].split;
+    const int split = P.net[0].l0_f16 ? 4 : P.net[0].split;   // 4: one f16 part (a0_put / a0_put8)
+    const bool l0_tmem = P.net[0].l0_tmem != 0;
     const bool sampler = (P.mode == kModeSampler);
     const int xdim = P.xdim;
     // state pieces (8 columns) of this row owned by this thread: [piece_lo, piece_lo + n_own)
@@ -673,7 +712,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
         for (int i = 0; i < kOwn; ++i) {
           if (i < n_own) {
             const int pc = piece_lo + i;
-            if (cdiffe) {   // the columns right after x hold y_t: touch only the x elements
+            if (l0_tmem) {   // one f16 part in tensor memory: 8 elements = 4 columns of this row's lane
+              const float* v = &xs[i * 8];
+              tmem_st4(lane_taddr + kTmemL0 + static_cast<uint32_t>(pc * 4),
+                       pack_f16x2(f16_clamp(v[0]), f16_clamp(v[1])), pack_f16x2(f16_clamp(v[2]), f16_clamp(v[3])),
+                       pack_f16x2(f16_clamp(v[4]), f16_clamp(v[5])), pack_f16x2(f16_clamp(v[6]), f16_clamp(v[7])));
+            } else if (cdiffe) {   // the columns right after x hold y_t: touch only the x elements
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if (pc * 8 + e < xdim) a0_put(sH, row, pc * 8 + e, dvp, split, xs[i * 8 + e]);
@@ -682,6 +726,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             }
           }
         }
+      };
+
+      // operand written: make it visible to the tensor core (shared-memory operand: async-proxy fence; tensor-memory
+      // operand: the stores have landed) and tell the issuer
+      auto publish_a0 = [&]() {
+        if (l0_tmem) {
+          tc_wait_st();
+          tc_fence_before();
+        } else {
+          fence_proxy_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.a0_ready);
       };
 
       // ---- tile init
@@ -735,9 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
           }
         }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(B.a0_ready);
+      publish_a0();
       tl_mark(tl, 0x500u);
 
       for (int step = 0; step < n_steps; ++step) {
@@ -854,11 +909,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
             sB0[et] = fmaf(tau_n, wt, u);
           }
           if (sampler) {
-            if (!last_pass) {
+            if (!last_pass && !l0_tmem) {
               put_x();   // DPS: same x for the likelihood net (H2 overwrote the operand)
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(B.a0_ready);
+              publish_a0();
             } else if (cdiffe && !last_step) {
               put_yt();
             }
@@ -890,6 +943,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               tc_wait_ld();
 #pragma unroll
               for (int e = 0; e < 8; ++e) stash[dps ? e : 0] = __uint_as_float(v[e]) + sB3[e];
+            }
+            if (l0_tmem) {   // the prior pass's output layer has read all of H3: its last columns take x again
+              put_x();
+              publish_a0();
             }
           } else {
             // CDE/CDiffE: mu = sqrt(beta) a + beta x / 2 (sdes.py:77-79, Q3);
@@ -934,9 +991,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
               }
             } else {
               put_x();   // next step's layer-0 operand
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(B.a0_ready);
+              publish_a0();
               tl_mark(tl, 0x500u);
               job_mark(tl, 0x500u);
             }
@@ -973,6 +1028,8 @@ int fill_net(const DmipMlp* net, const void* packed, int n_varying, int out_rows
   o->ksteps0 = g.k0pad / 16;
   o->dv = g.n_varying;
   o->split = g.split;
+  o->l0_f16 = g.l0_f16;
+  o->l0_tmem = 0;
   o->outpad = g.outpad;
   o->n_const = g.n_const;
   o->n_stages = g.n_stages;
@@ -1080,6 +1137,9 @@ int launch_sampler_tc(const DmipSampler* d, cudaStream_t s) {
     P.n_nets = 1;
     if ((rc = fill_net(&d->net, d->packed, dv, d->xdim, d->l0_split, &P.net[0]))) return rc;
   }
+  // tensor-memory layer-0 operand: one f16 part of <= 128 k, whole 8-element state pieces (CDE / DPS)
+  for (int p = 0; p < P.n_nets; ++p)
+    P.net[p].l0_tmem = (P.net[p].l0_f16 && d->variant != DMIP_CDIFFE && P.net[p].ksteps0 * 16 <= 128) ? 1 : 0;
   P.xdim = d->xdim;
   P.ydim = d->ydim;
   P.n_obs = d->n_obs;

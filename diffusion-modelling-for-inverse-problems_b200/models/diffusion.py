@@ -44,7 +44,7 @@ class BaseClassDiffusionModel():
         self.ydim = ydim
         self.sde = None                      # set by subclasses
         self.precision = 'bf16'
-        self.l0_split = 2
+        self.l0_split = 4                    # layer-0 operand: one f16 part (1: bf16, 2: bf16 hi + lo, 3: + W0 split)
         self._packed = (_lib.PackedNet(), _lib.PackedNet())
         self._seed_counter = 0
         self._stage = None                   # pinned host staging buffer of the sampler's result

@@ -123,7 +123,7 @@ class _ScoreMLP(nn.Sequential):
         self.add_module(str(len(self)), nn.Linear(widths[-1], output_dim))
         self._packed = _lib.PackedNet()
         self.precision = 'bf16'
-        self.l0_split = 2
+        self.l0_split = 4                    # layer-0 operand: one f16 part (1: bf16, 2: bf16 hi + lo, 3: + W0 split)
 
     def _fused(self, x, cond, t):
         L = _lib.require_gpu()

@@ -74,8 +74,10 @@ int dmip_device_ok(void);
  * Re-tiles one net into the bf16, 128B-swizzled, K-major stage images the sampler streams with bulk-TMA.
  * `n_varying` = leading input columns that vary per row and therefore enter the layer-0 GEMM (the rest —
  * y and/or t — are folded into an fp32 per-step bias by the kernel); `out_rows` = leading output rows kept
- * (CDiffE needs only the first xdim outputs, models/diffusion.py:177); `l0_split` in {1,2,3}: layer-0
- * operand splitting (1: bf16 x; 2: x = hi+lo, both bf16; 3: also W0 = hi+lo).  Call again after every
+ * (CDiffE needs only the first xdim outputs, models/diffusion.py:177); `l0_split` in {1,2,3,4}: layer-0
+ * operand splitting (1: bf16 x; 2: x = hi+lo, both bf16; 3: also W0 = hi+lo; 4: ONE f16 part — layer 0 is an f16 x f16
+ * product, 11 mantissa bits of the state at the MMA count of mode 1: as accurate as mode 2 in every sampler test
+ * because the bf16 hidden layers dominate the error, and 6 % faster; the Python classes default to it).  Call again after every
  * optimizer.step().  Replaces nothing in the reference (its weights are read in place by addmm). */
 size_t dmip_pack_bytes(const DmipMlp* net, int32_t n_varying, int32_t out_rows, int32_t l0_split);
 int dmip_pack_mlp(const DmipMlp* net, int32_t n_varying, int32_t out_rows, int32_t l0_split, void* packed,

@@ -49,7 +49,8 @@ def sw128_offset(row, k, kblock_bytes=16384):
 
 
 def case_pack(xdim=3, ydim=23, out_dim=3, split=2, seed=3):
-    """The packed image must hold exactly bf16(W) at the swizzled positions the UMMA descriptor expects."""
+    """The packed image must hold exactly bf16(W) — f16(W0) for layer 0 with l0_split = 4 — at the swizzled positions the
+    UMMA descriptor expects."""
     _, _lib = _dmip()
     L = _lib.require_gpu()
     in_dim = xdim + ydim + 1
@@ -61,7 +62,8 @@ def case_pack(xdim=3, ydim=23, out_dim=3, split=2, seed=3):
     dv = xdim
     buf = _lib.PackedNet().get(net, dv, out_dim, split).cpu().numpy()
     dvp = (dv + 7) // 8 * 8
-    k0 = (split - 1) * dvp + dv
+    parts = 1 if split == 4 else split              # l0_split = 4: one part, f16 instead of bf16
+    k0 = (parts - 1) * dvp + dv
     k0pad = (k0 + 15) // 16 * 16
     kb0 = (k0pad + 63) // 64
     n_stages = 4 * kb0 + 72
@@ -91,9 +93,12 @@ def case_pack(xdim=3, ydim=23, out_dim=3, split=2, seed=3):
         st = c * kb0
         kg = k
         part, idx = divmod(kg, dvp)
-        if part < split and idx < dv:
+        if part < parts and idx < dv:
             src = lo if part == 2 else hi
-            want = int(bf16_bits(src[c * 128 + r, idx]))
+            if split == 4:
+                want = int(W0[c * 128 + r, idx].half().view(torch.int16).item()) & 0xFFFF
+            else:
+                want = int(bf16_bits(src[c * 128 + r, idx]))
         else:
             want = 0
         bad += int(img[st, sw128_offset(r, k) // 2]) != want
@@ -146,7 +151,7 @@ def _model(kind, xdim, ydim, hidden, seed):
     return m
 
 
-def case_sampler(name, kind, precision, split=2):
+def case_sampler(name, kind, precision, split=4):
     """Injected-noise sampler parity vs the golden reference samples.
 
     These fixtures use *untrained* nets, whose reverse dynamics expand (|x| reaches ~1e2) and amplify any

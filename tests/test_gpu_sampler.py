@@ -16,7 +16,7 @@ def test_umma_building_block(mode, n, k):
     _ok(gc.case_umma(mode, n, k))
 
 
-@pytest.mark.parametrize("split", [1, 2, 3])
+@pytest.mark.parametrize("split", [1, 2, 3, 4])
 def test_pack_image(split):
     _ok(gc.case_pack(split=split))
 
@@ -38,7 +38,7 @@ def test_sampler_injected_noise(name, kind, precision):
     _ok(gc.case_sampler(name, kind, precision))
 
 
-@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("split", [1, 2, 3])
 def test_sampler_layer0_split_modes(split):
     _ok(gc.case_sampler("sampler_cde_linear", "CDE", "bf16", split))
 
