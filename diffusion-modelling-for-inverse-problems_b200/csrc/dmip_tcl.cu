@@ -402,6 +402,8 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
                                          bool tile_ok, int w, uint8_t* smem, uint32_t (&v)[32]) {
   tmem_ld32(taddr, v);
   tc_wait_ld();
+  const bool full = tile_ok && smp0 + C::SPW <= P.B;     // warp-uniform
+  float* sst0 = P.st[g] + (smp0 * C::NADJ) * 512 + n;
 #pragma unroll
   for (int j = 0; j < C::SPW; ++j) {
     const int base = j * C::NS;
@@ -436,10 +438,10 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
 #pragma unroll
       for (int k = 0; k < C::kNT; ++k) v[base + C::sS + k] = __float_as_uint(p1 * zs[k]);
     }
-    // derivative state the backward epilogue needs (fp32, coalesced; dmip_tcl.h: st)
-    const long long smp = smp0 + j;
-    if (tile_ok && smp < P.B) {
-      float* sst = P.st[g] + (smp * C::NADJ) * 512 + n;
+    // derivative state the backward epilogue needs (fp32, coalesced; dmip_tcl.h: st).  Offsets from one base pointer
+    // are compile-time constants; a window that lies inside the batch (all but the last tile) stores unpredicated.
+    if (full || (tile_ok && smp0 + j < P.B)) {
+      float* sst = sst0 + static_cast<size_t>(j) * (C::NADJ * 512);
       sst[0] = p1;
       if (C::kI) sst[512] = q1;
       if (C::kT) sst[(1 + C::kI) * 512] = cT;
@@ -465,9 +467,34 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
 // Second half of an item, AFTER the next layer's MMAs were told the K-blocks are there: the outputs of the adjoint streams
 // P | I | T (still in v[]) go to the IN_{g+1} stash image (bf16 hi/lo, backward geometry: weight-gradient operand).
 template <class C>
-__device__ __forceinline__ void fwd_stash(const TclDev& P, int g, int n, long long smp0, bool tile_ok, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void fwd_stash(const TclDev& P, int g, int n, long long tile, long long smp0, bool tile_ok, int w,
+                                          const uint32_t (&v)[32]) {
   const uint32_t nterm = (static_cast<uint32_t>(n) >> 6) * 8192u + (static_cast<uint32_t>(n) & 7u) * 2u;
   const uint32_t nchunk = (static_cast<uint32_t>(n) & 63u) >> 3;
+  if (C::NS == C::NADJ) {
+    // every stream is an adjoint stream (DSM, cScoreFPE, adjoint-route passes): the forward tile IS the stash block and
+    // window row r is block row w*32 + r — all offsets but the swizzle term are compile-time constants
+    if (!tile_ok) return;
+    uint8_t* ihi = P.in_img[g + 1][0] + static_cast<size_t>(tile) * (512 * 128) + nterm + static_cast<uint32_t>(w) * 4096u;
+    uint8_t* ilo = P.in_img[g + 1][1] + static_cast<size_t>(tile) * (512 * 128) + nterm + static_cast<uint32_t>(w) * 4096u;
+    const uint32_t nc4 = nchunk << 4;                  // swizzle term: one XOR with an immediate per row
+    const bool full = smp0 + C::SPW <= P.B;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t xo = i * 128u + (nc4 ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+      for (int q = 0; q < kWin / 8; ++q) {
+        const int r = q * 8 + i;
+        if (r < C::SPW * C::NS && (full || smp0 + r / C::NS < P.B)) {
+          unsigned short hi, lo;
+          split1(__uint_as_float(v[r]), hi, lo);
+          *reinterpret_cast<unsigned short*>(ihi + q * 1024u + xo) = hi;
+          *reinterpret_cast<unsigned short*>(ilo + q * 1024u + xo) = lo;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < C::SPW; ++j) {
     const long long smp = smp0 + j;
@@ -672,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&B.hready[c]);
-          fwd_stash<C>(P, g, n, smp0, tile_ok, v);
+          fwd_stash<C>(P, g, n, tile, smp0, tile_ok, w, v);
         }
         if (g == 1 && tb + tile_stride < n_tiles) {
           // GEMM 0 of this tile has retired (acc_full[0] above): the small operand region takes the next tile's inputs
@@ -833,22 +860,32 @@ __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, 
     if (lane == 0) mbar_arrive(hready);
   }
   if (tile_ok) {
-    uint8_t* ahi = P.adj_img[L][0] + blk;
-    uint8_t* alo = P.adj_img[L][1] + blk;
-    uint8_t* ihi = P.in_img[L + 1][0] + blk;
-    uint8_t* ilo = P.in_img[L + 1][1] + blk;
+    const uint32_t wo = static_cast<uint32_t>(w) * 4096u;           // window w starts 4 row-groups (4 KB) into the block
+    uint8_t* ahi = P.adj_img[L][0] + blk + wo;
+    uint8_t* alo = P.adj_img[L][1] + blk + wo;
+    uint8_t* ihi = P.in_img[L + 1][0] + blk + wo;
+    uint8_t* ilo = P.in_img[L + 1][1] + blk + wo;
+    const uint32_t kc4 = kchunk << 4;                               // swizzle term: one XOR with an immediate per row
+    const long long s_first = tile * (2 * C::SPWB) + w * C::SPWB;
+    const bool full = s_first + C::SPWB <= P.B;                     // warp-uniform: no row of a live sample is missing
+    // rows in the order (r & 7) outer, (r >> 3) inner: one swizzled chunk offset is live at a time
 #pragma unroll
-    for (int r = 0; r < kWin; ++r) {
-      unsigned short hi, lo;
-      split1(__uint_as_float(v[r]), hi, lo);
-      const uint32_t o = row_off(static_cast<uint32_t>(w * kWin + r));
-      *reinterpret_cast<unsigned short*>(ahi + o) = hi;
-      *reinterpret_cast<unsigned short*>(alo + o) = lo;
-      const int j = r / C::NADJ;
-      const bool dead = j >= C::SPWB || tile * (2 * C::SPWB) + w * C::SPWB + j >= P.B;
-      if (dead) {
-        *reinterpret_cast<unsigned short*>(ihi + o) = 0;
-        *reinterpret_cast<unsigned short*>(ilo + o) = 0;
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t xo = i * 128u + (kc4 ^ (static_cast<uint32_t>(i) << 4));
+#pragma unroll
+      for (int q = 0; q < kWin / 8; ++q) {
+        const int r = q * 8 + i;
+        unsigned short hi, lo;
+        split1(__uint_as_float(v[r]), hi, lo);
+        const uint32_t o = q * 1024u + xo;
+        *reinterpret_cast<unsigned short*>(ahi + o) = hi;
+        *reinterpret_cast<unsigned short*>(alo + o) = lo;
+        const int j = r / C::NADJ;
+        const bool dead = j >= C::SPWB || (!full && s_first + j >= P.B);
+        if (dead) {
+          *reinterpret_cast<unsigned short*>(ihi + o) = 0;
+          *reinterpret_cast<unsigned short*>(ilo + o) = 0;
+        }
       }
     }
   }
