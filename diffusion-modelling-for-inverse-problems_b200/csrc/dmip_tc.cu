@@ -59,6 +59,14 @@ constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
 // them, and the output layer (which reads all of H3) is complete before the next operand is written — so layer 0 runs
 // tensor-memory A operands (0.5 N + 13 cycles per instruction instead of 0.5 N + 46).
 constexpr uint32_t kTmemL0 = kTmemH + 192;
+// The same quarter serves layer 2: the epilogue of layer 1's LAST chunk (features 384-511 of H2 = layer 2's K-blocks 6, 7)
+// starts after every MMA of layer 1 has retired, so H1 is dead and that chunk can land in columns 192-255 instead of
+// shared memory; H3's chunk 3 replaces it only after layer 2's last MMA.  A quarter of layer 2's instructions then read a
+// tensor-memory A operand (0.5 N + 13 cycles instead of 0.5 N + 46).  -DDMIP_L2_TAIL_TMEM=0 restores all-shared H2.
+#ifndef DMIP_L2_TAIL_TMEM
+#define DMIP_L2_TAIL_TMEM 1
+#endif
+constexpr bool kL2TailTmem = DMIP_L2_TAIL_TMEM != 0;
 
 // shared-memory map (offsets from the 1024-aligned dynamic shared memory base; 231.6 of the 232.4 KB a CTA may have)
 constexpr int kOffH = 0;
@@ -585,13 +593,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                   const uint32_t b_lo = b_base + s * kPair16;
                   if (elect_one()) {
                     if (!(dbg & 2)) {
-                      if (l == 2) {          // A = H2 in shared memory
+                      if (l == 2 && !(kL2TailTmem && pr == 3)) {   // A = H2 in shared memory
                         const uint32_t a_lo = a_base + pr * kPair16;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                           umma_ss(d_tmem, desc_hi | (a_lo + (j >> 2) * kBlk16 + (j & 3) * 2),
                                   desc_hi | (b_lo + (j >> 2) * kBlk16 + (j & 3) * 2), idesc, (pr | j) != 0 ? 1u : 0u);
-                      } else {               // A = H1 / H3 in tensor memory
+                      } else {               // A = H1 / H3 (and the last quarter of H2) in tensor memory
                         const uint32_t a_tm = tmem_base + kTmemH + pr * 64;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -841,7 +849,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_mlp(const __grid_constant__ 
                   philox_normal4(gidx, here, kStreamState, pc * 2, P.seed, zdraw);
                   philox_normal4(gidx, here, kStreamState, pc * 2 + 1, P.seed, zdraw4);
                 };
-                if (l == 1) {
+                if (l == 1 && !(kL2TailTmem && c == 3)) {
                   if (draw_here)
                     epi_hidden<false, false>(lane_taddr, acc_col, cgp, row, c, lane, bias, sH, &B.acc_empty[buf], &B.hready[c], draw);
                   else
