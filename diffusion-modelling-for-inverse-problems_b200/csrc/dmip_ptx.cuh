@@ -186,6 +186,48 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// 16-byte store into the shared window of any CTA of the cluster (address from mapa_u32, or an own shared::cta address)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// generic-proxy writes into ANY CTA's shared memory of the cluster -> visible to the async proxy (tensor core operands)
+__device__ __forceinline__ void fence_proxy_async_cluster_smem() {
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
+// wait on an own mbarrier whose arrivals come from another CTA (release.cluster): acquire at cluster scope
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      g_watchdog_info[0] = 0xDEAD0000u | tag;
+      g_watchdog_info[1] = blockIdx.x;
+      g_watchdog_info[2] = threadIdx.x;
+      g_watchdog_info[3] = parity;
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// the same arrival without release semantics: for a thread that publishes nothing of its own (relay of a TMA completion),
+// or right after a fence that already ordered its stores (fence.proxy.async.shared::cluster carries a GPU-scope membar)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory operand descriptor, K-major, 128-byte swizzle, bf16:
 //   rows (M or N index) are 128 B apart inside an 8-row / 1024 B swizzle atom, atoms are SBO = 1024 B apart,

@@ -46,14 +46,27 @@ constexpr int kMmaWarp = 17;
 constexpr int kCluster = 2;
 constexpr int kRegsSmall = 32;
 constexpr int kRegsRow = 112;
-constexpr uint32_t kTmemCols = 512;       // two halves of 4 chunks x 64 columns
+constexpr uint32_t kTmemCols = 512;       // two halves of 4 chunks x 64 columns (pair mode: 2 chunks x 128 columns)
+// CTA-pair mode (default): the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 of M = 256, N = 128 per step instead
+// of two M = 128, N = 64 instructions each.  An N = 64 shared-memory-operand instruction occupies the tensor pipe 32 of
+// the ~96 cycles it takes (6 KB of operand reads); the pair instruction takes ~110 cycles for twice the work per SM.
+// Every CTA keeps ITS 64-row tile as before (inputs, B operand in its own shared memory, stashes, loss stage); what is
+// redistributed are the accumulators: CTA r holds the features of chunks r and r + 2 for the rows of BOTH tiles (128
+// columns), so its epilogue threads write half of their output rows into the peer's shared memory (st.shared::cluster)
+// and every "operand ready" barrier lives in the leader CTA (rank 0), which issues for the pair.  Each CTA streams only
+// the weight stages of its own chunks (no multicast); the peer's MMA warp relays "stage landed" to the leader.
+// -DDMIP_TCL_PAIR=0 builds the single-CTA kernels (cta_group::1, N = 64).
+#ifndef DMIP_TCL_PAIR
+#define DMIP_TCL_PAIR 1
+#endif
+constexpr bool kPair = DMIP_TCL_PAIR != 0;
 
 constexpr int kOffHhi = 0;
 constexpr int kOffHlo = kOffHhi + kHHalf;
 constexpr int kOffIn = kOffHlo + kHHalf;                 // hi at +0, lo at +kInHalf
 constexpr int kOffW = kOffIn + 2 * kInHalf;
 constexpr int kOffBar = kOffW + kSlots * kStage;
-constexpr int kNumBars = 2 * kSlots + 2 + 4 + 1;
+constexpr int kNumBars = 2 * kSlots + 2 + 4 + 1 + kSlots + 1;
 constexpr int kOffRed = kOffBar + ((kNumBars * 8 + 15) & ~15);   // float red[4], b3sum[64]
 constexpr int kOffTmem = kOffRed + (4 + kTclSmallF) * 4;
 constexpr int kSmemBytes = kOffTmem + 16;
@@ -66,6 +79,11 @@ struct Bars {
                        //           shared-memory input is dead
   uint64_t* hready;    // [4]       K-blocks 2c, 2c+1 of the next B operand written (8 row warps each)
   uint64_t* in_ready;  // [1]       operand of the tile's first GEMM written (16 row warps)
+  // pair mode: hready / in_ready are the LEADER's (arrivals from both CTAs: 16 row warps of the CTA that owns the chunk /
+  // 32 row warps), and
+  uint64_t* pfull;     // [kSlots]  leader: the peer's weight stage landed (relayed by the peer's MMA warp)
+  uint64_t* xfree;     // [1]       the PEER's row warps have finished reading their staged outputs (forward loss stage):
+                       //           its activation region may take the next tile's rows
 };
 
 __device__ __forceinline__ Bars make_bars(uint8_t* smem) {
@@ -76,6 +94,8 @@ __device__ __forceinline__ Bars make_bars(uint8_t* smem) {
   B.acc_full = b + 2 * kSlots;
   B.hready = B.acc_full + 2;
   B.in_ready = B.hready + 4;
+  B.pfull = B.in_ready + 1;
+  B.xfree = B.pfull + kSlots;
   return B;
 }
 
@@ -96,6 +116,23 @@ template <int kRegs>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 __device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// operand store of an epilogue thread: own shared memory, or (pair mode) the shared window of either CTA of the pair
+__device__ __forceinline__ void st_operand_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  if (kPair) st_cluster_v4(addr, a, b, c, d);
+  else asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// `remote`: the stores went to the peer's shared memory (the cluster-scope proxy fence carries a GPU-scope membar that
+// waits for every store of the thread in flight, global ones included — keep those AFTER this point)
+__device__ __forceinline__ void fence_operand_stores(bool remote = kPair) {
+  if (kPair && remote) fence_proxy_async_cluster_smem();
+  else fence_proxy_async_smem();
+}
+// arrival on a barrier of the leader CTA (pair mode: `leader_addr` = mapa of the barrier in CTA 0) or of this CTA
+// — always with release at CLUSTER scope there: the stores it publishes may have gone to the peer's shared memory
+__device__ __forceinline__ void arrive_issuer(uint64_t* bar, uint32_t leader_addr) {
+  if (kPair) mbar_arrive_remote_relaxed(leader_addr);   // after fence_operand_stores(): its membar is the release
+  else mbar_arrive(bar);
 }
 __device__ __forceinline__ void row_warps_sync() {   // named barrier over the 512 row-warp threads
   asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -195,25 +232,79 @@ __device__ __forceinline__ void bwd_row(long long smp, int a, long long& block, 
 
 // ------------------------------------------------------------------------------------------------ producer / issuer
 // Streams the n_stages weight stages of one tile pass, for every tile this CTA runs (whole warp, one elected lane issues).
+// Single-CTA mode: both CTAs of the cluster walk the whole image, each fetches half of every stage and multicasts it.
+// Pair mode: CTA r fetches, for every GEMM with four chunks, only the stages of ITS chunks r and r + 2 (image order: GEMM,
+// K-block, chunk, hi | lo), and all stages of a one-chunk GEMM (both CTAs compute that chunk: each reads its own rows).
+template <int kNG, int kLastChunks>
 __device__ __forceinline__ void tcl_producer(const uint8_t* stages, int n_stages, int tile_first, int n_tiles, int tile_stride,
                                              uint8_t* sW, const Bars& B, uint32_t crank, uint16_t cmask) {
   int s = 0;
   uint32_t ph = 0;
   constexpr uint32_t part = kStage / kCluster;
   for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
-    for (int st = 0; st < n_stages; ++st) {
-      mbar_wait(&B.empty[s], ph ^ 1u, 0xA00 + s);   // slot released by the issuers of ALL cluster CTAs
-      const uint8_t* g = stages + static_cast<size_t>(st) * kStage;
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&B.full[s], kStage);
-        if (kCluster == 1) bulk_g2s(sW + s * kStage, g, kStage, &B.full[s]);
-        else bulk_g2s_multicast(sW + s * kStage + crank * part, g + crank * part, part, &B.full[s], cmask);
+    if (!kPair) {
+      for (int st = 0; st < n_stages; ++st) {
+        mbar_wait(&B.empty[s], ph ^ 1u, 0xA00 + s);   // slot released by the issuers of ALL cluster CTAs
+        const uint8_t* g = stages + static_cast<size_t>(st) * kStage;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&B.full[s], kStage);
+          if (kCluster == 1) bulk_g2s(sW + s * kStage, g, kStage, &B.full[s]);
+          else bulk_g2s_multicast(sW + s * kStage + crank * part, g + crank * part, part, &B.full[s], cmask);
+        }
+        __syncwarp();
+        if (++s == kSlots) { s = 0; ph ^= 1u; }
       }
+    } else {
+      int base = 0;   // first stage of GEMM g in the image
+#pragma unroll 1
+      for (int g = 0; g < kNG; ++g) {
+        const int nkb = g == 0 ? 1 : 8;
+        const int nc = g == kNG - 1 ? kLastChunks : 4;
+        const int np = nc == 4 ? 2 : 1;
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb)
+#pragma unroll 1
+          for (int p = 0; p < np; ++p)
+#pragma unroll 1
+            for (int hl = 0; hl < 2; ++hl) {
+              const int c = nc == 4 ? static_cast<int>(crank) + 2 * p : 0;
+              const int st = base + (kb * nc + c) * 2 + hl;
+              mbar_wait(&B.empty[s], ph ^ 1u, 0xA00 + s);   // slot released by the leader's commit
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&B.full[s], kStage);
+                bulk_g2s(sW + s * kStage, stages + static_cast<size_t>(st) * kStage, kStage, &B.full[s]);
+              }
+              __syncwarp();
+              if (++s == kSlots) { s = 0; ph ^= 1u; }
+            }
+        base += nkb * nc * 2;
+      }
+    }
+  }
+}
+
+// Pair mode, MMA warp of the peer CTA (rank 1): tells the leader that a weight stage has landed in THIS CTA's ring.
+__device__ __forceinline__ void tcl_relay(int n_stages_cta, int tile_first, int n_tiles, int tile_stride, const Bars& B) {
+  int s = 0;
+  uint32_t ph = 0;
+  const uint32_t pfull0 = mapa_u32(&B.pfull[0], 0);
+  for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
+    for (int st = 0; st < n_stages_cta; ++st) {
+      mbar_wait(&B.full[s], ph, 0xA80 + s);
+      if (elect_one()) mbar_arrive_remote_relaxed(pfull0 + static_cast<uint32_t>(s) * 8u);
       __syncwarp();
       if (++s == kSlots) { s = 0; ph ^= 1u; }
     }
   }
 }
+// stages one CTA of a pair streams per tile
+template <int kNG, int kLastChunks>
+struct PairStages {
+  static_assert(kNG >= 2, "a small-K GEMM followed by 512-deep ones");
+  // GEMM 0: one K-block, two of its four chunks, hi | lo; the middle GEMMs: 8 K-blocks x 2 chunks x 2; the last GEMM:
+  // 8 K-blocks x (2 of 4 chunks, or its only chunk) x 2
+  static constexpr int value = 4 + (kNG - 2) * 32 + (kLastChunks == 4 ? 32 : 16);
+};
 
 // MMA issuer of one CTA: kNG GEMMs per tile; GEMM 0 reads the small operand (K = 16 k0steps), the others the 512-deep
 // activations; all K-outer over 64-feature K-blocks with (up to) four open accumulator chunks; the last GEMM has
@@ -290,6 +381,99 @@ __device__ __forceinline__ void tcl_issuer(int k0steps, int tile_first, int n_ti
   }
 }
 
+// MMA issuer of the LEADER CTA in pair mode: the same GEMM sequence with tcgen05.mma.cta_group::2 — M = 256 (chunk r + 2p
+// from CTA r's ring slot), N = 128 (64 rows from each CTA's operand region, same CTA-relative address), accumulator p at
+// columns p * 128 of the TMEM half in both CTAs.  A one-chunk GEMM runs with the same stage in both rings: each CTA ends
+// up with that chunk for all 128 rows and reads its own 64.  Every commit is multicast to both CTAs.
+template <int kNG, int kLastChunks>
+__device__ __forceinline__ void tcl_issuer_pair(int k0steps, int tile_first, int n_tiles, int tile_stride, uint8_t* smem,
+                                                uint32_t tmem_base, const Bars& B) {
+  int s = 0;
+  uint32_t ph = 0, hr_par = 0, in_par = 0;
+  uint32_t gc = 0;
+  const uint32_t in16 = (smem_u32(smem + kOffIn) & 0x3FFFFu) >> 4;
+  const uint32_t h16 = (smem_u32(smem + kOffHhi) & 0x3FFFFu) >> 4;
+  const uint32_t w16 = (smem_u32(smem + kOffW) & 0x3FFFFu) >> 4;
+  const uint64_t descA = umma_smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+  const uint64_t descB = umma_smem_desc(0, 1024, 1024);
+  constexpr uint32_t idesc = umma_idesc_bf16_major(256, 2 * kNR, 0, 1);
+  constexpr uint16_t both = 0x3;
+  for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
+#pragma unroll 1
+    for (int g = 0; g < kNG; ++g) {
+      const int nkb = g == 0 ? 1 : 8;
+      const int np = (g == kNG - 1 ? kLastChunks : 4) == 4 ? 2 : 1;
+      const int nk16 = g == 0 ? k0steps : 4;
+      const uint32_t b_base = g == 0 ? in16 : h16;
+      const uint32_t b_half = (g == 0 ? kInHalf : kHHalf) >> 4;
+      const uint32_t set = gc & 1u;
+      ++gc;
+      const uint32_t acc0 = tmem_base + set * 256u;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (g == 0) {
+          mbar_wait_cluster(B.in_ready, in_par, 0xB00);
+          in_par ^= 1u;
+        } else if ((kb & 1) == 0) {
+          const int c = kb >> 1;
+          mbar_wait_cluster(&B.hready[c], (hr_par >> c) & 1u, 0xB10 + c);
+          hr_par ^= 1u << c;
+        }
+        tc_fence_after();
+        const uint32_t b16 = b_base + static_cast<uint32_t>(kb) * 512u;
+#pragma unroll 1
+        for (int p = 0; p < np; ++p) {
+          const uint32_t d = acc0 + static_cast<uint32_t>(p) * (2 * kNR);
+          // hi stage x (B hi, B lo)
+          mbar_wait(&B.full[s], ph, 0xB20 + s);
+          mbar_wait_cluster(&B.pfull[s], ph, 0xB40 + s);
+          tc_fence_after();
+          uint32_t a16 = w16 + static_cast<uint32_t>(s) * (kStage >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nk16) {
+                umma_ss_pair(d, descA | (a16 + j * 2), descB | (b16 + j * 128), idesc, (kb | j) != 0 ? 1u : 0u);
+                umma_ss_pair(d, descA | (a16 + j * 2), descB | (b16 + b_half + j * 128), idesc, 1u);
+              }
+            tc_commit_pair(&B.empty[s], both);
+          }
+          __syncwarp();
+          if (++s == kSlots) { s = 0; ph ^= 1u; }
+          // lo stage x B hi
+          mbar_wait(&B.full[s], ph, 0xB30 + s);
+          mbar_wait_cluster(&B.pfull[s], ph, 0xB50 + s);
+          tc_fence_after();
+          a16 = w16 + static_cast<uint32_t>(s) * (kStage >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nk16) umma_ss_pair(d, descA | (a16 + j * 2), descB | (b16 + j * 128), idesc, 1u);
+            tc_commit_pair(&B.empty[s], both);
+            if (kb == nkb - 1 && p == np - 1) tc_commit_pair(&B.acc_full[set], both);
+          }
+          __syncwarp();
+          if (++s == kSlots) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  }
+}
+
+// the three service roles of the warps above the row warps
+template <int kNG, int kLastChunks>
+__device__ __forceinline__ void tcl_service_warps(int warp, const uint8_t* stages, int n_stages, int k0steps, int tile_first,
+                                                  int n_tiles, int tile_stride, uint8_t* smem, uint32_t tmem_base,
+                                                  const Bars& B, uint32_t crank, uint16_t cmask) {
+  if (warp == kProducerWarp) {
+    tcl_producer<kNG, kLastChunks>(stages, n_stages, tile_first, n_tiles, tile_stride, smem + kOffW, B, crank, cmask);
+  } else if (warp == kMmaWarp) {
+    if (!kPair) tcl_issuer<kNG, kLastChunks>(k0steps, tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
+    else if (crank == 0u) tcl_issuer_pair<kNG, kLastChunks>(k0steps, tile_first, n_tiles, tile_stride, smem, tmem_base, B);
+    else tcl_relay(PairStages<kNG, kLastChunks>::value, tile_first, n_tiles, tile_stride, B);
+  }
+}
+
 // one-time setup shared by both kernels; returns tmem_base
 __device__ __forceinline__ uint32_t tcl_setup(uint8_t* smem, const Bars& B, int warp, int lane) {
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -297,20 +481,32 @@ __device__ __forceinline__ uint32_t tcl_setup(uint8_t* smem, const Bars& B, int 
   if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&B.full[i], 1);
-      mbar_init(&B.empty[i], static_cast<uint32_t>(kCluster));
+      mbar_init(&B.empty[i], kPair ? 1u : static_cast<uint32_t>(kCluster));   // pair mode: the leader's commit only
+      mbar_init(&B.pfull[i], 1);
     }
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], 8);    // 4 lane quarters x 2 windows
-    mbar_init(B.in_ready, kNumRowWarps);
+    // single-CTA: 4 lane quarters x 2 windows; pair: all 16 row warps of the CTA that owns the chunk
+    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], kPair ? kNumRowWarps : 8);
+    mbar_init(B.in_ready, kPair ? 2 * kNumRowWarps : kNumRowWarps);
+    mbar_init(B.xfree, kNumRowWarps);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_holder);
+  if (!kPair && warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_holder);
   // the operand regions must hold finite values from the start (zero rows / zero K padding meet zero weights)
   for (int i = threadIdx.x; i < kOffW / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   float* red = reinterpret_cast<float*>(smem + kOffRed);
   for (int i = threadIdx.x; i < 4 + kTclSmallF; i += kThreads) red[i] = 0.f;
   fence_proxy_async_smem();
+  if (kPair) {
+    // both CTAs exist and their mbarriers are initialised before the pair allocation (one warp in EACH CTA)
+    cluster_sync_all();
+    if (warp == kMmaWarp) tmem_alloc_pair<kTmemCols>(tmem_holder);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    return __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -325,7 +521,8 @@ __device__ __forceinline__ void tcl_teardown(uint32_t tmem_base, int warp) {
   if (kCluster > 1) cluster_sync_all();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (kPair) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -399,7 +596,7 @@ __device__ __forceinline__ void fwd_build_input(const TclDev& P, long long tile,
 // One (layer, chunk, window) item of the forward epilogue: thread = feature n of the layer's output.
 template <class C, bool kFirst>
 __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr, int n, float bias, long long smp0,
-                                         bool tile_ok, int w, uint8_t* smem, uint32_t (&v)[32]) {
+                                         bool tile_ok, int w, uint32_t hdst, uint32_t (&v)[32]) {
   tmem_ld32(taddr, v);
   tc_wait_ld();
   const bool full = tile_ok && smp0 + C::SPW <= P.B;     // warp-uniform
@@ -440,7 +637,8 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
     }
     // derivative state the backward epilogue needs (fp32, coalesced; dmip_tcl.h: st).  Offsets from one base pointer
     // are compile-time constants; a window that lies inside the batch (all but the last tile) stores unpredicated.
-    if (full || (tile_ok && smp0 + j < P.B)) {
+    // Pair mode, layers 1 and 2: stored by fwd_state_from_outputs AFTER the operand fence instead.
+    if ((!kPair || kFirst) && (full || (tile_ok && smp0 + j < P.B))) {
       float* sst = sst0 + static_cast<size_t>(j) * (C::NADJ * 512);
       sst[0] = p1;
       if (C::kI) sst[512] = q1;
@@ -449,8 +647,9 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
   }
 #pragma unroll
   for (int r = C::SPW * C::NS; r < kWin; ++r) v[r] = 0u;   // padding rows of the window
-  // next layer's B operand: feature n, rows w*32 .. w*32+31 = four 16-byte chunks, hi and lo
-  uint8_t* hrow = smem + kOffHhi + (static_cast<uint32_t>(n) >> 3) * 1024u + (static_cast<uint32_t>(n) & 7u) * 128u;
+  // next layer's B operand: feature n, rows w*32 .. w*32+31 = four 16-byte chunks, hi and lo (hdst: the hi activation
+  // region of the CTA that owns the rows — this CTA, or in pair mode either one)
+  const uint32_t hrow = hdst + (static_cast<uint32_t>(n) >> 3) * 1024u + (static_cast<uint32_t>(n) & 7u) * 128u;
   const uint32_t line = static_cast<uint32_t>(n) & 7u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -459,8 +658,29 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
     for (int e = 0; e < 4; ++e)
       split2(__uint_as_float(v[i * 8 + 2 * e]), __uint_as_float(v[i * 8 + 2 * e + 1]), hi[e], lo[e]);
     const uint32_t co = ((static_cast<uint32_t>(w * 4 + i) ^ line) << 4);
-    st_shared_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
-    st_shared_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
+    st_operand_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
+    st_operand_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// Pair mode, tanh layers: the derivative state of fwd_item from the layer's OUTPUTS still in v[] (h, h_I, p1 zd_T):
+//   phi'(z_P) = 1 - h^2,  phi'(z_I) = 1 - h_I^2,  phi''(z_P) zd_T = -2 h (p1 zd_T)  — after the next layer's MMAs were
+// released, so that the operand fence does not wait for these global stores.
+template <class C>
+__device__ __forceinline__ void fwd_state_from_outputs(const TclDev& P, int g, int n, long long smp0, bool tile_ok,
+                                                       const uint32_t (&v)[32]) {
+  const bool full = tile_ok && smp0 + C::SPW <= P.B;
+  float* sst0 = P.st[g] + (smp0 * C::NADJ) * 512 + n;
+#pragma unroll
+  for (int j = 0; j < C::SPW; ++j) {
+    if (full || (tile_ok && smp0 + j < P.B)) {
+      const int base = j * C::NS;
+      float* sst = sst0 + static_cast<size_t>(j) * (C::NADJ * 512);
+      const float h = __uint_as_float(v[base]);
+      sst[0] = 1.f - h * h;
+      if (C::kI) { const float hI = __uint_as_float(v[base + C::sI]); sst[512] = 1.f - hI * hI; }
+      if (C::kT) sst[(1 + C::kI) * 512] = -2.f * h * __uint_as_float(v[base + C::sT]);
+    }
   }
 }
 
@@ -648,17 +868,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
 
   if (warp >= kNumRowWarps) {
     reg_dealloc<kRegsSmall>();
-    if (warp == kProducerWarp) {
-      tcl_producer(keep(P.stages_fwd), kTclFwdStages, tile_first, n_tiles, tile_stride, smem + kOffW, B, crank, cmask);
-    } else if (warp == kMmaWarp) {
-      tcl_issuer<4, 1>(keep(P.k0steps_fwd), tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
-    }
+    tcl_service_warps<4, 1>(warp, keep(P.stages_fwd), kTclFwdStages, keep(P.k0steps_fwd), tile_first, n_tiles, tile_stride,
+                            smem, tmem_base, B, crank, cmask);
   } else {
     reg_alloc<kRegsRow>();
     const int q = warp & 3, cgp = warp >> 2;
-    const int w = cgp & 1, c_first = cgp >> 1;          // this warp's window; its chunks are c_first and c_first + 2
+    // single-CTA: this warp's window w of the CTA's tile; its chunks are c_first and c_first + 2.
+    // pair: the CTA's chunks are crank and crank + 2; the warp takes window w of the tile of CTA `tsel` (columns
+    // tsel * 64 + w * 32 of the 128-column accumulators).
+    const int w = cgp & 1;
+    const int c_first = kPair ? static_cast<int>(crank) : cgp >> 1;
+    const int tsel = kPair ? cgp >> 1 : static_cast<int>(crank);
     const int t = threadIdx.x;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t hdst = kPair ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel)) : smem_u32(smem + kOffHhi);
+    const uint32_t in_ready_leader = kPair ? mapa_u32(B.in_ready, 0) : 0u;
+    const uint32_t hready_leader = kPair ? mapa_u32(&B.hready[0], 0) : 0u;
+    const uint32_t xfree_peer = kPair ? mapa_u32(B.xfree, crank ^ 1u) : 0u;
+    uint32_t xpar = 0;
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* b3sum = red + 4;
     float* outs = reinterpret_cast<float*>(smem + kOffHhi);
@@ -671,53 +898,64 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
     {
       const bool ok = tile_first + static_cast<int>(crank) < n_tiles;
       fwd_build_input<C>(P, tile_first + static_cast<int>(crank), ok, smem + kOffIn, t);
-      fence_proxy_async_smem();
+      fence_operand_stores(false);
       __syncwarp();
-      if (lane == 0) mbar_arrive(B.in_ready);
+      if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
     }
     for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
-      const bool tile_ok = tb + static_cast<int>(crank) < n_tiles;
+      const bool tile_ok = tb + static_cast<int>(crank) < n_tiles;      // this CTA's own tile (inputs, loss stage)
       const long long tile = tb + static_cast<int>(crank);
       const long long s0 = tile * (2 * C::SPW);
-      const long long smp0 = s0 + w * C::SPW;
+      const long long etile = tb + tsel;                                // the tile whose rows this warp's items hold
+      const bool etile_ok = etile < n_tiles;
+      const long long smp0 = etile * (2 * C::SPW) + w * C::SPW;
 #pragma unroll 1
       for (int g = 0; g < 3; ++g) {
         if (g & 1) { mbar_wait(&B.acc_full[1], par1, 0xC01); par1 ^= 1u; }
         else { mbar_wait(&B.acc_full[0], par0, 0xC00); par0 ^= 1u; }
         tc_fence_after();
+        if (kPair && g == 0 && tb != tile_first && tsel != static_cast<int>(crank)) {
+          // the peer's activation region still holds its staged outputs of the previous tile until its loss stage is done
+          mbar_wait_cluster(B.xfree, xpar, 0xC10);
+          xpar ^= 1u;
+        }
 #pragma unroll 1
         for (int ci = 0; ci < 2; ++ci) {
           const int c = c_first + 2 * ci;
           const int n = c * 128 + q * 32 + lane;
-          const uint32_t taddr = lane_taddr + static_cast<uint32_t>((g & 1) * 256 + c * kNR + w * kWin);
+          const uint32_t taddr = lane_taddr + static_cast<uint32_t>((g & 1) * 256) +
+                                 (kPair ? static_cast<uint32_t>(ci * 2 * kNR + tsel * kNR + w * kWin)
+                                        : static_cast<uint32_t>(c * kNR + w * kWin));
           // register select (the loops stay rolled: six copies of the item body would not fit the instruction cache)
           const float bs = g == 0 ? (ci ? bias[0][1] : bias[0][0]) : g == 1 ? (ci ? bias[1][1] : bias[1][0]) : (ci ? bias[2][1] : bias[2][0]);
           uint32_t v[32];
-          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, tile_ok, w, smem, v);
-          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, tile_ok, w, smem, v);
-          fence_proxy_async_smem();
+          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, etile_ok, w, hdst, v);
+          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, etile_ok, w, hdst, v);
+          fence_operand_stores(tsel != static_cast<int>(crank));
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&B.hready[c]);
-          fwd_stash<C>(P, g, n, tile, smp0, tile_ok, w, v);
+          if (lane == 0) arrive_issuer(&B.hready[c], hready_leader + static_cast<uint32_t>(c) * 8u);
+          if (kPair && g != 0) fwd_state_from_outputs<C>(P, g, n, smp0, etile_ok, v);
+          fwd_stash<C>(P, g, n, etile, smp0, etile_ok, w, v);
         }
         if (g == 1 && tb + tile_stride < n_tiles) {
           // GEMM 0 of this tile has retired (acc_full[0] above): the small operand region takes the next tile's inputs
           const int nt = tb + tile_stride + static_cast<int>(crank);
           fwd_build_input<C>(P, nt, nt < n_tiles, smem + kOffIn, t);
-          fence_proxy_async_smem();
+          fence_operand_stores(false);
           __syncwarp();
-          if (lane == 0) mbar_arrive(B.in_ready);
+          if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
         }
       }
-      // ---- output layer: accumulator chunk 0 of TMEM half 1 -> staged outputs (the activation region is dead now)
+      // ---- output layer: accumulator chunk 0 of TMEM half 1 -> staged outputs (the activation region is dead now).
+      // Pair mode: both CTAs hold chunk 0 for all 128 rows; each reads the columns of its own tile.
       mbar_wait(&B.acc_full[1], par1, 0xC02);
       par1 ^= 1u;
       tc_fence_after();
       const int od = P.out_dim;
-      if (c_first == 0 && q * 32 < od) {
+      if ((kPair ? tsel == 0 : c_first == 0) && q * 32 < od) {
         uint32_t v[32];
-        tmem_ld32(lane_taddr + 256u + static_cast<uint32_t>(w * kWin), v);
+        tmem_ld32(lane_taddr + 256u + static_cast<uint32_t>((kPair ? static_cast<int>(crank) * kNR : 0) + w * kWin), v);
         tc_wait_ld();
         const int j = q * 32 + lane;
         if (j < od) {
@@ -734,6 +972,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
       row_warps_sync();
       fwd_loss_stage<C>(P, s0, tile_ok, outs, red, b3sum, t);
       row_warps_sync();   // nobody overwrites the staged outputs (next tile's layer-0 epilogue) while they are read
+      if (kPair && tb + tile_stride < n_tiles) {
+        // ... nor does the peer, whose layer-0 epilogue of the next tile writes this CTA's rows: tell it
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(xfree_peer);
+      }
     }
     // ---- flush the CTA's loss sums and output-bias gradient
     if (t == 0) {
@@ -835,13 +1078,14 @@ __device__ __forceinline__ float bwd_math(const TclDev& P, uint32_t taddr, long 
 // well) and, for L > 0, the B operand of the next GEMM
 template <class C>
 __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, int k, long long tile, bool tile_ok, int w,
-                                          const uint32_t (&v)[32], uint8_t* smem, uint64_t* hready, int lane) {
+                                          const uint32_t (&v)[32], uint32_t hdst, bool remote, uint64_t* hready,
+                                          uint32_t hready_leader, int lane) {
   const uint32_t kterm = (static_cast<uint32_t>(k) >> 6) * 8192u + (static_cast<uint32_t>(k) & 7u) * 2u;
   const uint32_t kchunk = (static_cast<uint32_t>(k) & 63u) >> 3;
   const size_t blk = static_cast<size_t>(tile) * (512 * 128) + kterm;
   auto row_off = [&](uint32_t r) { return (r >> 3) * 1024u + (r & 7u) * 128u + ((kchunk ^ (r & 7u)) << 4); };
   if (to_smem) {
-    uint8_t* hrow = smem + kOffHhi + (static_cast<uint32_t>(k) >> 3) * 1024u + (static_cast<uint32_t>(k) & 7u) * 128u;
+    const uint32_t hrow = hdst + (static_cast<uint32_t>(k) >> 3) * 1024u + (static_cast<uint32_t>(k) & 7u) * 128u;
     const uint32_t line = static_cast<uint32_t>(k) & 7u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -850,14 +1094,14 @@ __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, 
       for (int e = 0; e < 4; ++e)
         split2(__uint_as_float(v[i * 8 + 2 * e]), __uint_as_float(v[i * 8 + 2 * e + 1]), hi[e], lo[e]);
       const uint32_t co = ((static_cast<uint32_t>(w * 4 + i) ^ line) << 4);
-      st_shared_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
-      st_shared_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
+      st_operand_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
+      st_operand_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
     }
     // the next GEMM may read these K-blocks now; the global stash stores below are off its critical path
-    fence_proxy_async_smem();
+    fence_operand_stores(remote);
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(hready);
+    if (lane == 0) arrive_issuer(hready, hready_leader);
   }
   if (tile_ok) {
     const uint32_t wo = static_cast<uint32_t>(w) * 4096u;           // window w starts 4 row-groups (4 KB) into the block
@@ -908,32 +1152,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
 
   if (warp >= kNumRowWarps) {
     reg_dealloc<kRegsSmall>();
-    if (warp == kProducerWarp) {
-      tcl_producer(keep(P.stages_bwd), kGradIn ? kTclBwdStagesIn : kTclBwdStages, tile_first, n_tiles, tile_stride,
-                   smem + kOffW, B, crank, cmask);
-    } else if (warp == kMmaWarp) {
-      if (kGradIn) tcl_issuer<4, 1>(keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
-      else tcl_issuer<3, 4>(keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
-    }
+    if (kGradIn)
+      tcl_service_warps<4, 1>(warp, keep(P.stages_bwd), kTclBwdStagesIn, keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride,
+                              smem, tmem_base, B, crank, cmask);
+    else
+      tcl_service_warps<3, 4>(warp, keep(P.stages_bwd), kTclBwdStages, keep(P.k0steps_bwd), tile_first, n_tiles, tile_stride,
+                              smem, tmem_base, B, crank, cmask);
   } else {
     reg_alloc<kRegsRow>();
     const int q = warp & 3, cgp = warp >> 2;
-    const int w = cgp & 1, c_first = cgp >> 1;
+    const int w = cgp & 1;                                             // window; chunks / tile as in k_tcl_fwd
+    const int c_first = kPair ? static_cast<int>(crank) : cgp >> 1;
+    const int tsel = kPair ? cgp >> 1 : static_cast<int>(crank);
     const int t = threadIdx.x;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t hdst = kPair ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel)) : smem_u32(smem + kOffHhi);
+    const uint32_t in_ready_leader = kPair ? mapa_u32(B.in_ready, 0) : 0u;
+    const uint32_t hready_leader = kPair ? mapa_u32(&B.hready[0], 0) : 0u;
     uint32_t par = 0;   // bit s: phase of acc_full[s]
     uint32_t gc = 0;    // running GEMM counter (three GEMMs per tile: the TMEM half of a GEMM is gc & 1, as in tcl_issuer)
     float bsum[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // bias gradients of layers 2, 1, 0 for this thread's two features
     {
       const bool ok = tile_first + static_cast<int>(crank) < n_tiles;
       bwd_build_input<C>(P, tile_first + static_cast<int>(crank), ok, smem + kOffIn, t);
-      fence_proxy_async_smem();
+      fence_operand_stores(false);
       __syncwarp();
-      if (lane == 0) mbar_arrive(B.in_ready);
+      if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
     }
     for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
-      const bool tile_ok = tb + static_cast<int>(crank) < n_tiles;
+      const bool tile_ok = tb + static_cast<int>(crank) < n_tiles;     // this CTA's own tile
       const long long tile = tb + static_cast<int>(crank);
+      const long long etile = tb + tsel;                               // the tile whose rows this warp's items hold
+      const bool etile_ok = etile < n_tiles;
+      // accumulator columns of this warp's two items inside a TMEM half
+      const uint32_t col0 = kPair ? static_cast<uint32_t>(tsel * kNR + w * kWin) : static_cast<uint32_t>(c_first * kNR + w * kWin);
+      constexpr uint32_t kColStep = 2 * kNR;                           // second item: chunk c_first + 2
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         const int L = 2 - g;
@@ -944,34 +1197,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
         // item's results are stored
         float pre[C::SPWB * C::NADJ];
         uint32_t v[32];
-        bwd_prefetch<C>(P, L, k0, tile, w, pre);
+        bwd_prefetch<C>(P, L, k0, etile_ok ? etile : tile, w, pre);
         mbar_wait(&B.acc_full[set], (par >> set) & 1u, 0xD00 + set);
         par ^= 1u << set;
         tc_fence_after();
-        const uint32_t t0 = lane_taddr + set * 256u + static_cast<uint32_t>(c_first * kNR + w * kWin);
-        bsum[g][0] += bwd_math<C>(P, t0, tile, tile_ok, w, pre, v);
-        bwd_prefetch<C>(P, L, k1, tile, w, pre);
-        bwd_store<C>(P, L, L != 0 || kGradIn, k0, tile, tile_ok, w, v, smem, &B.hready[c_first], lane);
-        bsum[g][1] += bwd_math<C>(P, t0 + 2 * kNR, tile, tile_ok, w, pre, v);
-        bwd_store<C>(P, L, L != 0 || kGradIn, k1, tile, tile_ok, w, v, smem, &B.hready[c_first + 2], lane);
+        const uint32_t t0 = lane_taddr + set * 256u + col0;
+        bsum[g][0] += bwd_math<C>(P, t0, etile, etile_ok, w, pre, v);
+        bwd_prefetch<C>(P, L, k1, etile_ok ? etile : tile, w, pre);
+        bwd_store<C>(P, L, L != 0 || kGradIn, k0, etile, etile_ok, w, v, hdst, tsel != static_cast<int>(crank), &B.hready[c_first],
+                     hready_leader + static_cast<uint32_t>(c_first) * 8u, lane);
+        bsum[g][1] += bwd_math<C>(P, t0 + kColStep, etile, etile_ok, w, pre, v);
+        bwd_store<C>(P, L, L != 0 || kGradIn, k1, etile, etile_ok, w, v, hdst, tsel != static_cast<int>(crank), &B.hready[c_first + 2],
+                     hready_leader + static_cast<uint32_t>(c_first + 2) * 8u, lane);
         if (g == 1 && tb + tile_stride < n_tiles) {
           const int nt = tb + tile_stride + static_cast<int>(crank);
           bwd_build_input<C>(P, nt, nt < n_tiles, smem + kOffIn, t);
-          fence_proxy_async_smem();
+          fence_operand_stores(false);
           __syncwarp();
-          if (lane == 0) mbar_arrive(B.in_ready);
+          if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
         }
       }
       if (kGradIn) {
-        // ---- gradient w.r.t. the inputs: accumulator chunk 0 = (input column, row); rows are samples (one adjoint stream)
+        // ---- gradient w.r.t. the inputs: accumulator chunk 0 = (input column, row); rows are samples (one adjoint stream).
+        // Pair mode: both CTAs hold the chunk for all 128 rows; each reads the columns of its own tile.
         const uint32_t set = gc & 1u;
         ++gc;
         mbar_wait(&B.acc_full[set], (par >> set) & 1u, 0xD10 + set);
         par ^= 1u << set;
         tc_fence_after();
-        if (c_first == 0 && q * 32 < P.in_dim) {
+        if ((kPair ? tsel == 0 : c_first == 0) && q * 32 < P.in_dim) {
           uint32_t v[32];
-          tmem_ld32(lane_taddr + set * 256u + static_cast<uint32_t>(w * kWin), v);
+          tmem_ld32(lane_taddr + set * 256u + static_cast<uint32_t>((kPair ? static_cast<int>(crank) * kNR : 0) + w * kWin), v);
           tc_wait_ld();
           const int k = q * 32 + lane;
           if (k < P.in_dim && tile_ok) {
