@@ -17,7 +17,9 @@
 // IN PLACE with the next layer's input; the two TMEM halves alternate between consecutive layers, and the next layer's
 // MMAs start as soon as its first K-blocks are written.
 // Weight stream: hi / lo stages of 16 KB (128 features x 64 k, K-major, the sampler's stage format) in consumption
-// order, bulk-TMA into a 5-slot ring, multicast across the CTA pair of a cluster (both CTAs walk the same sequence).
+// order, bulk-TMA into a 5-slot ring.
+// CTA pairs (kPair, the default): the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256, N = 128) over
+// their two tiles; see the comment at kPair for what moves between the CTAs.
 //
 // Three kernels + pack:  k_tcl_fwd  (jets forward, per-sample loss terms, output adjoints, stashes for the backward),
 //                        k_tcl_bwd  (adjoint rows P | I | T back through the layers, bias gradients),
@@ -114,9 +116,6 @@ template <int kRegs>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 // operand store of an epilogue thread: own shared memory, or (pair mode) the shared window of either CTA of the pair
 __device__ __forceinline__ void st_operand_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   if (kPair) st_cluster_v4(addr, a, b, c, d);
