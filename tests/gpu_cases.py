@@ -880,6 +880,45 @@ def case_loss_at_baseline_batch(kind, B=65536, chunk=4096):
     return max(err / 3e-4, e_g), 1.0, dict(loss=loss.item(), ref=tot, e_loss=err, e_grad=e_g)
 
 
+def case_loss_repeats(kind, B=65536 + 37, reps=12):
+    """Stand-in for compute-sanitizer racecheck (closed on this pool) on the cross-CTA protocol of the CTA-pair loss
+    kernels: the same fused step, `reps` times on the same inputs, at a batch that leaves the last tile pair ragged (one
+    CTA of the last cluster runs an empty tile).  Every repeat must give the loss and every gradient of the first one
+    up to the reordering of fp32 atomics (3e-5 relative to each tensor's largest entry): an operand read before its rows
+    were written, or a stale weight stage, would show as a wrong result, not as rounding."""
+    from dmip import losses as dl
+    from dmip.linear_problem import LinearForwardProblem
+    from dmip.models.diffusion import CDE
+    lin = LinearForwardProblem()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 2, generator=g)
+    y = lin(x) + 0.3 * torch.randn(B, 2, generator=g)
+    t = torch.rand(B, 1, generator=g) * (1 - 2e-4) + 1e-4
+    eps = torch.randn(B, 2, generator=g)
+    torch.manual_seed(3)
+    m = CDE(2, 2, [512, 512, 512])
+    m.sde.to(DEV)
+    xd, yd, td, ed = (v.to(DEV) for v in (x, y, t, eps))
+    icd = lin.score_posterior(x, y).to(DEV)
+    loss_fn = dl.PINNLoss(lambda xx, yy: icd, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+    first, worst = None, 0.0
+    for _ in range(reps):
+        if kind == "DSM":
+            loss, _ = dl.dsm_fused(m, xd, yd, td, ed)
+        else:
+            loss, _ = loss_fn(m.sde, xd, yd, xd, td, ed, None, None)
+        m.sde.a.zero_grad()
+        loss.backward()
+        cur = [loss.detach().double().reshape(1)] + [p.grad.detach().double().clone() for p in m.sde.a.parameters()]
+        if first is None:
+            first = cur
+            continue
+        for a_, r_ in zip(cur, first):
+            worst = max(worst, ((a_ - r_).abs().max() / r_.abs().max().clamp_min(1e-30)).item())
+    ok = all(torch.isfinite(v).all().item() for v in first)
+    return (worst if ok else float("inf")), 3e-5, dict(reps=reps, batch=B, loss=first[0].item())
+
+
 def case_sampler_trained_1000_steps(precision):
     """Trained linear CDE at S = 1000 steps (5x the reference default: bf16 rounding accumulates 5x longer), N = 512,
     the keyed Philox stream injected, against the CPU oracle sampler on the same noise: fp32 5e-4, bf16 1e-2 max abs

@@ -74,6 +74,12 @@ def test_fused_loss_at_baseline_batch_65536(kind, loss_path):
     _ok(gc.case_loss_at_baseline_batch(kind))
 
 
+@pytest.mark.parametrize("kind", ["DSM", "PINN"])
+def test_fused_loss_repeats_bit_for_bit_up_to_atomics(kind):
+    """the same step twelve times at a ragged batch: the cross-CTA protocol of the pair kernels has no timing dependence"""
+    _ok(gc.case_loss_repeats(kind))
+
+
 def test_kernels_stay_inside_their_buffers():
     """canary-guarded outputs and workspaces over ragged sizes (the stand-in for compute-sanitizer, closed on this pool)"""
     _ok(gc.case_guarded_buffers())
