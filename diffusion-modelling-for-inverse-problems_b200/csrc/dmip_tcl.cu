@@ -1196,13 +1196,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
         // item's results are stored
         float pre[C::SPWB * C::NADJ];
         uint32_t v[32];
-        bwd_prefetch<C>(P, L, k0, etile_ok ? etile : tile, w, pre);
+        bwd_prefetch<C>(P, L, k0, etile, w, pre);
         mbar_wait(&B.acc_full[set], (par >> set) & 1u, 0xD00 + set);
         par ^= 1u << set;
         tc_fence_after();
         const uint32_t t0 = lane_taddr + set * 256u + col0;
         bsum[g][0] += bwd_math<C>(P, t0, etile, etile_ok, w, pre, v);
-        bwd_prefetch<C>(P, L, k1, etile_ok ? etile : tile, w, pre);
+        bwd_prefetch<C>(P, L, k1, etile, w, pre);
         bwd_store<C>(P, L, L != 0 || kGradIn, k0, etile, etile_ok, w, v, hdst, tsel != static_cast<int>(crank), &B.hready[c_first],
                      hready_leader + static_cast<uint32_t>(c_first) * 8u, lane);
         bsum[g][1] += bwd_math<C>(P, t0 + kColStep, etile, etile_ok, w, pre, v);
