@@ -50,7 +50,10 @@ constexpr int kNumRowWarps = 16;
 constexpr int kRowThreads = 512;
 constexpr int kProducerWarp = 16;
 constexpr int kMmaWarp = 17;
-constexpr int kCluster = 2;          // CTAs per cluster sharing one multicast weight stream
+#ifndef DMIP_CLUSTER
+#define DMIP_CLUSTER 2
+#endif
+constexpr int kCluster = DMIP_CLUSTER;   // CTAs per cluster sharing one multicast weight stream (2; 4 is a build-time experiment)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemH = 0;       // 256 columns: 128 x 512 bf16 activations (A operand)
 constexpr uint32_t kTmemAcc = 256;   // 2 x 128 columns: fp32 accumulator chunks
@@ -1083,7 +1086,7 @@ int launch(TcParams& P, cudaStream_t s) {
   P.cluster = C;
   P.dbg = g_dbg;
   const long long want_clusters = (P.n_tiles + C - 1) / C;
-  const long long max_clusters = n_sm / C;
+  const long long max_clusters = n_sm / C;   // pairs: all 74 are co-resident (tools/probe/cluster_probe.cu; 4: only 33)
   const long long n_clusters = want_clusters < max_clusters ? want_clusters : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * C));
