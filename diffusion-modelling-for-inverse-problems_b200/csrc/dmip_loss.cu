@@ -278,10 +278,11 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
             l_ic = P.lam * r * r;
             abP = P.inv_B * P.lam * 2.f * r * alpha;
           } else {
-            // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                            (losses.py:49-52, Q3)
+            // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                            (losses.py:49-52, Q3);
+            // PINNLoss2 only reports it ('DSM_eval', losses.py:291): no adjoint
             const float r = aj / sb * sd + epsj;
             l_dsm = 0.5f * r * r;
-            abP = P.inv_B * r * sd / sb;
+            abP = P.kind == DMIP_LOSS_PINN2 ? 0.f : P.inv_B * r * sd / sb;
           }
           if (P.has_I) {                           // initial condition at t = 0          (losses.py:221-230)
             const float g0 = sqrtf(P.bmin);
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_jets_fwd(const __grid_constant
       atomicAdd(&P.losses[1], red[1] * P.inv_B);
       atomicAdd(&P.losses[2], red[2] * P.inv_B);
       atomicAdd(&P.losses[3], red[3] * P.inv_B);
-      atomicAdd(&P.losses[0], (red[1] + red[2] + red[3]) * P.inv_B);
+      atomicAdd(&P.losses[0], ((P.kind == DMIP_LOSS_PINN2 ? 0.f : red[1]) + red[2] + red[3]) * P.inv_B);
     }
     __syncthreads();
   }
@@ -774,8 +775,9 @@ int plan_pass(const PassCfg& c, LossPlan* p) {
 // DmipLoss -> PassCfg (CDE / CDiffE losses), with the reference's argument checks
 int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
   DMIP_REQUIRE(q != nullptr, "descriptor is NULL");
-  DMIP_REQUIRE(q->kind == DMIP_LOSS_DSM || q->kind == DMIP_LOSS_DSM_PDE || q->kind == DMIP_LOSS_PINN,
-               "No valid loss_fn was specified. Options are DMIP_LOSS_DSM, DMIP_LOSS_DSM_PDE, DMIP_LOSS_PINN.");
+  DMIP_REQUIRE(q->kind == DMIP_LOSS_DSM || q->kind == DMIP_LOSS_DSM_PDE || q->kind == DMIP_LOSS_PINN ||
+               q->kind == DMIP_LOSS_PINN2,
+               "No valid loss_fn was specified. Options are DMIP_LOSS_DSM, DMIP_LOSS_DSM_PDE, DMIP_LOSS_PINN, DMIP_LOSS_PINN2.");
   DMIP_REQUIRE(q->model == DMIP_CDE || q->model == DMIP_CDIFFE, "model must be DMIP_CDE or DMIP_CDIFFE");
   DMIP_REQUIRE(q->xdim >= 1 && q->ydim >= 1 && q->batch >= 0, "xdim/ydim must be positive, batch >= 0");
   int rc = check_net(q->net, q->xdim + q->ydim + 1, "net");
@@ -793,11 +795,12 @@ int cfg_from_loss(const DmipLoss* q, PassCfg* c) {
     DMIP_REQUIRE(q->pde_metric == DMIP_L1 || q->pde_metric == DMIP_L2,
                  "No valid metric specified. Metric should be one of \"L1\" or \"L2\"");
   }
-  if (q->kind == DMIP_LOSS_PINN) {
+  const bool pinn = q->kind == DMIP_LOSS_PINN || q->kind == DMIP_LOSS_PINN2;
+  if (pinn) {
     DMIP_REQUIRE(q->ic_metric == DMIP_L1 || q->ic_metric == DMIP_L2, "ic_metric should be one of \"L1\" or \"L2\"");
     DMIP_REQUIRE(q->ic_target != nullptr || q->batch == 0, "PINNLoss needs ic_target = initial_condition(x, y)");
   }
-  c->has_I = q->kind == DMIP_LOSS_PINN;
+  c->has_I = pinn;
   c->has_T = pde;
   const bool fpe = pde && q->pde_loss == DMIP_PDE_FPE;
   if (fpe) {

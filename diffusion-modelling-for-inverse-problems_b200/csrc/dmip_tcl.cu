@@ -780,10 +780,11 @@ __device__ __forceinline__ void fwd_loss_stage(const TclDev& P, long long s0, bo
         l_ic = P.lam * r * r;
         abP = P.inv_B * P.lam * 2.f * r * alpha;
       } else {
-        // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                                         (losses.py:49-52, Q3)
+        // DSM: 1/2 sum (s std + eps)^2, s = a / sqrt(beta)                                         (losses.py:49-52, Q3);
+        // PINNLoss2 only reports it ('DSM_eval', losses.py:291): no adjoint
         const float r = aj / sb * sd + epsj;
         l_dsm = 0.5f * r * r;
-        abP = P.inv_B * r * sd / sb;
+        abP = P.kind == DMIP_LOSS_PINN2 ? 0.f : P.inv_B * r * sd / sb;
       }
       if (C::kI) {                                   // initial condition at t = 0                 (losses.py:221-230)
         const float g0 = sqrtf(P.bmin);
@@ -982,7 +983,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
       atomicAdd(&P.losses[1], red[1] * P.inv_B);
       atomicAdd(&P.losses[2], red[2] * P.inv_B);
       atomicAdd(&P.losses[3], red[3] * P.inv_B);
-      atomicAdd(&P.losses[0], (red[1] + red[2] + red[3]) * P.inv_B);
+      atomicAdd(&P.losses[0], ((P.kind == DMIP_LOSS_PINN2 ? 0.f : red[1]) + red[2] + red[3]) * P.inv_B);
     }
     if (t < P.out_dim) atomicAdd(&P.grad[P.off_b[3] + t], b3sum[t]);
   }

@@ -1,5 +1,5 @@
 """Drop-in for the reference's `losses.py`: DSMLoss, ScoreFPELoss, ConditionalScoreFPELoss, DSM_PDELoss, PINNLoss,
-PosteriorLoss — same class names, constructor arguments, `.name` dispatch keys and `forward` signatures.
+PINNLoss2, PosteriorLoss — same class names, constructor arguments, `.name` dispatch keys and `forward` signatures.
 
 The reference builds these losses out of 2d+1 `torch.autograd.grad(create_graph=True)` passes and then runs
 `loss.backward()` through the double-backward graph (losses.py:14-26, 77-98, 214-242).  Here the composite losses
@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib
 
-_LOSS_DSM, _LOSS_DSM_PDE, _LOSS_PINN = 0, 1, 2
+_LOSS_DSM, _LOSS_DSM_PDE, _LOSS_PINN, _LOSS_PINN2 = 0, 1, 2, 3
 _METRIC = {'L1': 1, 'L2': 2}
 _DIVERGENCE = {'exact': 0, 'hutchinson': 1, 'approx': 1, 'approximate': 1, 'exact_adjoint': 2}
 
@@ -259,6 +259,38 @@ class PINNLoss(nn.Module):
         out, cfg = _fused(model, cfg, x, y, t, target, ic_target)
         self.last_launch_count = cfg['launches']
         return out[0], {'PDE-Loss': out[3].detach(), 'Initial Condition': out[2].detach(), 'DSM-Loss': out[1].detach()}
+
+
+class PINNLoss2(nn.Module):
+    """PINNLoss without the data-driven DSM term: mean(lam2 * initial condition + lam * PDE residual); the DSM loss is only
+    reported ('DSM_eval').  Constructor as upstream (losses.py:250-261) — so `utils.get_model_from_args`, which passes an
+    unsupported `pde_metric=` (utils.py:38), fails with the same TypeError — plus the attribute upstream's forward reads
+    but never sets (`ic_metric`, losses.py:276), as a keyword-only argument (default 'L1', PINNLoss's default).  The pde
+    losses keep their default metrics (ScoreFPELoss 'L1', ConditionalScoreFPELoss 'L2')."""
+
+    def __init__(self, initial_condition, lam=1., lam2=1., pde_loss='FPE', *, ic_metric='L1', divergence_method='exact'):
+        super().__init__()
+        self.lam = lam
+        self.lam2 = lam2
+        self.initial_condition = initial_condition
+        self.pde_loss = ScoreFPELoss() if pde_loss == 'FPE' else ConditionalScoreFPELoss()
+        self.eval_metric = DSMLoss()
+        self.name = 'PINNLoss2'
+        self.ic_metric = ic_metric
+        self.divergence_method = divergence_method
+
+    def forward(self, model, x, y, diffused_samples, t, target, std, g):
+        div, probe = _divergence(self, diffused_samples)
+        cfg = dict(kind=_LOSS_PINN2, model=_model_kind(x, diffused_samples), lam=float(self.lam), lam2=float(self.lam2),
+                   pde_loss=0 if self.pde_loss.name == 'FPELoss' else 1, pde_metric=_metric(self.pde_loss.metric),
+                   ic_metric=_metric(self.ic_metric), divergence=div, hutch_v=probe,
+                   batch_global=getattr(self, 'batch_global', 0), grad_out=getattr(self, 'grad_out', None))
+        _check_diffused(model, x, y, diffused_samples, t, target, std)
+        with torch.no_grad():
+            ic_target = self.initial_condition(x, y)
+        out, cfg = _fused(model, cfg, x, y, t, target, ic_target)
+        self.last_launch_count = cfg['launches']
+        return out[0], {'PDE-Loss': out[3].detach(), 'Initial Condition': out[2].detach(), 'DSM_eval': out[1].detach()}
 
 
 class PosteriorLoss(nn.Module):

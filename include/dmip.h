@@ -191,6 +191,8 @@ int dmip_mlp_backward(const DmipMlpGrad* d, void* stream);
 #define DMIP_LOSS_DSM 0     /* loss_fn.name == 'DSMLoss'                                   */
 #define DMIP_LOSS_DSM_PDE 1 /* DSM_PDELoss                                                 */
 #define DMIP_LOSS_PINN 2    /* PINNLoss                                                    */
+#define DMIP_LOSS_PINN2 3   /* PINNLoss2 (losses.py:245-291): PINNLoss WITHOUT the DSM term in the objective — total =
+                               lam2 ic + lam pde; out_losses[1] still reports the mean DSM loss (its 'DSM_eval' entry)  */
 #define DMIP_PDE_FPE 0      /* pde_loss = 'FPE'  (exact divergence: d = xdim [+ydim for CDiffE] <= 31) */
 #define DMIP_PDE_CFPE 1     /* pde_loss = 'cScoreFPE'                                      */
 /* divergence_method of ScoreFPELoss.forward (losses.py:81-86).  EXACT: d <= 4 runs forward-only (d + d(d+1)/2 tangent

@@ -160,6 +160,26 @@ def pinn_loss(params, model_kind, x, y, t, eps, ic_target, lam=1.0, lam2=1.0,
     return loss, {"PDE-Loss": l_pde.mean(), "Initial Condition": l_ic.mean(), "DSM-Loss": l_dsm.mean()}
 
 
+def pinn2_loss(params, model_kind, x, y, t, eps, ic_target, lam=1.0, lam2=1.0,
+               pde_loss="FPE", ic_metric="L1", probe=None):
+    """PINNLoss2.forward (losses.py:263-291): PINNLoss without the data-driven DSM term —
+    mean(lam2 ic + lam pde); the DSM loss is only reported ('DSM_eval').  Upstream the class
+    reads an attribute it never sets (self.ic_metric, :276) — `ic_metric` here is that
+    attribute; its pde losses are built with their default metrics (:256-259: ScoreFPELoss()
+    'L1', ConditionalScoreFPELoss() 'L2')."""
+    B, xdim = x.shape
+    z0, cond, z_t, std = _split(model_kind, x, y, t, eps)
+    t0 = torch.zeros_like(t)
+    s0 = onets.mlp(params, x, y, t0) / vp.beta(t0) ** 0.5               # :268-270
+    terms = score_and_fpe_terms(params, z_t, cond, t, z0, eps, need_space=(pde_loss != "cScoreFPE"), probe=probe)
+    diff = s0[:, :xdim] - ic_target
+    l_ic = lam2 * ((diff ** 2).mean(1, keepdim=True) if ic_metric == "L2" else diff.abs().mean(1, keepdim=True))
+    l_pde = lam * _pde(terms, t, eps, std, pde_loss, "L2" if pde_loss == "cScoreFPE" else "L1")
+    loss = l_ic.mean() + l_pde.mean()                                   # :289 (Q10 for the (B,)+(B,1) case)
+    return loss, {"PDE-Loss": l_pde.mean(), "Initial Condition": l_ic.mean(),
+                  "DSM_eval": dsm(terms["s"], std, eps).mean()}
+
+
 def posterior_loss(prior_params, lik_params, surr_params, x, y, t, eps, lam,
                    a=scat.A_NOISE, b=scat.B_NOISE):
     """PosteriorLoss.forward (losses.py:372-386) with likelihood_target (:349-371)

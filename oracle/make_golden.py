@@ -256,6 +256,12 @@ def fx_loss(name, model_kind, problem, loss_kind, hidden, seed, B, full_grads=Fa
         loss_fn = ref_losses.PINNLoss(ic_fn, **kw)
     elif loss_kind == "DSM_PDE":
         loss_fn = ref_losses.DSM_PDELoss(**kw)
+    elif loss_kind == "PINN2":
+        # the class as shipped reads self.ic_metric, which its constructor never sets (losses.py:250-261, :276;
+        # SURVEY.md App. C): the attribute is supplied here, everything else is the reference's code
+        ic_metric = kw.pop("ic_metric")
+        loss_fn = ref_losses.PINNLoss2(ic_fn, **kw)
+        loss_fn.ic_metric = ic_metric
     if probe is not None:
         # ScoreFPELoss.forward(..., divergence_method=...) is the reference's own argument (losses.py:77-86); the
         # composite losses never pass it, so it is bound here; rademacher_like (losses.py:7-11) hands out the stored probe
@@ -279,7 +285,7 @@ def fx_loss(name, model_kind, problem, loss_kind, hidden, seed, B, full_grads=Fa
     loss.backward()
     arrs = dict(x=x, y=y, t=t, eps=eps, loss=loss.detach(),
                 meta=np.array([seed, xdim, ydim, B] + list(hidden)))
-    if loss_kind == "PINN":
+    if loss_kind in ("PINN", "PINN2"):
         arrs["ic_target"] = ic_fn(x, y)
     if probe is not None:
         arrs["probe"] = probe
@@ -309,6 +315,8 @@ fx_loss("loss_dsmpde_cde_linear_cfpe", "CDE", "linear", "DSM_PDE", H, 41, 128, l
 fx_loss("loss_pinn_small", "CDE", "linear", "PINN", (64, 64), 42, 64, full_grads=True,
         lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
 fx_loss("loss_dsm_small", "CDE", "linear", "DSM", (64, 64), 43, 64, full_grads=True)
+fx_loss("loss_pinn2_cde_linear", "CDE", "linear", "PINN2", H, 47, 128, lam=0.01, lam2=0.1, pde_loss="FPE", ic_metric="L2")
+fx_loss("loss_pinn2_cde_scat_cfpe", "CDE", "scat", "PINN2", H, 48, 96, lam=0.02, lam2=0.05, pde_loss="cScoreFPE", ic_metric="L1")
 # d = 26 (CDiffE on scatterometry): exact divergence = 53 double-backward passes upstream; and the Hutchinson estimator
 fx_loss("loss_pinn_cdiffe_scat", "CDiffE", "scat", "PINN", H, 44, 48,
         lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1")

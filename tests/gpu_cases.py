@@ -224,6 +224,9 @@ LOSS_CASES = {
     "loss_pinn_small": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="FPE", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear_cfpe": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="cScoreFPE", pde_metric="L1"), 1.0),
+    # PINNLoss2 (losses.py:245-291) with the attribute its forward reads but never sets supplied (oracle/make_golden.py)
+    "loss_pinn2_cde_linear": ("CDE", "PINN2", dict(lam=0.01, lam2=0.1, pde_loss="FPE", ic_metric="L2"), 1.0),
+    "loss_pinn2_cde_scat_cfpe": ("CDE", "PINN2", dict(lam=0.02, lam2=0.05, pde_loss="cScoreFPE", ic_metric="L1"), 1.0),
     "loss_pinn_cdiffe_scat": ("CDiffE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
     "loss_pinn_cde_scat_hutch": ("CDE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1",
                                                      divergence_method="hutchinson"), 1.0),
@@ -257,6 +260,9 @@ def case_loss(name, route=None):
         if kind == "PINN":
             ic = fx["ic_target"].to(DEV)
             loss_fn = dl.PINNLoss(lambda xx, yy: ic, **kw)
+        elif kind == "PINN2":
+            ic = fx["ic_target"].to(DEV)
+            loss_fn = dl.PINNLoss2(lambda xx, yy: ic, **kw)
         else:
             loss_fn = dl.DSM_PDELoss(**kw)
         if "probe" in fx:

@@ -81,6 +81,9 @@ LOSS_CASES = {
     "loss_pinn_small": ("CDE", "PINN", dict(lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="FPE", pde_metric="L1"), 1.0),
     "loss_dsmpde_cde_linear_cfpe": ("CDE", "DSM_PDE", dict(lam=0.1, pde_loss="cScoreFPE", pde_metric="L1"), 1.0),
+    # PINNLoss2 (losses.py:245-291) with the attribute its forward reads but never sets supplied (oracle/make_golden.py)
+    "loss_pinn2_cde_linear": ("CDE", "PINN2", dict(lam=0.01, lam2=0.1, pde_loss="FPE", ic_metric="L2"), 1.0),
+    "loss_pinn2_cde_scat_cfpe": ("CDE", "PINN2", dict(lam=0.02, lam2=0.05, pde_loss="cScoreFPE", ic_metric="L1"), 1.0),
     "loss_pinn_cdiffe_scat": ("CDiffE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1"), 1.0),
     "loss_pinn_cde_scat_hutch": ("CDE", "PINN", dict(lam=0.01, lam2=0.001, pde_loss="FPE", ic_metric="L2", pde_metric="L1",
                                                      divergence_method="hutchinson"), 1.0),
@@ -105,6 +108,8 @@ def test_losses(name):
         loss, info = ol.dsm_loss(params, model, x, y, t, eps), {}
     elif kind == "PINN":
         loss, info = ol.pinn_loss(params, model, x, y, t, eps, fx["ic_target"], **kw)
+    elif kind == "PINN2":
+        loss, info = ol.pinn2_loss(params, model, x, y, t, eps, fx["ic_target"], **kw)
     else:
         loss, info = ol.dsm_pde_loss(params, model, x, y, t, eps, **kw)
     assert abs(loss.item() - fx["loss"].item()) <= 2e-4 * abs(fx["loss"].item()) + 1e-6
