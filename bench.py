@@ -111,10 +111,11 @@ def cpu_params(in_dim, out_dim, seed=0):
 _REF_MODEL = {}
 
 
-def _reference_cde(xdim, ydim):
+def _reference_cde(xdim, ydim, cls="CDE"):
     """The stock reference class on CPU (baseline/_ref = unmodified reference files; oracle/shims for the three modules
-    the reference tree does not contain).  None if the staged sources are missing."""
-    key = (xdim, ydim)
+    the reference tree does not contain).  None if the staged sources are missing.  For cls != 'CDE' the reference's
+    losses module is attached as `model.ref_losses` (the training arm needs its DSMLoss)."""
+    key = (xdim, ydim, cls)
     if key in _REF_MODEL:
         return _REF_MODEL[key]
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
@@ -131,8 +132,10 @@ def _reference_cde(xdim, ydim):
             torch.cuda.is_available = lambda: False        # the reference picks its device at import time: keep it on CPU
             mod = importlib.import_module("models.diffusion")
             torch.manual_seed(0)
-            model = mod.CDE(xdim, ydim, list(HIDDEN))
-            model.sde.eval()
+            model = getattr(mod, cls)(xdim, ydim, list(HIDDEN))
+            model.ref_losses = importlib.import_module("losses")
+            if cls == "CDE":
+                model.sde.eval()
         except Exception as e:                             # noqa: BLE001 — fall back to the port, and say so
             print("reference arm: stock classes unavailable:", repr(e), file=sys.stderr)
             model = None
@@ -466,6 +469,60 @@ def also_train(kind, B, steps=5, warmup=3, dist=None, rank=0, world=1):
     return out
 
 
+def also_config0(batch=1000, n_batches=90, cpu_batches=12):
+    """BASELINE configs[0]: the linear toy problem, CDiffE with the DSM loss, at the sizes of config/config_linear.yml
+    (batch 1000, 90 000 training rows -> 90 batches per epoch, Adam lr 1e-4) through the drop-in `model.train_epoch`:
+    at this batch a step is a handful of short launches, so what is measured is the host path (device-side t draw,
+    fused loss call, optimizer step on the gradient bucket — no autograd round trip).  The same epoch body of the stock
+    reference classes runs on the host cores for `cpu_batches` batches."""
+    import torch
+    from dmip import losses as dl
+    from dmip.models.diffusion import CDiffE
+    torch.manual_seed(0)
+    model = CDiffE(2, 2, HIDDEN)
+    opt = torch.optim.Adam(model.sde.a.parameters(), lr=1e-4)      # the reference's optimizer (main_diffusion_linear.py:160)
+    x, y, _ = linear_batch(batch * n_batches, 7)
+    xd, yd = x.cuda(), y.cuda()
+
+    def loader():
+        for i in range(0, xd.shape[0], batch):
+            yield xd[i:i + batch], yd[i:i + batch]
+
+    loss_fn = dl.DSMLoss()
+    model.train_epoch(opt, loss_fn, loader)                        # warm-up epoch (Adam state, bucket, kernel attributes)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss, _ = model.train_epoch(opt, loss_fn, loader)
+    lv = float(loss)                                               # device -> host read of the epoch's result
+    dt = time.perf_counter() - t0
+    out = {"config": f"configs[0]: linear CDiffE + DSMLoss, config_linear.yml sizes: one train_epoch of {n_batches} batches "
+                     f"of {batch} (wall clock through model.train_epoch, data resident on the GPU as in the reference's loader)",
+           "value": batch * n_batches / dt, "unit": "samples/s", "ms": dt / n_batches * 1e3, "dtype": "bf16x3 (fp32-accurate split)",
+           "loss": lv, "gpu_launches": getattr(loss_fn, "last_launch_count", 0) * n_batches,
+           "roofline": {"bound": "host", "achieved": None, "peak": None, "unit": "ms/step", "frac": None, "traffic": None,
+                        "note": "launch-bound: ~0.15 ms of kernels per step; see tools/small_batch_steps.py"},
+           "e2e": {"value": batch * n_batches / dt, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    del model, opt
+    ref = _reference_cde(2, 2, "CDiffE")
+    if ref is not None:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ropt = torch.optim.Adam(ref.sde.a.parameters(), lr=1e-4)
+        rloss = ref.ref_losses.DSMLoss()
+
+        def cpu_loader(nb):
+            return lambda: ((x[i:i + batch], y[i:i + batch]) for i in range(0, nb * batch, batch))
+
+        ref.train_epoch(ropt, rloss, cpu_loader(2))                # warm-up
+        t0 = time.perf_counter()
+        ref.train_epoch(ropt, rloss, cpu_loader(cpu_batches))
+        cdt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": batch * cpu_batches / cdt, "unit": "samples/s", "cores": cores, "kind": "reference",
+                               "ms_per_step": cdt / cpu_batches * 1e3,
+                               "sample": f"{cpu_batches} batches of {batch}: the stock reference CDiffE.train_epoch + DSMLoss, torch CPU fp32"}
+    return out
+
+
 def also_posterior_loss(B=16384, steps=5, warmup=3):
     """PosteriorDiffusionEstimator.train_epoch body (models/diffusion.py:204-229): PosteriorLoss forward + backward +
     Adam on both nets, scatterometry shapes, random-init surrogate of the reference's architecture."""
@@ -565,6 +622,7 @@ def run_also(args, flush):
             also[name] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
 
+    guard("config0_linear_cdiffe_dsm", also_config0)
     guard("cdiffe_scat", lambda: also_sampler("cdiffe_scat", 1 << 20, 1000, flush))
     guard("dps_scat", lambda: also_sampler("dps_scat", 1 << 16, 1000, flush))
     guard("pinn_linear", lambda: also_train("PINN", 65536))

@@ -156,6 +156,18 @@ def mlp_desc(net, keep):
     return d
 
 
+def mlp_desc_cached(net):
+    """`mlp_desc` once per set of parameter storages: (descriptor, kept tensors).  Optimizer steps update the parameters in
+    place, so during training the pointers — all the descriptor holds — do not change from step to step."""
+    layers = linear_layers(net)
+    key = tuple(p.data_ptr() for lin in layers for p in (lin.weight, lin.bias))
+    hit = net.__dict__.get('_dmip_desc')
+    if hit is None or hit[0] != key:
+        keep = []
+        hit = net.__dict__['_dmip_desc'] = (key, mlp_desc(net, keep), keep)
+    return hit[1], hit[2]
+
+
 class PackedNet:
     """Cache of the tcgen05 operand image of one net; re-packed when a parameter changes.
 

@@ -226,6 +226,14 @@ int dmip_hist_kl(const void* hist_p, const void* hist_q, int64_t n_bins_total, d
   return launch_hist_kl(hist_p, hist_q, n_bins_total, epsilon, out, static_cast<cudaStream_t>(stream));
 }
 
+int dmip_sample_t(const float* u, float* t, int64_t n, int32_t debias, float beta_min, float beta_max, float t_epsilon,
+                  float T, float eps_add, void* stream) {
+  reset_launch_count();
+  int rc = require_device();
+  if (rc) return rc;
+  return launch_sample_t(u, t, n, debias, beta_min, beta_max, t_epsilon, T, eps_add, static_cast<cudaStream_t>(stream));
+}
+
 #if defined(DMIP_DEBUG) || defined(DMIP_JOBMARKS)
 void dmip_debug_set_timeline(void* device_buf, int32_t capacity) {
   debug_set_timeline(static_cast<unsigned long long*>(device_buf), capacity);

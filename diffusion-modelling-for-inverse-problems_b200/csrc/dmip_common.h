@@ -77,6 +77,8 @@ size_t surrogate_workspace(const DmipSurrogate* d);
 int launch_surrogate(const DmipSurrogate* d, cudaStream_t s);
 size_t metropolis_workspace(const DmipMetropolis* d);
 int launch_metropolis(const DmipMetropolis* d, cudaStream_t s);
+int launch_sample_t(const float* u, float* t, long long n, int debias, float beta_min, float beta_max, float t_epsilon,
+                    float T, float eps_add, cudaStream_t s);
 size_t sampler_tc_workspace();
 void debug_set_timeline(unsigned long long* buf, int cap);
 }  // namespace dmip

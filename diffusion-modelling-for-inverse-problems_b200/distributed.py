@@ -128,16 +128,19 @@ def _bucket_nets(model):
     return [a]
 
 
-def train_step_data_parallel(model, optimizer, loss_fn, x, y, t=None, group=None, batch_global=None):
-    """One optimisation step of CDE/CDiffE/PosteriorDiffusionEstimator.train_epoch (models/diffusion.py:80-102) with the
-    batch split across ranks: x, y are THIS rank's rows; the loss means run over the global batch.
+def fused_optimizer_step(model, optimizer, loss_fn, x, y, t=None, *, data_parallel=False, group=None, batch_global=None):
+    """`optimizer.zero_grad(); loss.backward(); optimizer.step()` of the reference's train loops (models/diffusion.py:
+    100-102, :150-152, :223-225) without autograd in between: the fused loss kernels write the gradient into the model's
+    GradBucket, whose slices ARE the parameters' `.grad`, and the optimizer steps on that memory.  The gradient is the
+    one `loss.backward()` after `zero_grad()` leaves behind; what is saved is host time (at the reference's batch of
+    1000 the autograd round trip is a third of the step).  Returns (loss, info) as device tensors.
 
-    `batch_global`: rows of the whole batch over all ranks.  Default: this rank's rows x world size (equal shards — what
-    `shard_range` gives when the batch divides evenly); pass it explicitly for ragged shards.  It is a host integer: no
-    collective and no device->host read is spent on it.  The step: fused loss kernels write the gradient into the
-    model's GradBucket, ONE all-reduce (gradients + loss scalars), optimizer.step()."""
+    data_parallel=True: x, y are THIS rank's rows, the loss means run over the global batch (`batch_global` rows over all
+    ranks; default: this rank's rows x world size — what `shard_range` gives when the batch divides evenly; a host
+    integer, so no collective and no device->host read is spent on it), and ONE all-reduce sums gradients and loss
+    scalars of all ranks in the bucket before the optimizer steps."""
     from .losses import fused_train_step
-    rank, ws = world()
+    ws = world()[1] if data_parallel else 1
     bucket = getattr(model, '_grad_bucket', None)
     if bucket is None:
         bucket = model._grad_bucket = GradBucket(_bucket_nets(model))
@@ -149,9 +152,12 @@ def train_step_data_parallel(model, optimizer, loss_fn, x, y, t=None, group=None
     try:
         with torch.no_grad():
             loss, info = fused_train_step(model, loss_fn, x, y, t)
-    finally:                                          # module state must not leak into a later single-process train_epoch
+    finally:                                          # module state must not leak into a later call
         loss_fn.batch_global = 0
         loss_fn.grad_out = None
+    if ws == 1:
+        optimizer.step()
+        return loss, info
     keys = sorted(info)
     sc = bucket.scalars
     sc.zero_()
@@ -162,3 +168,10 @@ def train_step_data_parallel(model, optimizer, loss_fn, x, y, t=None, group=None
     optimizer.step()
     out = bucket.scalars.clone()
     return out[0], {k: out[1 + i] for i, k in enumerate(keys)}
+
+
+def train_step_data_parallel(model, optimizer, loss_fn, x, y, t=None, group=None, batch_global=None):
+    """One optimisation step of CDE/CDiffE/PosteriorDiffusionEstimator.train_epoch (models/diffusion.py:80-102) with the
+    batch split across ranks (see fused_optimizer_step)."""
+    return fused_optimizer_step(model, optimizer, loss_fn, x, y, t, data_parallel=True, group=group,
+                                batch_global=batch_global)

@@ -79,13 +79,12 @@ def _launch_fused(net, cfg, x, y, t, eps, ic_target, grad_out=None):
     in its all-reduce bucket, whose slices ARE the parameters' .grad (dmip.distributed.GradBucket)."""
     L = _bind()
     dev = x.device
-    keep = []
     d = DmipLoss()
     d.kind, d.model = cfg['kind'], cfg['model']
     d.xdim, d.ydim = x.shape[1], y.shape[1]
     d.batch = x.shape[0]
     d.batch_global = cfg.get('batch_global', 0) or x.shape[0]
-    d.net = _lib.mlp_desc(net, keep)
+    d.net, keep = _lib.mlp_desc_cached(net)
     d.beta_min, d.beta_max = cfg['beta_min'], cfg['beta_max']
     d.lam, d.lam2 = cfg.get('lam', 0.0), cfg.get('lam2', 0.0)
     d.pde_loss, d.pde_metric, d.ic_metric = cfg.get('pde_loss', 0), cfg.get('pde_metric', 1), cfg.get('ic_metric', 1)
@@ -112,8 +111,11 @@ def _launch_fused(net, cfg, x, y, t, eps, ic_target, grad_out=None):
         _lib.check(-1)
     ws = guard.empty(nbytes, torch.uint8, dev)
     d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
-    with torch.cuda.device(dev):
+    if torch.cuda.current_device() == dev.index:
         _lib.check(L.dmip_loss_fwd_bwd(C.byref(d), _lib.stream_ptr()))
+    else:
+        with torch.cuda.device(dev):
+            _lib.check(L.dmip_loss_fwd_bwd(C.byref(d), _lib.stream_ptr()))
     guard.check("dmip_loss_fwd_bwd")
     return losses, grad, L.dmip_last_launch_count()
 
@@ -130,11 +132,13 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        scale = gout[0]                       # only losses[0] (the total) is differentiable; the rest is the info dict
+        # only losses[0] (the total) is differentiable; the rest is the info dict.  ONE multiply over the flat gradient;
+        # the parameters get views of the product (AccumulateGrad adopts them when .grad is None: no copies)
+        flat = ctx.flat * gout[0]
         grads, off = [], 0
         for shp in ctx.shapes:
             n = shp.numel()
-            grads.append((ctx.flat[off:off + n] * scale).view(shp))
+            grads.append(flat[off:off + n].view(shp))
             off += n
         return (None, None, None, None, None, None, None, *grads)
 

@@ -27,12 +27,28 @@ from torch import nn
 
 from .. import _lib
 from .. import sdes
+from ..distributed import _bucket_nets, fused_optimizer_step
 from ..losses import PosteriorLoss, fused_train_step
 from ..nets import MLP, MLP2, PosteriorScore
 
 device = 'cuda' if torch.cuda.is_available() else 'cpu'
 
 _VARIANT = {'CDE': _lib.CDE, 'CDiffE': _lib.CDIFFE, 'Posterior': _lib.DPS}
+
+
+def _owns_all_grads(model, optimizer):
+    """True when `optimizer.zero_grad(); loss.backward(); optimizer.step()` can be replaced by the fused step that writes
+    the gradient straight into the parameters' `.grad` (dmip.distributed.fused_optimizer_step): every parameter of the
+    optimizer is a trainable parameter of the model's score net(s) without gradient hooks — nothing else would get, or
+    keep, a gradient from this loss.  Cached per (optimizer, parameter count)."""
+    key = (id(optimizer), sum(len(g['params']) for g in optimizer.param_groups))
+    cache = model.__dict__.setdefault('_fused_step_ok', {})
+    if key not in cache:
+        mine = {id(p): p for net in _bucket_nets(model) for lin in _lib.linear_layers(net) for p in (lin.weight, lin.bias)}
+        theirs = [p for g in optimizer.param_groups for p in g['params']]
+        cache[key] = (len(theirs) == len(mine) and all(id(p) in mine for p in theirs)
+                      and all(p.requires_grad and not p._backward_hooks and p.is_cuda for p in mine.values()))
+    return cache[key]
 
 
 class BaseClassDiffusionModel():
@@ -183,6 +199,14 @@ class BaseClassDiffusionModel():
 
     # ------------------------------------------------------------------ training
     def sample_t(self, x, eps=1e-4):
+        base = self.sde.base_sde
+        if x.is_cuda and hasattr(base, 'sample_t_device'):
+            # the reference draws t on the CPU and copies it over every batch; at its own batch size that is a third of
+            # the step's host time — same distribution, drawn where it is used
+            t_ = base.sample_t_device([x.size(0), ] + [1 for _ in range(x.ndim - 1)], x.device, self.sde.debias, eps)
+            t_ = t_.to(x.dtype)
+            t_.requires_grad = True
+            return t_
         if self.sde.debias:
             t_ = self.sde.base_sde.sample_debiasing_t([x.size(0), ] + [1 for _ in range(x.ndim - 1)]) + eps
             t_ = torch.where(t_ > self.sde.T, t_ - eps, t_).to(x)
@@ -197,14 +221,28 @@ class BaseClassDiffusionModel():
         logger_info = {}
         for k, (x, y) in enumerate(epoch_data_loader()):
             t = self.sample_t(x)
-            loss, loss_info = fused_train_step(self, loss_fn, x, y, t)
-            for key, value in loss_info.items():
-                logger_info[key] = logger_info.get(key, 0) * k / (k + 1) + value.item() / (k + 1)
-            optimizer.zero_grad()
-            loss.backward()
-            optimizer.step()
+            if x.is_cuda and _owns_all_grads(self, optimizer):
+                # zero_grad / backward / step without the autograd round trip (dmip.distributed.fused_optimizer_step)
+                loss, loss_info = fused_optimizer_step(self, optimizer, loss_fn, x, y, t)
+                stepped = True
+            else:
+                loss, loss_info = fused_train_step(self, loss_fn, x, y, t)
+                stepped = False
+            # running means as upstream (models/diffusion.py:90-92, :103), kept on the device in float64 — the arithmetic
+            # of upstream's Python floats — as ONE vector, and read back once per epoch instead of one .item() per
+            # entry per batch
+            if loss_info:
+                keys = list(loss_info)
+                vals = torch.stack([loss_info[key].detach() for key in keys]).double()
+                logger_info = (logger_info * k / (k + 1) if k else 0) + vals / (k + 1)
+            if not stepped:
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()
             mean_loss = mean_loss * k / (k + 1) + loss.detach() / (k + 1)
-        return mean_loss, logger_info
+        if not torch.is_tensor(logger_info):
+            return mean_loss, {}
+        return mean_loss, dict(zip(keys, logger_info.tolist()))
 
 
 class CDE(BaseClassDiffusionModel):

@@ -73,6 +73,26 @@ class VariancePreservingSDE(torch.nn.Module):
         u = torch.rand(*shape)
         return vp_truncated_inverse_cdf(u.view(-1), self.beta_min, self.beta_max, self.t_epsilon, self.T).view(*shape)
 
+    def sample_t_device(self, shape, device, debias=True, eps=1e-4):
+        """`sample_t` of the models (models/diffusion.py:48-58: the draw above + eps, folded back where it exceeds T; or
+        eps + u T without debiasing) entirely on `device`: one torch.rand and one kernel (`dmip_sample_t`) instead of ten
+        CPU ops and a host-to-device copy per batch.  Same distribution, the CUDA generator's stream."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.require_gpu()
+        if not getattr(L, '_sample_t_bound', False):
+            L.dmip_sample_t.restype = C.c_int
+            L.dmip_sample_t.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_float, C.c_void_p]
+            L._sample_t_bound = True
+        u = torch.rand(*shape, device=device, dtype=torch.float32)
+        t = torch.empty_like(u)
+        with torch.cuda.device(device):
+            _lib.check(L.dmip_sample_t(u.data_ptr(), t.data_ptr(), u.numel(), 1 if debias else 0, float(self.beta_min),
+                                       float(self.beta_max), float(self.t_epsilon), float(self.T), float(eps),
+                                       _lib.stream_ptr()))
+        return t
+
 
 class VarianceExplodingSDE(torch.nn.Module):
     """VE-SDE of Song et al. 2021 (eq. 30-31): dy = sqrt(d[sigma^2(t)]/dt) dW, sigma(t) = sigma_min (sigma_max/sigma_min)^t.

@@ -342,6 +342,14 @@ typedef struct DmipHistogram {
 int dmip_histogramdd(const DmipHistogram* d, void* stream);
 int dmip_hist_kl(const void* hist_p, const void* hist_q, int64_t n_bins_total, double epsilon, double* out, void* stream);
 
+/* ---- training-time draw of t on the device ---------------------------------------------------------------------------
+ * BaseClassDiffusionModel.sample_t (models/diffusion.py:48-58): t[i] from the uniform u[i] (both device float[n]).
+ * debias != 0: the inverse CDF of VariancePreservingSDE.sample_debiasing_t (sdes.py:51-57; q(t) ~ beta(t)/var(t),
+ * constant below t_epsilon), then + eps_add, minus eps_add again where the sum exceeds T; debias == 0: eps_add + u T,
+ * clamped to T - eps_add.  The reference draws on the CPU and copies t over every batch. */
+int dmip_sample_t(const float* u, float* t, int64_t n, int32_t debias, float beta_min, float beta_max, float t_epsilon,
+                  float T, float eps_add, void* stream);
+
 /* ---- debug hook (exists only in -DDMIP_DEBUG / -DDMIP_JOBMARKS builds of the library; the tcgen05 building-block
  * self-tests and micro-benchmarks live in tools/probe/, outside the product) ------------------------------------------
  * Timeline: when set, CTA 0 of the tcgen05 sampler records (clock64 << 16 | event code) entries into

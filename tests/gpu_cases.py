@@ -925,6 +925,38 @@ def case_loss_repeats(kind, B=65536 + 37, reps=12):
     return (worst if ok else float("inf")), 3e-5, dict(reps=reps, batch=B, loss=first[0].item())
 
 
+def case_sample_t_device():
+    """dmip_sample_t against the host mirror (dmip.sdes.vp_truncated_inverse_cdf + the eps handling of
+    models/diffusion.py:48-58) on the same uniforms, including u = 0, the kink at t_epsilon and u -> 1; and
+    `model.sample_t` on a CUDA batch: shape, dtype, leaf with requires_grad, range (eps, T]."""
+    import ctypes as C
+    from dmip import _lib, sdes
+    from dmip.models.diffusion import CDE
+    sde = sdes.VariancePreservingSDE()
+    u = torch.cat([torch.tensor([0.0, 1e-7, 1e-4, 1.0 - 6e-8]), torch.rand(100000, generator=torch.Generator().manual_seed(5))])
+    worst = 0.0
+    for debias in (True, False):
+        ud = u.to(DEV)
+        sde.sample_t_device([1], DEV)                                   # binds the entry point
+        L = _lib.require_gpu()
+        t = torch.empty_like(ud)
+        _lib.check(L.dmip_sample_t(ud.data_ptr(), t.data_ptr(), ud.numel(), int(debias), float(sde.beta_min),
+                                   float(sde.beta_max), float(sde.t_epsilon), float(sde.T), 1e-4, _lib.stream_ptr()))
+        if debias:
+            ref = sdes.vp_truncated_inverse_cdf(u.double(), sde.beta_min, sde.beta_max, sde.t_epsilon, sde.T) + 1e-4
+            ref = torch.where(ref.float() > sde.T, ref - 1e-4, ref)
+        else:
+            ref = 1e-4 + u.double() * sde.T
+            ref = torch.where(ref.float() > sde.T, torch.full_like(ref, sde.T - 1e-4), ref)
+        worst = max(worst, (t.cpu().double() - ref).abs().max().item())
+    m = CDE(2, 2, [512, 512, 512])
+    x = torch.randn(1000, 2, device=DEV)
+    tt = m.sample_t(x)
+    ok = (tt.shape == (1000, 1) and tt.dtype == torch.float32 and tt.is_cuda and tt.requires_grad and tt.is_leaf
+          and tt.min().item() > 1e-4 and tt.max().item() <= 1.0)
+    return (worst if ok else float("inf")), 2e-7, dict(worst=worst)
+
+
 def case_sampler_trained_1000_steps(precision):
     """Trained linear CDE at S = 1000 steps (5x the reference default: bf16 rounding accumulates 5x longer), N = 512,
     the keyed Philox stream injected, against the CPU oracle sampler on the same noise: fp32 5e-4, bf16 1e-2 max abs

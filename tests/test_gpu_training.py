@@ -26,3 +26,9 @@ def test_data_parallel_two_ranks_nccl(kind):
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     err, tol, extra = gc.case_data_parallel_nccl(kind)
     assert err <= tol, extra
+
+
+def test_sample_t_on_the_device_matches_the_host_mirror():
+    """models/diffusion.py:48-58 + sdes.py:51-57 as one kernel (no CPU draw, no host-to-device copy per batch)"""
+    err, tol, extra = gc.case_sample_t_device()
+    assert err <= tol, extra
