@@ -40,15 +40,16 @@ def _owns_all_grads(model, optimizer):
     """True when `optimizer.zero_grad(); loss.backward(); optimizer.step()` can be replaced by the fused step that writes
     the gradient straight into the parameters' `.grad` (dmip.distributed.fused_optimizer_step): every parameter of the
     optimizer is a trainable parameter of the model's score net(s) without gradient hooks — nothing else would get, or
-    keep, a gradient from this loss.  Cached per (optimizer, parameter count)."""
-    key = (id(optimizer), sum(len(g['params']) for g in optimizer.param_groups))
-    cache = model.__dict__.setdefault('_fused_step_ok', {})
-    if key not in cache:
+    keep, a gradient from this loss.  The verdict is cached ON the optimizer (for this model and parameter count)."""
+    key = (id(model), sum(len(g['params']) for g in optimizer.param_groups))
+    hit = optimizer.__dict__.get('_dmip_fused_step_ok')
+    if hit is None or hit[0] != key:
         mine = {id(p): p for net in _bucket_nets(model) for lin in _lib.linear_layers(net) for p in (lin.weight, lin.bias)}
         theirs = [p for g in optimizer.param_groups for p in g['params']]
-        cache[key] = (len(theirs) == len(mine) and all(id(p) in mine for p in theirs)
-                      and all(p.requires_grad and not p._backward_hooks and p.is_cuda for p in mine.values()))
-    return cache[key]
+        ok = (len(theirs) == len(mine) and all(id(p) in mine for p in theirs)
+              and all(p.requires_grad and not p._backward_hooks and p.is_cuda for p in mine.values()))
+        hit = optimizer.__dict__['_dmip_fused_step_ok'] = (key, ok)
+    return hit[1]
 
 
 class BaseClassDiffusionModel():

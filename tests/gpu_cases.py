@@ -925,6 +925,53 @@ def case_loss_repeats(kind, B=65536 + 37, reps=12):
     return (worst if ok else float("inf")), 3e-5, dict(reps=reps, batch=B, loss=first[0].item())
 
 
+def case_train_epoch_paths_agree(loss_name):
+    """`train_epoch` with the fused optimizer step (the optimizer holds exactly the net's parameters) against the literal
+    zero_grad / backward / step triple (taken when it holds anything else — here one extra parameter): same seeds, so
+    the same t and noise draws; after an epoch of 6 batches of 1000 the parameters agree up to fp32 atomics, the
+    returned loss and info dict too; and the fast path was the one that ran (p.grad aliases the gradient bucket)."""
+    from dmip import losses as dl
+    from dmip.linear_problem import LinearForwardProblem
+    from dmip.models.diffusion import CDE
+    lin = LinearForwardProblem()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(6000, 2, generator=g)
+    y = lin(x) + 0.3 * torch.randn(6000, 2, generator=g)
+    xd, yd = x.to(DEV), y.to(DEV)
+
+    def loader():
+        for i in range(0, 6000, 1000):
+            yield xd[i:i + 1000], yd[i:i + 1000]
+
+    res = []
+    for extra in (False, True):
+        torch.manual_seed(4)
+        m = CDE(2, 2, [512, 512, 512])
+        params = list(m.sde.a.parameters())
+        dummy = torch.nn.Parameter(torch.zeros(3, device=DEV))
+        opt = torch.optim.Adam(params + ([dummy] if extra else []), lr=1e-3)
+        if loss_name == "DSM":
+            loss_fn = dl.DSMLoss()
+        else:
+            ic = lin.score_posterior(x, y).to(DEV)
+            table = {}
+            loss_fn = dl.PINNLoss(lambda xx, yy: ic[table.setdefault(xx.data_ptr(), len(table)) * 1000:][:1000],
+                                  lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
+        torch.manual_seed(9)
+        loss, info = m.train_epoch(opt, loss_fn, loader)
+        fast = hasattr(m, "_grad_bucket") and params[0].grad is not None and \
+            params[0].grad.data_ptr() == m._grad_bucket.flat.data_ptr()
+        res.append((loss.item(), info, [p.detach().clone() for p in params], fast))
+    (l0, i0, p0, f0), (l1, i1, p1, f1) = res
+    err = abs(l0 - l1) / abs(l1)
+    for k in i1:
+        err = max(err, abs(i0[k] - i1[k]) / max(abs(i1[k]), 1e-12))
+    for a_, b_ in zip(p0, p1):
+        err = max(err, ((a_ - b_).abs().max() / b_.abs().max()).item())
+    ok = f0 and not f1 and set(i0) == set(i1) and all(isinstance(v, float) for v in i0.values())
+    return (err if ok else float("inf")), 2e-5, dict(loss_fast=l0, loss_literal=l1, fast_path=(f0, f1))
+
+
 def case_sample_t_device():
     """dmip_sample_t against the host mirror (dmip.sdes.vp_truncated_inverse_cdf + the eps handling of
     models/diffusion.py:48-58) on the same uniforms, including u = 0, the kink at t_epsilon and u -> 1; and

@@ -32,3 +32,9 @@ def test_sample_t_on_the_device_matches_the_host_mirror():
     """models/diffusion.py:48-58 + sdes.py:51-57 as one kernel (no CPU draw, no host-to-device copy per batch)"""
     err, tol, extra = gc.case_sample_t_device()
     assert err <= tol, extra
+
+
+@pytest.mark.parametrize("loss_name", ["DSM", "PINN"])
+def test_train_epoch_fused_optimizer_step_equals_the_literal_triple(loss_name):
+    err, tol, extra = gc.case_train_epoch_paths_agree(loss_name)
+    assert err <= tol, extra
