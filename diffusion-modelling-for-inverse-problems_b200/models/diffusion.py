@@ -27,7 +27,7 @@ from torch import nn
 
 from .. import _lib
 from .. import sdes
-from ..distributed import _bucket_nets, fused_optimizer_step
+from ..distributed import GraphedTrainStep, _bucket_nets, fused_optimizer_step
 from ..losses import PosteriorLoss, fused_train_step
 from ..nets import MLP, MLP2, PosteriorScore
 
@@ -217,17 +217,39 @@ class BaseClassDiffusionModel():
         t_.requires_grad = True
         return t_
 
-    def train_epoch(self, optimizer, loss_fn, epoch_data_loader):
+    def _graphed_step_for(self, optimizer, loss_fn, x, y):
+        """The captured step for this (optimizer, loss, batch shape): captured on first sight; a batch of another shape
+        (the ragged last one of an epoch) runs eagerly unless that shape comes back, which replaces the capture."""
+        if len(optimizer.state) == 0:
+            return None       # the optimizer creates its state on its first step: that step runs eagerly, outside any capture
+        key = GraphedTrainStep.key_of(optimizer, loss_fn, x, y)
+        gs = self.__dict__.get('_graphed_step')
+        if gs is not None and gs.key == key:
+            return gs
+        if gs is None or self.__dict__.get('_graph_miss') == key:
+            self._graphed_step = GraphedTrainStep(self, optimizer, loss_fn, x, y)
+            return self._graphed_step
+        self._graph_miss = key
+        return None
+
+    def train_epoch(self, optimizer, loss_fn, epoch_data_loader, *, graph=False):
+        """Upstream's epoch loop.  graph=True (keyword-only extra): batches of a repeating shape run as one CUDA-graph
+        replay each (dmip.distributed.GraphedTrainStep — the launch-bound regime of small batches); anything the graph
+        cannot serve (other shapes, an optimizer with foreign parameters) takes the eager path below."""
         mean_loss = 0
         logger_info = {}
         for k, (x, y) in enumerate(epoch_data_loader()):
-            t = self.sample_t(x)
-            if x.is_cuda and _owns_all_grads(self, optimizer):
+            fused_ok = x.is_cuda and _owns_all_grads(self, optimizer)
+            replay = self._graphed_step_for(optimizer, loss_fn, x, y) if graph and fused_ok else None
+            if replay is not None:
+                loss, loss_info = replay(x, y)
+                stepped = True
+            elif fused_ok:
                 # zero_grad / backward / step without the autograd round trip (dmip.distributed.fused_optimizer_step)
-                loss, loss_info = fused_optimizer_step(self, optimizer, loss_fn, x, y, t)
+                loss, loss_info = fused_optimizer_step(self, optimizer, loss_fn, x, y, self.sample_t(x))
                 stepped = True
             else:
-                loss, loss_info = fused_train_step(self, loss_fn, x, y, t)
+                loss, loss_info = fused_train_step(self, loss_fn, x, y, self.sample_t(x))
                 stepped = False
             # running means as upstream (models/diffusion.py:90-92, :103), kept on the device in float64 — the arithmetic
             # of upstream's Python floats — as ONE vector, and read back once per epoch instead of one .item() per

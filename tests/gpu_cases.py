@@ -497,7 +497,7 @@ def case_edge_shapes():
 
 
 # ------------------------------------------------------------------------------------------- training loop (a10)
-def case_train_epoch(loss_name):
+def case_train_epoch(loss_name, graph=False, capturable=False):
     """CDE.train_epoch with the reference's call signature (models/diffusion.py:74-105) on the linear toy problem
     (linear_problem.py:10-16: y = A x + b + 0.3 eps): Adam steps through the fused loss kernels must reduce the loss,
     and the DSM-trained net's posterior mean must move to the analytic posterior (linear_problem.py:41-46)."""
@@ -513,15 +513,16 @@ def case_train_epoch(loss_name):
     Y = X @ A.T + b + sig * torch.randn(16000, 2, generator=g)
     X, Y = X.to(DEV), Y.to(DEV)
     m = CDE(2, 2, [512, 512, 512])
-    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3 if loss_name == "DSM" else 3e-4)
+    opt = torch.optim.Adam(m.sde.a.parameters(), lr=1e-3 if loss_name == "DSM" else 3e-4, capturable=capturable)
     if loss_name == "DSM":
         loss_fn = dl.DSMLoss()
     else:
         cov = torch.linalg.inv(torch.eye(2) + A.T @ A / sig ** 2).to(DEV)
+        At_d, b_d, prec_t = A.T.to(DEV), b.to(DEV), torch.linalg.inv(cov).T.contiguous()
 
-        def score_posterior(x, y):              # analytic posterior score (linear_problem.py:61-65)
-            mean = (cov @ (A.T.to(DEV) @ (y - b.to(DEV)).T / sig ** 2)).T
-            return -(x - mean) @ torch.linalg.inv(cov).T
+        def score_posterior(x, y):              # analytic posterior score (linear_problem.py:61-65), device code only
+            mean = (cov @ (At_d @ (y - b_d).T / sig ** 2)).T
+            return -(x - mean) @ prec_t
 
         loss_fn = dl.PINNLoss(score_posterior, lam=0.001, lam2=0.1, pde_loss="FPE", ic_metric="L2", pde_metric="L1")
 
@@ -533,9 +534,12 @@ def case_train_epoch(loss_name):
 
     losses = []
     for epoch in range(12 if loss_name == "DSM" else 4):
-        loss, info = m.train_epoch(opt, loss_fn, loader)
+        loss, info = m.train_epoch(opt, loss_fn, loader, graph=graph) if graph else m.train_epoch(opt, loss_fn, loader)
         losses.append(float(loss))
     assert all(np.isfinite(losses)), losses
+    if graph:
+        gs = m._graphed_step
+        assert gs.step_in_graph == capturable and isinstance(gs.graph, torch.cuda.CUDAGraph)
     if loss_name != "DSM":
         assert set(info) == {"PDE-Loss", "Initial Condition", "DSM-Loss"}
         return (0.0 if losses[-1] < losses[0] else 1.0), 0.5, dict(first=losses[0], last=losses[-1])

@@ -38,3 +38,10 @@ def test_sample_t_on_the_device_matches_the_host_mirror():
 def test_train_epoch_fused_optimizer_step_equals_the_literal_triple(loss_name):
     err, tol, extra = gc.case_train_epoch_paths_agree(loss_name)
     assert err <= tol, extra
+
+
+@pytest.mark.parametrize("loss_name,capturable", [("DSM", False), ("DSM", True), ("PINN", False)])
+def test_train_epoch_as_cuda_graph_replays(loss_name, capturable):
+    """graph=True: every batch is one replay of the captured step (eager or captured optimizer); same learning criteria"""
+    err, tol, extra = gc.case_train_epoch(loss_name, graph=True, capturable=capturable)
+    assert err <= tol, extra

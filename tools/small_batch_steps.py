@@ -20,7 +20,7 @@ def run(kind, B, path, steps=100):
     x = torch.randn(B, 2)
     y = lin(x) + 0.3 * torch.randn(B, 2)
     xd, yd = x.cuda(), y.cuda()
-    loss_fn = dl.DSMLoss() if kind == "DSM" else dl.PINNLoss(lin.score_posterior, lam=0.001, lam2=0.1, pde_loss="FPE",
+    loss_fn = dl.DSMLoss() if kind == "DSM" else dl.PINNLoss(lambda xx, yy: -xx, lam=0.001, lam2=0.1, pde_loss="FPE",
                                                               ic_metric="L2", pde_metric="L1")
 
     def step_bucket():
@@ -35,14 +35,16 @@ def run(kind, B, path, steps=100):
         opt.step()
         return loss
 
-    if path == "train_epoch":            # the drop-in method itself, 50 batches per call
+    if path in ("train_epoch", "graph"):   # the drop-in method itself, 50 batches per call; "graph": graph=True
+        kw = dict(graph=True) if path == "graph" else {}
+
         def loader():
             for _ in range(50):
                 yield xd, yd
-        m.train_epoch(opt, loss_fn, loader)
+        m.train_epoch(opt, loss_fn, loader, **kw)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        m.train_epoch(opt, loss_fn, loader)
+        m.train_epoch(opt, loss_fn, loader, **kw)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / 50 * 1e3
     fn = step_bucket if path == "bucket" else step_reference_loop
@@ -61,4 +63,5 @@ if __name__ == "__main__":
         for B in (1000, 4096, 16384):
             print(f"{kind:4s} batch {B:6d}: zero_grad / backward / step loop {run(kind, B, 'loop'):7.3f} ms/step   "
                   f"fused optimizer step {run(kind, B, 'bucket'):7.3f} ms/step   model.train_epoch "
-                  f"{run(kind, B, 'train_epoch'):7.3f} ms/step", flush=True)
+                  f"{run(kind, B, 'train_epoch'):7.3f} ms/step   train_epoch(graph=True) {run(kind, B, 'graph'):7.3f} ms/step",
+                  flush=True)
