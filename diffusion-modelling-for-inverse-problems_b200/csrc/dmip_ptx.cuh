@@ -191,6 +191,15 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
 }
+// asynchronous 16-byte store into ANOTHER CTA's shared memory; its completion is counted (16 bytes) on an mbarrier of that
+// same CTA — the writer neither fences nor arrives (both addresses from mapa_u32 with the destination's rank)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   cluster_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_mbar)
+               : "memory");
+}
 // generic-proxy writes into ANY CTA's shared memory of the cluster -> visible to the async proxy (tensor core operands)
 __device__ __forceinline__ void fence_proxy_async_cluster_smem() {
   asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");

@@ -54,9 +54,11 @@ constexpr uint32_t kTmemCols = 512;       // two halves of 4 chunks x 64 columns
 // the ~96 cycles it takes (6 KB of operand reads); the pair instruction takes ~110 cycles for twice the work per SM.
 // Every CTA keeps ITS 64-row tile as before (inputs, B operand in its own shared memory, stashes, loss stage); what is
 // redistributed are the accumulators: CTA r holds the features of chunks r and r + 2 for the rows of BOTH tiles (128
-// columns), so its epilogue threads write half of their output rows into the peer's shared memory (st.shared::cluster)
-// and every "operand ready" barrier lives in the leader CTA (rank 0), which issues for the pair.  Each CTA streams only
-// the weight stages of its own chunks (no multicast); the peer's MMA warp relays "stage landed" to the leader.
+// columns), so its epilogue threads write half of their output rows into the peer's shared memory — with st.async,
+// whose completion bytes are counted on the peer's `rready` barrier: the writer neither fences nor arrives, the peer's
+// receiver warp (18) forwards "rows landed" — and every "operand ready" barrier lives in the leader CTA (rank 0), which
+// issues for the pair.  Each CTA streams only the weight stages of its own chunks (no multicast); the peer's MMA warp
+// relays "stage landed" to the leader.
 // -DDMIP_TCL_PAIR=0 builds the single-CTA kernels (cta_group::1, N = 64).
 #ifndef DMIP_TCL_PAIR
 #define DMIP_TCL_PAIR 1
@@ -68,7 +70,7 @@ constexpr int kOffHlo = kOffHhi + kHHalf;
 constexpr int kOffIn = kOffHlo + kHHalf;                 // hi at +0, lo at +kInHalf
 constexpr int kOffW = kOffIn + 2 * kInHalf;
 constexpr int kOffBar = kOffW + kSlots * kStage;
-constexpr int kNumBars = 2 * kSlots + 2 + 4 + 1 + kSlots + 1;
+constexpr int kNumBars = 2 * kSlots + 2 + 4 + 1 + kSlots + 1 + 4;
 constexpr int kOffRed = kOffBar + ((kNumBars * 8 + 15) & ~15);   // float red[4], b3sum[64]
 constexpr int kOffTmem = kOffRed + (4 + kTclSmallF) * 4;
 constexpr int kSmemBytes = kOffTmem + 16;
@@ -86,6 +88,8 @@ struct Bars {
   uint64_t* pfull;     // [kSlots]  leader: the peer's weight stage landed (relayed by the peer's MMA warp)
   uint64_t* xfree;     // [1]       the PEER's row warps have finished reading their staged outputs (forward loss stage):
                        //           its activation region may take the next tile's rows
+  uint64_t* rready;    // [4]       this CTA's rows of chunk c, written by the PEER with st.async, have landed (32 KB of
+                       //           transaction bytes per phase, armed and forwarded to hready[c] by the receiver warp)
 };
 
 __device__ __forceinline__ Bars make_bars(uint8_t* smem) {
@@ -98,6 +102,7 @@ __device__ __forceinline__ Bars make_bars(uint8_t* smem) {
   B.in_ready = B.hready + 4;
   B.pfull = B.in_ready + 1;
   B.xfree = B.pfull + kSlots;
+  B.rready = B.xfree + 1;
   return B;
 }
 
@@ -116,17 +121,17 @@ template <int kRegs>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-// operand store of an epilogue thread: own shared memory, or (pair mode) the shared window of either CTA of the pair
-__device__ __forceinline__ void st_operand_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  if (kPair) st_cluster_v4(addr, a, b, c, d);
+// operand store of an epilogue thread: own shared memory, or (pair mode, rmbar != 0) an asynchronous store into the
+// peer's shared memory whose arrival is counted on the peer's `rready` barrier — the writer neither fences nor arrives
+__device__ __forceinline__ void st_operand_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rmbar) {
+  if (kPair && rmbar != 0u) st_async_v4(addr, a, b, c, d, rmbar);
+  else if (kPair) st_cluster_v4(addr, a, b, c, d);
   else asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// `remote`: the stores went to the peer's shared memory (the cluster-scope proxy fence carries a GPU-scope membar that
-// waits for every store of the thread in flight, global ones included — keep those AFTER this point)
-__device__ __forceinline__ void fence_operand_stores(bool remote = kPair) {
-  if (kPair && remote) fence_proxy_async_cluster_smem();
-  else fence_proxy_async_smem();
-}
+constexpr uint32_t kRemoteChunkBytes = 8u * 32u * 8u * 16u;   // 8 warps x 32 features x (4 row chunks x hi, lo) x 16 B
+// (a cluster-scope proxy fence would carry a GPU-scope membar that waits for every store of the thread in flight, global
+// ones included: the first pair version spent 13 % of its warp samples there — rows of the peer's tile go by st.async)
+__device__ __forceinline__ void fence_operand_stores() { fence_proxy_async_smem(); }
 // arrival on a barrier of the leader CTA (pair mode: `leader_addr` = mapa of the barrier in CTA 0) or of this CTA
 // — always with release at CLUSTER scope there: the stores it publishes may have gone to the peer's shared memory
 __device__ __forceinline__ void arrive_issuer(uint64_t* bar, uint32_t leader_addr) {
@@ -459,6 +464,28 @@ __device__ __forceinline__ void tcl_issuer_pair(int k0steps, int tile_first, int
   }
 }
 
+// Pair mode, warp 18 of each CTA: per layer that produces an operand, and per chunk owned by the PEER, arm this CTA's rready
+// barrier with the bytes the peer's st.async stores will deliver, wait for them, make them visible to the tensor core
+// and tell the leader's issuer (hready[c]).
+constexpr int kReceiverWarp = 18;
+__device__ __forceinline__ void tcl_receiver(int n_operand_layers, int tile_first, int n_tiles, int tile_stride, const Bars& B,
+                                             uint32_t crank) {
+  uint32_t par = 0;
+  const uint32_t hready_leader = mapa_u32(&B.hready[0], 0);
+  for (int tb = tile_first; tb < n_tiles; tb += tile_stride)
+    for (int l = 0; l < n_operand_layers; ++l)
+      for (int ci = 0; ci < 2; ++ci) {
+        const uint32_t c = (1u - crank) + 2u * static_cast<uint32_t>(ci);
+        if (elect_one()) mbar_arrive_expect_tx(&B.rready[c], kRemoteChunkBytes);
+        __syncwarp();
+        mbar_wait_cluster(&B.rready[c], (par >> c) & 1u, 0xA90 + c);
+        par ^= 1u << c;
+        fence_proxy_async_smem();
+        if (elect_one()) mbar_arrive_remote_relaxed(hready_leader + c * 8u);
+        __syncwarp();
+      }
+}
+
 // the three service roles of the warps above the row warps
 template <int kNG, int kLastChunks>
 __device__ __forceinline__ void tcl_service_warps(int warp, const uint8_t* stages, int n_stages, int k0steps, int tile_first,
@@ -470,6 +497,9 @@ __device__ __forceinline__ void tcl_service_warps(int warp, const uint8_t* stage
     if (!kPair) tcl_issuer<kNG, kLastChunks>(k0steps, tile_first, n_tiles, tile_stride, smem, tmem_base, B, cmask);
     else if (crank == 0u) tcl_issuer_pair<kNG, kLastChunks>(k0steps, tile_first, n_tiles, tile_stride, smem, tmem_base, B);
     else tcl_relay(PairStages<kNG, kLastChunks>::value, tile_first, n_tiles, tile_stride, B);
+  } else if (kPair && warp == kReceiverWarp) {
+    // every GEMM but the last is followed by an epilogue that writes the next operand
+    tcl_receiver(kNG - 1, tile_first, n_tiles, tile_stride, B, crank);
   }
 }
 
@@ -486,7 +516,9 @@ __device__ __forceinline__ uint32_t tcl_setup(uint8_t* smem, const Bars& B, int 
     mbar_init(&B.acc_full[0], 1);
     mbar_init(&B.acc_full[1], 1);
     // single-CTA: 4 lane quarters x 2 windows; pair: all 16 row warps of the CTA that owns the chunk
-    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], kPair ? kNumRowWarps : 8);
+    // (pair: the 8 warps of the chunk's owner whose rows are local + the receiver warp of the CTA that got the other rows)
+    for (int i = 0; i < 4; ++i) mbar_init(&B.hready[i], kPair ? 9 : 8);
+    for (int i = 0; i < 4; ++i) mbar_init(&B.rready[i], 1);
     mbar_init(B.in_ready, kPair ? 2 * kNumRowWarps : kNumRowWarps);
     mbar_init(B.xfree, kNumRowWarps);
     fence_barrier_init();
@@ -595,7 +627,7 @@ __device__ __forceinline__ void fwd_build_input(const TclDev& P, long long tile,
 // One (layer, chunk, window) item of the forward epilogue: thread = feature n of the layer's output.
 template <class C, bool kFirst>
 __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr, int n, float bias, long long smp0,
-                                         bool tile_ok, int w, uint32_t hdst, uint32_t (&v)[32]) {
+                                         bool tile_ok, int w, uint32_t hdst, uint32_t rmbar, uint32_t (&v)[32]) {
   tmem_ld32(taddr, v);
   tc_wait_ld();
   const bool full = tile_ok && smp0 + C::SPW <= P.B;     // warp-uniform
@@ -657,8 +689,8 @@ __device__ __forceinline__ void fwd_item(const TclDev& P, int g, uint32_t taddr,
     for (int e = 0; e < 4; ++e)
       split2(__uint_as_float(v[i * 8 + 2 * e]), __uint_as_float(v[i * 8 + 2 * e + 1]), hi[e], lo[e]);
     const uint32_t co = ((static_cast<uint32_t>(w * 4 + i) ^ line) << 4);
-    st_operand_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
-    st_operand_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
+    st_operand_v4(hrow + co, hi[0], hi[1], hi[2], hi[3], rmbar);
+    st_operand_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3], rmbar);
   }
 }
 
@@ -885,6 +917,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
     const uint32_t in_ready_leader = kPair ? mapa_u32(B.in_ready, 0) : 0u;
     const uint32_t hready_leader = kPair ? mapa_u32(&B.hready[0], 0) : 0u;
     const uint32_t xfree_peer = kPair ? mapa_u32(B.xfree, crank ^ 1u) : 0u;
+    const bool remote = kPair && tsel != static_cast<int>(crank);       // this warp's rows live in the peer's shared memory
+    const uint32_t rready_dst = remote ? mapa_u32(&B.rready[0], static_cast<uint32_t>(tsel)) : 0u;
     uint32_t xpar = 0;
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* b3sum = red + 4;
@@ -898,7 +932,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
     {
       const bool ok = tile_first + static_cast<int>(crank) < n_tiles;
       fwd_build_input<C>(P, tile_first + static_cast<int>(crank), ok, smem + kOffIn, t);
-      fence_operand_stores(false);
+      fence_operand_stores();
       __syncwarp();
       if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
     }
@@ -929,12 +963,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
           // register select (the loops stay rolled: six copies of the item body would not fit the instruction cache)
           const float bs = g == 0 ? (ci ? bias[0][1] : bias[0][0]) : g == 1 ? (ci ? bias[1][1] : bias[1][0]) : (ci ? bias[2][1] : bias[2][0]);
           uint32_t v[32];
-          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, etile_ok, w, hdst, v);
-          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, etile_ok, w, hdst, v);
-          fence_operand_stores(tsel != static_cast<int>(crank));
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_issuer(&B.hready[c], hready_leader + static_cast<uint32_t>(c) * 8u);
+          const uint32_t rmbar = remote ? rready_dst + static_cast<uint32_t>(c) * 8u : 0u;
+          if (g == 0) fwd_item<C, true>(P, g, taddr, n, bs, smp0, etile_ok, w, hdst, rmbar, v);
+          else fwd_item<C, false>(P, g, taddr, n, bs, smp0, etile_ok, w, hdst, rmbar, v);
+          if (!remote) {   // remote rows: the peer's receiver warp sees them land (rready) and tells the issuer
+            fence_operand_stores();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_issuer(&B.hready[c], hready_leader + static_cast<uint32_t>(c) * 8u);
+          }
           if (kPair && g != 0) fwd_state_from_outputs<C>(P, g, n, smp0, etile_ok, v);
           fwd_stash<C>(P, g, n, etile, smp0, etile_ok, w, v);
         }
@@ -942,7 +979,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
           // GEMM 0 of this tile has retired (acc_full[0] above): the small operand region takes the next tile's inputs
           const int nt = tb + tile_stride + static_cast<int>(crank);
           fwd_build_input<C>(P, nt, nt < n_tiles, smem + kOffIn, t);
-          fence_operand_stores(false);
+          fence_operand_stores();
           __syncwarp();
           if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
         }
@@ -1078,7 +1115,7 @@ __device__ __forceinline__ float bwd_math(const TclDev& P, uint32_t taddr, long 
 // well) and, for L > 0, the B operand of the next GEMM
 template <class C>
 __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, int k, long long tile, bool tile_ok, int w,
-                                          const uint32_t (&v)[32], uint32_t hdst, bool remote, uint64_t* hready,
+                                          const uint32_t (&v)[32], uint32_t hdst, uint32_t rmbar, uint64_t* hready,
                                           uint32_t hready_leader, int lane) {
   const uint32_t kterm = (static_cast<uint32_t>(k) >> 6) * 8192u + (static_cast<uint32_t>(k) & 7u) * 2u;
   const uint32_t kchunk = (static_cast<uint32_t>(k) & 63u) >> 3;
@@ -1094,14 +1131,16 @@ __device__ __forceinline__ void bwd_store(const TclDev& P, int L, bool to_smem, 
       for (int e = 0; e < 4; ++e)
         split2(__uint_as_float(v[i * 8 + 2 * e]), __uint_as_float(v[i * 8 + 2 * e + 1]), hi[e], lo[e]);
       const uint32_t co = ((static_cast<uint32_t>(w * 4 + i) ^ line) << 4);
-      st_operand_v4(hrow + co, hi[0], hi[1], hi[2], hi[3]);
-      st_operand_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3]);
+      st_operand_v4(hrow + co, hi[0], hi[1], hi[2], hi[3], rmbar);
+      st_operand_v4(hrow + kHHalf + co, lo[0], lo[1], lo[2], lo[3], rmbar);
     }
     // the next GEMM may read these K-blocks now; the global stash stores below are off its critical path
-    fence_operand_stores(remote);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) arrive_issuer(hready, hready_leader);
+    if (rmbar == 0u) {   // remote rows (st.async): the peer's receiver warp tells the issuer
+      fence_operand_stores();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_issuer(hready, hready_leader);
+    }
   }
   if (tile_ok) {
     const uint32_t wo = static_cast<uint32_t>(w) * 4096u;           // window w starts 4 row-groups (4 KB) into the block
@@ -1169,13 +1208,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
     const uint32_t hdst = kPair ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel)) : smem_u32(smem + kOffHhi);
     const uint32_t in_ready_leader = kPair ? mapa_u32(B.in_ready, 0) : 0u;
     const uint32_t hready_leader = kPair ? mapa_u32(&B.hready[0], 0) : 0u;
+    const uint32_t rready_dst = (kPair && tsel != static_cast<int>(crank)) ? mapa_u32(&B.rready[0], static_cast<uint32_t>(tsel)) : 0u;
     uint32_t par = 0;   // bit s: phase of acc_full[s]
     uint32_t gc = 0;    // running GEMM counter (three GEMMs per tile: the TMEM half of a GEMM is gc & 1, as in tcl_issuer)
     float bsum[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // bias gradients of layers 2, 1, 0 for this thread's two features
     {
       const bool ok = tile_first + static_cast<int>(crank) < n_tiles;
       bwd_build_input<C>(P, tile_first + static_cast<int>(crank), ok, smem + kOffIn, t);
-      fence_operand_stores(false);
+      fence_operand_stores();
       __syncwarp();
       if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
     }
@@ -1204,15 +1244,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
         const uint32_t t0 = lane_taddr + set * 256u + col0;
         bsum[g][0] += bwd_math<C>(P, t0, etile, etile_ok, w, pre, v);
         bwd_prefetch<C>(P, L, k1, etile, w, pre);
-        bwd_store<C>(P, L, L != 0 || kGradIn, k0, etile, etile_ok, w, v, hdst, tsel != static_cast<int>(crank), &B.hready[c_first],
+        bwd_store<C>(P, L, L != 0 || kGradIn, k0, etile, etile_ok, w, v, hdst, rready_dst ? rready_dst + c_first * 8u : 0u, &B.hready[c_first],
                      hready_leader + static_cast<uint32_t>(c_first) * 8u, lane);
         bsum[g][1] += bwd_math<C>(P, t0 + kColStep, etile, etile_ok, w, pre, v);
-        bwd_store<C>(P, L, L != 0 || kGradIn, k1, etile, etile_ok, w, v, hdst, tsel != static_cast<int>(crank), &B.hready[c_first + 2],
+        bwd_store<C>(P, L, L != 0 || kGradIn, k1, etile, etile_ok, w, v, hdst, rready_dst ? rready_dst + (c_first + 2) * 8u : 0u, &B.hready[c_first + 2],
                      hready_leader + static_cast<uint32_t>(c_first + 2) * 8u, lane);
         if (g == 1 && tb + tile_stride < n_tiles) {
           const int nt = tb + tile_stride + static_cast<int>(crank);
           bwd_build_input<C>(P, nt, nt < n_tiles, smem + kOffIn, t);
-          fence_operand_stores(false);
+          fence_operand_stores();
           __syncwarp();
           if (lane == 0) arrive_issuer(B.in_ready, in_ready_leader);
         }
