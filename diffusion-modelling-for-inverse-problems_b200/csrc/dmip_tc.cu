@@ -1123,9 +1123,11 @@ size_t sampler_tc_workspace() {
   return 256;   // the state lives in registers, activations in shared / tensor memory: no device scratch is needed
 }
 
+void tcl_debug_set_timeline(unsigned long long* buf, int cap);   // dmip_tcl.cu
 void debug_set_timeline(unsigned long long* buf, int cap) {
   g_tl = buf;
   g_tl_cap = cap;
+  tcl_debug_set_timeline(buf, cap);
 }
 
 int launch_sampler_tc(const DmipSampler* d, cudaStream_t s) {

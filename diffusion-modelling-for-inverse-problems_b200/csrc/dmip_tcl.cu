@@ -160,10 +160,8 @@ __device__ __forceinline__ float join1(unsigned short hi, unsigned short lo) {
 __device__ __forceinline__ uint32_t img_off(uint32_t row, uint32_t f) {
   return (f >> 6) * 8192u + (row >> 3) * 1024u + (row & 7u) * 128u + ((((f & 63u) >> 3) ^ (row & 7u)) << 4) + (f & 7u) * 2u;
 }
-// byte offset of (feature k, row) in the MN-major B operand of a tile ([k / 8] atoms of 1 KB: 8 k lines x 64 rows)
-__device__ __forceinline__ uint32_t bop_off(uint32_t k, uint32_t row) {
-  return (k >> 3) * 1024u + (k & 7u) * 128u + (((row >> 3) ^ (k & 7u)) << 4) + (row & 7u) * 2u;
-}
+// (feature k, row) of the MN-major B operand of a tile sits at byte (k / 8) * 1024 + (k % 8) * 128 + (((row / 8) ^ (k % 8)) << 4)
+// + (row % 8) * 2: atoms of 1 KB = 8 k lines x 64 rows (the build_input functions and the epilogues write it that way)
 
 // tanh to fp32 accuracy without the branch of tanhf: 1 - 2 / (e^{2|x|} + 1) on the two MUFU ops (ex2, rcp; absolute
 // error ~3e-7, where the quotient cancels) and the odd Taylor polynomial below |x| = 0.04 (relative error < 1e-7 there).
@@ -233,6 +231,36 @@ __device__ __forceinline__ void bwd_row(long long smp, int a, long long& block, 
   const int wb = rem / C::SPWB, jb = rem - wb * C::SPWB;
   row = static_cast<uint32_t>(wb * kWin + jb * C::NADJ + a);
 }
+
+// ---- timeline of CTA 0 (timing builds -DDMIP_JOBMARKS only; tools/tcl_timeline.py): four roles x [count, (clock << 16 | code)...]
+#ifdef DMIP_JOBMARKS
+__device__ unsigned long long* g_tcl_tl = nullptr;
+__device__ int g_tcl_tl_cap = 0;
+struct Tl {
+  unsigned long long* p;
+  unsigned int n, cap;
+};
+__device__ __forceinline__ Tl tl_open(int role, bool on) {
+  Tl r = {nullptr, 0u, 0u};
+  if (on && blockIdx.x == 0 && g_tcl_tl != nullptr) {
+    const int seg = g_tcl_tl_cap / 4;
+    r.p = g_tcl_tl + static_cast<size_t>(role) * seg;
+    r.cap = static_cast<unsigned int>(seg - 1);
+  }
+  return r;
+}
+__device__ __forceinline__ void tl_mark(Tl& r, unsigned int code) {
+  if (r.p != nullptr && r.n < r.cap) { r.p[1 + r.n] = (static_cast<unsigned long long>(clock64()) << 16) | code; ++r.n; }
+}
+__device__ __forceinline__ void tl_close(const Tl& r) { if (r.p != nullptr) r.p[0] = r.n; }
+#define TL_OPEN(name, role, on) Tl name = tl_open(role, on)
+#define TL_MARK(name, code) tl_mark(name, code)
+#define TL_CLOSE(name) tl_close(name)
+#else
+#define TL_OPEN(name, role, on) ((void)0)
+#define TL_MARK(name, code) ((void)0)
+#define TL_CLOSE(name) ((void)0)
+#endif
 
 // ------------------------------------------------------------------------------------------------ producer / issuer
 // Streams the n_stages weight stages of one tile pass, for every tile this CTA runs (whole warp, one elected lane issues).
@@ -402,9 +430,11 @@ __device__ __forceinline__ void tcl_issuer_pair(int k0steps, int tile_first, int
   const uint64_t descB = umma_smem_desc(0, 1024, 1024);
   constexpr uint32_t idesc = umma_idesc_bf16_major(256, 2 * kNR, 0, 1);
   constexpr uint16_t both = 0x3;
+  TL_OPEN(tl, 0, (threadIdx.x & 31) == 0 && kNG == 4);   // the forward pass (the backward pass of a loss has three GEMMs)
   for (int tb = tile_first; tb < n_tiles; tb += tile_stride) {
 #pragma unroll 1
     for (int g = 0; g < kNG; ++g) {
+      TL_MARK(tl, 0x100u | g);
       const int nkb = g == 0 ? 1 : 8;
       const int np = (g == kNG - 1 ? kLastChunks : 4) == 4 ? 2 : 1;
       const int nk16 = g == 0 ? k0steps : 4;
@@ -422,6 +452,7 @@ __device__ __forceinline__ void tcl_issuer_pair(int k0steps, int tile_first, int
           const int c = kb >> 1;
           mbar_wait_cluster(&B.hready[c], (hr_par >> c) & 1u, 0xB10 + c);
           hr_par ^= 1u << c;
+          TL_MARK(tl, 0x200u | (g << 4) | c);
         }
         tc_fence_after();
         const uint32_t b16 = b_base + static_cast<uint32_t>(kb) * 512u;
@@ -460,8 +491,10 @@ __device__ __forceinline__ void tcl_issuer_pair(int k0steps, int tile_first, int
           if (++s == kSlots) { s = 0; ph ^= 1u; }
         }
       }
+      TL_MARK(tl, 0x300u | g);
     }
   }
+  TL_CLOSE(tl);
 }
 
 // Pair mode, warp 18 of each CTA: per layer that produces an operand, and per chunk owned by the PEER, arm this CTA's rready
@@ -563,64 +596,86 @@ __device__ __forceinline__ void tcl_teardown(uint32_t tmem_base, int warp) {
 // walk the input columns (coalesced stash rows), warps walk the rows.
 template <class C>
 __device__ __forceinline__ void fwd_build_input(const TclDev& P, long long tile, bool tile_ok, uint8_t* sIn, int t) {
-  const int k = t & 63;             // input column (K index of GEMM 0), 64 of them
+  // One row x 8 consecutive input columns per thread (512 threads = 64 rows x 8 column groups): the per-sample terms
+  // (two expf, a sqrt, the loads of t / x / y / eps) are evaluated once per row, only the warps of a column group below
+  // in_dim do any arithmetic, and a stash row is two 16-byte stores.  (One column x 8 rows per thread — the first version —
+  // left the five lanes with k < in_dim walking 8 rows of dependent loads serially: 15 K cycles per tile on the warps the
+  // next layer's epilogue was waiting for, tools/tcl_timeline.py.)
+  const int row = t & 63, kg = t >> 6;
   const int d = P.d;
-  const bool is_I_net = false;
-  (void)is_I_net;
-#pragma unroll 1
-  for (int row = t >> 6; row < kNR; row += kRowThreads / 64) {
-    const int w = row >> 5, rw = row & 31;
-    const int j = rw / C::NS, st = rw - j * C::NS;
-    const long long smp = tile * (2 * C::SPW) + w * C::SPW + j;
-    float v = 0.f;
-    const bool live = tile_ok && j < C::SPW && smp < P.B && k < P.in_dim;
-    if (live && P.post == 4) {
+  const int w = row >> 5, rw = row & 31;
+  const int j = rw / C::NS, st = rw - j * C::NS;
+  const long long smp = tile * (2 * C::SPW) + w * C::SPW + j;
+  const bool live_row = tile_ok && j < C::SPW && smp < P.B;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (live_row && kg * 8 < P.in_dim) {
+    if (P.post == 4) {
       // plain net forward: cat[x, cond, t] as given (nets.py:32-35, :52-57)
-      if (k < P.xdim) v = P.x[smp * P.xdim + k];
-      else if (k < P.xdim + P.ydim) v = P.y[smp * P.ydim + (k - P.xdim)];
-      else v = P.t[smp];
-    } else if (live) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kg * 8 + e;
+        if (k < P.xdim) v[e] = P.x[smp * P.xdim + k];
+        else if (k < P.xdim + P.ydim) v[e] = P.y[smp * P.ydim + (k - P.xdim)];
+        else if (k < P.in_dim) v[e] = P.t[smp];
+      }
+    } else {
       const float tt = P.t[smp];
       float beta, alpha, var;
       vp_terms(tt, P.bmin, P.bmax, beta, alpha, var);
       const float sd = sqrtf(var);
-      // clean / diffused state component k (k < d): CDE: z0 = x; CDiffE: z0 = [x, y]   (models/diffusion.py:80,129)
-      float z0k = 0.f, epsk = 0.f;
-      if (k < d) {
-        z0k = (k < P.xdim) ? P.x[smp * P.xdim + k] : P.y[smp * P.ydim + (k - P.xdim)];
-        epsk = P.eps[smp * d + k];
-      }
-      if (st == 0) {                                   // P: [z_t, cond, t]           (sdes.py:43-46)
-        if (k < d) v = epsk * sd + alpha * z0k;
-        else if (k < d + P.cdim) v = P.y[smp * P.ydim + (k - d)];
-        else v = tt;
-      } else if (C::kI && st == C::sI) {               // I: [x, y, 0]                (losses.py:221-223)
-        if (k < P.xdim) v = P.x[smp * P.xdim + k];
-        else if (k < P.xdim + P.ydim) v = P.y[smp * P.ydim + (k - P.xdim)];
-        else v = 0.f;
-      } else if (C::kT && st == C::sT) {               // T: (dz_t/dt, 0, 1)          
-        if (k < d) v = epsk * beta * (1.f - var) / (2.f * sd) - 0.5f * beta * alpha * z0k;
-        else if (k < d + P.cdim) v = 0.f;
-        else v = 1.f;
-      } else if (C::kNT > 0 && st >= C::sS && st < C::sQ) {
-        v = (k == st - C::sS) ? 1.f : 0.f;             // S_k: e_k;   Q: zero input
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kg * 8 + e;
+        if (k >= P.in_dim) continue;
+        // clean / diffused state component k (k < d): CDE: z0 = x; CDiffE: z0 = [x, y]   (models/diffusion.py:80,129)
+        float z0k = 0.f, epsk = 0.f;
+        if (k < d) {
+          z0k = (k < P.xdim) ? P.x[smp * P.xdim + k] : P.y[smp * P.ydim + (k - P.xdim)];
+          epsk = P.eps[smp * d + k];
+        }
+        float val = 0.f;
+        if (st == 0) {                                   // P: [z_t, cond, t]           (sdes.py:43-46)
+          if (k < d) val = epsk * sd + alpha * z0k;
+          else if (k < d + P.cdim) val = P.y[smp * P.ydim + (k - d)];
+          else val = tt;
+        } else if (C::kI && st == C::sI) {               // I: [x, y, 0]                (losses.py:221-223)
+          if (k < P.xdim) val = P.x[smp * P.xdim + k];
+          else if (k < P.xdim + P.ydim) val = P.y[smp * P.ydim + (k - P.xdim)];
+          else val = 0.f;
+        } else if (C::kT && st == C::sT) {               // T: (dz_t/dt, 0, 1)          
+          if (k < d) val = epsk * beta * (1.f - var) / (2.f * sd) - 0.5f * beta * alpha * z0k;
+          else if (k < d + P.cdim) val = 0.f;
+          else val = 1.f;
+        } else if (C::kNT > 0 && st >= C::sS && st < C::sQ) {
+          val = (k == st - C::sS) ? 1.f : 0.f;           // S_k: e_k;   Q: zero input
+        }
+        v[e] = val;
       }
     }
-    unsigned short hi, lo;
-    split1(v, hi, lo);
-    const uint32_t off = bop_off(static_cast<uint32_t>(k), static_cast<uint32_t>(row));
-    *reinterpret_cast<unsigned short*>(sIn + off) = hi;
-    *reinterpret_cast<unsigned short*>(sIn + kInHalf + off) = lo;
-    // inputs of layer 0 for the adjoint streams (weight-gradient operand), in the backward geometry
-    const int a = (st == 0) ? 0 : (C::kI && st == C::sI) ? 1 : (C::kT && st == C::sT) ? (1 + C::kI) : -1;
-    if (tile_ok && j < C::SPW && smp < P.B && a >= 0) {
-      long long blk;
-      uint32_t rb;
-      bwd_row<C>(smp, a, blk, rb);
-      const size_t o = static_cast<size_t>(blk) * (kTclSmallF * 128) + img_off(rb, static_cast<uint32_t>(k));
-      *reinterpret_cast<unsigned short*>(P.in_img[0][0] + o) = hi;
-      *reinterpret_cast<unsigned short*>(P.in_img[0][1] + o) = lo;
-    }
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  // MN-major B operand: column k = kg * 8 + e is line e of atom kg; this row's element sits in chunk (row / 8) ^ e
+  uint8_t* atom = sIn + kg * 1024 + (row & 7) * 2;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    uint8_t* q = atom + e * 128 + (((row >> 3) ^ e) << 4);
+    const uint32_t h2 = hi[e >> 1], l2 = lo[e >> 1];
+    *reinterpret_cast<unsigned short*>(q) = static_cast<unsigned short>((e & 1) ? (h2 >> 16) : (h2 & 0xFFFFu));
+    *reinterpret_cast<unsigned short*>(q + kInHalf) = static_cast<unsigned short>((e & 1) ? (l2 >> 16) : (l2 & 0xFFFFu));
+  }
+  // inputs of layer 0 for the adjoint streams (weight-gradient operand), in the backward geometry: 8 features = 16 bytes
+  const int a = (st == 0) ? 0 : (C::kI && st == C::sI) ? 1 : (C::kT && st == C::sT) ? (1 + C::kI) : -1;
+  if (live_row && a >= 0) {
+    long long blk;
+    uint32_t rb;
+    bwd_row<C>(smp, a, blk, rb);
+    const size_t o = static_cast<size_t>(blk) * (kTclSmallF * 128) + img_off(rb, static_cast<uint32_t>(kg * 8));
+    *reinterpret_cast<uint4*>(P.in_img[0][0] + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(P.in_img[0][1] + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -920,6 +975,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
     const bool remote = kPair && tsel != static_cast<int>(crank);       // this warp's rows live in the peer's shared memory
     const uint32_t rready_dst = remote ? mapa_u32(&B.rready[0], static_cast<uint32_t>(tsel)) : 0u;
     uint32_t xpar = 0;
+    TL_OPEN(tl, warp == 0 ? 1 : warp == 8 ? 2 : 3, lane == 0 && (warp == 0 || warp == 8 || warp == 15));
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* b3sum = red + 4;
     float* outs = reinterpret_cast<float*>(smem + kOffHhi);
@@ -948,6 +1004,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
         if (g & 1) { mbar_wait(&B.acc_full[1], par1, 0xC01); par1 ^= 1u; }
         else { mbar_wait(&B.acc_full[0], par0, 0xC00); par0 ^= 1u; }
         tc_fence_after();
+        TL_MARK(tl, 0x400u | g);
         if (kPair && g == 0 && tb != tile_first && tsel != static_cast<int>(crank)) {
           // the peer's activation region still holds its staged outputs of the previous tile until its loss stage is done
           mbar_wait_cluster(B.xfree, xpar, 0xC10);
@@ -972,8 +1029,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
             __syncwarp();
             if (lane == 0) arrive_issuer(&B.hready[c], hready_leader + static_cast<uint32_t>(c) * 8u);
           }
+          TL_MARK(tl, 0x500u | (g << 4) | ci);
           if (kPair && g != 0) fwd_state_from_outputs<C>(P, g, n, smp0, etile_ok, v);
           fwd_stash<C>(P, g, n, etile, smp0, etile_ok, w, v);
+          TL_MARK(tl, 0x600u | (g << 4) | ci);
         }
         if (g == 1 && tb + tile_stride < n_tiles) {
           // GEMM 0 of this tile has retired (acc_full[0] above): the small operand region takes the next tile's inputs
@@ -1006,13 +1065,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
         }
       }
       tc_fence_before();
+      TL_MARK(tl, 0x700u);
       row_warps_sync();
+      TL_MARK(tl, 0x710u);
       fwd_loss_stage<C>(P, s0, tile_ok, outs, red, b3sum, t);
       row_warps_sync();   // nobody overwrites the staged outputs (next tile's layer-0 epilogue) while they are read
+      TL_MARK(tl, 0x720u);
       if (kPair && tb + tile_stride < n_tiles) {
         // ... nor does the peer, whose layer-0 epilogue of the next tile writes this CTA's rows: tell it
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(xfree_peer);
+        // relaxed: the loss stage's reads of the staged outputs were consumed before the barrier above, and a release at
+        // cluster scope is a GPU-scope membar (~2 K cycles per tile on every row warp)
+        if (lane == 0) mbar_arrive_remote_relaxed(xfree_peer);
       }
     }
     // ---- flush the CTA's loss sums and output-bias gradient
@@ -1023,6 +1087,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
       atomicAdd(&P.losses[0], ((P.kind == DMIP_LOSS_PINN2 ? 0.f : red[1]) + red[2] + red[3]) * P.inv_B);
     }
     if (t < P.out_dim) atomicAdd(&P.grad[P.off_b[3] + t], b3sum[t]);
+    TL_CLOSE(tl);
   }
   tcl_teardown(tmem_base, warp);
 }
@@ -1034,29 +1099,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
 // matching rows of the IN_0 stash block are zeroed here too (the forward writes only live rows).
 template <class C>
 __device__ __forceinline__ void bwd_build_input(const TclDev& P, long long tile, bool tile_ok, uint8_t* sIn, int t) {
-  const int j = t & 63;             // output component (K index of GEMM 0)
+  // one row x 8 consecutive output components per thread (see fwd_build_input)
+  const int row = t & 63, jg = t >> 6;
   const int od = P.out_dim;
-#pragma unroll 1
-  for (int row = t >> 6; row < kNR; row += kRowThreads / 64) {
-    const int w = row >> 5, rw = row & 31;
-    const int sj = rw / C::NADJ, a = rw - sj * C::NADJ;
-    const long long smp = tile * (2 * C::SPWB) + w * C::SPWB + sj;
-    const bool live = tile_ok && sj < C::SPWB && smp < P.B;
-    float v = 0.f;
-    if (live && j < od) v = P.abar[(smp * C::NADJ + a) * od + j];
-    unsigned short hi, lo;
-    split1(v, hi, lo);
-    const uint32_t off = bop_off(static_cast<uint32_t>(j), static_cast<uint32_t>(row));
-    *reinterpret_cast<unsigned short*>(sIn + off) = hi;
-    *reinterpret_cast<unsigned short*>(sIn + kInHalf + off) = lo;
-    if (tile_ok) {
-      const size_t o = static_cast<size_t>(tile) * (kTclSmallF * 128) + img_off(static_cast<uint32_t>(row), static_cast<uint32_t>(j));
-      *reinterpret_cast<unsigned short*>(P.adj_img[3][0] + o) = hi;
-      *reinterpret_cast<unsigned short*>(P.adj_img[3][1] + o) = lo;
-      if (!live) {
-        *reinterpret_cast<unsigned short*>(P.in_img[0][0] + o) = 0;
-        *reinterpret_cast<unsigned short*>(P.in_img[0][1] + o) = 0;
-      }
+  const int w = row >> 5, rw = row & 31;
+  const int sj = rw / C::NADJ, a = rw - sj * C::NADJ;
+  const long long smp = tile * (2 * C::SPWB) + w * C::SPWB + sj;
+  const bool live = tile_ok && sj < C::SPWB && smp < P.B;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int j = jg * 8 + e;
+    v[e] = (live && j < od) ? P.abar[(smp * C::NADJ + a) * od + j] : 0.f;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  uint8_t* atom = sIn + jg * 1024 + (row & 7) * 2;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    uint8_t* q = atom + e * 128 + (((row >> 3) ^ e) << 4);
+    const uint32_t h2 = hi[e >> 1], l2 = lo[e >> 1];
+    *reinterpret_cast<unsigned short*>(q) = static_cast<unsigned short>((e & 1) ? (h2 >> 16) : (h2 & 0xFFFFu));
+    *reinterpret_cast<unsigned short*>(q + kInHalf) = static_cast<unsigned short>((e & 1) ? (l2 >> 16) : (l2 & 0xFFFFu));
+  }
+  if (tile_ok) {
+    const size_t o = static_cast<size_t>(tile) * (kTclSmallF * 128) + img_off(static_cast<uint32_t>(row), static_cast<uint32_t>(jg * 8));
+    *reinterpret_cast<uint4*>(P.adj_img[3][0] + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(P.adj_img[3][1] + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (!live) {
+      *reinterpret_cast<uint4*>(P.in_img[0][0] + o) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(P.in_img[0][1] + o) = make_uint4(0, 0, 0, 0);
     }
   }
 }
@@ -1513,6 +1586,16 @@ int launch_clustered(K kernel, long long n_tiles, const TclDev& P, cudaStream_t 
 }
 
 }  // namespace
+
+void tcl_debug_set_timeline(unsigned long long* buf, int cap) {
+#ifdef DMIP_JOBMARKS
+  cudaMemcpyToSymbol(g_tcl_tl, &buf, sizeof(buf));
+  cudaMemcpyToSymbol(g_tcl_tl_cap, &cap, sizeof(cap));
+#else
+  (void)buf;
+  (void)cap;
+#endif
+}
 
 bool tcl_streams_supported(const TclStreams& s) {
 #define X(i, t, n, q) if (s.has_I == i && s.has_T == t && s.n_tan == n && s.has_Q == q) return true;

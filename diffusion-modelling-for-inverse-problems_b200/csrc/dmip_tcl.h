@@ -68,5 +68,7 @@ int tcl_launch_fwd(const TclDev& P, cudaStream_t s);
 int tcl_launch_bwd(const TclDev& P, cudaStream_t s);
 // dW_l for all four layers: four split-K tcgen05 GEMMs over the stash images, fp32 atomics into P.grad
 int tcl_launch_wgrad(const TclDev& P, cudaStream_t s);
+// timing builds (-DDMIP_JOBMARKS): CTA 0 of k_tcl_fwd records (clock << 16 | code) entries; no-op otherwise
+void tcl_debug_set_timeline(unsigned long long* buf, int cap);
 
 }  // namespace dmip
