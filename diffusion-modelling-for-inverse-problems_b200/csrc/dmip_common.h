@@ -75,6 +75,9 @@ int launch_histogramdd(const DmipHistogram* d, cudaStream_t s);
 int launch_hist_kl(const void* hp, const void* hq, long long m, double epsilon, double* out, cudaStream_t s);
 size_t surrogate_workspace(const DmipSurrogate* d);
 int launch_surrogate(const DmipSurrogate* d, cudaStream_t s);
+bool surrogate_tc_supported(const DmipMlp& net);
+size_t surrogate_tc_workspace();
+int launch_surrogate_tc(const DmipSurrogate* d, void* images, cudaStream_t s);
 size_t metropolis_workspace(const DmipMetropolis* d);
 int launch_metropolis(const DmipMetropolis* d, cudaStream_t s);
 int launch_sample_t(const float* u, float* t, long long n, int debias, float beta_min, float beta_max, float t_epsilon,

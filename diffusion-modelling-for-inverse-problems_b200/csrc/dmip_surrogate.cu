@@ -362,7 +362,11 @@ int launch_metropolis(const DmipMetropolis* d, cudaStream_t s) {
   return DMIP_OK;
 }
 
-size_t surrogate_workspace(const DmipSurrogate* d) { return align_up(surr_wt_floats(&d->net) * sizeof(float)); }
+// [transposed fp32 weights of the FFMA kernel | packed bf16 hi / lo images of the tensor-core kernel], each part 1 KB aligned
+static size_t surrogate_ffma_bytes(const DmipSurrogate* d) {
+  return (align_up(surr_wt_floats(&d->net) * sizeof(float)) + 1023) / 1024 * 1024;
+}
+size_t surrogate_workspace(const DmipSurrogate* d) { return surrogate_ffma_bytes(d) + surrogate_tc_workspace() + 1024; }
 
 int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
   const DmipMlp& net = d->net;
@@ -377,6 +381,11 @@ int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
   if (!d->workspace || d->workspace_bytes < surrogate_workspace(d)) {
     set_error("workspace too small: need %zu bytes", surrogate_workspace(d));
     return DMIP_EWORKSPACE;
+  }
+  if (surrogate_tc_supported(net)) {
+    // tcgen05 path (dmip_surrogate_tc.cu): its weight images sit behind the FFMA kernel's part, at the next 1 KB boundary
+    const uintptr_t base = reinterpret_cast<uintptr_t>(d->workspace) + surrogate_ffma_bytes(d);
+    return launch_surrogate_tc(d, reinterpret_cast<void*>((base + 1023) / 1024 * 1024), s);
   }
   static int n_sm = 0;
   static bool ready[64] = {};   // cudaFuncSetAttribute is per device
