@@ -601,12 +601,21 @@ def also_surrogate(rows=256 * 65536, steps=3, warmup=2):
         gh = gr.cpu()
     e2e_s = time.perf_counter() - t0
     ach = rows / (ms * 1e-3) * SURR_FLOP / 1e12
-    pk = measured_fp32_tflops()
+    ffma = os.environ.get("DMIP_SURROGATE_PATH") == "ffma"
+    if ffma:
+        pk = measured_fp32_tflops()
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                "peak_source": "measured cuBLAS SGEMM (TF32 off) on this GPU (DMIP_SURROGATE_PATH=ffma: the fp32 FFMA kernel)",
+                "flop_per_row": SURR_FLOP, "kernel": "k_surrogate"}
+    else:
+        # the two 256 x 256 layers (forward + reverse: 524,288 of the 550,912 FLOP / row) and the output layer run as
+        # bf16x3 split products on the tensor cores: 3 issued FLOP per algorithmic FLOP
+        roof = tensor_roofline(ach, sustained=False, flop_per_row=SURR_FLOP,
+                               kernel="k_surrogate_tc (bf16x3 split: 3 tensor-core FLOP per algorithmic FLOP)",
+                               tensor_flops_issued_tflops=3 * ach)
     return {"config": f"K4 surrogate energy + score, {rows} rows (256 observations x 65,536 particles), in calls of {chunk} rows",
-            "value": rows / (ms * 1e-3), "unit": "rows/s", "ms": ms, "dtype": "f32", "gpu_launches": n_chunks * steps,
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
-                         "peak_source": "measured cuBLAS SGEMM (TF32 off) on this GPU: k_surrogate is fp32 FFMA by design "
-                                        "(the energy has 1/b^2 = 1e4 terms)", "flop_per_row": SURR_FLOP, "kernel": "k_surrogate"},
+            "value": rows / (ms * 1e-3), "unit": "rows/s", "ms": ms, "dtype": "f32" if ffma else "bf16x3",
+            "gpu_launches": n_chunks * steps * (5 if ffma else 2), "roofline": roof,
             "e2e": {"value": rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": rows * 26 * 4, "d2h_bytes_per_step": rows * 12}}
 
 

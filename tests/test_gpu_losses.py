@@ -42,12 +42,18 @@ def test_tensor_core_loss_path_is_the_one_that_runs():
     _ok(gc.case_loss_path_taken())
 
 
-def test_surrogate_energy_and_score():
-    _ok(gc.case_surrogate_energy())
+@pytest.mark.parametrize("path", ["tc", "ffma"])
+def test_surrogate_energy_and_score(path):
+    _ok(gc.case_surrogate_energy(path))
 
 
-def test_surrogate_likelihood_vjp():
-    _ok(gc.case_surrogate_vjp())
+@pytest.mark.parametrize("path", ["tc", "ffma"])
+def test_surrogate_likelihood_vjp(path):
+    _ok(gc.case_surrogate_vjp(path))
+
+
+def test_surrogate_tensor_core_kernel_matches_the_fp32_kernel_on_100003_rows():
+    _ok(gc.case_surrogate_tc_vs_ffma())
 
 
 def test_histogram_kl_matches_numpy_bit_for_bit():
