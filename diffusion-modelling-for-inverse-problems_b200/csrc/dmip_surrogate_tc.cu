@@ -7,9 +7,9 @@
 // operand; the surrogate fixture is met with a 10x margin on E and the gradient, tools/study_k4_split.py) of
 // tcgen05.mma M = 128, N = 128, K = 16 with the A operand in TENSOR MEMORY:
 //   TMEM = two regions X, Y of 256 columns.  A GEMM reads its A operand from one region and accumulates into the other;
-//   the epilogue turns each group of 32 fp32 accumulator columns IN PLACE into 16 columns of bf16 hi pairs + 16 columns
-//   of bf16 lo pairs — the A operand of the next GEMM — so the regions swap roles layer by layer and no activation ever
-//   touches shared memory.  The whole shared memory is the weight ring.
+//   the epilogue turns each unit of 16 fp32 accumulator columns IN PLACE into 8 columns of bf16 hi pairs + 8 columns
+//   of bf16 lo pairs — the A operand of one k-step of the next GEMM — so the regions swap roles layer by layer and no
+//   activation ever touches shared memory.  The whole shared memory is the weight ring.
 //   Weights: ONE packed image per matrix (128 out x 64 in tiles, K-major, 128-byte swizzle, hi and lo), read K-major by
 //   the forward GEMMs and MN-major — the same bytes — by the reverse sweep (W^T), streamed from L2 by bulk-TMA in
 //   32 KB stages.
@@ -18,9 +18,10 @@
 //   likelihood cotangent, and the ReLU masks (bits in registers) stay in the row's thread.
 // Per tile: P0 | G1 P1 | G2 P2 | G3 P3 | G4 P4 | G5 P5 | G6 P6.  Each 256 x 256 GEMM runs its stages in the order
 // (kb0 kb1) x c0, (kb0 kb1) x c1, (kb2 kb3) x c0, (kb2 kb3) x c1 (kb = 64-wide K block, c = 128-wide N chunk): chunk 0
-// is complete after 3/4 of the GEMM and its epilogue (row warps 0-3) runs under the rest; the next GEMM starts on the
-// K blocks chunk 0 produced while row warps 4-7 convert chunk 1.
-// Warps: 0-7 rows (warp & 3 = TMEM lane quarter, warp >> 2 = chunk), 8 producer, 9 MMA issuer.
+// is complete after 3/4 of the GEMM and its epilogue (row warps 0-7) runs under the rest; the next GEMM starts on the
+// K blocks chunk 0 produced while row warps 8-15 convert chunk 1.
+// Warps: 0-15 rows (warp & 3 = TMEM lane quarter, warp >> 2 = feature quarter: 64 features per thread), 16 producer,
+// 17 MMA issuer.
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,7 +32,7 @@ namespace dmip {
 namespace {
 
 constexpr int kTRows = 128;
-constexpr int kTThreads = 320;
+constexpr int kTThreads = 576;               // warps 0-15 rows, 16 producer, 17 MMA issuer
 constexpr int kTStage = 32768;                 // hi 16 KB + lo 16 KB
 constexpr int kTRing = 6;
 constexpr int kImgW = 262144;                  // one 256 x 256 matrix: [part][c][kb] tiles of 16 KB
@@ -42,8 +43,9 @@ constexpr int kOffW0 = kTRing * kTStage;       // float4[256]: W0[f][0..2], b0[f
 constexpr int kOffB1 = kOffW0 + 4096;          // float[256]
 constexpr int kOffB2 = kOffB1 + 1024;
 constexpr int kOffB3 = kOffB2 + 1024;          // float[32]
-constexpr int kOffPart = kOffB3 + 128;         // float4[128]: chunk 1's share of the input gradient
-constexpr int kOffMask = kOffPart + 2048;      // uint32[3 layers][4 groups][256 row threads]: ReLU patterns of the row's chunk
+constexpr int kOffPart = kOffB3 + 128;         // float4[4][128]: the four feature quarters' shares of the input gradient
+constexpr int kOffE = kOffPart + 8192;         // float[128]: energy share of outputs 16.. (second output unit)
+constexpr int kOffMask = kOffE + 512;          // uint32[3 layers][2 words][512 row threads]: ReLU patterns of the thread's 64 features
 constexpr int kOffBars = kOffMask + 12288;     // full[6] empty[6] a_ready[2] acc_full[2], tmem holder
 constexpr int kTSmem = kOffBars + 256;
 
@@ -95,68 +97,71 @@ struct TBars {
   uint64_t *full, *empty, *a_ready, *acc_full;
 };
 
-// 32 fp32 values of one feature group -> 16 columns of hi pairs + 16 columns of lo pairs at the group's own columns
-__device__ __forceinline__ void store_group(uint32_t taddr, const float (&v)[32]) {
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) split_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-  tmem_st16(taddr, hi);
-  tmem_st16(taddr + 16, lo);
+// m |= (v > 0) << e as one predicated OR (the C expression made ptxas park the values in local memory)
+__device__ __forceinline__ void mask_bit(uint32_t& m, float v, int e) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(m) : "f"(v), "r"(1u << e));
 }
-// the A operand of this warp's rows and chunk is complete
+// One UNIT = 16 features = the K of one MMA = 16 fp32 accumulator columns, which the epilogue replaces IN PLACE by 8
+// columns of bf16 hi pairs + 8 columns of bf16 lo pairs: the A operand of k-step s of the next GEMM sits at columns
+// 16 s (hi) and 16 s + 8 (lo) of the region.
+__device__ __forceinline__ void store_unit(uint32_t taddr, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  tmem_st8(taddr, hi);
+  tmem_st8(taddr + 8, lo);
+}
+// the A operand of this warp's rows and features is complete
 __device__ __forceinline__ void publish(uint64_t* a_ready, int lane) {
   tc_wait_st();
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(a_ready);
 }
-// m |= (v > 0) << e as one predicated OR (the C expression made ptxas park the 32 values in local memory)
-__device__ __forceinline__ void mask_bit(uint32_t& m, float v, int e) {
-  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(m) : "f"(v), "r"(1u << e));
-}
-// The row-warp phases below are ROLLED loops over the four 32-feature groups of a chunk (one group = one tcgen05.ld of 32
-// columns), with the ReLU patterns in shared memory: fully unrolled, the eight row warps walked 200 KB of code at
-// different places and spent half of their issue slots waiting for instructions (ncu: stall_no_inst).
-// The accumulator load of group j + 1 is issued as soon as group j's values have left the load registers.
+// The row-warp phases are ROLLED loops over the thread's four units, with the ReLU patterns in shared memory (two words
+// per layer and thread): fully unrolled over 128 features per thread, the row warps walked 200 KB of code at different
+// places and spent half of their issue slots waiting for instructions (ncu: stall_no_inst).  The accumulator load of
+// unit i + 1 is issued as soon as unit i's values have left the load registers.
 
 // forward epilogue of a hidden layer: z = acc + bias, ReLU pattern, relu, in place
-__device__ __forceinline__ void hidden_fwd(uint32_t region, const float* bias, uint32_t* mask /* [j * 256] */) {
-  uint32_t u[32];
-  tmem_ld32(region, u);
+__device__ __forceinline__ void hidden_fwd(uint32_t cols, const float* bias, uint32_t* mask /* [word * 512] */) {
+  uint32_t u[16];
+  tmem_ld16(cols, u);
+  uint32_t m = 0;
 #pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
+  for (int i = 0; i < 4; ++i) {
     tc_wait_ld();
-    float v[32];
-    uint32_t m = 0;
+    float v[16];
 #pragma unroll
-    for (int e4 = 0; e4 < 8; ++e4) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + 32 * j + 4 * e4);
-      const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int e = 4 * e4 + i;
-        v[e] = fmaxf(__uint_as_float(u[e]) + bb[i], 0.f);
-        mask_bit(m, v[e], e);
-      }
+    for (int e4 = 0; e4 < 4; ++e4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + 16 * i + 4 * e4);
+      v[4 * e4 + 0] = fmaxf(__uint_as_float(u[4 * e4 + 0]) + b.x, 0.f);
+      v[4 * e4 + 1] = fmaxf(__uint_as_float(u[4 * e4 + 1]) + b.y, 0.f);
+      v[4 * e4 + 2] = fmaxf(__uint_as_float(u[4 * e4 + 2]) + b.z, 0.f);
+      v[4 * e4 + 3] = fmaxf(__uint_as_float(u[4 * e4 + 3]) + b.w, 0.f);
     }
-    if (j < 3) tmem_ld32(region + 32 * (j + 1), u);
-    mask[j * 256] = m;
-    store_group(region + 32 * j, v);
+    if (i < 3) tmem_ld16(cols + 16 * (i + 1), u);
+    uint32_t mu = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) mask_bit(mu, v[e], e);
+    m |= mu << (16 * (i & 1));
+    if (i & 1) { mask[(i >> 1) * 512] = m; m = 0; }
+    store_unit(cols + 16 * i, v);
   }
 }
 // reverse epilogue of a hidden layer: hbar masked by the layer's ReLU pattern, in place
-__device__ __forceinline__ void hidden_bwd(uint32_t region, const uint32_t* mask) {
-  uint32_t u[32];
-  tmem_ld32(region, u);
+__device__ __forceinline__ void hidden_bwd(uint32_t cols, const uint32_t* mask) {
+  uint32_t u[16];
+  tmem_ld16(cols, u);
 #pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t m = mask[j * 256];
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t m = mask[(i >> 1) * 512] >> (16 * (i & 1));
     tc_wait_ld();
-    float v[32];
+    float v[16];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = ((m >> e) & 1u) ? __uint_as_float(u[e]) : 0.f;
-    if (j < 3) tmem_ld32(region + 32 * (j + 1), u);
-    store_group(region + 32 * j, v);
+    for (int e = 0; e < 16; ++e) v[e] = ((m >> e) & 1u) ? __uint_as_float(u[e]) : 0.f;
+    if (i < 3) tmem_ld16(cols + 16 * (i + 1), u);
+    store_unit(cols + 16 * i, v);
   }
 }
 
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       mbar_init(&B.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&B.a_ready[i], 4);
+      mbar_init(&B.a_ready[i], 8);
       mbar_init(&B.acc_full[i], 1);
     }
     fence_barrier_init();
@@ -197,14 +202,14 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
     sB2[f] = P.b2[f];
     if (f < 32) sB3[f] = f < P.out_dim ? P.b3[f] : 0.f;
   }
-  if (warp == 9) tmem_alloc<512>(holder);
+  if (warp == 17) tmem_alloc<512>(holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder;
   const long long n_tiles = (P.n + kTRows - 1) / kTRows;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ---------------------------------------------------------------------------------------------- producer
     int s = 0;
     uint32_t ph = 0;
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ---------------------------------------------------------------------------------------------- MMA issuer
     int s = 0;
     uint32_t ph = 0;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           if (elect_one()) {
 #pragma unroll
             for (int k16 = 0; k16 < 16; ++k16) {
-              const uint32_t a_hi = A + 32u * (k16 >> 1) + 8u * (k16 & 1), a_lo = a_hi + 16u;
+              const uint32_t a_hi = A + 16u * k16, a_lo = a_hi + 8u;
               const uint64_t b_hi = dK | (st16 + (k16 >> 2) * 256u + (k16 & 3) * 2u), b_lo = b_hi + 1024u;
               umma_ts(D, a_hi, b_hi, iF3, k16 > 0 ? 1u : 0u);
               umma_ts(D, a_hi, b_lo, iF3, 1u);
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_hi = A + 8u * ks, a_lo = a_hi + 16u;
+                const uint32_t a_hi = A + 16u * ks, a_lo = a_hi + 8u;
                 const uint64_t b_hi = dMN3 | (st16 + c * 512u + ks * 128u), b_lo = b_hi + 1024u;
                 umma_ts(D + 128u * c, a_hi, b_hi, iB, ks > 0 ? 1u : 0u);
                 umma_ts(D + 128u * c, a_hi, b_lo, iB, 1u);
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const int sg = 4 * kb + ks;
-              const uint32_t a_hi = A + 32u * (sg >> 1) + 8u * (sg & 1), a_lo = a_hi + 16u;
+              const uint32_t a_hi = A + 16u * sg, a_lo = a_hi + 8u;
               const uint64_t b_hi = bwd ? (dMN | (st16 + ks * 128u)) : (dK | (st16 + ks * 2u));
               const uint64_t b_lo = b_hi + 1024u;
               const uint32_t idesc = bwd ? iB : iF;
@@ -360,15 +365,18 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
     }
   } else {
     // ---------------------------------------------------------------------------------------------- row warps
-    const int q = warp & 3, c = warp >> 2;
+    // warp = 4 sub + q: q = TMEM lane quarter (rows 32 q ..), sub = feature quarter: chunk c = sub >> 1, features
+    // [64 sub, 64 sub + 64) of every 256-wide layer = four units per thread
+    const int q = warp & 3, sub = warp >> 2, c = sub >> 1;
     const int row = q * 32 + lane;
     const uint32_t lt = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t X = lt + 128u * c, Y = lt + 256u + 128u * c;   // this warp's chunk of the two regions
-    uint32_t* mk = reinterpret_cast<uint32_t*>(smem + kOffMask) + threadIdx.x;   // [layer * 1024 + j * 256]
+    const uint32_t X = lt + 64u * sub, Y = lt + 256u + 64u * sub;   // this thread's columns of the two regions
+    uint32_t* mk = reinterpret_cast<uint32_t*>(smem + kOffMask) + threadIdx.x;   // [layer * 1024 + word * 512]
+    float* sE = reinterpret_cast<float*>(smem + kOffE);
     uint32_t nw = 0;             // waits done on acc_full[c]
     const int od = P.out_dim, idim = P.in_dim, mode = P.mode;
     const float a2 = P.a2, bb2 = P.bb2, lambd = P.lambd;
-    const float4* w0 = sW0 + c * 128;
+    const float4* w0 = sW0 + 64 * sub;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long grow = tile * kTRows + row;
       const bool live = grow < P.n;
@@ -379,18 +387,22 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
         if (idim > 2) x2 = P.x[grow * idim + 2];
       }
       // ---- P0: h1 = relu(W0 x + b0)
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        float v[32];
+      {
         uint32_t m = 0;
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          float v[16];
+          uint32_t mu = 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float4 w = w0[j * 32 + e];
-          v[e] = fmaxf(fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, w.w))), 0.f);
-          mask_bit(m, v[e], e);
+          for (int e = 0; e < 16; ++e) {
+            const float4 w = w0[i * 16 + e];
+            v[e] = fmaxf(fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, w.w))), 0.f);
+            mask_bit(mu, v[e], e);
+          }
+          m |= mu << (16 * (i & 1));
+          if (i & 1) { mk[(i >> 1) * 512] = m; m = 0; }
+          store_unit(X + 16 * i, v);
         }
-        mk[j * 256] = m;
-        store_group(X + 32 * j, v);
       }
       publish(&B.a_ready[c], lane);
       // ---- P1: h2 = relu(acc + b1) (G1 accumulates into Y);  P2: h3 = relu(acc + b2) (G2 -> X)
@@ -398,24 +410,26 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       for (int l = 1; l <= 2; ++l) {
         mbar_wait(&B.acc_full[c], nw & 1u, 0x300 + c); ++nw;
         tc_fence_after();
-        hidden_fwd(l == 1 ? Y : X, (l == 1 ? sB1 : sB2) + c * 128, mk + l * 1024);
+        hidden_fwd(l == 1 ? Y : X, (l == 1 ? sB1 : sB2) + 64 * sub, mk + l * 1024);
         publish(&B.a_ready[c], lane);
       }
-      // ---- P3: f = acc + b3 (G3 -> Y[0, 32)), energy, cotangent  (the rows' chunk-0 threads only)
+      // ---- P3: f = acc + b3 (G3 -> Y[0, 32)), energy, cotangent: outputs [0, 16) by the sub 0 thread of the row,
+      //      outputs [16, 32) by its sub 1 thread
       if (c == 0) {
         mbar_wait(&B.acc_full[0], nw & 1u, 0x320); ++nw;
         tc_fence_after();
-        uint32_t u[32];
-        tmem_ld32(lt + 256u, u);
+        uint32_t u[16];
+        tmem_ld16(lt + 256u + 16u * sub, u);
         tc_wait_ld();
-        float w[32];
+        float w[16];
         float E = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int e = 0; e < 16; ++e) {
           float we = 0.f;
-          if (e < od) {
-            const float f = __uint_as_float(u[e]) + sB3[e];
-            const float yv = live ? P.y[grow * od + e] : 0.f;
+          const int o = 16 * sub + e;
+          if (o < od) {
+            const float f = __uint_as_float(u[e]) + sB3[o];
+            const float yv = live ? P.y[grow * od + o] : 0.f;
             const float p = a2 * f * f + bb2;
             const float ip = __frcp_rn(p);
             const float r = yv - f;
@@ -425,17 +439,22 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
             } else {
               we = (-a2 * f + r + a2 * r * r * f) * ip;                       // -a^2 v1 + v2 + a^2 v3  (losses.py:354-368)
             }
-            if (live && P.fx) P.fx[grow * od + e] = f;
+            if (live && P.fx) P.fx[grow * od + o] = f;
           }
           w[e] = we;
         }
-        if (mode == 0 && live && P.energy) {
-          E += lambd * (fmaxf(x0 - 1.f, 0.f) + fmaxf(-1.f - x0, 0.f) + fmaxf(x1 - 1.f, 0.f) + fmaxf(-1.f - x1, 0.f) +
-                        fmaxf(x2 - 1.f, 0.f) + fmaxf(-1.f - x2, 0.f));
-          P.energy[grow] = E;
-        }
-        store_group(lt + 256u, w);
+        store_unit(lt + 256u + 16u * sub, w);
         publish(&B.a_ready[0], lane);
+        if (mode == 0 && P.energy) {
+          if (sub == 1) sE[row] = E;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (sub == 0 && live) {
+            E += sE[row];
+            E += lambd * (fmaxf(x0 - 1.f, 0.f) + fmaxf(-1.f - x0, 0.f) + fmaxf(x1 - 1.f, 0.f) + fmaxf(-1.f - x1, 0.f) +
+                          fmaxf(x2 - 1.f, 0.f) + fmaxf(-1.f - x2, 0.f));
+            P.energy[grow] = E;
+          }
+        }
       }
       // ---- P4: h3bar = acc masked by h3 > 0 (G4 -> X);  P5: h2bar (G5 -> Y)
 #pragma unroll 1
@@ -450,19 +469,19 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       tc_fence_after();
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
       {
-        uint32_t u[32];
-        tmem_ld32(X, u);
+        uint32_t u[16];
+        tmem_ld16(X, u);
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t m = mk[j * 256];
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t m = mk[(i >> 1) * 512] >> (16 * (i & 1));
           tc_wait_ld();
-          float v[32];
+          float v[16];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = ((m >> e) & 1u) ? __uint_as_float(u[e]) : 0.f;
-          if (j < 3) tmem_ld32(X + 32 * (j + 1), u);
+          for (int e = 0; e < 16; ++e) v[e] = ((m >> e) & 1u) ? __uint_as_float(u[e]) : 0.f;
+          if (i < 3) tmem_ld16(X + 16 * (i + 1), u);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float4 w = w0[j * 32 + e];
+          for (int e = 0; e < 16; ++e) {
+            const float4 w = w0[i * 16 + e];
             g0 = fmaf(v[e], w.x, g0);
             g1 = fmaf(v[e], w.y, g1);
             g2 = fmaf(v[e], w.z, g2);
@@ -470,11 +489,14 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
         }
       }
       tc_fence_before();
-      if (c == 1) sPart[row] = make_float4(g0, g1, g2, 0.f);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (c == 0 && live) {
-        const float4 o = sPart[row];
-        g0 += o.x; g1 += o.y; g2 += o.z;
+      if (sub != 0) sPart[(sub - 1) * 128 + row] = make_float4(g0, g1, g2, 0.f);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (sub == 0 && live) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 o = sPart[k * 128 + row];
+          g0 += o.x; g1 += o.y; g2 += o.z;
+        }
         if (mode == 0) {
           g0 += lambd * ((x0 > 1.f ? 1.f : 0.f) - (x0 < -1.f ? 1.f : 0.f));
           g1 += lambd * ((x1 > 1.f ? 1.f : 0.f) - (x1 < -1.f ? 1.f : 0.f));
@@ -488,7 +510,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
