@@ -18,10 +18,9 @@
 //   likelihood cotangent, and the ReLU masks (bits in registers) stay in the row's thread.
 // Per tile: P0 | G1 P1 | G2 P2 | G3 P3 | G4 P4 | G5 P5 | G6 P6.  Each 256 x 256 GEMM runs its stages in the order
 // (kb0 kb1) x c0, (kb0 kb1) x c1, (kb2 kb3) x c0, (kb2 kb3) x c1 (kb = 64-wide K block, c = 128-wide N chunk): chunk 0
-// is complete after 3/4 of the GEMM and its epilogue (row warps 0-7) runs under the rest; the next GEMM starts on the
-// K blocks chunk 0 produced while row warps 8-15 convert chunk 1.
-// Warps: 0-15 rows (warp & 3 = TMEM lane quarter, warp >> 2 = feature quarter: 64 features per thread), 16 producer,
-// 17 MMA issuer.
+// is complete after 3/4 of the GEMM and its epilogue (all row warps) runs under the rest; the next GEMM starts on the
+// K blocks chunk 0 produced while the row warps convert chunk 1.
+// Warps: 0-15 rows (warp & 3 = TMEM lane quarter; 32 features of each chunk per thread), 16 producer, 17 MMA issuer.
 #include <stdlib.h>
 #include <string.h>
 
@@ -118,18 +117,19 @@ __device__ __forceinline__ void publish(uint64_t* a_ready, int lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive(a_ready);
 }
-// The row-warp phases are ROLLED loops over the thread's four units, with the ReLU patterns in shared memory (two words
-// per layer and thread): fully unrolled over 128 features per thread, the row warps walked 200 KB of code at different
-// places and spent half of their issue slots waiting for instructions (ncu: stall_no_inst).  The accumulator load of
-// unit i + 1 is issued as soon as unit i's values have left the load registers.
+// A row thread owns 32 features of chunk 0 and 32 features of chunk 1 of every 256-wide layer (two units each): ALL
+// sixteen row warps convert chunk 0 as soon as it is complete (3/4 into the GEMM) and then chunk 1 — the next GEMM waits
+// for half an epilogue, not a whole one.  The ReLU patterns live in shared memory (one word per layer, part and thread);
+// the phases are small loops: fully unrolled over 128 features per thread, the row warps walked 200 KB of code at
+// different places and spent half of their issue slots waiting for instructions (ncu: stall_no_inst).
 
-// forward epilogue of a hidden layer: z = acc + bias, ReLU pattern, relu, in place
-__device__ __forceinline__ void hidden_fwd(uint32_t cols, const float* bias, uint32_t* mask /* [word * 512] */) {
+// forward epilogue of one part (two units) of a hidden layer: z = acc + bias, ReLU pattern, relu, in place
+__device__ __forceinline__ void fwd_part(uint32_t cols, const float* bias, uint32_t* mask_word) {
   uint32_t u[16];
   tmem_ld16(cols, u);
   uint32_t m = 0;
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
     tc_wait_ld();
     float v[16];
 #pragma unroll
@@ -140,27 +140,24 @@ __device__ __forceinline__ void hidden_fwd(uint32_t cols, const float* bias, uin
       v[4 * e4 + 2] = fmaxf(__uint_as_float(u[4 * e4 + 2]) + b.z, 0.f);
       v[4 * e4 + 3] = fmaxf(__uint_as_float(u[4 * e4 + 3]) + b.w, 0.f);
     }
-    if (i < 3) tmem_ld16(cols + 16 * (i + 1), u);
-    uint32_t mu = 0;
+    if (i == 0) tmem_ld16(cols + 16, u);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) mask_bit(mu, v[e], e);
-    m |= mu << (16 * (i & 1));
-    if (i & 1) { mask[(i >> 1) * 512] = m; m = 0; }
+    for (int e = 0; e < 16; ++e) mask_bit(m, v[e], 16 * i + e);
     store_unit(cols + 16 * i, v);
   }
+  *mask_word = m;
 }
-// reverse epilogue of a hidden layer: hbar masked by the layer's ReLU pattern, in place
-__device__ __forceinline__ void hidden_bwd(uint32_t cols, const uint32_t* mask) {
+// reverse epilogue of one part of a hidden layer: hbar masked by the layer's ReLU pattern, in place
+__device__ __forceinline__ void bwd_part(uint32_t cols, uint32_t m) {
   uint32_t u[16];
   tmem_ld16(cols, u);
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t m = mask[(i >> 1) * 512] >> (16 * (i & 1));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
     tc_wait_ld();
     float v[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = ((m >> e) & 1u) ? __uint_as_float(u[e]) : 0.f;
-    if (i < 3) tmem_ld16(cols + 16 * (i + 1), u);
+    for (int e = 0; e < 16; ++e) v[e] = ((m >> (16 * i + e)) & 1u) ? __uint_as_float(u[e]) : 0.f;
+    if (i == 0) tmem_ld16(cols + 16, u);
     store_unit(cols + 16 * i, v);
   }
 }
@@ -187,7 +184,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       mbar_init(&B.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&B.a_ready[i], 8);
+      mbar_init(&B.a_ready[i], 16);
       mbar_init(&B.acc_full[i], 1);
     }
     fence_barrier_init();
@@ -365,18 +362,23 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
     }
   } else {
     // ---------------------------------------------------------------------------------------------- row warps
-    // warp = 4 sub + q: q = TMEM lane quarter (rows 32 q ..), sub = feature quarter: chunk c = sub >> 1, features
-    // [64 sub, 64 sub + 64) of every 256-wide layer = four units per thread
-    const int q = warp & 3, sub = warp >> 2, c = sub >> 1;
+    // warp = 4 sub + q: q = TMEM lane quarter (rows 32 q ..); the thread owns features [32 sub, +32) of chunk 0 (part 0)
+    // and [128 + 32 sub, +32) of chunk 1 (part 1) of every 256-wide layer
+    const int q = warp & 3, sub = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lt = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t X = lt + 64u * sub, Y = lt + 256u + 64u * sub;   // this thread's columns of the two regions
-    uint32_t* mk = reinterpret_cast<uint32_t*>(smem + kOffMask) + threadIdx.x;   // [layer * 1024 + word * 512]
+    const uint32_t X = lt + 32u * sub, Y = lt + 256u + 32u * sub;   // part p of a region: + 128 p
+    uint32_t* mk = reinterpret_cast<uint32_t*>(smem + kOffMask) + threadIdx.x;   // [layer * 1024 + part * 512]
     float* sE = reinterpret_cast<float*>(smem + kOffE);
-    uint32_t nw = 0;             // waits done on acc_full[c]
+    uint32_t nw0 = 0, nw1 = 0;   // waits done on acc_full[0], acc_full[1]
     const int od = P.out_dim, idim = P.in_dim, mode = P.mode;
     const float a2 = P.a2, bb2 = P.bb2, lambd = P.lambd;
-    const float4* w0 = sW0 + 64 * sub;
+    const float4* w0 = sW0 + 32 * sub;
+    auto wait_part = [&](int p, uint32_t tag) {
+      if (p == 0) { mbar_wait(&B.acc_full[0], nw0 & 1u, tag); ++nw0; }
+      else { mbar_wait(&B.acc_full[1], nw1 & 1u, tag + 1); ++nw1; }
+      tc_fence_after();
+    };
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long grow = tile * kTRows + row;
       const bool live = grow < P.n;
@@ -387,37 +389,37 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
         if (idim > 2) x2 = P.x[grow * idim + 2];
       }
       // ---- P0: h1 = relu(W0 x + b0)
-      {
-        uint32_t m = 0;
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
+      for (int p = 0; p < 2; ++p) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
           float v[16];
-          uint32_t mu = 0;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float4 w = w0[i * 16 + e];
+            const float4 w = w0[128 * p + 16 * i + e];
             v[e] = fmaxf(fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, w.w))), 0.f);
-            mask_bit(mu, v[e], e);
+            mask_bit(m, v[e], 16 * i + e);
           }
-          m |= mu << (16 * (i & 1));
-          if (i & 1) { mk[(i >> 1) * 512] = m; m = 0; }
-          store_unit(X + 16 * i, v);
+          store_unit(X + 128 * p + 16 * i, v);
         }
+        mk[p * 512] = m;
+        publish(&B.a_ready[p], lane);
       }
-      publish(&B.a_ready[c], lane);
       // ---- P1: h2 = relu(acc + b1) (G1 accumulates into Y);  P2: h3 = relu(acc + b2) (G2 -> X)
 #pragma unroll 1
       for (int l = 1; l <= 2; ++l) {
-        mbar_wait(&B.acc_full[c], nw & 1u, 0x300 + c); ++nw;
-        tc_fence_after();
-        hidden_fwd(l == 1 ? Y : X, (l == 1 ? sB1 : sB2) + 64 * sub, mk + l * 1024);
-        publish(&B.a_ready[c], lane);
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+          wait_part(p, 0x300);
+          fwd_part((l == 1 ? Y : X) + 128 * p, (l == 1 ? sB1 : sB2) + 128 * p + 32 * sub, mk + l * 1024 + p * 512);
+          publish(&B.a_ready[p], lane);
+        }
       }
       // ---- P3: f = acc + b3 (G3 -> Y[0, 32)), energy, cotangent: outputs [0, 16) by the sub 0 thread of the row,
       //      outputs [16, 32) by its sub 1 thread
-      if (c == 0) {
-        mbar_wait(&B.acc_full[0], nw & 1u, 0x320); ++nw;
-        tc_fence_after();
+      wait_part(0, 0x320);
+      if (sub < 2) {
         uint32_t u[16];
         tmem_ld16(lt + 256u + 16u * sub, u);
         tc_wait_ld();
@@ -455,33 +457,39 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
             P.energy[grow] = E;
           }
         }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B.a_ready[0]);
       }
       // ---- P4: h3bar = acc masked by h3 > 0 (G4 -> X);  P5: h2bar (G5 -> Y)
 #pragma unroll 1
       for (int l = 2; l >= 1; --l) {
-        mbar_wait(&B.acc_full[c], nw & 1u, 0x330 + c); ++nw;
-        tc_fence_after();
-        hidden_bwd(l == 2 ? X : Y, mk + l * 1024);
-        publish(&B.a_ready[c], lane);
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+          wait_part(p, 0x330);
+          bwd_part((l == 2 ? X : Y) + 128 * p, mk[l * 1024 + p * 512]);
+          publish(&B.a_ready[p], lane);
+        }
       }
       // ---- P6: h1bar (G6 -> X) masked, xbar = W0^T h1bar
-      mbar_wait(&B.acc_full[c], nw & 1u, 0x350 + c); ++nw;
-      tc_fence_after();
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      {
-        uint32_t u[16];
-        tmem_ld16(X, u);
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t m = mk[(i >> 1) * 512] >> (16 * (i & 1));
+      for (int p = 0; p < 2; ++p) {
+        wait_part(p, 0x350);
+        const uint32_t m = mk[p * 512];
+        uint32_t u[16];
+        tmem_ld16(X + 128 * p, u);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
           tc_wait_ld();
           float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = ((m >> e) & 1u) ? __uint_as_float(u[e]) : 0.f;
-          if (i < 3) tmem_ld16(X + 16 * (i + 1), u);
+          for (int e = 0; e < 16; ++e) v[e] = ((m >> (16 * i + e)) & 1u) ? __uint_as_float(u[e]) : 0.f;
+          if (i == 0) tmem_ld16(X + 128 * p + 16, u);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float4 w = w0[i * 16 + e];
+            const float4 w = w0[128 * p + 16 * i + e];
             g0 = fmaf(v[e], w.x, g0);
             g1 = fmaf(v[e], w.y, g1);
             g2 = fmaf(v[e], w.z, g2);
