@@ -393,33 +393,39 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       else { mbar_wait(&B.acc_full[1], nw1 & 1u, tag + 1); ++nw1; }
       tc_fence_after();
     };
+    // P0 of one part: h1 = relu(W0 x + b0) for this thread's 32 features of chunk p, straight into region X
+    auto p0_part = [&](int p, float x0, float x1, float x2) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float4 w = w0[128 * p + 16 * i + e];
+          v[e] = fmaxf(fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, w.w))), 0.f);
+          mask_bit(m, v[e], 16 * i + e);
+        }
+        store_unit(X + 128 * p + 16 * i, v);
+      }
+      mk[p * 512] = m;
+      publish(&B.a_ready[p], lane);
+    };
+    auto load_x = [&](long long g, float& x0, float& x1, float& x2) {
+      x0 = x1 = x2 = 0.f;
+      if (g < P.n) {
+        x0 = P.x[g * idim];
+        if (idim > 1) x1 = P.x[g * idim + 1];
+        if (idim > 2) x2 = P.x[g * idim + 2];
+      }
+    };
+    float x0, x1, x2;
+    load_x(static_cast<long long>(blockIdx.x) * kTRows + row, x0, x1, x2);
+    // ---- P0 of the CTA's first tile; every later tile's P0 runs inside the previous tile's P6 (below)
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) p0_part(p, x0, x1, x2);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long grow = tile * kTRows + row;
       const bool live = grow < P.n;
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-      if (live) {
-        x0 = P.x[grow * idim];
-        if (idim > 1) x1 = P.x[grow * idim + 1];
-        if (idim > 2) x2 = P.x[grow * idim + 2];
-      }
-      // ---- P0: h1 = relu(W0 x + b0)
-#pragma unroll 1
-      for (int p = 0; p < 2; ++p) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float4 w = w0[128 * p + 16 * i + e];
-            v[e] = fmaxf(fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, w.w))), 0.f);
-            mask_bit(m, v[e], 16 * i + e);
-          }
-          store_unit(X + 128 * p + 16 * i, v);
-        }
-        mk[p * 512] = m;
-        publish(&B.a_ready[p], lane);
-      }
       // ---- P1: h2 = relu(acc + b1) (G1 accumulates into Y);  P2: h3 = relu(acc + b2) (G2 -> X)
 #pragma unroll 1
       for (int l = 1; l <= 2; ++l) {
@@ -486,7 +492,12 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           publish(&B.a_ready[p], lane);
         }
       }
-      // ---- P6: h1bar (G6 -> X) masked, xbar = W0^T h1bar
+      // ---- P6: h1bar (G6 -> X) masked, xbar = W0^T h1bar — and, part by part, the NEXT tile's P0 into the columns this
+      //      thread has just read (its own 32 columns of the part), so that G1 of the next tile starts under this tile's tail
+      const long long ntile = tile + gridDim.x;
+      const bool has_next = ntile < n_tiles;
+      float nx0, nx1, nx2;
+      load_x(has_next ? ntile * kTRows + row : P.n, nx0, nx1, nx2);
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
@@ -509,6 +520,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
             g2 = fmaf(v[e], w.z, g2);
           }
         }
+        if (has_next) p0_part(p, nx0, nx1, nx2);
       }
       tc_fence_before();
       if (sub != 0) sPart[(sub - 1) * 128 + row] = make_float4(g0, g1, g2, 0.f);
@@ -528,6 +540,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
         if (idim > 1) P.grad[grow * idim + 1] = g1;
         if (idim > 2) P.grad[grow * idim + 2] = g2;
       }
+      x0 = nx0; x1 = nx1; x2 = nx2;
     }
   }
   tc_fence_before();
