@@ -17,7 +17,7 @@
 //   transpose (K = 32) are small tcgen05 GEMMs; the per-row energy, its cotangent dE/df or the merged
 //   likelihood cotangent, and the ReLU masks (bits in registers) stay in the row's thread.
 // Per tile: P0 | G1 P1 | G2 P2 | G3 P3 | G4 P4 | G5 P5 | G6 P6.  Each 256 x 256 GEMM runs its stages in the order
-// (kb0 kb1) x c0, (kb0 kb1) x c1, (kb2 kb3) x c0, (kb2 kb3) x c1 (kb = 64-wide K block, c = 128-wide N chunk): chunk 0
+// (kb0 kb1) x both chunks (N = 256 instructions), (kb2 kb3) x c0, (kb2 kb3) x c1 (kb = 64-wide K block, c = 128-wide N chunk): chunk 0
 // is complete after 3/4 of the GEMM and its epilogue (all row warps) runs under the rest; the next GEMM starts on the
 // K blocks chunk 0 produced while the row warps convert chunk 1.
 // Warps: 0-15 rows (warp & 3 = TMEM lane quarter; 32 features of each chunk per thread), 16 producer, 17 MMA issuer.
@@ -228,8 +228,39 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
         }
         const uint8_t* img = P.img + ((g == 1 || g == 6) ? 0 : kImgW);
         const bool bwd = g >= 5;
+        // K blocks 0, 1 (they need only chunk 0 of the operand): DOUBLE stages (two ring slots, 64 KB) for N = 256
+        // instructions; slots are consumed in even numbers per GEMM, so a double stage starts on an even slot
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);
+          mbar_wait(&B.empty[s + 1], ph ^ 1u, 0x101 + s);
+          if (elect_one()) {
+            uint8_t* st = smem + s * kTStage;
+            mbar_arrive_expect_tx(&B.full[s], 2 * kTStage);
+            mbar_arrive(&B.full[s + 1]);   // nobody waits for it: the slot's barrier just keeps step with the ring's phase
+            if (!bwd) {
+              // forward: all 256 out features x in features [64 kb, +64): [hi c0 | hi c1 | lo c0 | lo c1]
+#pragma unroll
+              for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                  bulk_g2s(st + p * 32768 + c * 16384, img + ((p * 2 + c) * 4 + kb) * 16384, 16384, &B.full[s]);
+            } else {
+              // reverse: K = out features [64 kb, +64), N = all 256 in features = four MN groups of 64, 8 KB apart
+              const int ct = kb >> 1, half = kb & 1;
+#pragma unroll
+              for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi)
+                  bulk_g2s(st + p * 32768 + gi * 8192, img + ((p * 2 + ct) * 4 + gi) * 16384 + half * 8192, 8192, &B.full[s]);
+            }
+          }
+          __syncwarp();
+          s += 2;
+          if (s == kTRing) { s = 0; ph ^= 1u; }
+        }
+#pragma unroll 1
+        for (int i = 4; i < 8; ++i) {
           const int kb = c_kb[i], c = c_ch[i];
           mbar_wait(&B.empty[s], ph ^ 1u, 0x100 + s);
           if (elect_one()) {
@@ -270,6 +301,8 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
     constexpr uint32_t iF = umma_idesc_bf16(128, 128);
     constexpr uint32_t iF3 = umma_idesc_bf16(128, 32);
     constexpr uint32_t iB = umma_idesc_bf16_major(128, 128, 0, 1);
+    constexpr uint32_t iF2 = umma_idesc_bf16(128, 256);
+    constexpr uint32_t iB2 = umma_idesc_bf16_major(128, 256, 0, 1);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
       for (int g = 1; g <= 6; ++g) {
@@ -343,10 +376,34 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           continue;
         }
         const bool bwd = g >= 5;
+        mbar_wait(&B.a_ready[0], ka0 & 1u, 0x210); ++ka0;
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
+        for (int kb = 0; kb < 2; ++kb) {   // K blocks 0, 1 for both chunks at once: N = 256 from a double stage
+          mbar_wait(&B.full[s], ph, 0x220 + s);
+          tc_fence_after();
+          const uint32_t st16 = base16 + static_cast<uint32_t>(s) * (kTStage >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const int sg = 4 * kb + ks;
+              const uint32_t a_hi = A + 16u * sg, a_lo = a_hi + 8u;
+              const uint64_t b_hi = bwd ? (dMN | (st16 + ks * 128u)) : (dK | (st16 + ks * 2u));
+              const uint64_t b_lo = b_hi + 2048u;
+              const uint32_t idesc = bwd ? iB2 : iF2;
+              umma_ts(D, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+              umma_ts(D, a_hi, b_lo, idesc, 1u);
+              umma_ts(D, a_lo, b_hi, idesc, 1u);
+            }
+            tc_commit(&B.empty[s]);
+            tc_commit(&B.empty[s + 1]);
+          }
+          __syncwarp();
+          s += 2;
+          if (s == kTRing) { s = 0; ph ^= 1u; }
+        }
+#pragma unroll 1
+        for (int i = 4; i < 8; ++i) {
           const int kb = c_kb[i], c = c_ch[i];
-          if (i == 0) { mbar_wait(&B.a_ready[0], ka0 & 1u, 0x210); ++ka0; }
           if (i == 4) { mbar_wait(&B.a_ready[1], ka1 & 1u, 0x211); ++ka1; }
           mbar_wait(&B.full[s], ph, 0x220 + s);
           tc_fence_after();
@@ -359,7 +416,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
               const uint64_t b_hi = bwd ? (dMN | (st16 + ks * 128u)) : (dK | (st16 + ks * 2u));
               const uint64_t b_lo = b_hi + 1024u;
               const uint32_t idesc = bwd ? iB : iF;
-              umma_ts(D + 128u * c, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+              umma_ts(D + 128u * c, a_hi, b_hi, idesc, 1u);
               umma_ts(D + 128u * c, a_hi, b_lo, idesc, 1u);
               umma_ts(D + 128u * c, a_lo, b_hi, idesc, 1u);
             }
