@@ -26,6 +26,7 @@ struct SurrDev {
   const float* b[DMIP_MAX_LAYERS];
   float a, bb, lambd;
   long long n;
+  long long rpo;        // rows per observation (0: one y row per x row)
   const float* x;
   const float* y;
   float* energy;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_surrogate(const __grid_constan
       float E = 0.f;
       for (int j = 0; j < P.out_dim; ++j) {
         const float f = in[j * kLd + t];
-        const float yv = live ? P.y[row * P.out_dim + j] : 0.f;
+        const float yv = live ? P.y[(P.rpo > 0 ? row / P.rpo : row) * P.out_dim + j] : 0.f;
         const float p = a2 * f * f + P.bb * P.bb;
         const float r = yv - f;
         float w;
@@ -375,7 +376,7 @@ int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
   for (int l = 0; l < net.n_layers; ++l)
     DMIP_REQUIRE(net.width[l] >= 1 && net.width[l] <= kMaxW && net.W[l] && net.b[l], "surrogate layer %d: bad width or NULL", l);
   DMIP_REQUIRE(d->mode == 0 || d->mode == 1, "surrogate mode must be 0 (energy + gradient) or 1 (likelihood VJP)");
-  DMIP_REQUIRE(d->n >= 0, "negative row count");
+  DMIP_REQUIRE(d->n >= 0 && d->rows_per_obs >= 0, "negative row count / rows_per_obs");
   if (d->n == 0) return DMIP_OK;
   DMIP_REQUIRE(d->x && d->y && d->grad, "x / y / grad is NULL");
   if (!d->workspace || d->workspace_bytes < surrogate_workspace(d)) {
@@ -421,6 +422,7 @@ int launch_surrogate(const DmipSurrogate* d, cudaStream_t s) {
   P.bb = d->b;
   P.lambd = d->lambd_bd;
   P.n = d->n;
+  P.rpo = d->rows_per_obs;
   P.x = d->x;
   P.y = d->y;
   P.energy = d->energy;

@@ -50,7 +50,7 @@ constexpr int kTSmem = kOffBars + 256;
 
 struct SurrTc {
   int mode, in_dim, out_dim;
-  long long n;
+  long long n, rpo;     // rows, rows per observation (0: one y row per x row)
   const float *W0, *b0, *W1, *b1, *W2, *b2, *W3, *b3;
   uint8_t* img;
   float a2, bb2, lambd;
@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       //      outputs [16, 32) by its sub 1 thread
       wait_part(0, 0x320);
       if (sub < 2) {
+        const float* yrow = P.y + (P.rpo > 0 ? grow / P.rpo : grow) * od;
         uint32_t u[16];
         tmem_ld16(lt + 256u + 16u * sub, u);
         tc_wait_ld();
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           const int o = 16 * sub + e;
           if (o < od) {
             const float f = __uint_as_float(u[e]) + sB3[o];
-            const float yv = live ? P.y[grow * od + o] : 0.f;
+            const float yv = live ? yrow[o] : 0.f;
             const float p = a2 * f * f + bb2;
             const float ip = __frcp_rn(p);
             const float r = yv - f;
@@ -638,6 +639,7 @@ int launch_surrogate_tc(const DmipSurrogate* d, void* images, cudaStream_t s) {
   P.in_dim = net.in_dim;
   P.out_dim = net.out_dim;
   P.n = d->n;
+  P.rpo = d->rows_per_obs;
   P.W0 = net.W[0]; P.b0 = net.b[0];
   P.W1 = net.W[1]; P.b1 = net.b[1];
   P.W2 = net.W[2]; P.b2 = net.b[2];

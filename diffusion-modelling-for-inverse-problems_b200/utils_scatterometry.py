@@ -22,7 +22,8 @@ SURR_ENERGY, SURR_LIK_VJP = 0, 1
 class DmipSurrogate(C.Structure):
     _fields_ = [("mode", C.c_int32), ("net", _lib.DmipMlp), ("a", C.c_float), ("b", C.c_float), ("lambd_bd", C.c_float),
                 ("n", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p), ("energy", C.c_void_p), ("grad", C.c_void_p),
-                ("fx", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("fx", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("rows_per_obs", C.c_int64)]
 
 
 def _bind():
@@ -57,15 +58,23 @@ def surrogate_call(forward_model, x, y, a, b, lambd_bd=0.0, mode=SURR_ENERGY, wa
     x = x.detach().float().contiguous()
     n = x.shape[0]
     y = torch.as_tensor(y, dtype=torch.float32, device=x.device)
-    if y.ndim == 1 or y.shape[0] != n:
-        y = y.reshape(-1, y.shape[-1]).expand(n, -1)     # one observation for all rows, as the reference broadcasts
-    y = y.contiguous()
+    y = y.reshape(-1, y.shape[-1]).contiguous()
+    # one observation per row, or k observations for k equal blocks of rows (k = 1: the reference's broadcast of one
+    # observation over all samples) — the kernel indexes y by row / rows_per_obs, nothing is expanded
+    k = y.shape[0]
+    if k == n:
+        rows_per_obs = 0
+    elif n % k == 0:
+        rows_per_obs = n // k
+    else:
+        raise ValueError(f"y has {k} rows for {n} samples: need one row per sample or a divisor of the sample count")
     keep = [x, y]
     d = DmipSurrogate()
     d.mode = mode
     d.net = _lib.mlp_desc(forward_model, keep)
     d.a, d.b, d.lambd_bd = float(a), float(b), float(lambd_bd)
     d.n = n
+    d.rows_per_obs = rows_per_obs
     d.x, d.y = x.data_ptr(), y.data_ptr()
     energy = torch.empty(n, device=x.device) if mode == SURR_ENERGY else None
     grad = torch.empty_like(x)

@@ -251,12 +251,16 @@ typedef struct DmipSurrogate {
   float a, b, lambd_bd; /* noise model p = (a f)^2 + b^2 and boundary weight (utils_scatterometry.py:19-21) */
   int64_t n;
   const float* x;       /* device (n, in_dim)  */
-  const float* y;       /* device (n, out_dim) */
+  const float* y;       /* device (n, out_dim), or (ceil(n / rows_per_obs), out_dim) when rows_per_obs > 0 */
   float* energy;        /* device (n,) or NULL */
   float* grad;          /* device (n, in_dim)  */
   float* fx;            /* device (n, out_dim) or NULL */
   void* workspace;      /* device, dmip_surrogate_workspace_bytes() */
   size_t workspace_bytes;
+  int64_t rows_per_obs; /* 0: y holds n rows, one per row of x.  > 0: row i belongs to observation i / rows_per_obs and y
+                           holds ceil(n / rows_per_obs) rows — batches of n_obs x n_per_obs rows laid out as DmipSampler
+                           lays out its particles; rows_per_obs = n is the reference's broadcast of ONE observation
+                           over all samples (utils_scatterometry.py:30-38 with ys of shape (1, ydim)) */
 } DmipSurrogate;
 
 size_t dmip_surrogate_workspace_bytes(const DmipSurrogate* d);

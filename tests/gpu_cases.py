@@ -396,6 +396,37 @@ def case_surrogate_vjp(path="tc"):
     return worst, 1.0, {}
 
 
+def case_surrogate_observation_blocks(path="tc"):
+    """rows_per_obs of the C ABI: y given as ONE row (the reference's broadcast of one observation over all samples,
+    utils_scatterometry.py:30-38) or as 4 rows for 4 equal blocks of samples must give exactly what the expanded
+    (n, ydim) tensor gives — same kernel, same arithmetic: bit-identical."""
+    from dmip import utils_scatterometry as us
+    fx = load_golden("scat_energy")
+    fm, _ = _surrogate_module()
+    x = fx["x"].to(DEV)
+    worst = 0.0
+    _surrogate_path(path)
+    try:
+        for k in (1, 4):
+            yk = fx["y"][:k].to(DEV)
+            full = yk.repeat_interleave(512 // k, dim=0)
+            for mode in (us.SURR_ENERGY, us.SURR_LIK_VJP):
+                a = us.surrogate_call(fm, x, yk, 0.2, 0.01, 1000.0, mode=mode, want_fx=True)
+                b = us.surrogate_call(fm, x, full, 0.2, 0.01, 1000.0, mode=mode, want_fx=True)
+                for u, v in zip(a, b):
+                    if u is not None:
+                        worst = max(worst, (u - v).abs().max().item())
+        bad = 0.0
+        try:
+            us.surrogate_call(fm, x, fx["y"][:5].to(DEV), 0.2, 0.01, 1000.0)
+            bad = 1.0            # 5 does not divide 512: must raise
+        except ValueError:
+            pass
+    finally:
+        _surrogate_path("tc")
+    return max(worst, bad), 0.0, {}
+
+
 def case_surrogate_tc_vs_ffma(n=100003):
     """The tensor-core kernel against the fp32 FFMA kernel on `n` random rows of the prior box and beyond (|x| <= 1.2:
     boundary terms on), one observation per row — both modes, a ragged last tile, many tiles per CTA: f 2e-5, E 2e-4 rel

@@ -52,6 +52,11 @@ def test_surrogate_likelihood_vjp(path):
     _ok(gc.case_surrogate_vjp(path))
 
 
+@pytest.mark.parametrize("path", ["tc", "ffma"])
+def test_surrogate_one_observation_per_block_of_rows(path):
+    _ok(gc.case_surrogate_observation_blocks(path))
+
+
 def test_surrogate_tensor_core_kernel_matches_the_fp32_kernel_on_100003_rows():
     _ok(gc.case_surrogate_tc_vs_ffma())
 
