@@ -204,12 +204,21 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, u
 __device__ __forceinline__ void fence_proxy_async_cluster_smem() {
   asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
 }
-// wait on an own mbarrier whose arrivals come from another CTA (release.cluster): acquire at cluster scope
+// wait on an own mbarrier whose arrivals come from another CTA (release.cluster): acquire at cluster scope.
+// (Every successful wait then invalidates L1 — CCTL.IVALL, 6 % of the forward loss kernel's warp samples.  With
+// -DDMIP_CTA_ACQUIRE the acquire stays at CTA scope, as in CUTLASS' ClusterBarrier::wait — sufficient for waiters that
+// only issue tcgen05.mma on async-proxy data afterwards; measured: no change of the step time (3.89 / 3.88 ms PINN,
+// 1.171 / 1.183 ms DSM), so the formally stronger form stays.)
+#ifdef DMIP_CTA_ACQUIRE
+#define DMIP_TRY_WAIT_CLUSTER "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
+#define DMIP_TRY_WAIT_CLUSTER "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      DMIP_TRY_WAIT_CLUSTER
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)

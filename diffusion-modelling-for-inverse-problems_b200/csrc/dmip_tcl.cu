@@ -124,8 +124,9 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 // operand store of an epilogue thread: own shared memory, or (pair mode, rmbar != 0) an asynchronous store into the
 // peer's shared memory whose arrival is counted on the peer's `rready` barrier — the writer neither fences nor arrives
 __device__ __forceinline__ void st_operand_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rmbar) {
+  // (local rows take a plain st.shared on the CTA's own address: a st.shared::cluster on the mapa address of the own rank
+  // is a GENERIC store — ST.E.128 behind an S2R SR_SWINHI per store, 6 % of the forward kernel's warp samples)
   if (kPair && rmbar != 0u) st_async_v4(addr, a, b, c, d, rmbar);
-  else if (kPair) st_cluster_v4(addr, a, b, c, d);
   else asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 constexpr uint32_t kRemoteChunkBytes = 8u * 32u * 8u * 16u;   // 8 warps x 32 features x (4 row chunks x hi, lo) x 16 B
@@ -968,7 +969,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_fwd(const __grid_constant__
     const int tsel = kPair ? cgp >> 1 : static_cast<int>(crank);
     const int t = threadIdx.x;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t hdst = kPair ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel)) : smem_u32(smem + kOffHhi);
+    const uint32_t hdst = (kPair && tsel != static_cast<int>(crank)) ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel))
+                                                                      : smem_u32(smem + kOffHhi);
     const uint32_t in_ready_leader = kPair ? mapa_u32(B.in_ready, 0) : 0u;
     const uint32_t hready_leader = kPair ? mapa_u32(&B.hready[0], 0) : 0u;
     const uint32_t xfree_peer = kPair ? mapa_u32(B.xfree, crank ^ 1u) : 0u;
@@ -1278,7 +1280,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tcl_bwd(const __grid_constant__
     const int tsel = kPair ? cgp >> 1 : static_cast<int>(crank);
     const int t = threadIdx.x;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t hdst = kPair ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel)) : smem_u32(smem + kOffHhi);
+    const uint32_t hdst = (kPair && tsel != static_cast<int>(crank)) ? mapa_u32(smem + kOffHhi, static_cast<uint32_t>(tsel))
+                                                                      : smem_u32(smem + kOffHhi);
     const uint32_t in_ready_leader = kPair ? mapa_u32(B.in_ready, 0) : 0u;
     const uint32_t hready_leader = kPair ? mapa_u32(&B.hready[0], 0) : 0u;
     const uint32_t rready_dst = (kPair && tsel != static_cast<int>(crank)) ? mapa_u32(&B.rready[0], static_cast<uint32_t>(tsel)) : 0u;
