@@ -427,6 +427,44 @@ def case_surrogate_observation_blocks(path="tc"):
     return max(worst, bad), 0.0, {}
 
 
+def case_surrogate_other_shapes():
+    """The tensor-core kernel's other admissible shapes — [in <= 3] -> 256 -> 256 -> 256 -> [out <= 32] — on random nets:
+    (in 2, out 5), (in 1, out 16), (in 3, out 32), 1000 rows, against the FFMA kernel (same tolerances as above); and a
+    net outside them ([3] -> 128 -> 128 -> [23]) must take the FFMA kernel (5 launches... here 4: three transposes)."""
+    from dmip import utils_scatterometry as us
+    worst, info = 0.0, {}
+    for in_dim, out_dim in ((2, 5), (1, 16), (3, 32)):
+        torch.manual_seed(10 * in_dim + out_dim)
+        fm = torch.nn.Sequential(torch.nn.Linear(in_dim, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                                 torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, out_dim)).to(DEV)
+        for p in fm.parameters():
+            p.requires_grad = False
+        sp = [(m.weight.detach().cpu(), m.bias.detach().cpu()) for m in fm if isinstance(m, torch.nn.Linear)]
+        x = torch.rand(1000, in_dim) * 2.4 - 1.2
+        with torch.no_grad():
+            y = fm(x.to(DEV)) + 0.05 * torch.randn(1000, out_dim, device=DEV)
+        keep = ~_kink_rows(sp, x)
+        for mode in (us.SURR_ENERGY, us.SURR_LIK_VJP):
+            _surrogate_path("tc")
+            E, g, f = us.surrogate_call(fm, x.to(DEV), y, 0.2, 0.01, 1000.0, mode=mode, want_fx=True)
+            n_tc = us.surrogate_call.last_launch_count
+            _surrogate_path("ffma")
+            try:
+                E2, g2, f2 = us.surrogate_call(fm, x.to(DEV), y, 0.2, 0.01, 1000.0, mode=mode, want_fx=True)
+            finally:
+                _surrogate_path("tc")
+            e_f = (f - f2).abs().max().item() / (1e-5 * max(1.0, f2.abs().max().item()))
+            e_E = ((E - E2).abs() / (2e-4 * E2.abs() + 1e-2)).max().item() if E is not None else 0.0
+            e_g = (g - g2).cpu()[keep].abs().max().item() / (2e-4 * g2.abs().max().item())
+            info[f"{in_dim}_{out_dim}_{mode}"] = max(e_f, e_E, e_g)
+            worst = max(worst, e_f, e_E, e_g, 0.0 if n_tc == 2 else 2.0, 0.0 if keep.float().mean().item() >= 0.9 else 2.0)
+    small = torch.nn.Sequential(torch.nn.Linear(3, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
+                                torch.nn.Linear(128, 23)).to(DEV)
+    us.surrogate_call(small, torch.rand(64, 3, device=DEV), torch.rand(64, 23, device=DEV), 0.2, 0.01, 1000.0)
+    worst = max(worst, 0.0 if us.surrogate_call.last_launch_count == 4 else 2.0)
+    return worst, 1.0, info
+
+
 def case_surrogate_tc_vs_ffma(n=100003):
     """The tensor-core kernel against the fp32 FFMA kernel on `n` random rows of the prior box and beyond (|x| <= 1.2:
     boundary terms on), one observation per row — both modes, a ragged last tile, many tiles per CTA: f 2e-5, E 2e-4 rel

@@ -57,6 +57,10 @@ def test_surrogate_one_observation_per_block_of_rows(path):
     _ok(gc.case_surrogate_observation_blocks(path))
 
 
+def test_surrogate_tensor_core_kernel_other_input_and_output_widths():
+    _ok(gc.case_surrogate_other_shapes())
+
+
 def test_surrogate_tensor_core_kernel_matches_the_fp32_kernel_on_100003_rows():
     _ok(gc.case_surrogate_tc_vs_ffma())
 
