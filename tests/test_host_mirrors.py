@@ -95,3 +95,66 @@ def test_debiased_t_sampler_follows_its_analytic_distribution():
     edges = np.array([te, 0.01, 0.05, 0.2, 0.5, 1.0])
     emp = np.histogram(draws, bins=edges)[0] / len(draws)
     assert np.allclose(emp, np.diff(cdf(edges)), atol=0.012)
+
+
+def test_bf16x3_split_products_meet_the_surrogate_tolerances_on_the_reference_fixture():
+    """The arithmetic of the tensor-core K4 kernel (csrc/dmip_surrogate_tc.cu), emulated on the CPU: the two 256 x 256
+    layers and the output layer as bf16x3 split products (x = hi + lo, both bf16; hi hi + hi lo + lo hi), layer 0 and the
+    input gradient in fp32 — against the reference's autograd values of scat_energy.npz in the units of the GPU test:
+    f 2e-5, E 2e-4 rel (+1e-2), gradient 2e-4 of its scale on the rows away from a ReLU kink.  Plain bf16 operands must
+    MISS them (that is why the kernel splits)."""
+    import numpy as np
+    from util import surrogate_params
+    fx = load_golden("scat_energy")
+    sp = [(W.double().numpy(), b.double().numpy()) for W, b in surrogate_params()]
+    x, y = fx["x"].double().numpy(), fx["y"].double().numpy()
+
+    def bf(v):
+        return torch.from_numpy(np.asarray(v, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).double().numpy()
+
+    def mm(A, B, parts):
+        if parts == 0:
+            return (A.astype(np.float32) @ B.astype(np.float32)).astype(np.float64)
+        a_hi, b_hi = bf(A), bf(B)
+        if parts == 1:
+            return (a_hi @ b_hi).astype(np.float32).astype(np.float64)
+        a_lo, b_lo = bf(A.astype(np.float32).astype(np.float64) - a_hi), bf(B.astype(np.float32).astype(np.float64) - b_hi)
+        return (a_hi @ b_hi + a_hi @ b_lo + a_lo @ b_hi).astype(np.float32).astype(np.float64)
+
+    def run(parts):
+        f32 = lambda v: v.astype(np.float32).astype(np.float64)
+        z, h = [], x
+        for l, (W, b) in enumerate(sp):
+            zz = f32(mm(h, W.T, 0 if l == 0 else parts) + b)
+            z.append(zz)
+            h = np.maximum(zz, 0) if l < 3 else zz
+        f = h
+        pre = (0.2 * f) ** 2 + 0.01 ** 2
+        E = 0.5 * np.log(pre).sum(1) + 0.5 * ((y - f) ** 2 / pre).sum(1) + 1000.0 * (np.maximum(x - 1, 0) + np.maximum(-1 - x, 0)).sum(1)
+        g = f32(0.04 * f / pre - (y - f) / pre - (y - f) ** 2 * 0.04 * f / pre ** 2)
+        for l in (3, 2, 1, 0):
+            g = f32(mm(g, sp[l][0], 0 if l == 0 else parts))
+            if l > 0:
+                g = g * (z[l - 1] > 0)
+        g = g + 1000.0 * ((x > 1).astype(float) - (x < -1).astype(float))
+        return f, E, g
+
+    # rows away from a ReLU kink (tests/gpu_cases.py:_kink_rows)
+    h, mn = x, np.full(x.shape[0], np.inf)
+    for W, b in sp[:-1]:
+        zz = h @ W.T + b
+        mn = np.minimum(mn, np.abs(zz).min(1))
+        h = np.maximum(zz, 0)
+    keep = mn >= 2e-5
+    assert keep.mean() >= 0.95
+    ref_f, ref_E, ref_g = fx["fx"].double().numpy(), fx["E"].double().numpy(), fx["grad"].double().numpy()
+
+    def errs(parts):
+        f, E, g = run(parts)
+        return (np.abs(f - ref_f).max() / 2e-5, (np.abs(E - ref_E) / (2e-4 * np.abs(ref_E) + 1e-2)).max(),
+                np.abs(g - ref_g)[keep].max() / (2e-4 * np.abs(ref_g).max()))
+
+    e3 = errs(3)
+    assert max(e3) < 0.5, e3          # bf16x3: inside every tolerance with a factor 2 to spare
+    e1 = errs(1)
+    assert min(e1) > 10.0, e1         # plain bf16 operands: outside every tolerance by more than 10x
