@@ -7,6 +7,8 @@ bit-identical to a single-GPU run of the same seed.  Training is data parallel: 
 its slice of the batch with means taken over the GLOBAL batch (`batch_global`), so one SUM all-reduce of the flat
 gradient (2-4 MB, NCCL over NVLink) plus the 4 loss scalars reproduces the single-process step.
 """
+import gc
+
 import torch
 import torch.distributed as dist
 
@@ -199,8 +201,17 @@ class GraphedTrainStep:
                 self._body(step=False)
         torch.cuda.current_stream(x.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.info = self._body(step=self.step_in_graph)
+        # No garbage collection inside the capture: collecting an older model's captured step there destroys ITS graph
+        # while this stream is capturing, which invalidates the capture (seen with a second model in one process).
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss, self.info = self._body(step=self.step_in_graph)
+        finally:
+            if gc_was_on:
+                gc.enable()
 
     @staticmethod
     def key_of(optimizer, loss_fn, x, y):

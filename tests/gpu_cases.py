@@ -1514,3 +1514,25 @@ def case_mlp_autograd(which):
         e = ((a.double() - b).abs().max() / b.abs().max()).item()
         worst = max(worst, e / (2e-5 if i == 0 else 3e-4))
     return worst, 1.0, {}
+
+
+def case_graphed_steps_of_successive_models():
+    """Three models in one process, each with a captured training step (eager Adam, capturable Adam, eager Adam): the
+    capture of a later model must not be invalidated by the collection of an earlier model's graph (GraphedTrainStep
+    keeps the garbage collector out of the capture) — the config0 bench line's loop.  Every epoch must lower the loss."""
+    from dmip import losses as dl
+    from dmip.models.diffusion import CDiffE
+    worst = 0.0
+    for capturable in (False, True, False):
+        torch.manual_seed(0)
+        model = CDiffE(2, 2, [512, 512, 512])
+        model.sde.to(DEV)
+        opt = torch.optim.Adam(model.sde.a.parameters(), lr=1e-3, capturable=capturable)
+        g = torch.Generator().manual_seed(2)
+        x = torch.randn(4000, 2, generator=g).to(DEV)
+        y = (x + 0.3 * torch.randn(4000, 2, generator=g).to(DEV))
+        loader = lambda: ((x[i:i + 1000], y[i:i + 1000]) for i in range(0, 4000, 1000))
+        losses = [float(model.train_epoch(opt, dl.DSMLoss(), loader, graph=True)[0]) for _ in range(6)]
+        captured = model.__dict__.get('_graphed_step') is not None
+        worst = max(worst, 0.0 if (captured and losses[-1] < losses[0] and all(np.isfinite(losses))) else 1.0)
+    return worst, 0.0, {}

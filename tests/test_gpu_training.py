@@ -45,3 +45,8 @@ def test_train_epoch_as_cuda_graph_replays(loss_name, capturable):
     """graph=True: every batch is one replay of the captured step (eager or captured optimizer); same learning criteria"""
     err, tol, extra = gc.case_train_epoch(loss_name, graph=True, capturable=capturable)
     assert err <= tol, extra
+
+
+def test_graphed_steps_of_successive_models_in_one_process():
+    err, tol, extra = gc.case_graphed_steps_of_successive_models()
+    assert err <= tol, extra
