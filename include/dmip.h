@@ -241,7 +241,11 @@ int dmip_loss_fwd_bwd(const DmipLoss* d, void* stream);
  *                           (main_diffusion_scatterometry.py:142-145) and the drift of the Metropolis reference chain.
  *   mode DMIP_SURR_LIK_VJP  grad[i] = J_f(x_i)^T (-a^2 v1 + v2 + a^2 v3), the three surrogate VJPs of
  *                           PosteriorLoss.likelihood_target (losses.py:349-371) merged; `energy` unused.
- * fx (optional): f(x) (n, out_dim).  Any widths <= 512, 2..DMIP_MAX_LAYERS layers. */
+ * fx (optional): f(x) (n, out_dim).  Any widths <= 512, 2..DMIP_MAX_LAYERS layers.
+ * Nets of the reference's surrogate shape — [in <= 3] -> 256 -> 256 -> 256 -> [out <= 32] — run the tcgen05 kernel
+ * (csrc/dmip_surrogate_tc.cu: bf16x3 split products, fp32 accumulate: f to ~5e-6 relative, energy and gradient within 2e-4;
+ * the gradient of a row within rounding distance of a ReLU kink may take the other side's value), every other net the
+ * fp32 FFMA kernel; DMIP_SURROGATE_PATH=ffma in the environment forces the FFMA kernel. */
 #define DMIP_SURR_ENERGY 0
 #define DMIP_SURR_LIK_VJP 1
 
