@@ -76,16 +76,18 @@ def surrogate_call(forward_model, x, y, a, b, lambd_bd=0.0, mode=SURR_ENERGY, wa
     d.n = n
     d.rows_per_obs = rows_per_obs
     d.x, d.y = x.data_ptr(), y.data_ptr()
-    energy = torch.empty(n, device=x.device) if mode == SURR_ENERGY else None
-    grad = torch.empty_like(x)
-    fx = torch.empty(n, d.net.out_dim, device=x.device) if want_fx else None
+    guard = _lib.Guarded()                 # DMIP_GUARD=1: canaries around every buffer the kernels write (debugging)
+    energy = guard.empty(n, torch.float32, x.device) if mode == SURR_ENERGY else None
+    grad = guard.empty(x.numel(), torch.float32, x.device).view_as(x)
+    fx = guard.empty(n * d.net.out_dim, torch.float32, x.device).view(n, d.net.out_dim) if want_fx else None
     d.energy = energy.data_ptr() if energy is not None else None
     d.grad = grad.data_ptr()
     d.fx = fx.data_ptr() if fx is not None else None
-    ws = torch.empty(max(L.dmip_surrogate_workspace_bytes(C.byref(d)), 16), dtype=torch.uint8, device=x.device)
+    ws = guard.empty(max(L.dmip_surrogate_workspace_bytes(C.byref(d)), 16), torch.uint8, x.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     with torch.cuda.device(x.device):
         _lib.check(L.dmip_surrogate_score(C.byref(d), _lib.stream_ptr()))
+    guard.check("dmip_surrogate_score")
     surrogate_call.last_launch_count = L.dmip_last_launch_count()
     return energy, grad, fx
 

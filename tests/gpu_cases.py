@@ -1391,7 +1391,7 @@ def case_guarded_buffers():
     with DMIP_GUARD=1 every output / scratch buffer handed to the library is wrapped in 4 KB canaries that are verified
     after the call (dmip._lib.Guarded) — the packed workspace of the tcgen05 loss path (images, stashes, adjoints), the
     flat gradient, the loss scalars and the sampler's output, over ragged batch sizes (tile tails, masked cluster CTAs)
-    and all three sampler variants."""
+    and all three sampler variants; the surrogate kernels' outputs and workspace (weight images) at ragged row counts."""
     import os
     from dmip import losses as dl
     from dmip.models.diffusion import CDE
@@ -1418,8 +1418,20 @@ def case_guarded_buffers():
             for N in (1, 127, 129, 300):
                 for prec in ("bf16", "fp32"):
                     ms(yv, num_samples=N, num_steps=3, precision=prec, seed=1, n_corrector=1)
+        # K4, both kernel families: ragged row counts, with and without the optional outputs, one observation for all rows
+        from dmip import utils_scatterometry as us
+        fm, _ = _surrogate_module()
+        fxs = load_golden("scat_energy")
+        for path in ("tc", "ffma"):
+            _surrogate_path(path)
+            for n in (1, 127, 128, 129, 512):
+                xs, ysn = fxs["x"][:n].to(DEV), fxs["y"][:n].to(DEV)
+                us.surrogate_call(fm, xs, ysn, 0.2, 0.01, 1000.0, want_fx=True)
+                us.surrogate_call(fm, xs, ysn[:1], 0.2, 0.01, 1000.0, mode=us.SURR_LIK_VJP)
+        _surrogate_path("tc")
     finally:
         os.environ.pop("DMIP_GUARD", None)
+        os.environ.pop("DMIP_SURROGATE_PATH", None)
         os.environ.pop("DMIP_LOSS_PATH", None)
     return 0.0, 0.5, {}
 
