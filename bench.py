@@ -620,6 +620,8 @@ def also_surrogate(rows=256 * 65536, steps=3, warmup=2):
         roof = tensor_roofline(ach, sustained=False, flop_per_row=SURR_FLOP,
                                kernel="k_surrogate_tc (bf16x3 split: 3 tensor-core FLOP per algorithmic FLOP)",
                                tensor_flops_issued_tflops=3 * ach)
+        tr = load_traffic().get("k_surrogate_tc_dram_bytes_per_launch", {})
+        roof["traffic"] = tr.get(f"{chunk}_rows")          # per launch (one 4M-row call), like `achieved`'s launch duration
     return {"config": f"K4 surrogate energy + score, {rows} rows (256 observations x 65,536 particles), in calls of {chunk} rows",
             "value": rows / (ms * 1e-3), "unit": "rows/s", "ms": ms, "dtype": "f32" if ffma else "bf16x3",
             "gpu_launches": n_chunks * steps * (5 if ffma else 2), "roofline": roof,
