@@ -43,8 +43,8 @@ constexpr int kOffB1 = kOffW0 + 4096;          // float[256]
 constexpr int kOffB2 = kOffB1 + 1024;
 constexpr int kOffB3 = kOffB2 + 1024;          // float[32]
 constexpr int kOffPart = kOffB3 + 128;         // float4[4][128]: the four feature quarters' shares of the input gradient
-constexpr int kOffE = kOffPart + 8192;         // float[128]: energy share of outputs 16.. (second output unit)
-constexpr int kOffMask = kOffE + 512;          // uint32[3 layers][2 words][512 row threads]: ReLU patterns of the thread's 64 features
+constexpr int kOffE = kOffPart + 8192;         // float[3][128]: energy shares of outputs 8.., 16.., 24.. (threads sub 1-3 of a row)
+constexpr int kOffMask = kOffE + 2048;          // uint32[3 layers][2 words][512 row threads]: ReLU patterns of the thread's 64 features
 constexpr int kOffBars = kOffMask + 12288;     // full[6] empty[6] a_ready[2] acc_full[2], tmem holder
 constexpr int kTSmem = kOffBars + 256;
 
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_hi = A + 16u * ks, a_lo = a_hi + 8u;
+                const uint32_t a_hi = A + 32u + 16u * ks, a_lo = a_hi + 8u;   // fbar sits beside f: columns 32-63
                 const uint64_t b_hi = dMN3 | (st16 + c * 512u + ks * 128u), b_lo = b_hi + 1024u;
                 umma_ts(D + 128u * c, a_hi, b_hi, iB, ks > 0 ? 1u : 0u);
                 umma_ts(D + 128u * c, a_hi, b_lo, iB, 1u);
@@ -493,20 +493,21 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           publish(&B.a_ready[p], lane);
         }
       }
-      // ---- P3: f = acc + b3 (G3 -> Y[0, 32)), energy, cotangent: outputs [0, 16) by the sub 0 thread of the row,
-      //      outputs [16, 32) by its sub 1 thread
+      // ---- P3: f = acc + b3 (G3 -> Y[0, 32)), energy, cotangent: the four threads of a row take 8 outputs each and write
+      //      their share of the cotangent operand (two units: hi 8 + lo 8 columns each) BESIDE f, into Y[32, 64) — nobody
+      //      overwrites a column another thread of the row still has to read
       wait_part(0, 0x320);
-      if (sub < 2) {
+      {
         const float* yrow = P.y + (P.rpo > 0 ? grow / P.rpo : grow) * od;
-        uint32_t u[16];
-        tmem_ld16(lt + 256u + 16u * sub, u);
+        uint32_t u[8];
+        tmem_ld8(lt + 256u + 8u * sub, u);
         tc_wait_ld();
-        float w[16];
+        float w[8];
         float E = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 8; ++e) {
           float we = 0.f;
-          const int o = 16 * sub + e;
+          const int o = 8 * sub + e;
           if (o < od) {
             const float f = __uint_as_float(u[e]) + sB3[o];
             const float yv = live ? yrow[o] : 0.f;
@@ -523,22 +524,23 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           }
           w[e] = we;
         }
-        store_unit(lt + 256u + 16u * sub, w);
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_pair(w[2 * e], w[2 * e + 1], hi[e], lo[e]);
+        const uint32_t dst = lt + 256u + 32u + 16u * (sub >> 1) + 4u * (sub & 1);   // unit sub / 2, pairs 4 (sub % 2) ..
+        tmem_st4(dst, hi[0], hi[1], hi[2], hi[3]);
+        tmem_st4(dst + 8u, lo[0], lo[1], lo[2], lo[3]);
         publish(&B.a_ready[0], lane);
         if (mode == 0 && P.energy) {
-          if (sub == 1) sE[row] = E;
-          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (sub != 0) sE[(sub - 1) * 128 + row] = E;
+          asm volatile("bar.sync 2, 512;" ::: "memory");
           if (sub == 0 && live) {
-            E += sE[row];
+            E += sE[row] + sE[128 + row] + sE[256 + row];
             E += lambd * (fmaxf(x0 - 1.f, 0.f) + fmaxf(-1.f - x0, 0.f) + fmaxf(x1 - 1.f, 0.f) + fmaxf(-1.f - x1, 0.f) +
                           fmaxf(x2 - 1.f, 0.f) + fmaxf(-1.f - x2, 0.f));
             P.energy[grow] = E;
           }
         }
-      } else {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&B.a_ready[0]);
       }
       // ---- P4: h3bar = acc masked by h3 > 0 (G4 -> X);  P5: h2bar (G5 -> Y)
 #pragma unroll 1
