@@ -496,9 +496,13 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
       // ---- P3: f = acc + b3 (G3 -> Y[0, 32)), energy, cotangent: the four threads of a row take 8 outputs each and write
       //      their share of the cotangent operand (two units: hi 8 + lo 8 columns each) BESIDE f, into Y[32, 64) — nobody
       //      overwrites a column another thread of the row still has to read
-      wait_part(0, 0x320);
       {
+        // the observation's 8 values first: their latency runs under the wait for the output layer's GEMM
         const float* yrow = P.y + (P.rpo > 0 ? grow / P.rpo : grow) * od;
+        float yv8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv8[e] = (live && 8 * sub + e < od) ? yrow[8 * sub + e] : 0.f;
+        wait_part(0, 0x320);
         uint32_t u[8];
         tmem_ld8(lt + 256u + 8u * sub, u);
         tc_wait_ld();
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_surrogate_tc(const __grid_cons
           const int o = 8 * sub + e;
           if (o < od) {
             const float f = __uint_as_float(u[e]) + sB3[o];
-            const float yv = live ? yrow[o] : 0.f;
+            const float yv = yv8[e];
             const float p = a2 * f * f + bb2;
             const float ip = __frcp_rn(p);
             const float r = yv - f;
